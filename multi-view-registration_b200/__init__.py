@@ -1,0 +1,315 @@
+"""Python binding of libmvr_b200.so -- the B200-native ICP alignment path.
+
+This package is a thin ctypes layer over the C ABI in include/mvr_b200.h (the drop-in boundary for
+the PCL calls the reference makes in mvr/src/registrator.cpp).  It contains no arithmetic of its own
+and NO fallback: if the CUDA library is missing or no CUDA device is usable, it raises.
+
+The directory name contains '-', so import it through the `mvr_b200` shim at the repo root.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmvr_b200.so")
+
+K_NAMES = ["morton", "sort", "table", "nn", "corr", "reduce", "transform", "normals"]
+K_COUNT = 8
+(OK, ERR_BAD_ARG, ERR_TOO_FEW, ERR_CUDA, ERR_NO_INPUT, ERR_NOT_SPD, ERR_ALLOC) = range(7)
+TARGET, SOURCE = 0, 1
+POINT_TO_POINT, POINT_TO_PLANE = 0, 1
+
+
+class MvrError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("mvr status %d: %s" % (status, msg))
+        self.status = status
+
+
+class IcpParams(C.Structure):
+    _fields_ = [
+        ("max_iterations", C.c_int),
+        ("max_correspondence_distance", C.c_double),
+        ("transformation_epsilon", C.c_double),
+        ("euclidean_fitness_epsilon", C.c_double),
+        ("use_reciprocal_correspondences", C.c_int),
+        ("estimator", C.c_int),
+        ("fixed_iterations", C.c_int),
+        ("min_correspondences", C.c_int),
+    ]
+
+
+class IcpReport(C.Structure):
+    _fields_ = [
+        ("iterations", C.c_int),
+        ("converged", C.c_int),
+        ("reason", C.c_int),
+        ("n_correspondences", C.c_int),
+        ("mse", C.c_double),
+        ("gpu_ms", C.c_double),
+        ("nn_queries", C.c_uint64),
+    ]
+
+
+class IcpIteration(C.Structure):
+    _fields_ = [("iteration", C.c_int), ("n_correspondences", C.c_int), ("mse", C.c_double), ("delta", C.c_float * 16)]
+
+
+class Grid(C.Structure):
+    _fields_ = [("origin", C.c_float * 3), ("inv_cell", C.c_float), ("cell", C.c_float), ("bits", C.c_int)]
+
+
+class KernelStat(C.Structure):
+    _fields_ = [("launches", C.c_uint64), ("ms", C.c_double), ("bytes", C.c_double), ("units", C.c_double)]
+
+
+class TurntableParams(C.Structure):
+    _fields_ = [
+        ("n_views", C.c_int),
+        ("pivot", C.c_double * 3),
+        ("axis", C.c_double * 3),
+        ("icp", IcpParams),
+        ("repeat_times", C.c_int),
+        ("loop_closure", C.c_int),
+        ("lum_iterations", C.c_int),
+        ("pair_begin", C.c_int),
+        ("pair_end", C.c_int),
+    ]
+
+
+class PairReport(C.Structure):
+    _fields_ = [
+        ("source_view", C.c_int),
+        ("target_view", C.c_int),
+        ("status", C.c_int),
+        ("iterations", C.c_int),
+        ("n_correspondences", C.c_int),
+        ("mse", C.c_double),
+        ("gpu_ms", C.c_double),
+        ("nn_queries", C.c_uint64),
+        ("pose", C.c_float * 16),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load libmvr_b200.so; raises if it has not been built (there is no other implementation)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libmvr_b200.so is not built: run `python __graft_entry__.py build` "
+                          "(the CUDA library is the only implementation; there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, fp, ip, up = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_uint32)
+    L.mvr_version.restype = C.c_char_p
+    L.mvr_status_string.restype = C.c_char_p
+    L.mvr_status_string.argtypes = [C.c_int]
+    L.mvr_icp_params_default.argtypes = [C.POINTER(IcpParams)]
+    L.mvr_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.mvr_ctx_destroy.argtypes = [vp]
+    L.mvr_ctx_set_stream.argtypes = [vp, vp]
+    L.mvr_ctx_synchronize.argtypes = [vp]
+    L.mvr_last_error.argtypes = [vp]
+    L.mvr_last_error.restype = C.c_char_p
+    L.mvr_ctx_set_profiling.argtypes = [vp, C.c_int]
+    L.mvr_ctx_get_kernel_stats.argtypes = [vp, C.POINTER(KernelStat), C.c_int]
+    L.mvr_ctx_set_index_options.argtypes = [vp, C.c_float, C.c_int]
+    for name in ("mvr_set_target", "mvr_set_source", "mvr_set_target_device", "mvr_set_source_device", "mvr_set_target_normals"):
+        getattr(L, name).argtypes = [vp, vp, C.c_size_t]
+    L.mvr_index_build.argtypes = [vp, C.c_int, C.POINTER(Grid)]
+    L.mvr_index_export.argtypes = [vp, C.c_int, C.POINTER(Grid), up, ip, up]
+    L.mvr_nn_query.argtypes = [vp, fp, C.c_size_t, ip, fp]
+    L.mvr_nn_query_device.argtypes = [vp, vp, C.c_size_t, vp, vp]
+    L.mvr_correspondences.argtypes = [vp, C.c_double, C.c_int, ip, ip, fp, C.POINTER(C.c_size_t)]
+    L.mvr_icp_align.argtypes = [vp, C.POINTER(IcpParams), fp, fp, vp, C.POINTER(IcpReport)]
+    L.mvr_icp_get_iterations.argtypes = [vp, C.POINTER(IcpIteration), C.c_int, C.POINTER(C.c_int)]
+    L.mvr_fitness_score.argtypes = [vp, C.c_double, C.POINTER(C.c_double)]
+    L.mvr_estimate_normals.argtypes = [vp, C.c_int, C.c_int, fp, fp, ip]
+    _lib = L
+    return L
+
+
+def default_params(**kw):
+    """mvr_icp_params with PCL's defaults, overridden by keyword (reference settings:
+    mvr/src/registrator.cpp:551-560)."""
+    p = IcpParams()
+    lib().mvr_icp_params_default(C.byref(p))
+    alias = {"max_dist": "max_correspondence_distance", "reciprocal": "use_reciprocal_correspondences"}
+    for k, v in kw.items():
+        setattr(p, alias.get(k, k), v)
+    return p
+
+
+def _pts(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] != 4:
+        raise ValueError("points must be n x 4 float32 (pcl::PointXYZ layout)")
+    return a
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _up(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint32))
+
+
+def pose_to_numpy(flat16):
+    """column-major float[16] (Eigen::Matrix4f) -> 4x4 numpy (row-major view of the same matrix)."""
+    return np.asarray(flat16, dtype=np.float32).reshape(4, 4).T.copy()
+
+
+def pose_from_numpy(M):
+    return np.ascontiguousarray(np.asarray(M, dtype=np.float32).T).reshape(16)
+
+
+class Context:
+    """One CUDA device + stream; mirrors a pcl::IterativeClosestPoint instance holding its
+    source/target (Registrator::icp_, mvr/include/registrator.h:91)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().mvr_ctx_create(int(device), C.byref(self._h))
+        if rc != OK:
+            raise MvrError(rc, "mvr_ctx_create failed (no usable CUDA device %d; there is no CPU fallback)" % device)
+        self._keep = {}
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().mvr_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, allow=()):
+        if rc != OK and rc not in allow:
+            raise MvrError(rc, (lib().mvr_last_error(self._h) or b"").decode() or lib().mvr_status_string(rc).decode())
+        return rc
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(lib().mvr_ctx_set_stream(self._h, C.c_void_p(int(cuda_stream_ptr))))
+
+    def synchronize(self):
+        self._ck(lib().mvr_ctx_synchronize(self._h))
+
+    def set_profiling(self, on):
+        self._ck(lib().mvr_ctx_set_profiling(self._h, int(bool(on))))
+
+    def kernel_stats(self, reset=False):
+        arr = (KernelStat * K_COUNT)()
+        self._ck(lib().mvr_ctx_get_kernel_stats(self._h, arr, int(bool(reset))))
+        return {K_NAMES[i]: dict(launches=int(arr[i].launches), ms=arr[i].ms, bytes=arr[i].bytes, units=arr[i].units)
+                for i in range(K_COUNT)}
+
+    def set_index_options(self, cell_edge=0.0, max_bits=8):
+        self._ck(lib().mvr_ctx_set_index_options(self._h, C.c_float(cell_edge), int(max_bits)))
+
+    # -- inputs --------------------------------------------------------------------------------
+    def set_target(self, pts):
+        pts = _pts(pts)
+        self._ck(lib().mvr_set_target(self._h, pts.ctypes.data, len(pts)))
+
+    def set_source(self, pts):
+        pts = _pts(pts)
+        self._ck(lib().mvr_set_source(self._h, pts.ctypes.data, len(pts)))
+
+    def set_target_device(self, ptr, n, keepalive=None):
+        self._keep["tgt"] = keepalive
+        self._ck(lib().mvr_set_target_device(self._h, C.c_void_p(int(ptr)), int(n)))
+
+    def set_source_device(self, ptr, n, keepalive=None):
+        self._keep["src"] = keepalive
+        self._ck(lib().mvr_set_source_device(self._h, C.c_void_p(int(ptr)), int(n)))
+
+    def set_target_normals(self, nrm):
+        nrm = _pts(nrm)
+        self._ck(lib().mvr_set_target_normals(self._h, nrm.ctypes.data, len(nrm)))
+
+    # -- index ---------------------------------------------------------------------------------
+    def index_build(self, which=TARGET, grid=None):
+        g = None
+        if grid is not None:
+            g = Grid()
+            g.origin[:] = [float(x) for x in grid["origin"]]
+            g.inv_cell = float(grid["inv_cell"])
+            g.cell = float(grid.get("cell", 1.0 / grid["inv_cell"]))
+            g.bits = int(grid["bits"])
+        self._ck(lib().mvr_index_build(self._h, int(which), C.byref(g) if g is not None else None))
+
+    def index_export(self, which, n):
+        g = Grid()
+        self._ck(lib().mvr_index_export(self._h, int(which), C.byref(g), None, None, None))
+        keys = np.empty(n, dtype=np.uint32)
+        perm = np.empty(n, dtype=np.int32)
+        start = np.empty((1 << (3 * g.bits)) + 1, dtype=np.uint32)
+        self._ck(lib().mvr_index_export(self._h, int(which), C.byref(g), _up(keys), _ip(perm), _up(start)))
+        grid = dict(origin=np.array(g.origin[:], dtype=np.float32), inv_cell=np.float32(g.inv_cell), cell=np.float32(g.cell), bits=g.bits)
+        return grid, keys, perm, start
+
+    # -- queries -------------------------------------------------------------------------------
+    def nn_query(self, q):
+        q = _pts(q)
+        idx = np.empty(len(q), dtype=np.int32)
+        d2 = np.empty(len(q), dtype=np.float32)
+        self._ck(lib().mvr_nn_query(self._h, _fp(q), len(q), _ip(idx), _fp(d2)))
+        return idx, d2
+
+    def nn_query_device(self, q_ptr, n, idx_ptr, d2_ptr):
+        self._ck(lib().mvr_nn_query_device(self._h, C.c_void_p(int(q_ptr)), int(n), C.c_void_p(int(idx_ptr)), C.c_void_p(int(d2_ptr))))
+
+    def correspondences(self, n_source, max_dist, reciprocal):
+        q = np.empty(max(n_source, 1), dtype=np.int32)
+        m = np.empty(max(n_source, 1), dtype=np.int32)
+        d = np.empty(max(n_source, 1), dtype=np.float32)
+        cnt = C.c_size_t(0)
+        self._ck(lib().mvr_correspondences(self._h, float(max_dist), int(bool(reciprocal)), _ip(q), _ip(m), _fp(d), C.byref(cnt)))
+        c = cnt.value
+        return q[:c].copy(), m[:c].copy(), d[:c].copy()
+
+    # -- ICP -----------------------------------------------------------------------------------
+    def icp_align(self, params, guess=None, n_source=None, want_cloud=False):
+        """Returns dict(status, final 4x4, cloud or None, iterations, converged, reason, n_corr, mse,
+        gpu_ms, nn_queries, log).  status MVR_ERR_TOO_FEW_CORRESPONDENCES is reported, not raised."""
+        g = pose_from_numpy(guess) if guess is not None else None
+        fin = np.empty(16, dtype=np.float32)
+        cloud = np.empty((n_source, 4), dtype=np.float32) if want_cloud else None
+        rep = IcpReport()
+        rc = lib().mvr_icp_align(self._h, C.byref(params), _fp(g) if g is not None else None, _fp(fin),
+                                 cloud.ctypes.data if cloud is not None else None, C.byref(rep))
+        self._ck(rc, allow=(ERR_TOO_FEW, ERR_NOT_SPD))
+        cnt = C.c_int(0)
+        lib().mvr_icp_get_iterations(self._h, None, 0, C.byref(cnt))
+        recs = (IcpIteration * max(cnt.value, 1))()
+        lib().mvr_icp_get_iterations(self._h, recs, cnt.value, C.byref(cnt))
+        log = [dict(iteration=recs[k].iteration, n_corr=recs[k].n_correspondences, mse=recs[k].mse,
+                    delta=pose_to_numpy(recs[k].delta[:])) for k in range(cnt.value)]
+        return dict(status=rc, final=pose_to_numpy(fin), cloud=cloud, iterations=rep.iterations, converged=rep.converged,
+                    reason=rep.reason, n_corr=rep.n_correspondences, mse=rep.mse, gpu_ms=rep.gpu_ms,
+                    nn_queries=int(rep.nn_queries), log=log)
+
+    def fitness_score(self, max_range=None):
+        import sys
+        s = C.c_double(0)
+        self._ck(lib().mvr_fitness_score(self._h, sys.float_info.max if max_range is None else float(max_range), C.byref(s)))
+        return s.value
+
+    def estimate_normals(self, which, n, k, viewpoint=(0.0, 0.0, 0.0), want_neighbours=False):
+        vp = np.ascontiguousarray(viewpoint, dtype=np.float32)
+        out = np.empty((n, 4), dtype=np.float32)
+        nbr = np.empty((n, k), dtype=np.int32) if want_neighbours else None
+        self._ck(lib().mvr_estimate_normals(self._h, int(which), int(k), _fp(vp), _fp(out), _ip(nbr) if nbr is not None else None))
+        return (out, nbr) if want_neighbours else out

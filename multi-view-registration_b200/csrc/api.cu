@@ -1,0 +1,811 @@
+// api.cu -- context, host-side ICP loop and the extern "C" boundary declared in include/mvr_b200.h.
+//
+// Host logic mirrors pcl::IterativeClosestPoint::computeTransformation + DefaultConvergenceCriteria
+// as configured by the reference (mvr/src/registrator.cpp:551-560, 768-771, 901-904):
+// the correspondence search, rejection and estimator sums run in CUDA kernels, the 3x3 SVD / 6x6
+// Cholesky solve and the convergence test run here on 18-29 doubles per iteration.
+// There is no CPU fallback for any device stage.
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mvr_b200.h"
+#include "launch.h"
+#include "small_solve.h"
+
+using namespace mvr;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return (T*)p; }
+};
+
+struct Cloud {
+  const float4* pts = nullptr;
+  DevBuf own;
+  int n = 0;
+  float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  int n_bad = 0;
+  uint64_t gen = 0;
+  // index
+  bool index_valid = false;
+  uint64_t index_gen = 0;
+  mvr_grid grid{};
+  GridDev gd{};
+  DevBuf keys, vals, keys_alt, vals_alt, hist, sorted, table;
+  uint32_t* sorted_keys = nullptr;
+  uint32_t* perm = nullptr;
+  IndexDev dev() const {
+    IndexDev ix;
+    ix.pts = sorted.as<float4>(); ix.start = table.as<uint32_t>(); ix.g = gd; ix.n_valid = n - n_bad;
+    return ix;
+  }
+  void release() { own.release(); keys.release(); vals.release(); keys_alt.release(); vals_alt.release(); hist.release(); sorted.release(); table.release(); }
+};
+
+struct ProfRec { int kind; cudaEvent_t a, b; double bytes, units; };
+
+}  // namespace
+
+struct mvr_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  Cloud tgt, src;
+  DevBuf normals; bool has_normals = false;
+  DevBuf cur, corr_j, corr_d2, partials, sums, out_cloud, qtmp, itmp, ftmp, scratch, misc;
+  double* h_sums = nullptr;      // pinned, REDUCE_MAX_VALS
+  uint32_t* h_small = nullptr;   // pinned, 16 words
+  std::string err;
+  bool profiling = false;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  mvr_kernel_stat stats[MVR_K_COUNT] = {};
+  std::vector<mvr_icp_iteration> iters;
+  bool have_out = false;         // out_cloud holds transform(source, final) of the last align
+  float cell_edge_opt = 0.f;
+  int max_bits_opt = 8;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+};
+
+namespace {
+
+#define CK(expr)                                                                                 \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      ctx->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                             \
+      return MVR_ERR_CUDA;                                                                       \
+    }                                                                                            \
+  } while (0)
+
+int fail(mvr_ctx* ctx, int code, const char* msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+cudaEvent_t get_event(mvr_ctx* ctx) {
+  if (!ctx->ev_pool.empty()) { cudaEvent_t e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct ProfScope {
+  mvr_ctx* ctx; int idx;
+  ProfScope(mvr_ctx* c, int kind, double bytes, double units) : ctx(c), idx(-1) {
+    if (!c->profiling) return;
+    ProfRec r{kind, get_event(c), get_event(c), bytes, units};
+    cudaEventRecord(r.a, c->stream);
+    c->prof.push_back(r);
+    idx = (int)c->prof.size() - 1;
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(ctx->prof[idx].b, ctx->stream); }
+};
+
+void prof_flush(mvr_ctx* ctx) {
+  for (ProfRec& r : ctx->prof) {
+    cudaEventSynchronize(r.b);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      mvr_kernel_stat& s = ctx->stats[r.kind];
+      s.launches += 1; s.ms += ms; s.bytes += r.bytes; s.units += r.units;
+    }
+    ctx->ev_pool.push_back(r.a); ctx->ev_pool.push_back(r.b);
+  }
+  ctx->prof.clear();
+}
+
+// ---- grid selection ---------------------------------------------------------------------------
+// Surface-density heuristic: a scan is a 2-manifold, so the number of occupied cells of edge e is
+// about 1.5 * area / e^2 with area ~ half the bounding-box surface; solve for `ppc` points per cell.
+double density_cell_edge(const float lo[3], const float hi[3], int n, double ppc) {
+  double ex = std::max(0.0, (double)hi[0] - lo[0]), ey = std::max(0.0, (double)hi[1] - lo[1]), ez = std::max(0.0, (double)hi[2] - lo[2]);
+  double area = ex * ey + ey * ez + ex * ez;  // = 0.5 * box surface
+  double ext = std::max(ex, std::max(ey, ez));
+  if (n <= 0 || ext <= 0) return 1.0;
+  if (area <= 0) return ext / std::min(1024.0, std::max(1.0, (double)n / ppc));
+  return std::sqrt(1.5 * ppc * area / (double)n);
+}
+
+mvr_grid make_grid(const float lo[3], const float hi[3], double cell, int max_bits) {
+  mvr_grid g{};
+  double ext = 0;
+  for (int a = 0; a < 3; ++a) ext = std::max(ext, (double)hi[a] - (double)lo[a]);
+  if (!(ext > 0) || !std::isfinite(ext)) ext = 1.0;
+  if (!(cell > 0) || !std::isfinite(cell)) cell = ext;
+  if (max_bits < 1) max_bits = 1;
+  if (max_bits > 10) max_bits = 10;
+  int bits = 1;
+  while (bits < max_bits && cell * (double)(1 << bits) < ext * 1.0001) ++bits;
+  if (cell * (double)(1 << bits) < ext * 1.0001) cell = ext * 1.0001 / (double)(1 << bits);
+  for (int a = 0; a < 3; ++a) g.origin[a] = lo[a];
+  g.inv_cell = (float)(1.0 / cell);
+  g.cell = (float)cell;
+  g.bits = bits;
+  return g;
+}
+
+GridDev to_dev(const mvr_grid& g) {
+  GridDev d;
+  d.ox = g.origin[0]; d.oy = g.origin[1]; d.oz = g.origin[2];
+  d.inv_cell = g.inv_cell;
+  double c = (1.0 / (double)g.inv_cell) * (1.0 - 1e-6);
+  d.cell_lo = std::nextafterf((float)c, 0.0f);
+  d.bits = g.bits;
+  d.G = 1 << g.bits;
+  return d;
+}
+
+bool same_grid(const mvr_grid& a, const mvr_grid& b) {
+  return std::memcmp(a.origin, b.origin, sizeof(a.origin)) == 0 && a.inv_cell == b.inv_cell && a.bits == b.bits;
+}
+
+// ---- clouds -----------------------------------------------------------------------------------
+int cloud_bbox(mvr_ctx* ctx, Cloud& c) {
+  for (int a = 0; a < 3; ++a) { c.lo[a] = 0; c.hi[a] = 0; }
+  c.n_bad = 0;
+  if (c.n <= 0) return MVR_OK;
+  CK(ctx->misc.ensure(64));
+  uint32_t* d = ctx->misc.as<uint32_t>();
+  CK(launch_bbox_init(d, ctx->stream));
+  CK(launch_bbox(c.pts, c.n, d, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_small, d, 7 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  c.n_bad = (int)ctx->h_small[6];
+  if (c.n_bad < c.n)
+    for (int a = 0; a < 3; ++a) { c.lo[a] = bbox_decode(ctx->h_small[a]); c.hi[a] = bbox_decode(ctx->h_small[3 + a]); }
+  return MVR_OK;
+}
+
+int cloud_set(mvr_ctx* ctx, Cloud& c, const float* xyzw, size_t n, bool device_ptr) {
+  if (n > (size_t)INT_MAX / 2) return fail(ctx, MVR_ERR_BAD_ARG, "cloud too large");
+  if (n > 0 && !xyzw) return fail(ctx, MVR_ERR_BAD_ARG, "null point pointer");
+  c.index_valid = false;
+  c.gen++;
+  c.n = (int)n;
+  if (device_ptr) {
+    c.pts = (const float4*)xyzw;
+  } else {
+    CK(c.own.ensure(std::max<size_t>(n, 1) * sizeof(float4)));
+    if (n) CK(cudaMemcpyAsync(c.own.p, xyzw, n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    c.pts = c.own.as<float4>();
+  }
+  return cloud_bbox(ctx, c);
+}
+
+// Build the Morton-sorted grid index of `pts` (n points of cloud c) with grid g.
+int build_index(mvr_ctx* ctx, Cloud& c, const float4* pts, const mvr_grid& g) {
+  const int n = c.n;
+  const size_t cells = (size_t)1 << (3 * g.bits);
+  CK(c.keys.ensure(std::max(n, 1) * sizeof(uint32_t)));
+  CK(c.vals.ensure(std::max(n, 1) * sizeof(uint32_t)));
+  CK(c.keys_alt.ensure(std::max(n, 1) * sizeof(uint32_t)));
+  CK(c.vals_alt.ensure(std::max(n, 1) * sizeof(uint32_t)));
+  CK(c.hist.ensure((size_t)256 * radix_num_blocks(n) * sizeof(uint32_t)));
+  CK(c.sorted.ensure(std::max(n, 1) * sizeof(float4)));
+  CK(c.table.ensure((cells + 2) * sizeof(uint32_t)));
+  c.grid = g;
+  c.gd = to_dev(g);
+  {
+    ProfScope ps(ctx, MVR_K_MORTON, 24.0 * n, n);
+    CK(launch_morton_keys(pts, n, c.gd, c.keys.as<uint32_t>(), c.vals.as<uint32_t>(), ctx->stream));
+  }
+  int key_bits = 3 * g.bits + (c.n_bad > 0 ? 1 : 0);
+  SortScratch sc{c.keys_alt.as<uint32_t>(), c.vals_alt.as<uint32_t>(), c.hist.as<uint32_t>()};
+  {
+    ProfScope ps(ctx, MVR_K_SORT, 16.0 * n, n);
+    CK(launch_radix_sort(c.keys.as<uint32_t>(), c.vals.as<uint32_t>(), n, key_bits, sc, &c.sorted_keys, &c.perm, ctx->stream));
+  }
+  {
+    ProfScope ps(ctx, MVR_K_TABLE, 36.0 * n + 4.0 * (double)cells, n);
+    CK(launch_gather_sorted(pts, c.perm, n, c.sorted.as<float4>(), ctx->stream));
+    CK(launch_cell_table(c.sorted_keys, n, g.bits, c.table.as<uint32_t>(), ctx->stream));
+  }
+  c.index_valid = true;
+  c.index_gen = c.gen;
+  return MVR_OK;
+}
+
+mvr_grid auto_grid(mvr_ctx* ctx, const Cloud& c) {
+  double e = ctx->cell_edge_opt > 0 ? ctx->cell_edge_opt : density_cell_edge(c.lo, c.hi, c.n - c.n_bad, 4.0);
+  return make_grid(c.lo, c.hi, e, ctx->max_bits_opt);
+}
+
+int ensure_target_index(mvr_ctx* ctx, const mvr_grid* want) {
+  Cloud& t = ctx->tgt;
+  if (t.index_valid && t.index_gen == t.gen && (!want || same_grid(*want, t.grid))) return MVR_OK;
+  mvr_grid g = want ? *want : auto_grid(ctx, t);
+  return build_index(ctx, t, t.pts, g);
+}
+
+void mat_identity(float* m) { for (int k = 0; k < 16; ++k) m[k] = (k % 5 == 0) ? 1.f : 0.f; }
+
+void matmul4d(const double* A, const double* B, double* C) {
+  double t[16];
+  for (int c = 0; c < 4; ++c)
+    for (int r = 0; r < 4; ++r) {
+      double s = 0;
+      for (int k = 0; k < 4; ++k) s += A[k * 4 + r] * B[c * 4 + k];
+      t[c * 4 + r] = s;
+    }
+  std::memcpy(C, t, sizeof(t));
+}
+
+// Grid for an align / correspondence pass: covers target and (guess-transformed) source boxes.
+mvr_grid pair_grid(mvr_ctx* ctx, const float* G, double max_dist) {
+  const Cloud &t = ctx->tgt, &s = ctx->src;
+  float lo[3], hi[3];
+  for (int a = 0; a < 3; ++a) { lo[a] = t.lo[a]; hi[a] = t.hi[a]; }
+  if (s.n - s.n_bad > 0) {
+    for (int corner = 0; corner < 8; ++corner) {
+      double p[3] = {(corner & 1) ? s.hi[0] : s.lo[0], (corner & 2) ? s.hi[1] : s.lo[1], (corner & 4) ? s.hi[2] : s.lo[2]};
+      for (int a = 0; a < 3; ++a) {
+        double v = G[a] * p[0] + G[4 + a] * p[1] + G[8 + a] * p[2] + G[12 + a];
+        if (std::isfinite(v)) { lo[a] = std::min(lo[a], (float)v); hi[a] = std::max(hi[a], (float)v); }
+      }
+    }
+  }
+  double e_den = density_cell_edge(t.lo, t.hi, t.n - t.n_bad, 48.0);
+  double e = e_den;
+  if (max_dist > 0 && std::isfinite(max_dist) && max_dist < e_den) e = max_dist;
+  if (ctx->cell_edge_opt > 0) e = ctx->cell_edge_opt;
+  for (int a = 0; a < 3; ++a) { lo[a] -= (float)e; hi[a] += (float)e; }
+  return make_grid(lo, hi, e, ctx->max_bits_opt);
+}
+
+float gate_float(double max_dist) {
+  double m2 = max_dist * max_dist;
+  if (!(m2 < (double)FLT_MAX)) return INFINITY;
+  float f = (float)m2;
+  if ((double)f < m2) f = std::nextafterf(f, INFINITY);
+  return std::nextafterf(f, INFINITY);
+}
+
+int ensure_pinned(mvr_ctx* ctx) {
+  if (!ctx->h_sums) CK(cudaMallocHost((void**)&ctx->h_sums, REDUCE_MAX_VALS * sizeof(double)));
+  if (!ctx->h_small) CK(cudaMallocHost((void**)&ctx->h_small, 64 * sizeof(uint32_t)));
+  return MVR_OK;
+}
+
+// One correspondence pass source -> target on the current source coordinates `cur`.
+// reciprocal: re-index `cur` in the pair grid first (PCL rebuilds the source kd-tree every iteration).
+int correspond_pass(mvr_ctx* ctx, const float4* cur, bool need_keys_done, const mvr_grid& g, bool reciprocal, double max_dist) {
+  Cloud& s = ctx->src;
+  const int n = s.n;
+  const double max2 = max_dist * max_dist;
+  const float max_d2f = gate_float(max_dist);
+  CK(ctx->corr_j.ensure(std::max(n, 1) * sizeof(int32_t)));
+  CK(ctx->corr_d2.ensure(std::max(n, 1) * sizeof(float)));
+  IndexDev tix = ctx->tgt.dev();
+  const double tbytes = 16.0 * ctx->tgt.n + 4.0 * (double)((size_t)1 << (3 * g.bits));
+  if (reciprocal) {
+    (void)need_keys_done;
+    int key_bits = 3 * g.bits + (s.n_bad > 0 ? 1 : 0);
+    SortScratch sc{s.keys_alt.as<uint32_t>(), s.vals_alt.as<uint32_t>(), s.hist.as<uint32_t>()};
+    {
+      ProfScope ps(ctx, MVR_K_SORT, 16.0 * n, n);
+      CK(launch_radix_sort(s.keys.as<uint32_t>(), s.vals.as<uint32_t>(), n, key_bits, sc, &s.sorted_keys, &s.perm, ctx->stream));
+    }
+    {
+      ProfScope ps(ctx, MVR_K_TABLE, 36.0 * n + 4.0 * (double)((size_t)1 << (3 * g.bits)), n);
+      CK(launch_gather_sorted(cur, s.perm, n, s.sorted.as<float4>(), ctx->stream));
+      CK(launch_cell_table(s.sorted_keys, n, g.bits, s.table.as<uint32_t>(), ctx->stream));
+    }
+    s.grid = g; s.gd = to_dev(g);
+    IndexDev six = s.dev();
+    ProfScope ps(ctx, MVR_K_CORR, 24.0 * n + tbytes + 16.0 * n, 2.0 * n);
+    CK(launch_correspond(s.sorted.as<float4>(), n, true, tix, ctx->tgt.pts, six, true, max2, max_d2f,
+                         ctx->corr_j.as<int32_t>(), ctx->corr_d2.as<float>(), ctx->stream));
+  } else {
+    IndexDev six{};
+    ProfScope ps(ctx, MVR_K_CORR, 24.0 * n + tbytes, n);
+    CK(launch_correspond(cur, n, false, tix, ctx->tgt.pts, six, false, max2, max_d2f, ctx->corr_j.as<int32_t>(),
+                         ctx->corr_d2.as<float>(), ctx->stream));
+  }
+  return MVR_OK;
+}
+
+int ensure_source_index_buffers(mvr_ctx* ctx, const mvr_grid& g) {
+  Cloud& s = ctx->src;
+  const int n = std::max(s.n, 1);
+  const size_t cells = (size_t)1 << (3 * g.bits);
+  CK(s.keys.ensure(n * sizeof(uint32_t)));
+  CK(s.vals.ensure(n * sizeof(uint32_t)));
+  CK(s.keys_alt.ensure(n * sizeof(uint32_t)));
+  CK(s.vals_alt.ensure(n * sizeof(uint32_t)));
+  CK(s.hist.ensure((size_t)256 * radix_num_blocks(s.n) * sizeof(uint32_t)));
+  CK(s.sorted.ensure(n * sizeof(float4)));
+  CK(s.table.ensure((cells + 2) * sizeof(uint32_t)));
+  return MVR_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* mvr_version(void) { return "mvr_b200 0.1 (sm_100a)"; }
+
+const char* mvr_status_string(int s) {
+  switch (s) {
+    case MVR_OK: return "ok";
+    case MVR_ERR_BAD_ARG: return "bad argument";
+    case MVR_ERR_TOO_FEW_CORRESPONDENCES: return "not enough correspondences";
+    case MVR_ERR_CUDA: return "CUDA error";
+    case MVR_ERR_NO_INPUT: return "input cloud not set";
+    case MVR_ERR_NOT_SPD: return "normal equations not positive definite";
+    case MVR_ERR_ALLOC: return "allocation failed";
+    default: return "unknown status";
+  }
+}
+
+void mvr_icp_params_default(mvr_icp_params* p) {
+  if (!p) return;
+  p->max_iterations = 10;
+  p->max_correspondence_distance = std::sqrt(DBL_MAX);
+  p->transformation_epsilon = 0.0;
+  p->euclidean_fitness_epsilon = -DBL_MAX;
+  p->use_reciprocal_correspondences = 0;
+  p->estimator = MVR_POINT_TO_POINT;
+  p->fixed_iterations = 0;
+  p->min_correspondences = 3;
+}
+
+int mvr_ctx_create(int device, mvr_ctx** out) {
+  if (!out) return MVR_ERR_BAD_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return MVR_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return MVR_ERR_CUDA;
+  mvr_ctx* ctx = new mvr_ctx();
+  ctx->device = device;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MVR_ERR_CUDA; }
+  ctx->own_stream = true;
+  cudaEventCreate(&ctx->ev_a);
+  cudaEventCreate(&ctx->ev_b);
+  if (ensure_pinned(ctx) != MVR_OK) { mvr_ctx_destroy(ctx); return MVR_ERR_CUDA; }
+  *out = ctx;
+  return MVR_OK;
+}
+
+int mvr_ctx_destroy(mvr_ctx* ctx) {
+  if (!ctx) return MVR_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  prof_flush(ctx);
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+  if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+  ctx->tgt.release(); ctx->src.release(); ctx->normals.release();
+  DevBuf* bufs[] = {&ctx->cur, &ctx->corr_j, &ctx->corr_d2, &ctx->partials, &ctx->sums, &ctx->out_cloud, &ctx->qtmp,
+                    &ctx->itmp, &ctx->ftmp, &ctx->scratch, &ctx->misc};
+  for (DevBuf* b : bufs) b->release();
+  if (ctx->h_sums) cudaFreeHost(ctx->h_sums);
+  if (ctx->h_small) cudaFreeHost(ctx->h_small);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return MVR_OK;
+}
+
+int mvr_ctx_set_stream(mvr_ctx* ctx, void* s) {
+  if (!ctx) return MVR_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)s;
+  ctx->own_stream = false;
+  return MVR_OK;
+}
+
+int mvr_ctx_synchronize(mvr_ctx* ctx) {
+  if (!ctx) return MVR_ERR_BAD_ARG;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MVR_OK;
+}
+
+const char* mvr_last_error(mvr_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int mvr_ctx_set_profiling(mvr_ctx* ctx, int on) {
+  if (!ctx) return MVR_ERR_BAD_ARG;
+  ctx->profiling = on != 0;
+  return MVR_OK;
+}
+
+int mvr_ctx_get_kernel_stats(mvr_ctx* ctx, mvr_kernel_stat* out, int reset) {
+  if (!ctx || !out) return MVR_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  CK(cudaStreamSynchronize(ctx->stream));
+  prof_flush(ctx);
+  std::memcpy(out, ctx->stats, sizeof(ctx->stats));
+  if (reset) std::memset(ctx->stats, 0, sizeof(ctx->stats));
+  return MVR_OK;
+}
+
+int mvr_ctx_set_index_options(mvr_ctx* ctx, float cell_edge, int max_bits) {
+  if (!ctx) return MVR_ERR_BAD_ARG;
+  if (max_bits < 1 || max_bits > 10) return fail(ctx, MVR_ERR_BAD_ARG, "max_bits must be in 1..10");
+  ctx->cell_edge_opt = cell_edge > 0 ? cell_edge : 0.f;
+  ctx->max_bits_opt = max_bits;
+  ctx->tgt.index_valid = false;
+  ctx->src.index_valid = false;
+  return MVR_OK;
+}
+
+int mvr_set_target(mvr_ctx* ctx, const float* xyzw, size_t n) {
+  if (!ctx) return MVR_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  ctx->has_normals = false;
+  return cloud_set(ctx, ctx->tgt, xyzw, n, false);
+}
+int mvr_set_source(mvr_ctx* ctx, const float* xyzw, size_t n) {
+  if (!ctx) return MVR_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  ctx->have_out = false;
+  return cloud_set(ctx, ctx->src, xyzw, n, false);
+}
+int mvr_set_target_device(mvr_ctx* ctx, const float* d, size_t n) {
+  if (!ctx) return MVR_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  ctx->has_normals = false;
+  return cloud_set(ctx, ctx->tgt, d, n, true);
+}
+int mvr_set_source_device(mvr_ctx* ctx, const float* d, size_t n) {
+  if (!ctx) return MVR_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  ctx->have_out = false;
+  return cloud_set(ctx, ctx->src, d, n, true);
+}
+
+int mvr_set_target_normals(mvr_ctx* ctx, const float* nxyzc, size_t n) {
+  if (!ctx || !nxyzc) return MVR_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  if ((int)n != ctx->tgt.n) return fail(ctx, MVR_ERR_BAD_ARG, "normals count differs from target size");
+  CK(ctx->normals.ensure(std::max<size_t>(n, 1) * sizeof(float4)));
+  CK(cudaMemcpyAsync(ctx->normals.p, nxyzc, n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->has_normals = true;
+  return MVR_OK;
+}
+
+int mvr_index_build(mvr_ctx* ctx, int which, const mvr_grid* grid) {
+  if (!ctx || (which != MVR_CLOUD_TARGET && which != MVR_CLOUD_SOURCE)) return MVR_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  Cloud& c = which == MVR_CLOUD_TARGET ? ctx->tgt : ctx->src;
+  if (!c.pts && c.n == 0 && c.gen == 0) return fail(ctx, MVR_ERR_NO_INPUT, "cloud not set");
+  mvr_grid g;
+  if (grid) {
+    if (grid->bits < 1 || grid->bits > 10 || !(grid->inv_cell > 0)) return fail(ctx, MVR_ERR_BAD_ARG, "bad grid");
+    g = *grid;
+  } else {
+    g = auto_grid(ctx, c);
+  }
+  return build_index(ctx, c, c.pts, g);
+}
+
+int mvr_index_export(mvr_ctx* ctx, int which, mvr_grid* grid, uint32_t* sorted_keys, int32_t* perm, uint32_t* cell_start) {
+  if (!ctx || (which != MVR_CLOUD_TARGET && which != MVR_CLOUD_SOURCE)) return MVR_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  Cloud& c = which == MVR_CLOUD_TARGET ? ctx->tgt : ctx->src;
+  if (!c.index_valid) return fail(ctx, MVR_ERR_NO_INPUT, "index not built");
+  if (grid) *grid = c.grid;
+  if (sorted_keys && c.n) CK(cudaMemcpyAsync(sorted_keys, c.sorted_keys, c.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (perm && c.n) CK(cudaMemcpyAsync(perm, c.perm, c.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (cell_start) CK(cudaMemcpyAsync(cell_start, c.table.p, (((size_t)1 << (3 * c.grid.bits)) + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MVR_OK;
+}
+
+int mvr_nn_query_device(mvr_ctx* ctx, const float* d_q, size_t n, int32_t* d_idx, float* d_d2) {
+  if (!ctx || (n && (!d_q || !d_idx || !d_d2))) return MVR_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->tgt.gen == 0) return fail(ctx, MVR_ERR_NO_INPUT, "target not set");
+  int rc = ensure_target_index(ctx, nullptr);
+  if (rc) return rc;
+  const Cloud& t = ctx->tgt;
+  ProfScope ps(ctx, MVR_K_NN, 24.0 * n + 16.0 * t.n + 4.0 * (double)((size_t)1 << (3 * t.grid.bits)), (double)n);
+  CK(launch_nn_query((const float4*)d_q, (int)n, t.dev(), INFINITY, d_idx, d_d2, ctx->stream));
+  return MVR_OK;
+}
+
+int mvr_nn_query(mvr_ctx* ctx, const float* q, size_t n, int32_t* idx, float* d2) {
+  if (!ctx || (n && (!q || !idx || !d2))) return MVR_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->tgt.gen == 0) return fail(ctx, MVR_ERR_NO_INPUT, "target not set");
+  if (n == 0) return MVR_OK;
+  CK(ctx->qtmp.ensure(n * sizeof(float4)));
+  CK(ctx->itmp.ensure(n * sizeof(int32_t)));
+  CK(ctx->ftmp.ensure(n * sizeof(float)));
+  CK(cudaMemcpyAsync(ctx->qtmp.p, q, n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+  int rc = mvr_nn_query_device(ctx, ctx->qtmp.as<float>(), n, ctx->itmp.as<int32_t>(), ctx->ftmp.as<float>());
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(idx, ctx->itmp.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(d2, ctx->ftmp.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MVR_OK;
+}
+
+int mvr_correspondences(mvr_ctx* ctx, double max_dist, int reciprocal, int32_t* iq, int32_t* im, float* dist, size_t* count) {
+  if (!ctx || !count) return MVR_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  *count = 0;
+  if (ctx->tgt.gen == 0 || ctx->src.gen == 0) return fail(ctx, MVR_ERR_NO_INPUT, "source/target not set");
+  if (!(max_dist >= 0)) return fail(ctx, MVR_ERR_BAD_ARG, "max_dist must be >= 0");
+  const int n = ctx->src.n;
+  if (n == 0) return MVR_OK;
+  if (!iq || !im || !dist) return MVR_ERR_BAD_ARG;
+  float I[16];
+  mat_identity(I);
+  mvr_grid g = pair_grid(ctx, I, max_dist);
+  int rc = ensure_target_index(ctx, &g);
+  if (rc) return rc;
+  if (reciprocal) {
+    rc = ensure_source_index_buffers(ctx, g);
+    if (rc) return rc;
+    ProfScope ps(ctx, MVR_K_MORTON, 24.0 * n, n);
+    CK(launch_morton_keys(ctx->src.pts, n, to_dev(g), ctx->src.keys.as<uint32_t>(), ctx->src.vals.as<uint32_t>(), ctx->stream));
+  }
+  rc = correspond_pass(ctx, ctx->src.pts, true, g, reciprocal != 0, max_dist);
+  if (rc) return rc;
+  CK(ctx->scratch.ensure(compact_scratch_elems(n) * sizeof(uint32_t) + 64));
+  CK(ctx->itmp.ensure((size_t)2 * n * sizeof(int32_t)));
+  CK(ctx->ftmp.ensure((size_t)n * sizeof(float)));
+  CK(ctx->misc.ensure(64));
+  int32_t* dq = ctx->itmp.as<int32_t>();
+  int32_t* dm = dq + n;
+  CK(launch_compact_corr(ctx->corr_j.as<int32_t>(), ctx->corr_d2.as<float>(), n, ctx->scratch.as<uint32_t>(), dq, dm,
+                         ctx->ftmp.as<float>(), ctx->misc.as<uint32_t>(), ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_small, ctx->misc.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  size_t c = ctx->h_small[0];
+  if (c) {
+    CK(cudaMemcpyAsync(iq, dq, c * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(im, dm, c * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(dist, ctx->ftmp.p, c * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  *count = c;
+  return MVR_OK;
+}
+
+int mvr_icp_align(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, float* out_pose, float* out_xyzw,
+                  mvr_icp_report* report) {
+  if (!ctx || !prm) return MVR_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->tgt.gen == 0 || ctx->src.gen == 0) return fail(ctx, MVR_ERR_NO_INPUT, "source/target not set");
+  Cloud& s = ctx->src;
+  const int n = s.n;
+  if (n == 0 || ctx->tgt.n == 0) return fail(ctx, MVR_ERR_NO_INPUT, "empty source or target");
+  if (prm->estimator == MVR_POINT_TO_PLANE && !ctx->has_normals)
+    return fail(ctx, MVR_ERR_NO_INPUT, "point-to-plane needs target normals (mvr_set_target_normals / mvr_estimate_normals)");
+  if (!(prm->max_correspondence_distance >= 0)) return fail(ctx, MVR_ERR_BAD_ARG, "max_correspondence_distance");
+  float G[16];
+  if (guess) std::memcpy(G, guess, sizeof(G)); else mat_identity(G);
+  const bool reciprocal = prm->use_reciprocal_correspondences != 0;
+  const double max_dist = prm->max_correspondence_distance;
+  const int min_corr = prm->min_correspondences > 0 ? prm->min_correspondences : 3;
+  const bool p2l = prm->estimator == MVR_POINT_TO_PLANE;
+
+  mvr_grid g = pair_grid(ctx, G, max_dist);
+  int rc = ensure_target_index(ctx, &g);
+  if (rc) return rc;
+  if (reciprocal && (rc = ensure_source_index_buffers(ctx, g))) return rc;
+  CK(ctx->cur.ensure((size_t)n * sizeof(float4)));
+  CK(ctx->partials.ensure((size_t)REDUCE_BLOCKS * REDUCE_MAX_VALS * sizeof(double)));
+  CK(ctx->sums.ensure(REDUCE_MAX_VALS * sizeof(double)));
+  CK(ctx->out_cloud.ensure((size_t)n * sizeof(float4)));
+  float4* cur = ctx->cur.as<float4>();
+  CK(cudaEventRecord(ctx->ev_a, ctx->stream));
+  CK(cudaMemcpyAsync(cur, s.pts, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+
+  // provisional origin for the sums: centre of the target box (keeps the double sums well scaled)
+  double3 o = make_double3(0.5 * ((double)ctx->tgt.lo[0] + ctx->tgt.hi[0]), 0.5 * ((double)ctx->tgt.lo[1] + ctx->tgt.hi[1]),
+                           0.5 * ((double)ctx->tgt.lo[2] + ctx->tgt.hi[2]));
+  Mat4f M;
+  std::memcpy(M.m, G, sizeof(G));
+  double fin[16];
+  for (int k = 0; k < 16; ++k) fin[k] = G[k];
+  ctx->iters.clear();
+  ctx->have_out = false;
+  int iter = 0, reason = MVR_REASON_NONE, converged = 0, n_corr = 0;
+  double prev_mse = DBL_MAX, cur_mse = 0.0;
+  uint64_t queries = 0;
+  const double rot_thr = 1.0 - prm->transformation_epsilon, trans_thr = prm->transformation_epsilon;
+  const GridDev gd = to_dev(g);
+  int status = MVR_OK;
+  if (prm->max_iterations <= 0) { converged = 1; reason = MVR_REASON_ITERATIONS; }
+  while (!converged) {
+    {
+      ProfScope ps(ctx, MVR_K_TRANSFORM, (reciprocal ? 40.0 : 32.0) * n, n);
+      CK(launch_transform_keys(cur, n, M, gd, reciprocal ? s.keys.as<uint32_t>() : nullptr,
+                               reciprocal ? s.vals.as<uint32_t>() : nullptr, ctx->stream));
+    }
+    rc = correspond_pass(ctx, cur, true, g, reciprocal, max_dist);
+    if (rc) return rc;
+    {
+      ProfScope ps(ctx, MVR_K_REDUCE, 36.0 * n, n);
+      if (p2l)
+        CK(launch_reduce_p2l(cur, n, ctx->corr_j.as<int32_t>(), ctx->corr_d2.as<float>(), ctx->tgt.pts, ctx->normals.as<float4>(), o,
+                             ctx->partials.as<double>(), ctx->sums.as<double>(), ctx->stream));
+      else
+        CK(launch_reduce_p2p(cur, n, ctx->corr_j.as<int32_t>(), ctx->corr_d2.as<float>(), ctx->tgt.pts, o,
+                             ctx->partials.as<double>(), ctx->sums.as<double>(), ctx->stream));
+    }
+    CK(cudaMemcpyAsync(ctx->h_sums, ctx->sums.p, REDUCE_MAX_VALS * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const double* S = ctx->h_sums;
+    double T[16];
+    double cnt = p2l ? S[27] : S[0];
+    double d2sum = p2l ? S[28] : S[16];
+    queries += (uint64_t)n + (reciprocal ? (uint64_t)(p2l ? S[29] : S[17]) : 0);
+    n_corr = (int)cnt;
+    if (n_corr < min_corr) { reason = MVR_REASON_NO_CORRESPONDENCES; status = MVR_ERR_TOO_FEW_CORRESPONDENCES; break; }
+    if (p2l) {
+      double A[36], b[6], x[6];
+      int k = 0;
+      for (int a = 0; a < 6; ++a)
+        for (int c = a; c < 6; ++c) { A[a * 6 + c] = S[k]; A[c * 6 + a] = S[k]; ++k; }
+      for (int a = 0; a < 6; ++a) b[a] = S[21 + a];
+      if (!cholesky_solve6(A, b, x)) { reason = MVR_REASON_NO_CORRESPONDENCES; status = MVR_ERR_NOT_SPD; break; }
+      pose_from_6(x, T);
+    } else {
+      double mu_a[3] = {S[1] / cnt, S[2] / cnt, S[3] / cnt}, mu_b[3] = {S[4] / cnt, S[5] / cnt, S[6] / cnt};
+      double Sg[9];
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) Sg[r * 3 + c] = S[7 + r * 3 + c] / cnt - mu_b[r] * mu_a[c];
+      double mu_s[3] = {mu_a[0] + o.x, mu_a[1] + o.y, mu_a[2] + o.z}, mu_d[3] = {mu_b[0] + o.x, mu_b[1] + o.y, mu_b[2] + o.z};
+      umeyama_rigid(mu_s, mu_d, Sg, T);
+    }
+    float Tf[16];
+    for (int k = 0; k < 16; ++k) Tf[k] = (float)T[k];
+    Tf[3] = Tf[7] = Tf[11] = 0.f; Tf[15] = 1.f;
+    double Td[16];
+    for (int k = 0; k < 16; ++k) Td[k] = Tf[k];
+    matmul4d(Td, fin, fin);
+    ++iter;
+    cur_mse = d2sum / cnt;
+    mvr_icp_iteration rec;
+    rec.iteration = iter; rec.n_correspondences = n_corr; rec.mse = cur_mse;
+    std::memcpy(rec.delta, Tf, sizeof(Tf));
+    ctx->iters.push_back(rec);
+    std::memcpy(M.m, Tf, sizeof(Tf));
+    // DefaultConvergenceCriteria::hasConverged
+    if (iter >= prm->max_iterations) { converged = 1; reason = MVR_REASON_ITERATIONS; break; }
+    if (!prm->fixed_iterations) {
+      double cos_angle = 0.5 * (Td[0] + Td[5] + Td[10] - 1.0);
+      double t2 = Td[12] * Td[12] + Td[13] * Td[13] + Td[14] * Td[14];
+      if (cos_angle >= rot_thr && t2 <= trans_thr) { converged = 1; reason = MVR_REASON_TRANSFORM; break; }
+      if (std::fabs(cur_mse - prev_mse) < 1e-12) { converged = 1; reason = MVR_REASON_ABS_MSE; break; }
+      if (std::fabs(cur_mse - prev_mse) / prev_mse < prm->euclidean_fitness_epsilon) { converged = 1; reason = MVR_REASON_REL_MSE; break; }
+      prev_mse = cur_mse;
+    }
+  }
+  Mat4f F;
+  for (int k = 0; k < 16; ++k) F.m[k] = (float)fin[k];
+  {
+    ProfScope ps(ctx, MVR_K_TRANSFORM, 32.0 * n, n);
+    CK(launch_transform(s.pts, ctx->out_cloud.as<float4>(), n, F, ctx->stream));
+  }
+  CK(cudaEventRecord(ctx->ev_b, ctx->stream));
+  if (out_xyzw) CK(cudaMemcpyAsync(out_xyzw, ctx->out_cloud.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->have_out = true;
+  if (out_pose) std::memcpy(out_pose, F.m, sizeof(F.m));
+  if (report) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
+    report->iterations = iter; report->converged = converged; report->reason = reason; report->n_correspondences = n_corr;
+    report->mse = cur_mse; report->gpu_ms = ms; report->nn_queries = queries;
+  }
+  if (status == MVR_ERR_TOO_FEW_CORRESPONDENCES) ctx->err = "not enough correspondences";
+  return status;
+}
+
+int mvr_icp_get_iterations(mvr_ctx* ctx, mvr_icp_iteration* out, int max_records, int* count) {
+  if (!ctx || !count) return MVR_ERR_BAD_ARG;
+  int c = (int)ctx->iters.size();
+  if (out) {
+    int m = std::min(c, std::max(max_records, 0));
+    if (m) std::memcpy(out, ctx->iters.data(), (size_t)m * sizeof(mvr_icp_iteration));
+    *count = m;
+  } else {
+    *count = c;
+  }
+  return MVR_OK;
+}
+
+int mvr_fitness_score(mvr_ctx* ctx, double max_range, double* score) {
+  if (!ctx || !score) return MVR_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->tgt.gen == 0 || ctx->src.gen == 0) return fail(ctx, MVR_ERR_NO_INPUT, "source/target not set");
+  const int n = ctx->src.n;
+  *score = DBL_MAX;
+  if (n == 0 || ctx->tgt.n == 0) return MVR_OK;
+  int rc = ensure_target_index(ctx, nullptr);
+  if (rc) return rc;
+  const float4* cloud = ctx->have_out ? ctx->out_cloud.as<float4>() : ctx->src.pts;
+  CK(ctx->itmp.ensure((size_t)n * sizeof(int32_t)));
+  CK(ctx->ftmp.ensure((size_t)n * sizeof(float)));
+  CK(ctx->partials.ensure((size_t)REDUCE_BLOCKS * REDUCE_MAX_VALS * sizeof(double)));
+  CK(ctx->sums.ensure(REDUCE_MAX_VALS * sizeof(double)));
+  const Cloud& t = ctx->tgt;
+  {
+    ProfScope ps(ctx, MVR_K_NN, 24.0 * n + 16.0 * t.n + 4.0 * (double)((size_t)1 << (3 * t.grid.bits)), (double)n);
+    CK(launch_nn_query(cloud, n, t.dev(), INFINITY, ctx->itmp.as<int32_t>(), ctx->ftmp.as<float>(), ctx->stream));
+  }
+  CK(launch_reduce_fitness(ctx->itmp.as<int32_t>(), ctx->ftmp.as<float>(), n, max_range, ctx->partials.as<double>(),
+                           ctx->sums.as<double>(), ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_sums, ctx->sums.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->h_sums[1] > 0) *score = ctx->h_sums[0] / ctx->h_sums[1];
+  return MVR_OK;
+}
+
+int mvr_estimate_normals(mvr_ctx* ctx, int which, int k, const float viewpoint[3], float* out, int32_t* neighbours) {
+  if (!ctx || !out || (which != MVR_CLOUD_TARGET && which != MVR_CLOUD_SOURCE)) return MVR_ERR_BAD_ARG;
+  if (k < 3 || k > 32) return fail(ctx, MVR_ERR_BAD_ARG, "k must be in 3..32");
+  cudaSetDevice(ctx->device);
+  Cloud& c = which == MVR_CLOUD_TARGET ? ctx->tgt : ctx->src;
+  if (c.gen == 0) return fail(ctx, MVR_ERR_NO_INPUT, "cloud not set");
+  const int n = c.n;
+  if (n == 0) return MVR_OK;
+  if (!c.index_valid || c.index_gen != c.gen) {
+    // kNN wants about k points in the 27-neighbourhood: ~k/4 per occupied cell on a surface
+    double e = ctx->cell_edge_opt > 0 ? ctx->cell_edge_opt : density_cell_edge(c.lo, c.hi, n - c.n_bad, std::max(2.0, k / 4.0));
+    int rc = build_index(ctx, c, c.pts, make_grid(c.lo, c.hi, e, ctx->max_bits_opt));
+    if (rc) return rc;
+  }
+  float3 vp = viewpoint ? make_float3(viewpoint[0], viewpoint[1], viewpoint[2]) : make_float3(0.f, 0.f, 0.f);
+  DevBuf& nb = which == MVR_CLOUD_TARGET ? ctx->normals : ctx->qtmp;
+  CK(nb.ensure((size_t)n * sizeof(float4)));
+  int32_t* dn = nullptr;
+  if (neighbours) { CK(ctx->itmp.ensure((size_t)n * k * sizeof(int32_t))); dn = ctx->itmp.as<int32_t>(); }
+  {
+    ProfScope ps(ctx, MVR_K_NORMALS, 32.0 * n, n);
+    CK(launch_normals(c.dev(), c.pts, n, k, vp, nb.as<float4>(), dn, ctx->stream));
+  }
+  CK(cudaMemcpyAsync(out, nb.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  if (neighbours) CK(cudaMemcpyAsync(neighbours, dn, (size_t)n * k * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (which == MVR_CLOUD_TARGET) ctx->has_normals = true;
+  return MVR_OK;
+}
+
+}  // extern "C"

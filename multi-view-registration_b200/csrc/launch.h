@@ -1,0 +1,75 @@
+// launch.h -- host-callable launchers of the CUDA kernels (one per kernel family).
+// Every launcher enqueues on the given stream and returns the last CUDA error; none synchronises.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace mvr {
+
+// ---- index.cu ------------------------------------------------------------------------------
+// bbox: out[0..2] = min xyz, out[3..5] = max xyz (as order-preserving uint encodings), out[6] = count
+// of non-finite points.  `out` must be initialised with bbox_init().
+cudaError_t launch_bbox_init(uint32_t* out7, cudaStream_t s);
+cudaError_t launch_bbox(const float4* pts, int n, uint32_t* out7, cudaStream_t s);
+float bbox_decode(uint32_t enc);
+
+cudaError_t launch_morton_keys(const float4* pts, int n, GridDev g, uint32_t* keys, uint32_t* vals, cudaStream_t s);
+// In-place pinned transform of pts followed by key generation (ICP's per-iteration transformCloud).
+cudaError_t launch_transform_keys(float4* pts, int n, Mat4f M, GridDev g, uint32_t* keys, uint32_t* vals, cudaStream_t s);
+cudaError_t launch_transform(const float4* in, float4* out, int n, Mat4f M, cudaStream_t s);
+
+struct SortScratch {
+  uint32_t* keys_alt;   // n
+  uint32_t* vals_alt;   // n
+  uint32_t* hist;       // 256 * radix_num_blocks(n)
+};
+int radix_num_blocks(int n);
+// Stable LSD radix sort of (key, value) pairs on the low `key_bits` bits.  On return the sorted
+// pairs are in *keys_out / *vals_out (one of the two buffers, chosen by pass parity).
+cudaError_t launch_radix_sort(uint32_t* keys, uint32_t* vals, int n, int key_bits, SortScratch sc, uint32_t** keys_out,
+                              uint32_t** vals_out, cudaStream_t s);
+
+cudaError_t launch_gather_sorted(const float4* pts, const uint32_t* perm, int n, float4* sorted, cudaStream_t s);
+// start[c] = first sorted position with key >= c, for c in [0, 1 << 3*bits].
+cudaError_t launch_cell_table(const uint32_t* sorted_keys, int n, int bits, uint32_t* start, cudaStream_t s);
+
+// ---- nn.cu ---------------------------------------------------------------------------------
+// Exact 1-NN of each query in the index.  q_has_index: queries carry their original index in .w
+// (results are written at that index) or are in caller order.  max_d2 gates the SEARCH only (points
+// farther than the gate may be reported as -1); pass +inf for un-gated.
+cudaError_t launch_nn_query(const float4* q, int nq, IndexDev ix, float max_d2, int32_t* out_idx, float* out_d2,
+                            cudaStream_t s);
+
+// ---- icp.cu --------------------------------------------------------------------------------
+// Forward (+ optional reciprocal) correspondence search.  Queries are the Morton-sorted source
+// (src.pts, .w = original index) when reciprocal, else `q` in caller order.  Output is indexed by the
+// query's ORIGINAL index: corr_j[i] = matched target original index or -1, corr_d2[i] = float d2.
+cudaError_t launch_correspond(const float4* q, int nq, bool q_has_index, IndexDev tgt, const float4* tgt_orig,
+                              IndexDev src, bool reciprocal, double max_dist2, float max_d2f, int32_t* corr_j,
+                              float* corr_d2, cudaStream_t s);
+
+// Sums over kept correspondences for the point-to-point estimator (18 doubles, see icp.cu) or the
+// point-to-plane one (30 doubles).  partials: blocks x REDUCE_MAX_VALS doubles; out: REDUCE_MAX_VALS doubles.
+enum { REDUCE_P2P_VALS = 18, REDUCE_P2L_VALS = 30, REDUCE_MAX_VALS = 32, REDUCE_BLOCKS = 296 };
+cudaError_t launch_reduce_p2p(const float4* src_cur, int n, const int32_t* corr_j, const float* corr_d2,
+                              const float4* tgt_orig, double3 origin, double* partials, double* out, cudaStream_t s);
+cudaError_t launch_reduce_p2l(const float4* src_cur, int n, const int32_t* corr_j, const float* corr_d2,
+                              const float4* tgt_orig, const float4* tgt_normals, double3 origin, double* partials,
+                              double* out, cudaStream_t s);
+// sum and count of d2[i] with idx[i] >= 0 and d2 <= max_range  (getFitnessScore); out[0]=sum, out[1]=count
+cudaError_t launch_reduce_fitness(const int32_t* idx, const float* d2, int n, double max_range, double* partials,
+                                  double* out, cudaStream_t s);
+
+// Order-preserving compaction of the correspondences (ascending source index).
+// scratch: uint32[compact_scratch_elems(n)].  count_out: device uint32.
+size_t compact_scratch_elems(int n);
+cudaError_t launch_compact_corr(const int32_t* corr_j, const float* corr_d2, int n, uint32_t* scratch, int32_t* out_q,
+                                int32_t* out_m, float* out_d2, uint32_t* count_out, cudaStream_t s);
+
+// ---- normals.cu ----------------------------------------------------------------------------
+cudaError_t launch_normals(IndexDev ix, const float4* pts_orig, int n, int k, float3 viewpoint, float4* out_nxyzc,
+                           int32_t* out_nbr, cudaStream_t s);
+
+}  // namespace mvr
