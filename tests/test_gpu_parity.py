@@ -15,13 +15,15 @@ RMSE_REL_TOL = 1e-4
 
 
 def rot_angle(A, B):
+    """Angle of A*B^T from its skew part (sin(angle) = |vee(R - R^T)| / 2).  arccos(trace) is useless
+    here: float32-rounded rotations are orthogonal only to ~1e-7, which arccos turns into ~3e-4 rad."""
     R = A[:3, :3].astype(np.float64) @ B[:3, :3].astype(np.float64).T
-    return float(np.arccos(np.clip(0.5 * (np.trace(R) - 1.0), -1.0, 1.0)))
+    w = 0.5 * np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    return float(np.arcsin(min(1.0, np.linalg.norm(w))))
 
 
 def assert_pose_close(A, B, scale=None):
     ang = rot_angle(A, B)
-    # arccos near 1 resolves ~1e-8 in double; float32 pose entries quantise at ~6e-8
     assert ang <= ROT_TOL, "rotation differs by %g rad" % ang
     ta, tb = A[:3, 3].astype(np.float64), B[:3, 3].astype(np.float64)
     denom = scale if scale is not None else max(np.linalg.norm(tb), 1e-12)
