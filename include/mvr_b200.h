@@ -101,6 +101,8 @@ enum { MVR_K_MORTON = 0, MVR_K_SORT = 1, MVR_K_TABLE = 2, MVR_K_NN = 3, MVR_K_CO
        MVR_K_TRANSFORM = 6, MVR_K_NORMALS = 7, MVR_K_COUNT = 8 };
 
 const char* mvr_version(void);
+/* Number of CUDA kernels this library has launched in the calling process (all contexts). */
+uint64_t mvr_kernel_launch_count(void);
 const char* mvr_status_string(int status);
 void mvr_icp_params_default(mvr_icp_params* p);
 

@@ -106,6 +106,7 @@ def lib():
     L = C.CDLL(LIB_PATH)
     vp, fp, ip, up = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_uint32)
     L.mvr_version.restype = C.c_char_p
+    L.mvr_kernel_launch_count.restype = C.c_uint64
     L.mvr_status_string.restype = C.c_char_p
     L.mvr_status_string.argtypes = [C.c_int]
     L.mvr_icp_params_default.argtypes = [C.POINTER(IcpParams)]
@@ -131,6 +132,10 @@ def lib():
     L.mvr_estimate_normals.argtypes = [vp, C.c_int, C.c_int, fp, fp, ip]
     _lib = L
     return L
+
+
+def kernel_launch_count():
+    return int(lib().mvr_kernel_launch_count())
 
 
 def default_params(**kw):

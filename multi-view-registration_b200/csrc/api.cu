@@ -19,6 +19,13 @@
 
 using namespace mvr;
 
+#include <atomic>
+namespace mvr {
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+}  // namespace mvr
+
 namespace {
 
 struct DevBuf {
@@ -363,6 +370,8 @@ int ensure_source_index_buffers(mvr_ctx* ctx, const mvr_grid& g) {
 extern "C" {
 
 const char* mvr_version(void) { return "mvr_b200 0.1 (sm_100a)"; }
+
+uint64_t mvr_kernel_launch_count(void) { return (uint64_t)launch_count(); }
 
 const char* mvr_status_string(int s) {
   switch (s) {

@@ -58,6 +58,7 @@ cudaError_t launch_correspond(const float4* q, int nq, bool q_has_index, IndexDe
     if (q_has_index) k_correspond<false, true><<<grid, block, 0, s>>>(q, nq, tgt, tgt_orig, src, max_dist2, max_d2f, corr_j, corr_d2);
     else k_correspond<false, false><<<grid, block, 0, s>>>(q, nq, tgt, tgt_orig, src, max_dist2, max_d2f, corr_j, corr_d2);
   }
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -164,23 +165,23 @@ __global__ void __launch_bounds__(256) k_reduce_fitness(const int32_t* __restric
 
 cudaError_t launch_reduce_p2p(const float4* src_cur, int n, const int32_t* corr_j, const float* corr_d2,
                               const float4* tgt_orig, double3 origin, double* partials, double* out, cudaStream_t s) {
-  k_reduce_p2p<<<REDUCE_BLOCKS, 256, 0, s>>>(src_cur, n, corr_j, corr_d2, tgt_orig, origin, partials);
-  k_reduce_final<<<1, 32, 0, s>>>(partials, REDUCE_BLOCKS, REDUCE_P2P_VALS, out);
+  k_reduce_p2p<<<REDUCE_BLOCKS, 256, 0, s>>>(src_cur, n, corr_j, corr_d2, tgt_orig, origin, partials); count_launch();
+  k_reduce_final<<<1, 32, 0, s>>>(partials, REDUCE_BLOCKS, REDUCE_P2P_VALS, out); count_launch();
   return cudaGetLastError();
 }
 
 cudaError_t launch_reduce_p2l(const float4* src_cur, int n, const int32_t* corr_j, const float* corr_d2,
                               const float4* tgt_orig, const float4* tgt_normals, double3 origin, double* partials,
                               double* out, cudaStream_t s) {
-  k_reduce_p2l<<<REDUCE_BLOCKS, 256, 0, s>>>(src_cur, n, corr_j, corr_d2, tgt_orig, tgt_normals, origin, partials);
-  k_reduce_final<<<1, 32, 0, s>>>(partials, REDUCE_BLOCKS, REDUCE_P2L_VALS, out);
+  k_reduce_p2l<<<REDUCE_BLOCKS, 256, 0, s>>>(src_cur, n, corr_j, corr_d2, tgt_orig, tgt_normals, origin, partials); count_launch();
+  k_reduce_final<<<1, 32, 0, s>>>(partials, REDUCE_BLOCKS, REDUCE_P2L_VALS, out); count_launch();
   return cudaGetLastError();
 }
 
 cudaError_t launch_reduce_fitness(const int32_t* idx, const float* d2, int n, double max_range, double* partials,
                                   double* out, cudaStream_t s) {
-  k_reduce_fitness<<<REDUCE_BLOCKS, 256, 0, s>>>(idx, d2, n, max_range, partials);
-  k_reduce_final<<<1, 32, 0, s>>>(partials, REDUCE_BLOCKS, 2, out);
+  k_reduce_fitness<<<REDUCE_BLOCKS, 256, 0, s>>>(idx, d2, n, max_range, partials); count_launch();
+  k_reduce_final<<<1, 32, 0, s>>>(partials, REDUCE_BLOCKS, 2, out); count_launch();
   return cudaGetLastError();
 }
 
@@ -266,9 +267,9 @@ __global__ void __launch_bounds__(CP_THREADS) k_compact_write(const int32_t* __r
 cudaError_t launch_compact_corr(const int32_t* corr_j, const float* corr_d2, int n, uint32_t* scratch, int32_t* out_q,
                                 int32_t* out_m, float* out_d2, uint32_t* count_out, cudaStream_t s) {
   int nblk = n > 0 ? (n + CP_TILE - 1) / CP_TILE : 0;
-  if (nblk > 0) k_compact_count<<<nblk, CP_THREADS, 0, s>>>(corr_j, n, scratch);
-  k_compact_scan<<<1, 1024, 0, s>>>(scratch, nblk, count_out);
-  if (nblk > 0) k_compact_write<<<nblk, CP_THREADS, 0, s>>>(corr_j, corr_d2, n, scratch, out_q, out_m, out_d2);
+  if (nblk > 0) { k_compact_count<<<nblk, CP_THREADS, 0, s>>>(corr_j, n, scratch); count_launch(); }
+  k_compact_scan<<<1, 1024, 0, s>>>(scratch, nblk, count_out); count_launch();
+  if (nblk > 0) { k_compact_write<<<nblk, CP_THREADS, 0, s>>>(corr_j, corr_d2, n, scratch, out_q, out_m, out_d2); count_launch(); }
   return cudaGetLastError();
 }
 

@@ -66,14 +66,14 @@ __global__ void __launch_bounds__(256) k_bbox(const float4* __restrict__ pts, in
 }
 
 cudaError_t launch_bbox_init(uint32_t* out7, cudaStream_t s) {
-  k_bbox_init<<<1, 32, 0, s>>>(out7);
+  k_bbox_init<<<1, 32, 0, s>>>(out7); count_launch();
   return cudaGetLastError();
 }
 
 cudaError_t launch_bbox(const float4* pts, int n, uint32_t* out7, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   int blocks = min((n + 255) / 256, 148 * 4);
-  k_bbox<<<blocks, 256, 0, s>>>(pts, n, out7);
+  k_bbox<<<blocks, 256, 0, s>>>(pts, n, out7); count_launch();
   return cudaGetLastError();
 }
 
@@ -106,19 +106,19 @@ __global__ void __launch_bounds__(256) k_transform(const float4* __restrict__ in
 
 cudaError_t launch_morton_keys(const float4* pts, int n, GridDev g, uint32_t* keys, uint32_t* vals, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  k_morton_keys<<<(n + 255) / 256, 256, 0, s>>>(pts, n, g, keys, vals);
+  k_morton_keys<<<(n + 255) / 256, 256, 0, s>>>(pts, n, g, keys, vals); count_launch();
   return cudaGetLastError();
 }
 
 cudaError_t launch_transform_keys(float4* pts, int n, Mat4f M, GridDev g, uint32_t* keys, uint32_t* vals, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  k_transform_keys<<<(n + 255) / 256, 256, 0, s>>>(pts, n, M, g, keys, vals);
+  k_transform_keys<<<(n + 255) / 256, 256, 0, s>>>(pts, n, M, g, keys, vals); count_launch();
   return cudaGetLastError();
 }
 
 cudaError_t launch_transform(const float4* in, float4* out, int n, Mat4f M, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  k_transform<<<(n + 255) / 256, 256, 0, s>>>(in, out, n, M);
+  k_transform<<<(n + 255) / 256, 256, 0, s>>>(in, out, n, M); count_launch();
   return cudaGetLastError();
 }
 
@@ -238,9 +238,9 @@ cudaError_t launch_radix_sort(uint32_t* keys, uint32_t* vals, int n, int key_bit
   uint32_t *kin = keys, *vin = vals, *kout = sc.keys_alt, *vout = sc.vals_alt;
   for (int p = 0; p < passes; ++p) {
     int shift = 8 * p;
-    k_radix_hist<<<nblk, RS_THREADS, 0, s>>>(kin, n, shift, sc.hist, nblk);
-    k_radix_scan<<<1, 1024, 0, s>>>(sc.hist, 256 * nblk);
-    k_radix_scatter<<<nblk, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, sc.hist, nblk);
+    k_radix_hist<<<nblk, RS_THREADS, 0, s>>>(kin, n, shift, sc.hist, nblk); count_launch();
+    k_radix_scan<<<1, 1024, 0, s>>>(sc.hist, 256 * nblk); count_launch();
+    k_radix_scatter<<<nblk, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, sc.hist, nblk); count_launch();
     uint32_t* t = kin; kin = kout; kout = t;
     t = vin; vin = vout; vout = t;
   }
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(256) k_gather_sorted(const float4* __restrict_
 
 cudaError_t launch_gather_sorted(const float4* pts, const uint32_t* perm, int n, float4* sorted, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  k_gather_sorted<<<(n + 255) / 256, 256, 0, s>>>(pts, perm, n, sorted);
+  k_gather_sorted<<<(n + 255) / 256, 256, 0, s>>>(pts, perm, n, sorted); count_launch();
   return cudaGetLastError();
 }
 
@@ -292,7 +292,7 @@ cudaError_t launch_cell_table(const uint32_t* sorted_keys, int n, int bits, uint
   uint32_t C = 1u << (3 * bits);
   long long threads = (long long)n + 1;
   int blocks = (int)((threads + 255) / 256);
-  k_cell_table<<<blocks, 256, 0, s>>>(sorted_keys, n, C, start);
+  k_cell_table<<<blocks, 256, 0, s>>>(sorted_keys, n, C, start); count_launch();
   return cudaGetLastError();
 }
 

@@ -8,6 +8,10 @@
 
 namespace mvr {
 
+// Process-wide count of kernel launches issued by this library (bench.py reports it as gpu_launches).
+void count_launch(int n = 1);
+unsigned long long launch_count();
+
 // ---- index.cu ------------------------------------------------------------------------------
 // bbox: out[0..2] = min xyz, out[3..5] = max xyz (as order-preserving uint encodings), out[6] = count
 // of non-finite points.  `out` must be initialised with bbox_init().

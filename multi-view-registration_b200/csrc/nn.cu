@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(128) k_nn_query(const float4* __restrict__ q, 
 cudaError_t launch_nn_query(const float4* q, int nq, IndexDev ix, float max_d2, int32_t* out_idx, float* out_d2,
                             cudaStream_t s) {
   if (nq <= 0) return cudaSuccess;
-  k_nn_query<<<(nq + 127) / 128, 128, 0, s>>>(q, nq, ix, max_d2, out_idx, out_d2);
+  k_nn_query<<<(nq + 127) / 128, 128, 0, s>>>(q, nq, ix, max_d2, out_idx, out_d2); count_launch();
   return cudaGetLastError();
 }
 

@@ -111,7 +111,7 @@ cudaError_t launch_normals(IndexDev ix, const float4* pts_orig, int n, int k, fl
                            int32_t* out_nbr, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   if (k < 1 || k > KNN_MAX) return cudaErrorInvalidValue;
-  k_normals<<<(n + 127) / 128, 128, 0, s>>>(ix, pts_orig, n, k, viewpoint, out_nxyzc, out_nbr);
+  k_normals<<<(n + 127) / 128, 128, 0, s>>>(ix, pts_orig, n, k, viewpoint, out_nxyzc, out_nbr); count_launch();
   return cudaGetLastError();
 }
 

@@ -68,6 +68,8 @@ struct orc_icp_report {
   int reason;           // 0 none, 1 iterations, 2 transform, 3 abs mse, 4 rel mse, 5 no correspondences
   int n_correspondences;
   double mse;           // mean squared distance of the last correspondence set
+  unsigned long long nn_queries;  // tree queries answered: one per source point per iteration + one per
+                                  // gate-passing point when the reciprocal test is on
 };
 
 struct orc_iter_record {
@@ -294,19 +296,22 @@ void matmul4d(const double A[16], const double B[16], double C[16]) {  // column
 struct Corr { int q, m; float d2; };
 
 void correspondences_impl(const P4* src, int n, const P4* tgt, const KdTree& ttree, double max_dist, int reciprocal,
-                          std::vector<Corr>& out) {
+                          std::vector<Corr>& out, unsigned long long* n_queries = nullptr) {
   const double max2 = max_dist * max_dist;
   KdTree stree;
   if (reciprocal) stree.init(src, n);
   std::vector<int> fj(n); std::vector<float> fd(n); std::vector<char> keep(n, 0);
-#pragma omp parallel for schedule(dynamic, 1024)
+  unsigned long long nq = 0;
+#pragma omp parallel for schedule(dynamic, 1024) reduction(+ : nq)
   for (int i = 0; i < n; ++i) {
     int j; float d2;
     ttree.query(src[i], j, d2);
     fj[i] = j; fd[i] = d2;
+    ++nq;
     if (j < 0 || (double)d2 > max2) continue;
     if (reciprocal) {
       int ib; float db;
+      ++nq;
       stree.query(tgt[j], ib, db);
       if (ib != i || (double)db > max2) continue;
     }
@@ -314,6 +319,7 @@ void correspondences_impl(const P4* src, int n, const P4* tgt, const KdTree& ttr
   }
   out.clear();
   for (int i = 0; i < n; ++i) if (keep[i]) out.push_back(Corr{i, fj[i], fd[i]});
+  if (n_queries) *n_queries += nq;
 }
 
 void estimate_svd_impl(const P4* src, const P4* tgt, const std::vector<Corr>& corr, double T[16]) {
@@ -550,11 +556,12 @@ int orc_icp_align(const float* src_in, int n, const float* tgt_in, int m, const 
   int iter = 0, reason = 0, converged = 0;
   double prev_mse = DBL_MAX, cur_mse = 0;
   int nlog = 0;
+  unsigned long long queries = 0;
   const double rot_thr = 1.0 - prm->transformation_epsilon, trans_thr = prm->transformation_epsilon;
   const int min_corr = prm->min_correspondences > 0 ? prm->min_correspondences : 3;
   if (prm->max_iterations <= 0) { reason = 1; converged = 1; }
   while (!converged) {
-    correspondences_impl(cur.data(), n, tgt, ttree, prm->max_correspondence_distance, prm->use_reciprocal, corr);
+    correspondences_impl(cur.data(), n, tgt, ttree, prm->max_correspondence_distance, prm->use_reciprocal, corr, &queries);
     if ((int)corr.size() < min_corr) { reason = 5; converged = 0; break; }
     double T[16];
     if (prm->estimator == 1) {
@@ -595,7 +602,7 @@ int orc_icp_align(const float* src_in, int n, const float* tgt_in, int m, const 
     P4* o = (P4*)out_xyzw;
     for (int i = 0; i < n; ++i) o[i] = finite3(src0[i]) ? xform(finf, src0[i]) : src0[i];
   }
-  if (rep) { rep->iterations = iter; rep->converged = converged; rep->reason = reason; rep->n_correspondences = (int)corr.size(); rep->mse = cur_mse; }
+  if (rep) { rep->iterations = iter; rep->converged = converged; rep->reason = reason; rep->n_correspondences = (int)corr.size(); rep->mse = cur_mse; rep->nn_queries = queries; }
   if (n_log) *n_log = nlog;
   return reason == 5 ? 2 : 0;
 }

@@ -35,6 +35,7 @@ class IcpReport(C.Structure):
         ("reason", C.c_int),
         ("n_correspondences", C.c_int),
         ("mse", C.c_double),
+        ("nn_queries", C.c_ulonglong),
     ]
 
 
@@ -244,7 +245,7 @@ def icp_align(src, tgt, params, guess=None, tgt_normals=None, max_log=256):
                          delta=np.array(log[k].delta[:], dtype=np.float64).reshape(4, 4).T.copy()))
     return dict(status=rc, final=fin.reshape(4, 4).T.copy(), cloud=out,
                 iterations=rep.iterations, converged=rep.converged, reason=rep.reason,
-                n_corr=rep.n_correspondences, mse=rep.mse, log=recs)
+                n_corr=rep.n_correspondences, mse=rep.mse, nn_queries=int(rep.nn_queries), log=recs)
 
 
 def fitness_score(cloud, tgt, max_range=None):
