@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 HOST = os.path.join(HERE, "host")
 LIB = os.path.join(HERE, "libmvr_b200.so")
 
-CU_SOURCES = ["index.cu", "nn.cu", "icp.cu", "normals.cu", "api.cu"]
+CU_SOURCES = ["index.cu", "bin.cu", "nn.cu", "icp.cu", "normals.cu", "api.cu"]
 HOST_SOURCES = ["registrator.cpp", "lum.cpp", "capi.cpp"]
 
 NVCC_FLAGS = [
@@ -21,6 +21,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
     "-Xcompiler", "-fPIC",
+    "-fmad=false",          # IEEE add/mul everywhere: the device-side solves match the host arithmetic bit for bit
     "-Xcompiler", "-fno-fast-math",
 ]
 

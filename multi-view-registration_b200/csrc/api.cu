@@ -51,20 +51,30 @@ struct Cloud {
   float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
   int n_bad = 0;
   uint64_t gen = 0;
-  // index
+  // index: `sorted` (cell-ordered points, .w = original index) + `table` (cell starts).  Built either by
+  // the counting sort of bin.cu (order inside a cell unspecified) or by the stable radix sort of
+  // index.cu (mvr_index_build; `exportable`, keys/perm kept for mvr_index_export).
   bool index_valid = false;
+  bool exportable = false;
   uint64_t index_gen = 0;
   mvr_grid grid{};
   GridDev gd{};
-  DevBuf keys, vals, keys_alt, vals_alt, hist, sorted, table;
+  DevBuf keys, vals, keys_alt, vals_alt, hist, counters, sorted, table, occ;
   uint32_t* sorted_keys = nullptr;
   uint32_t* perm = nullptr;
+  bool has_occ = false;          // gate prefilter built for this index (IndexDev::occ)
+  int occ_shift = 0;
+  float occ_gate2 = 0.f;
   IndexDev dev() const {
     IndexDev ix;
     ix.pts = sorted.as<float4>(); ix.start = table.as<uint32_t>(); ix.g = gd; ix.n_valid = n - n_bad;
+    ix.occ = has_occ ? occ.as<uint8_t>() : nullptr; ix.occ_shift = occ_shift; ix.occ_gate2 = occ_gate2;
     return ix;
   }
-  void release() { own.release(); keys.release(); vals.release(); keys_alt.release(); vals_alt.release(); hist.release(); sorted.release(); table.release(); }
+  void release() {
+    own.release(); keys.release(); vals.release(); keys_alt.release(); vals_alt.release(); hist.release();
+    counters.release(); sorted.release(); table.release(); occ.release();
+  }
 };
 
 struct ProfRec { int kind; cudaEvent_t a, b; double bytes, units; };
@@ -75,9 +85,12 @@ struct mvr_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
-  Cloud tgt, src;
+  Cloud tgt, src, qry;          // qry: scratch cloud used to present queries in cell order
   DevBuf normals; bool has_normals = false;
-  DevBuf cur, corr_j, corr_d2, partials, sums, out_cloud, qtmp, itmp, ftmp, scratch, misc;
+  DevBuf cur, corr_j, corr_d2, partials, sums, out_cloud, qtmp, itmp, ftmp, scratch, misc, tiles, state, log;
+  uint32_t scan_epoch = 1;
+  IcpState* h_state = nullptr;   // pinned staging copy of the device IcpState
+  IterRec* h_log = nullptr;      // pinned, ICP_MAX_LOG records
   double* h_sums = nullptr;      // pinned, REDUCE_MAX_VALS
   uint32_t* h_small = nullptr;   // pinned, 16 words
   std::string err;
@@ -89,6 +102,7 @@ struct mvr_ctx {
   bool have_out = false;         // out_cloud holds transform(source, final) of the last align
   float cell_edge_opt = 0.f;
   int max_bits_opt = 8;
+  bool presort_queries = true;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
 };
 
@@ -247,6 +261,51 @@ int build_index(mvr_ctx* ctx, Cloud& c, const float4* pts, const mvr_grid& g) {
     CK(launch_cell_table(c.sorted_keys, n, g.bits, c.table.as<uint32_t>(), ctx->stream));
   }
   c.index_valid = true;
+  c.exportable = true;
+  c.has_occ = false;
+  c.index_gen = c.gen;
+  return MVR_OK;
+}
+
+// (Re)index cloud c's points `pts` (n = c.n) in grid g with the counting sort of bin.cu.  d_delta
+// (nullable, device float[16]) is applied to pts in place first; d_done (nullable) skips the work on
+// the device once an align has converged.
+int bin_index(mvr_ctx* ctx, Cloud& c, float4* pts, const mvr_grid& g, const float* d_delta, const int* d_done) {
+  const int n = c.n;
+  const size_t cells = (size_t)1 << (3 * g.bits);
+  const size_t nn = (size_t)std::max(n, 1);
+  CK(c.keys.ensure(nn * sizeof(uint32_t)));
+  CK(c.vals.ensure(nn * sizeof(uint32_t)));
+  CK(c.sorted.ensure(nn * sizeof(float4)));
+  CK(c.table.ensure((cells + 2) * sizeof(uint32_t)));
+  if ((cells + 1) * sizeof(uint32_t) > c.counters.cap) {
+    CK(c.counters.ensure((cells + 1) * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(c.counters.p, 0, c.counters.cap, ctx->stream));   // k_scan_cells keeps them zero afterwards
+  }
+  const size_t tiles = (size_t)scan_num_tiles(cells + 1);
+  if (tiles * sizeof(unsigned long long) > ctx->tiles.cap) {
+    CK(ctx->tiles.ensure(tiles * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(ctx->tiles.p, 0, ctx->tiles.cap, ctx->stream));
+  }
+  c.grid = g;
+  c.gd = to_dev(g);
+  {
+    ProfScope ps(ctx, MVR_K_TRANSFORM, (d_delta ? 40.0 : 24.0) * n, n);
+    CK(launch_transform_bin(pts, n, d_delta, d_done, c.gd, c.keys.as<uint32_t>(), c.vals.as<uint32_t>(), c.counters.as<uint32_t>(), ctx->stream));
+  }
+  {
+    ProfScope ps(ctx, MVR_K_TABLE, 8.0 * (double)(cells + 1), (double)cells);
+    CK(launch_scan_cells(c.counters.as<uint32_t>(), c.table.as<uint32_t>(), cells + 1, ctx->tiles.as<unsigned long long>(),
+                         ctx->scan_epoch, d_done, ctx->stream));
+    ctx->scan_epoch = (ctx->scan_epoch % 0x3fffffffu) + 1;
+  }
+  {
+    ProfScope ps(ctx, MVR_K_SORT, 44.0 * n, n);
+    CK(launch_bin_scatter(pts, n, c.keys.as<uint32_t>(), c.vals.as<uint32_t>(), c.table.as<uint32_t>(), d_done, c.sorted.as<float4>(), ctx->stream));
+  }
+  c.index_valid = true;
+  c.exportable = false;
+  c.has_occ = false;
   c.index_gen = c.gen;
   return MVR_OK;
 }
@@ -260,7 +319,18 @@ int ensure_target_index(mvr_ctx* ctx, const mvr_grid* want) {
   Cloud& t = ctx->tgt;
   if (t.index_valid && t.index_gen == t.gen && (!want || same_grid(*want, t.grid))) return MVR_OK;
   mvr_grid g = want ? *want : auto_grid(ctx, t);
-  return build_index(ctx, t, t.pts, g);
+  return bin_index(ctx, t, const_cast<float4*>(t.pts), g, nullptr, nullptr);
+}
+
+// Present `n` query points (device) in the cell order of the target grid: fills ctx->qry.
+int sort_queries(mvr_ctx* ctx, const float4* q, int n) {
+  Cloud& c = ctx->qry;
+  c.pts = q; c.n = n; c.n_bad = 0; c.gen++;
+  // the order only has to be coherent, so a coarse (<= 64^3) version of the target grid is enough and
+  // keeps the counting sort's table small; coarse Morton order is a prefix of the fine one
+  mvr_grid g = ctx->tgt.grid;
+  while (g.bits > 6) { g.bits -= 1; g.inv_cell *= 0.5f; g.cell *= 2.0f; }
+  return bin_index(ctx, c, const_cast<float4*>(q), g, nullptr, nullptr);
 }
 
 void mat_identity(float* m) { for (int k = 0; k < 16; ++k) m[k] = (k % 5 == 0) ? 1.f : 0.f; }
@@ -276,8 +346,20 @@ void matmul4d(const double* A, const double* B, double* C) {
   std::memcpy(C, t, sizeof(t));
 }
 
-// Grid for an align / correspondence pass: covers target and (guess-transformed) source boxes.
-mvr_grid pair_grid(mvr_ctx* ctx, const float* G, double max_dist) {
+float gate_float(double max_dist) {
+  double m2 = max_dist * max_dist;
+  if (!(m2 < (double)FLT_MAX)) return INFINITY;
+  float f = (float)m2;
+  if ((double)f < m2) f = std::nextafterf(f, INFINITY);
+  return std::nextafterf(f, INFINITY);
+}
+
+// Grids for an align / correspondence pass, both covering the target and the (guess-transformed)
+// source boxes so that clamping at the grid boundary stays rare:
+//   target grid: fine cells (~4 points per occupied cell) -- built once per align, searched 30 x n times;
+//   source grid: coarse cells (~16 points per cell) -- rebuilt every iteration, and the reciprocal
+//                search into it is seeded with a tight radius, so the cheap table matters more.
+void pair_grids(mvr_ctx* ctx, const float* G, mvr_grid* gt, mvr_grid* gs) {
   const Cloud &t = ctx->tgt, &s = ctx->src;
   float lo[3], hi[3];
   for (int a = 0; a < 3; ++a) { lo[a] = t.lo[a]; hi[a] = t.hi[a]; }
@@ -290,77 +372,61 @@ mvr_grid pair_grid(mvr_ctx* ctx, const float* G, double max_dist) {
       }
     }
   }
-  double e_den = density_cell_edge(t.lo, t.hi, t.n - t.n_bad, 48.0);
-  double e = e_den;
-  if (max_dist > 0 && std::isfinite(max_dist) && max_dist < e_den) e = max_dist;
-  if (ctx->cell_edge_opt > 0) e = ctx->cell_edge_opt;
-  for (int a = 0; a < 3; ++a) { lo[a] -= (float)e; hi[a] += (float)e; }
-  return make_grid(lo, hi, e, ctx->max_bits_opt);
+  double et = ctx->cell_edge_opt > 0 ? ctx->cell_edge_opt : density_cell_edge(t.lo, t.hi, t.n - t.n_bad, 4.0);
+  double es = ctx->cell_edge_opt > 0 ? ctx->cell_edge_opt : density_cell_edge(s.lo, s.hi, s.n - s.n_bad, 16.0);
+  float lt[3], ht[3], ls[3], hs[3];
+  for (int a = 0; a < 3; ++a) { lt[a] = lo[a] - (float)et; ht[a] = hi[a] + (float)et; ls[a] = lo[a] - (float)es; hs[a] = hi[a] + (float)es; }
+  *gt = make_grid(lt, ht, et, std::min(ctx->max_bits_opt, 7));
+  *gs = make_grid(ls, hs, es, std::min(ctx->max_bits_opt, 6));
 }
 
-float gate_float(double max_dist) {
-  double m2 = max_dist * max_dist;
-  if (!(m2 < (double)FLT_MAX)) return INFINITY;
-  float f = (float)m2;
-  if ((double)f < m2) f = std::nextafterf(f, INFINITY);
-  return std::nextafterf(f, INFINITY);
+// Gate prefilter of the target index for gates up to max_dist (no-op for an infinite gate).
+int ensure_target_occupancy(mvr_ctx* ctx, double max_dist) {
+  Cloud& t = ctx->tgt;
+  const double m2 = max_dist * max_dist;
+  if (!(m2 < 1e30) || t.n - t.n_bad <= 0) { t.has_occ = false; return MVR_OK; }
+  const double edge = 1.0 / (double)t.grid.inv_cell;
+  int shift = 0;
+  while (shift < t.grid.bits && edge * (double)(1 << shift) < 1.01 * max_dist) ++shift;
+  if (edge * (double)(1 << shift) < 1.01 * max_dist) { t.has_occ = false; return MVR_OK; }   // gate wider than the grid
+  const float g2 = gate_float(max_dist);
+  if (t.has_occ && t.occ_shift == shift && t.occ_gate2 >= g2) return MVR_OK;
+  CK(t.occ.ensure((size_t)1 << (3 * (t.grid.bits - shift))));
+  CK(launch_build_occupancy(t.table.as<uint32_t>(), t.grid.bits, shift, t.occ.as<uint8_t>(), ctx->stream));
+  t.has_occ = true; t.occ_shift = shift; t.occ_gate2 = g2;
+  return MVR_OK;
 }
 
 int ensure_pinned(mvr_ctx* ctx) {
   if (!ctx->h_sums) CK(cudaMallocHost((void**)&ctx->h_sums, REDUCE_MAX_VALS * sizeof(double)));
   if (!ctx->h_small) CK(cudaMallocHost((void**)&ctx->h_small, 64 * sizeof(uint32_t)));
+  if (!ctx->h_state) CK(cudaMallocHost((void**)&ctx->h_state, sizeof(IcpState)));
+  if (!ctx->h_log) CK(cudaMallocHost((void**)&ctx->h_log, ICP_MAX_LOG * sizeof(IterRec)));
   return MVR_OK;
 }
 
-// One correspondence pass source -> target on the current source coordinates `cur`.
-// reciprocal: re-index `cur` in the pair grid first (PCL rebuilds the source kd-tree every iteration).
-int correspond_pass(mvr_ctx* ctx, const float4* cur, bool need_keys_done, const mvr_grid& g, bool reciprocal, double max_dist) {
+// Algorithmic bytes of one correspondence launch: each query read once (16 B) and
+// its result written once (8 B), each target point once (16 B); the reciprocal test reads each source
+// point once more (16 B).  Cell-table entries are NOT counted (conservative).
+double corr_bytes(int n, int m, bool reciprocal) { return 24.0 * n + 16.0 * m + (reciprocal ? 16.0 * n : 0.0); }
+
+// One ICP iteration's search half on the current source coordinates `cur`: apply the pending delta
+// in place, re-index the source in the pair grid (PCL rebuilds the source kd-tree every iteration; we
+// also use the cell order to keep neighbouring threads on neighbouring queries), then search.
+int correspond_pass(mvr_ctx* ctx, float4* cur, const mvr_grid& gs, bool reciprocal, double max_dist, const float* d_delta,
+                    const int* d_done) {
   Cloud& s = ctx->src;
   const int n = s.n;
   const double max2 = max_dist * max_dist;
   const float max_d2f = gate_float(max_dist);
-  CK(ctx->corr_j.ensure(std::max(n, 1) * sizeof(int32_t)));
-  CK(ctx->corr_d2.ensure(std::max(n, 1) * sizeof(float)));
-  IndexDev tix = ctx->tgt.dev();
-  const double tbytes = 16.0 * ctx->tgt.n + 4.0 * (double)((size_t)1 << (3 * g.bits));
-  if (reciprocal) {
-    (void)need_keys_done;
-    int key_bits = 3 * g.bits + (s.n_bad > 0 ? 1 : 0);
-    SortScratch sc{s.keys_alt.as<uint32_t>(), s.vals_alt.as<uint32_t>(), s.hist.as<uint32_t>()};
-    {
-      ProfScope ps(ctx, MVR_K_SORT, 16.0 * n, n);
-      CK(launch_radix_sort(s.keys.as<uint32_t>(), s.vals.as<uint32_t>(), n, key_bits, sc, &s.sorted_keys, &s.perm, ctx->stream));
-    }
-    {
-      ProfScope ps(ctx, MVR_K_TABLE, 36.0 * n + 4.0 * (double)((size_t)1 << (3 * g.bits)), n);
-      CK(launch_gather_sorted(cur, s.perm, n, s.sorted.as<float4>(), ctx->stream));
-      CK(launch_cell_table(s.sorted_keys, n, g.bits, s.table.as<uint32_t>(), ctx->stream));
-    }
-    s.grid = g; s.gd = to_dev(g);
-    IndexDev six = s.dev();
-    ProfScope ps(ctx, MVR_K_CORR, 24.0 * n + tbytes + 16.0 * n, 2.0 * n);
-    CK(launch_correspond(s.sorted.as<float4>(), n, true, tix, ctx->tgt.pts, six, true, max2, max_d2f,
-                         ctx->corr_j.as<int32_t>(), ctx->corr_d2.as<float>(), ctx->stream));
-  } else {
-    IndexDev six{};
-    ProfScope ps(ctx, MVR_K_CORR, 24.0 * n + tbytes, n);
-    CK(launch_correspond(cur, n, false, tix, ctx->tgt.pts, six, false, max2, max_d2f, ctx->corr_j.as<int32_t>(),
-                         ctx->corr_d2.as<float>(), ctx->stream));
-  }
-  return MVR_OK;
-}
-
-int ensure_source_index_buffers(mvr_ctx* ctx, const mvr_grid& g) {
-  Cloud& s = ctx->src;
-  const int n = std::max(s.n, 1);
-  const size_t cells = (size_t)1 << (3 * g.bits);
-  CK(s.keys.ensure(n * sizeof(uint32_t)));
-  CK(s.vals.ensure(n * sizeof(uint32_t)));
-  CK(s.keys_alt.ensure(n * sizeof(uint32_t)));
-  CK(s.vals_alt.ensure(n * sizeof(uint32_t)));
-  CK(s.hist.ensure((size_t)256 * radix_num_blocks(s.n) * sizeof(uint32_t)));
-  CK(s.sorted.ensure(n * sizeof(float4)));
-  CK(s.table.ensure((cells + 2) * sizeof(uint32_t)));
+  CK(ctx->corr_j.ensure((size_t)std::max(n, 1) * sizeof(int32_t)));
+  CK(ctx->corr_d2.ensure((size_t)std::max(n, 1) * sizeof(float)));
+  int rc = bin_index(ctx, s, cur, gs, d_delta, d_done);
+  if (rc) return rc;
+  s.index_valid = false;   // the index describes `cur`, not the caller's source cloud
+  ProfScope ps(ctx, MVR_K_CORR, corr_bytes(n, ctx->tgt.n, reciprocal), (double)n);
+  CK(launch_correspond(s.sorted.as<float4>(), n, ctx->tgt.dev(), s.dev(), reciprocal, max2, max_d2f, ctx->corr_j.as<int32_t>(),
+                       ctx->corr_d2.as<float>(), d_done, ctx->stream));
   return MVR_OK;
 }
 
@@ -423,12 +489,14 @@ int mvr_ctx_destroy(mvr_ctx* ctx) {
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
-  ctx->tgt.release(); ctx->src.release(); ctx->normals.release();
+  ctx->tgt.release(); ctx->src.release(); ctx->qry.release(); ctx->normals.release();
   DevBuf* bufs[] = {&ctx->cur, &ctx->corr_j, &ctx->corr_d2, &ctx->partials, &ctx->sums, &ctx->out_cloud, &ctx->qtmp,
-                    &ctx->itmp, &ctx->ftmp, &ctx->scratch, &ctx->misc};
+                    &ctx->itmp, &ctx->ftmp, &ctx->scratch, &ctx->misc, &ctx->tiles, &ctx->state, &ctx->log};
   for (DevBuf* b : bufs) b->release();
   if (ctx->h_sums) cudaFreeHost(ctx->h_sums);
   if (ctx->h_small) cudaFreeHost(ctx->h_small);
+  if (ctx->h_state) cudaFreeHost(ctx->h_state);
+  if (ctx->h_log) cudaFreeHost(ctx->h_log);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return MVR_OK;
@@ -533,7 +601,7 @@ int mvr_index_export(mvr_ctx* ctx, int which, mvr_grid* grid, uint32_t* sorted_k
   if (!ctx || (which != MVR_CLOUD_TARGET && which != MVR_CLOUD_SOURCE)) return MVR_ERR_BAD_ARG;
   cudaSetDevice(ctx->device);
   Cloud& c = which == MVR_CLOUD_TARGET ? ctx->tgt : ctx->src;
-  if (!c.index_valid) return fail(ctx, MVR_ERR_NO_INPUT, "index not built");
+  if (!c.index_valid || !c.exportable) return fail(ctx, MVR_ERR_NO_INPUT, "index not built (call mvr_index_build first)");
   if (grid) *grid = c.grid;
   if (sorted_keys && c.n) CK(cudaMemcpyAsync(sorted_keys, c.sorted_keys, c.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   if (perm && c.n) CK(cudaMemcpyAsync(perm, c.perm, c.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -544,13 +612,21 @@ int mvr_index_export(mvr_ctx* ctx, int which, mvr_grid* grid, uint32_t* sorted_k
 
 int mvr_nn_query_device(mvr_ctx* ctx, const float* d_q, size_t n, int32_t* d_idx, float* d_d2) {
   if (!ctx || (n && (!d_q || !d_idx || !d_d2))) return MVR_ERR_BAD_ARG;
+  if (n > (size_t)INT_MAX / 2) return fail(ctx, MVR_ERR_BAD_ARG, "too many queries");
   cudaSetDevice(ctx->device);
   if (ctx->tgt.gen == 0) return fail(ctx, MVR_ERR_NO_INPUT, "target not set");
   int rc = ensure_target_index(ctx, nullptr);
   if (rc) return rc;
+  if (n == 0) return MVR_OK;
   const Cloud& t = ctx->tgt;
-  ProfScope ps(ctx, MVR_K_NN, 24.0 * n + 16.0 * t.n + 4.0 * (double)((size_t)1 << (3 * t.grid.bits)), (double)n);
-  CK(launch_nn_query((const float4*)d_q, (int)n, t.dev(), INFINITY, d_idx, d_d2, ctx->stream));
+  const float4* q = (const float4*)d_q;
+  if (ctx->presort_queries) {
+    // queries arrive in caller order; walking them in cell order keeps a warp inside a few cells
+    if ((rc = sort_queries(ctx, q, (int)n))) return rc;
+    q = ctx->qry.sorted.as<float4>();
+  }
+  ProfScope ps(ctx, MVR_K_NN, 24.0 * n + 16.0 * t.n, (double)n);
+  CK(launch_nn_query(q, (int)n, ctx->presort_queries, t.dev(), INFINITY, d_idx, d_d2, ctx->stream));
   return MVR_OK;
 }
 
@@ -582,16 +658,12 @@ int mvr_correspondences(mvr_ctx* ctx, double max_dist, int reciprocal, int32_t* 
   if (!iq || !im || !dist) return MVR_ERR_BAD_ARG;
   float I[16];
   mat_identity(I);
-  mvr_grid g = pair_grid(ctx, I, max_dist);
-  int rc = ensure_target_index(ctx, &g);
+  mvr_grid gt, gs;
+  pair_grids(ctx, I, &gt, &gs);
+  int rc = ensure_target_index(ctx, &gt);
   if (rc) return rc;
-  if (reciprocal) {
-    rc = ensure_source_index_buffers(ctx, g);
-    if (rc) return rc;
-    ProfScope ps(ctx, MVR_K_MORTON, 24.0 * n, n);
-    CK(launch_morton_keys(ctx->src.pts, n, to_dev(g), ctx->src.keys.as<uint32_t>(), ctx->src.vals.as<uint32_t>(), ctx->stream));
-  }
-  rc = correspond_pass(ctx, ctx->src.pts, true, g, reciprocal != 0, max_dist);
+  if ((rc = ensure_target_occupancy(ctx, max_dist))) return rc;
+  rc = correspond_pass(ctx, const_cast<float4*>(ctx->src.pts), gs, reciprocal != 0, max_dist, nullptr, nullptr);
   if (rc) return rc;
   CK(ctx->scratch.ensure(compact_scratch_elems(n) * sizeof(uint32_t) + 64));
   CK(ctx->itmp.ensure((size_t)2 * n * sizeof(int32_t)));
@@ -629,122 +701,94 @@ int mvr_icp_align(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, f
   if (guess) std::memcpy(G, guess, sizeof(G)); else mat_identity(G);
   const bool reciprocal = prm->use_reciprocal_correspondences != 0;
   const double max_dist = prm->max_correspondence_distance;
-  const int min_corr = prm->min_correspondences > 0 ? prm->min_correspondences : 3;
   const bool p2l = prm->estimator == MVR_POINT_TO_PLANE;
 
-  mvr_grid g = pair_grid(ctx, G, max_dist);
-  int rc = ensure_target_index(ctx, &g);
+  mvr_grid gt, gs;
+  pair_grids(ctx, G, &gt, &gs);
+  int rc = ensure_target_index(ctx, &gt);
   if (rc) return rc;
-  if (reciprocal && (rc = ensure_source_index_buffers(ctx, g))) return rc;
+  if ((rc = ensure_target_occupancy(ctx, max_dist))) return rc;
   CK(ctx->cur.ensure((size_t)n * sizeof(float4)));
   CK(ctx->partials.ensure((size_t)REDUCE_BLOCKS * REDUCE_MAX_VALS * sizeof(double)));
-  CK(ctx->sums.ensure(REDUCE_MAX_VALS * sizeof(double)));
   CK(ctx->out_cloud.ensure((size_t)n * sizeof(float4)));
+  CK(ctx->state.ensure(sizeof(IcpState)));
+  CK(ctx->log.ensure((size_t)ICP_MAX_LOG * sizeof(IterRec)));
   float4* cur = ctx->cur.as<float4>();
-  CK(cudaEventRecord(ctx->ev_a, ctx->stream));
-  CK(cudaMemcpyAsync(cur, s.pts, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+  IcpState* d_st = ctx->state.as<IcpState>();
+  IterRec* d_log = ctx->log.as<IterRec>();
+  const float* d_delta = (const float*)((const char*)d_st + offsetof(IcpState, delta));
+  const int* d_done = (const int*)((const char*)d_st + offsetof(IcpState, done));
 
+  // initial state: the guess is the first "delta" (ICP transforms the input by the guess, then iterates)
+  IcpState& h = *ctx->h_state;
+  std::memset(&h, 0, sizeof(h));
+  for (int k = 0; k < 16; ++k) { h.delta[k] = G[k]; h.fin[k] = G[k]; }
+  h.prev_mse = DBL_MAX;
+  h.rot_thr = 1.0 - prm->transformation_epsilon;
+  h.trans_thr = prm->transformation_epsilon;
+  h.fit_eps = prm->euclidean_fitness_epsilon;
   // provisional origin for the sums: centre of the target box (keeps the double sums well scaled)
-  double3 o = make_double3(0.5 * ((double)ctx->tgt.lo[0] + ctx->tgt.hi[0]), 0.5 * ((double)ctx->tgt.lo[1] + ctx->tgt.hi[1]),
-                           0.5 * ((double)ctx->tgt.lo[2] + ctx->tgt.hi[2]));
-  Mat4f M;
-  std::memcpy(M.m, G, sizeof(G));
-  double fin[16];
-  for (int k = 0; k < 16; ++k) fin[k] = G[k];
+  h.ox = 0.5 * ((double)ctx->tgt.lo[0] + ctx->tgt.hi[0]);
+  h.oy = 0.5 * ((double)ctx->tgt.lo[1] + ctx->tgt.hi[1]);
+  h.oz = 0.5 * ((double)ctx->tgt.lo[2] + ctx->tgt.hi[2]);
+  h.max_iter = prm->max_iterations;
+  h.fixed = prm->fixed_iterations != 0;
+  h.min_corr = prm->min_correspondences > 0 ? prm->min_correspondences : 3;
+  h.p2l = p2l; h.recip = reciprocal; h.n_src = n;
+  if (prm->max_iterations <= 0) { h.done = 1; h.reason = MVR_REASON_ITERATIONS; }
+
+  CK(cudaEventRecord(ctx->ev_a, ctx->stream));
+  CK(cudaMemcpyAsync(d_st, &h, sizeof(IcpState), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(cur, s.pts, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
   ctx->iters.clear();
   ctx->have_out = false;
-  int iter = 0, reason = MVR_REASON_NONE, converged = 0, n_corr = 0;
-  double prev_mse = DBL_MAX, cur_mse = 0.0;
-  uint64_t queries = 0;
-  const double rot_thr = 1.0 - prm->transformation_epsilon, trans_thr = prm->transformation_epsilon;
-  const GridDev gd = to_dev(g);
-  int status = MVR_OK;
-  if (prm->max_iterations <= 0) { converged = 1; reason = MVR_REASON_ITERATIONS; }
-  while (!converged) {
-    {
-      ProfScope ps(ctx, MVR_K_TRANSFORM, (reciprocal ? 40.0 : 32.0) * n, n);
-      CK(launch_transform_keys(cur, n, M, gd, reciprocal ? s.keys.as<uint32_t>() : nullptr,
-                               reciprocal ? s.vals.as<uint32_t>() : nullptr, ctx->stream));
-    }
-    rc = correspond_pass(ctx, cur, true, g, reciprocal, max_dist);
-    if (rc) return rc;
-    {
+
+  // Enqueue iterations in batches; after each batch read the state back.  Once the device raises
+  // `done` the remaining launches of a batch return immediately.
+  int enqueued = 0;
+  int batch = h.fixed ? 64 : 2;
+  bool done = h.done != 0;
+  while (!done) {
+    int todo = std::min(batch, std::max(prm->max_iterations - enqueued, 1));
+    for (int it = 0; it < todo; ++it) {
+      rc = correspond_pass(ctx, cur, gs, reciprocal, max_dist, d_delta, d_done);
+      if (rc) return rc;
       ProfScope ps(ctx, MVR_K_REDUCE, 36.0 * n, n);
-      if (p2l)
-        CK(launch_reduce_p2l(cur, n, ctx->corr_j.as<int32_t>(), ctx->corr_d2.as<float>(), ctx->tgt.pts, ctx->normals.as<float4>(), o,
-                             ctx->partials.as<double>(), ctx->sums.as<double>(), ctx->stream));
-      else
-        CK(launch_reduce_p2p(cur, n, ctx->corr_j.as<int32_t>(), ctx->corr_d2.as<float>(), ctx->tgt.pts, o,
-                             ctx->partials.as<double>(), ctx->sums.as<double>(), ctx->stream));
+      CK(launch_reduce_solve(cur, n, ctx->corr_j.as<int32_t>(), ctx->corr_d2.as<float>(), ctx->tgt.pts,
+                             p2l ? ctx->normals.as<float4>() : nullptr, ctx->partials.as<double>(), d_st, d_log, p2l, ctx->stream));
     }
-    CK(cudaMemcpyAsync(ctx->h_sums, ctx->sums.p, REDUCE_MAX_VALS * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    enqueued += todo;
+    CK(cudaMemcpyAsync(&h, d_st, sizeof(IcpState), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    const double* S = ctx->h_sums;
-    double T[16];
-    double cnt = p2l ? S[27] : S[0];
-    double d2sum = p2l ? S[28] : S[16];
-    queries += (uint64_t)n + (reciprocal ? (uint64_t)(p2l ? S[29] : S[17]) : 0);
-    n_corr = (int)cnt;
-    if (n_corr < min_corr) { reason = MVR_REASON_NO_CORRESPONDENCES; status = MVR_ERR_TOO_FEW_CORRESPONDENCES; break; }
-    if (p2l) {
-      double A[36], b[6], x[6];
-      int k = 0;
-      for (int a = 0; a < 6; ++a)
-        for (int c = a; c < 6; ++c) { A[a * 6 + c] = S[k]; A[c * 6 + a] = S[k]; ++k; }
-      for (int a = 0; a < 6; ++a) b[a] = S[21 + a];
-      if (!cholesky_solve6(A, b, x)) { reason = MVR_REASON_NO_CORRESPONDENCES; status = MVR_ERR_NOT_SPD; break; }
-      pose_from_6(x, T);
-    } else {
-      double mu_a[3] = {S[1] / cnt, S[2] / cnt, S[3] / cnt}, mu_b[3] = {S[4] / cnt, S[5] / cnt, S[6] / cnt};
-      double Sg[9];
-      for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) Sg[r * 3 + c] = S[7 + r * 3 + c] / cnt - mu_b[r] * mu_a[c];
-      double mu_s[3] = {mu_a[0] + o.x, mu_a[1] + o.y, mu_a[2] + o.z}, mu_d[3] = {mu_b[0] + o.x, mu_b[1] + o.y, mu_b[2] + o.z};
-      umeyama_rigid(mu_s, mu_d, Sg, T);
-    }
-    float Tf[16];
-    for (int k = 0; k < 16; ++k) Tf[k] = (float)T[k];
-    Tf[3] = Tf[7] = Tf[11] = 0.f; Tf[15] = 1.f;
-    double Td[16];
-    for (int k = 0; k < 16; ++k) Td[k] = Tf[k];
-    matmul4d(Td, fin, fin);
-    ++iter;
-    cur_mse = d2sum / cnt;
-    mvr_icp_iteration rec;
-    rec.iteration = iter; rec.n_correspondences = n_corr; rec.mse = cur_mse;
-    std::memcpy(rec.delta, Tf, sizeof(Tf));
-    ctx->iters.push_back(rec);
-    std::memcpy(M.m, Tf, sizeof(Tf));
-    // DefaultConvergenceCriteria::hasConverged
-    if (iter >= prm->max_iterations) { converged = 1; reason = MVR_REASON_ITERATIONS; break; }
-    if (!prm->fixed_iterations) {
-      double cos_angle = 0.5 * (Td[0] + Td[5] + Td[10] - 1.0);
-      double t2 = Td[12] * Td[12] + Td[13] * Td[13] + Td[14] * Td[14];
-      if (cos_angle >= rot_thr && t2 <= trans_thr) { converged = 1; reason = MVR_REASON_TRANSFORM; break; }
-      if (std::fabs(cur_mse - prev_mse) < 1e-12) { converged = 1; reason = MVR_REASON_ABS_MSE; break; }
-      if (std::fabs(cur_mse - prev_mse) / prev_mse < prm->euclidean_fitness_epsilon) { converged = 1; reason = MVR_REASON_REL_MSE; break; }
-      prev_mse = cur_mse;
-    }
+    done = h.done != 0;
+    batch = std::min(batch * 2, 64);
   }
-  Mat4f F;
-  for (int k = 0; k < 16; ++k) F.m[k] = (float)fin[k];
   {
     ProfScope ps(ctx, MVR_K_TRANSFORM, 32.0 * n, n);
-    CK(launch_transform(s.pts, ctx->out_cloud.as<float4>(), n, F, ctx->stream));
+    CK(launch_transform_final(s.pts, ctx->out_cloud.as<float4>(), n, d_st, ctx->stream));
   }
   CK(cudaEventRecord(ctx->ev_b, ctx->stream));
+  const int n_log = std::min(h.iter, (int)ICP_MAX_LOG);
+  if (n_log > 0) CK(cudaMemcpyAsync(ctx->h_log, d_log, (size_t)n_log * sizeof(IterRec), cudaMemcpyDeviceToHost, ctx->stream));
   if (out_xyzw) CK(cudaMemcpyAsync(out_xyzw, ctx->out_cloud.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->have_out = true;
-  if (out_pose) std::memcpy(out_pose, F.m, sizeof(F.m));
+  for (int k = 0; k < n_log; ++k) {
+    mvr_icp_iteration rec;
+    rec.iteration = ctx->h_log[k].iteration; rec.n_correspondences = ctx->h_log[k].n_corr; rec.mse = ctx->h_log[k].mse;
+    std::memcpy(rec.delta, ctx->h_log[k].delta, sizeof(rec.delta));
+    ctx->iters.push_back(rec);
+  }
+  if (out_pose) for (int k = 0; k < 16; ++k) out_pose[k] = (float)h.fin[k];
   if (report) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
-    report->iterations = iter; report->converged = converged; report->reason = reason; report->n_correspondences = n_corr;
-    report->mse = cur_mse; report->gpu_ms = ms; report->nn_queries = queries;
+    report->iterations = h.iter; report->converged = (h.done && h.status == 0) ? 1 : 0; report->reason = h.reason;
+    report->n_correspondences = h.n_corr; report->mse = h.cur_mse; report->gpu_ms = ms; report->nn_queries = h.queries;
   }
-  if (status == MVR_ERR_TOO_FEW_CORRESPONDENCES) ctx->err = "not enough correspondences";
-  return status;
+  if (h.status == MVR_ERR_TOO_FEW_CORRESPONDENCES) ctx->err = "not enough correspondences";
+  if (h.status == MVR_ERR_NOT_SPD) ctx->err = "point-to-plane normal equations not positive definite";
+  return h.status;
 }
 
 int mvr_icp_get_iterations(mvr_ctx* ctx, mvr_icp_iteration* out, int max_records, int* count) {
@@ -775,9 +819,10 @@ int mvr_fitness_score(mvr_ctx* ctx, double max_range, double* score) {
   CK(ctx->partials.ensure((size_t)REDUCE_BLOCKS * REDUCE_MAX_VALS * sizeof(double)));
   CK(ctx->sums.ensure(REDUCE_MAX_VALS * sizeof(double)));
   const Cloud& t = ctx->tgt;
+  if ((rc = sort_queries(ctx, cloud, n))) return rc;
   {
-    ProfScope ps(ctx, MVR_K_NN, 24.0 * n + 16.0 * t.n + 4.0 * (double)((size_t)1 << (3 * t.grid.bits)), (double)n);
-    CK(launch_nn_query(cloud, n, t.dev(), INFINITY, ctx->itmp.as<int32_t>(), ctx->ftmp.as<float>(), ctx->stream));
+    ProfScope ps(ctx, MVR_K_NN, 24.0 * n + 16.0 * t.n, (double)n);
+    CK(launch_nn_query(ctx->qry.sorted.as<float4>(), n, true, t.dev(), INFINITY, ctx->itmp.as<int32_t>(), ctx->ftmp.as<float>(), ctx->stream));
   }
   CK(launch_reduce_fitness(ctx->itmp.as<int32_t>(), ctx->ftmp.as<float>(), n, max_range, ctx->partials.as<double>(),
                            ctx->sums.as<double>(), ctx->stream));
@@ -798,7 +843,7 @@ int mvr_estimate_normals(mvr_ctx* ctx, int which, int k, const float viewpoint[3
   if (!c.index_valid || c.index_gen != c.gen) {
     // kNN wants about k points in the 27-neighbourhood: ~k/4 per occupied cell on a surface
     double e = ctx->cell_edge_opt > 0 ? ctx->cell_edge_opt : density_cell_edge(c.lo, c.hi, n - c.n_bad, std::max(2.0, k / 4.0));
-    int rc = build_index(ctx, c, c.pts, make_grid(c.lo, c.hi, e, ctx->max_bits_opt));
+    int rc = bin_index(ctx, c, const_cast<float4*>(c.pts), make_grid(c.lo, c.hi, e, ctx->max_bits_opt), nullptr, nullptr);
     if (rc) return rc;
   }
   float3 vp = viewpoint ? make_float3(viewpoint[0], viewpoint[1], viewpoint[2]) : make_float3(0.f, 0.f, 0.f);

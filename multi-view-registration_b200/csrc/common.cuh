@@ -26,6 +26,12 @@ struct IndexDev {
   const uint32_t* start;
   GridDev g;
   int n_valid;   // finite points (they occupy sorted positions [0, n_valid))
+  // Optional gate prefilter: occ[morton(cell >> occ_shift)] != 0 iff some indexed point lies in the
+  // 3x3x3 neighbourhood of that coarse cell.  Coarse edge >= 1.01 * sqrt(occ_gate2), so a query whose
+  // coarse cell reads 0 has no point within any gate <= occ_gate2.  nullptr: no prefilter.
+  const uint8_t* occ;
+  int occ_shift;
+  float occ_gate2;
 };
 
 struct Mat4f { float m[16]; };  // column-major

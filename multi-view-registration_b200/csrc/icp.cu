@@ -1,30 +1,36 @@
 // icp.cu -- per-iteration ICP kernels: correspondence search with gate + reciprocal test (K4+K5),
-// estimator sums (K6 point-to-point 3x3 cross-covariance, K9 point-to-plane 6x6 normal equations),
-// fitness reduction (K8) and order-preserving correspondence compaction.
+// estimator sums (K6 point-to-point 3x3 cross-covariance, K9 point-to-plane 6x6 normal equations)
+// with the solve and the convergence test in the reduction's last block, fitness reduction (K8) and
+// order-preserving correspondence compaction.
 //
 // Restates, for the GPU, what pcl::IterativeClosestPoint does per iteration inside icp.align()
 // (reference call sites mvr/src/registrator.cpp:569, 920, 1012, 1024; semantics SURVEY.md A3-A8):
-//   determine(Reciprocal)Correspondences -> TransformationEstimationSVD sums -> (host) SVD.
+//   determine(Reciprocal)Correspondences -> TransformationEstimationSVD -> transformCloud ->
+//   DefaultConvergenceCriteria.
+// The whole loop state lives in an IcpState on the device, so an align needs no host round trip per
+// iteration: the host only enqueues iterations and reads the state back when a batch has run.
 #include "launch.h"
 #include "nn_search.cuh"
+#include "small_solve.h"
 
 namespace mvr {
 
 // ---------------------------------------------------------------------------------------------
 // correspondences: source point i -> nearest target j, gate, optional reciprocal test
 // ---------------------------------------------------------------------------------------------
-template <bool RECIP, bool QIDX>
-__global__ void __launch_bounds__(128) k_correspond(const float4* __restrict__ q, int nq, IndexDev tgt,
-                                                    const float4* __restrict__ tgt_orig, IndexDev src, double max2,
-                                                    float max_d2f, int32_t* __restrict__ corr_j, float* __restrict__ corr_d2) {
+template <bool RECIP>
+__global__ void __launch_bounds__(128) k_correspond(const float4* __restrict__ q, int nq, IndexDev tgt, IndexDev src, double max2,
+                                                    float max_d2f, int32_t* __restrict__ corr_j, float* __restrict__ corr_d2,
+                                                    const int* __restrict__ done) {
+  if (done && *done) return;
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nq) return;
   float4 p = __ldg(q + k);
-  const int i = QIDX ? __float_as_int(p.w) : k;
+  const int i = __float_as_int(p.w);
   int j = -1;
   float d2 = MVR_INF;
   if (finite3(p)) {
-    NnBest b{MVR_INF, 0x7fffffff};
+    NnBest b{MVR_INF, 0x7fffffff, -1};
     nn_search(tgt, p.x, p.y, p.z, max_d2f, b);
     if (b.idx != 0x7fffffff && !((double)b.d2 > max2)) {   // PCL: if (distance > max_dist_sqr) continue;
       bool keep = true;
@@ -32,8 +38,8 @@ __global__ void __launch_bounds__(128) k_correspond(const float4* __restrict__ q
         // nearest source point of the matched target point; seeded with (d2, i), which is exactly
         // what the search would compute for source point i (fsub(a,b) == -fsub(b,a)), so the result
         // is i iff no other source point is lexicographically closer.
-        float4 t = __ldg(tgt_orig + b.idx);
-        NnBest rb{b.d2, i};
+        float4 t = __ldg(tgt.pts + b.pos);
+        NnBest rb{b.d2, i, -1};
         nn_search(src, t.x, t.y, t.z, b.d2, rb);
         keep = (rb.idx == i);
       }
@@ -46,25 +52,20 @@ __global__ void __launch_bounds__(128) k_correspond(const float4* __restrict__ q
   corr_d2[i] = d2;
 }
 
-cudaError_t launch_correspond(const float4* q, int nq, bool q_has_index, IndexDev tgt, const float4* tgt_orig,
-                              IndexDev src, bool reciprocal, double max_dist2, float max_d2f, int32_t* corr_j,
-                              float* corr_d2, cudaStream_t s) {
+cudaError_t launch_correspond(const float4* q, int nq, IndexDev tgt, IndexDev src, bool reciprocal, double max_dist2,
+                              float max_d2f, int32_t* corr_j, float* corr_d2, const int* d_done, cudaStream_t s) {
   if (nq <= 0) return cudaSuccess;
   dim3 grid((nq + 127) / 128), block(128);
-  if (reciprocal) {
-    if (q_has_index) k_correspond<true, true><<<grid, block, 0, s>>>(q, nq, tgt, tgt_orig, src, max_dist2, max_d2f, corr_j, corr_d2);
-    else k_correspond<true, false><<<grid, block, 0, s>>>(q, nq, tgt, tgt_orig, src, max_dist2, max_d2f, corr_j, corr_d2);
-  } else {
-    if (q_has_index) k_correspond<false, true><<<grid, block, 0, s>>>(q, nq, tgt, tgt_orig, src, max_dist2, max_d2f, corr_j, corr_d2);
-    else k_correspond<false, false><<<grid, block, 0, s>>>(q, nq, tgt, tgt_orig, src, max_dist2, max_d2f, corr_j, corr_d2);
-  }
+  if (reciprocal) k_correspond<true><<<grid, block, 0, s>>>(q, nq, tgt, src, max_dist2, max_d2f, corr_j, corr_d2, d_done);
+  else k_correspond<false><<<grid, block, 0, s>>>(q, nq, tgt, src, max_dist2, max_d2f, corr_j, corr_d2, d_done);
   count_launch();
   return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------
-// estimator sums: fixed topology (thread grid-stride -> warp shuffle tree -> 8 warps in order ->
-// REDUCE_BLOCKS partials summed in block order), so results are identical run to run.
+// estimator sums: fixed topology (thread grid-stride over ORIGINAL indices -> warp shuffle tree ->
+// 8 warps in order -> REDUCE_BLOCKS partials summed in block order by the last block to finish), so
+// results are identical run to run and do not depend on the order of points inside grid cells.
 // ---------------------------------------------------------------------------------------------
 template <int NV>
 __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* __restrict__ partials) {
@@ -86,31 +87,126 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* __re
   }
 }
 
-__global__ void k_reduce_final(const double* __restrict__ partials, int nblk, int nv, double* __restrict__ out) {
-  int t = threadIdx.x;
-  if (t >= nv) return;
-  double x = 0;
-  for (int b = 0; b < nblk; ++b) x += partials[(size_t)b * REDUCE_MAX_VALS + t];
-  out[t] = x;
+// True in exactly one block per launch: the one that finished last.  On return in that block every
+// block's partials are visible.
+__device__ __forceinline__ bool last_block_done(unsigned int* ticket) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+    if (is_last) *ticket = 0;
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
 }
 
-// Point-to-point sums about `origin` o (a = s - o, b = t - o, exact in double):
+// Ordered sum of the blocks' partials: 8 chunks of consecutive blocks summed in parallel (each in
+// block order), then the 8 chunk sums in chunk order.  Called by all 256 threads of the last block.
+template <int NV>
+__device__ __forceinline__ void ordered_total(const double* __restrict__ partials, int nblk, double* __restrict__ out) {
+  __shared__ double ch[8][REDUCE_MAX_VALS];
+  const int a = threadIdx.x & 31, c = threadIdx.x >> 5;
+  const int per = (nblk + 7) / 8;
+  if (a < NV) {
+    const int b0 = c * per, b1 = min(b0 + per, nblk);
+    double x = 0;
+#pragma unroll 8
+    for (int b = b0; b < b1; ++b) x += __ldcg(partials + (size_t)b * REDUCE_MAX_VALS + a);
+    ch[c][a] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double x = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x += ch[k][threadIdx.x];
+    out[threadIdx.x] = x;
+  }
+  __syncthreads();
+}
+
+// The tail of one ICP iteration, run by one thread: estimate the increment from the sums, compose it
+// into the accumulated transform, log, and evaluate DefaultConvergenceCriteria.
+__device__ __noinline__ void icp_finish_iteration(IcpState* st, IterRec* log) {
+  const double* S = st->sums;
+  const bool p2l = st->p2l != 0;
+  const double cnt = p2l ? S[27] : S[0];
+  const double d2sum = p2l ? S[28] : S[16];
+  st->queries += (unsigned long long)st->n_src + (st->recip ? (unsigned long long)(p2l ? S[29] : S[17]) : 0ull);
+  const int n_corr = (int)cnt;
+  st->n_corr = n_corr;
+  if (n_corr < st->min_corr) { st->reason = 5; st->status = 2; st->done = 1; return; }  // "Not enough correspondences"
+  double T[16];
+  if (p2l) {
+    double A[36], b[6], x[6];
+    int k = 0;
+    for (int a = 0; a < 6; ++a)
+      for (int c = a; c < 6; ++c) { A[a * 6 + c] = S[k]; A[c * 6 + a] = S[k]; ++k; }
+    for (int a = 0; a < 6; ++a) b[a] = S[21 + a];
+    if (!cholesky_solve6(A, b, x)) { st->reason = 5; st->status = 5; st->done = 1; return; }
+    pose_from_6(x, T);
+  } else {
+    double mu_a[3] = {S[1] / cnt, S[2] / cnt, S[3] / cnt}, mu_b[3] = {S[4] / cnt, S[5] / cnt, S[6] / cnt};
+    double Sg[9];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) Sg[r * 3 + c] = S[7 + r * 3 + c] / cnt - mu_b[r] * mu_a[c];
+    double mu_s[3] = {mu_a[0] + st->ox, mu_a[1] + st->oy, mu_a[2] + st->oz};
+    double mu_d[3] = {mu_b[0] + st->ox, mu_b[1] + st->oy, mu_b[2] + st->oz};
+    umeyama_rigid(mu_s, mu_d, Sg, T);
+  }
+  float Tf[16];
+  for (int k = 0; k < 16; ++k) Tf[k] = (float)T[k];
+  Tf[3] = Tf[7] = Tf[11] = 0.f; Tf[15] = 1.f;
+  double Td[16], F[16];
+  for (int k = 0; k < 16; ++k) Td[k] = Tf[k];
+  for (int c = 0; c < 4; ++c)
+    for (int r = 0; r < 4; ++r) {
+      double x = 0;
+      for (int k = 0; k < 4; ++k) x += Td[k * 4 + r] * st->fin[c * 4 + k];
+      F[c * 4 + r] = x;
+    }
+  for (int k = 0; k < 16; ++k) { st->fin[k] = F[k]; st->delta[k] = Tf[k]; }
+  const int iter = ++st->iter;
+  const double cur_mse = d2sum / cnt;
+  st->cur_mse = cur_mse;
+  if (iter <= ICP_MAX_LOG) {
+    IterRec& r = log[iter - 1];
+    r.iteration = iter; r.n_corr = n_corr; r.mse = cur_mse;
+    for (int k = 0; k < 16; ++k) r.delta[k] = Tf[k];
+  }
+  if (iter >= st->max_iter) { st->done = 1; st->reason = 1; return; }
+  if (!st->fixed) {
+    const double cos_angle = 0.5 * (Td[0] + Td[5] + Td[10] - 1.0);
+    const double t2 = Td[12] * Td[12] + Td[13] * Td[13] + Td[14] * Td[14];
+    if (cos_angle >= st->rot_thr && t2 <= st->trans_thr) { st->done = 1; st->reason = 2; return; }
+    if (fabs(cur_mse - st->prev_mse) < 1e-12) { st->done = 1; st->reason = 3; return; }
+    if (fabs(cur_mse - st->prev_mse) / st->prev_mse < st->fit_eps) { st->done = 1; st->reason = 4; return; }
+    st->prev_mse = cur_mse;
+  }
+}
+
+// Point-to-point sums about the origin o (a = s - o, b = t - o, exact in double):
 // [0] n, [1..3] sum a, [4..6] sum b, [7..15] sum b_r * a_c (row r, col c), [16] sum d2,
-// [17] number of source points that passed the distance gate (= reciprocal queries issued).
+// [17] number of source points that passed the distance gate (= reciprocal queries when enabled).
 __global__ void __launch_bounds__(256) k_reduce_p2p(const float4* __restrict__ src, int n, const int32_t* __restrict__ corr_j,
                                                     const float* __restrict__ corr_d2, const float4* __restrict__ tgt,
-                                                    double3 o, double* __restrict__ partials) {
+                                                    double* __restrict__ partials, IcpState* __restrict__ st, IterRec* __restrict__ log) {
+  if (st->done) return;
+  const double ox = st->ox, oy = st->oy, oz = st->oz;
   double v[REDUCE_P2P_VALS];
 #pragma unroll
   for (int a = 0; a < REDUCE_P2P_VALS; ++a) v[a] = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    int j = __ldg(corr_j + i);
+    const int j = __ldg(corr_j + i);
     if (j < -1) v[17] += 1.0;
     if (j < 0) continue;
     v[17] += 1.0;
-    float4 s = __ldg(src + i), t = __ldg(tgt + j);
-    double ax = (double)s.x - o.x, ay = (double)s.y - o.y, az = (double)s.z - o.z;
-    double bx = (double)t.x - o.x, by = (double)t.y - o.y, bz = (double)t.z - o.z;
+    const float4 s = __ldg(src + i);
+    const float4 t = __ldg(tgt + j);
+    double ax = (double)s.x - ox, ay = (double)s.y - oy, az = (double)s.z - oz;
+    double bx = (double)t.x - ox, by = (double)t.y - oy, bz = (double)t.z - oz;
     v[0] += 1.0;
     v[1] += ax; v[2] += ay; v[3] += az;
     v[4] += bx; v[5] += by; v[6] += bz;
@@ -120,23 +216,28 @@ __global__ void __launch_bounds__(256) k_reduce_p2p(const float4* __restrict__ s
     v[16] += (double)__ldg(corr_d2 + i);
   }
   block_reduce_store<REDUCE_P2P_VALS>(v, partials);
+  if (!last_block_done(&st->ticket)) return;
+  ordered_total<REDUCE_P2P_VALS>(partials, gridDim.x, st->sums);
+  if (threadIdx.x == 0) icp_finish_iteration(st, log);
 }
 
 // Point-to-plane normal equations: J = [cross(s, n), n], r = n.(d - s).
 // [0..20] upper triangle of J^T J row-major, [21..26] J^T r, [27] n, [28] sum d2, [29] gate-passing count.
 __global__ void __launch_bounds__(256) k_reduce_p2l(const float4* __restrict__ src, int n, const int32_t* __restrict__ corr_j,
                                                     const float* __restrict__ corr_d2, const float4* __restrict__ tgt,
-                                                    const float4* __restrict__ nrm, double3 o, double* __restrict__ partials) {
-  (void)o;
+                                                    const float4* __restrict__ nrm, double* __restrict__ partials,
+                                                    IcpState* __restrict__ st, IterRec* __restrict__ log) {
+  if (st->done) return;
   double v[REDUCE_P2L_VALS];
 #pragma unroll
   for (int a = 0; a < REDUCE_P2L_VALS; ++a) v[a] = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    int j = __ldg(corr_j + i);
+    const int j = __ldg(corr_j + i);
     if (j < -1) v[29] += 1.0;
     if (j < 0) continue;
     v[29] += 1.0;
-    float4 s = __ldg(src + i), t = __ldg(tgt + j), nn = __ldg(nrm + j);
+    const float4 s = __ldg(src + i);
+    const float4 t = __ldg(tgt + j), nn = __ldg(nrm + j);
     double sx = s.x, sy = s.y, sz = s.z, nx = nn.x, ny = nn.y, nz = nn.z;
     double J[6] = {nz * sy - ny * sz, nx * sz - nz * sx, ny * sx - nx * sy, nx, ny, nz};
     double r = nx * ((double)t.x - sx) + ny * ((double)t.y - sy) + nz * ((double)t.z - sz);
@@ -151,6 +252,18 @@ __global__ void __launch_bounds__(256) k_reduce_p2l(const float4* __restrict__ s
     v[28] += (double)__ldg(corr_d2 + i);
   }
   block_reduce_store<REDUCE_P2L_VALS>(v, partials);
+  if (!last_block_done(&st->ticket)) return;
+  ordered_total<REDUCE_P2L_VALS>(partials, gridDim.x, st->sums);
+  if (threadIdx.x == 0) icp_finish_iteration(st, log);
+}
+
+__global__ void k_reduce_final(const double* __restrict__ partials, int nblk, int nv, double* __restrict__ out) {
+  int t = threadIdx.x;
+  if (t >= nv) return;
+  double x = 0;
+#pragma unroll 8
+  for (int b = 0; b < nblk; ++b) x += partials[(size_t)b * REDUCE_MAX_VALS + t];
+  out[t] = x;
 }
 
 __global__ void __launch_bounds__(256) k_reduce_fitness(const int32_t* __restrict__ idx, const float* __restrict__ d2, int n,
@@ -163,18 +276,29 @@ __global__ void __launch_bounds__(256) k_reduce_fitness(const int32_t* __restric
   block_reduce_store<2>(v, partials);
 }
 
-cudaError_t launch_reduce_p2p(const float4* src_cur, int n, const int32_t* corr_j, const float* corr_d2,
-                              const float4* tgt_orig, double3 origin, double* partials, double* out, cudaStream_t s) {
-  k_reduce_p2p<<<REDUCE_BLOCKS, 256, 0, s>>>(src_cur, n, corr_j, corr_d2, tgt_orig, origin, partials); count_launch();
-  k_reduce_final<<<1, 32, 0, s>>>(partials, REDUCE_BLOCKS, REDUCE_P2P_VALS, out); count_launch();
+__global__ void __launch_bounds__(256) k_transform_final(const float4* __restrict__ in, float4* __restrict__ out, int n,
+                                                         const IcpState* __restrict__ st) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Mat4f M;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) M.m[k] = (float)st->fin[k];
+  float4 p = __ldg(in + i);
+  out[i] = finite3(p) ? xform_pinned(M, p) : p;
+}
+
+cudaError_t launch_reduce_solve(const float4* src_cur, int n, const int32_t* corr_j, const float* corr_d2,
+                                const float4* tgt_orig, const float4* tgt_normals, double* partials, IcpState* st,
+                                IterRec* log, bool p2l, cudaStream_t s) {
+  if (p2l) k_reduce_p2l<<<REDUCE_BLOCKS, 256, 0, s>>>(src_cur, n, corr_j, corr_d2, tgt_orig, tgt_normals, partials, st, log);
+  else k_reduce_p2p<<<REDUCE_BLOCKS, 256, 0, s>>>(src_cur, n, corr_j, corr_d2, tgt_orig, partials, st, log);
+  count_launch();
   return cudaGetLastError();
 }
 
-cudaError_t launch_reduce_p2l(const float4* src_cur, int n, const int32_t* corr_j, const float* corr_d2,
-                              const float4* tgt_orig, const float4* tgt_normals, double3 origin, double* partials,
-                              double* out, cudaStream_t s) {
-  k_reduce_p2l<<<REDUCE_BLOCKS, 256, 0, s>>>(src_cur, n, corr_j, corr_d2, tgt_orig, tgt_normals, origin, partials); count_launch();
-  k_reduce_final<<<1, 32, 0, s>>>(partials, REDUCE_BLOCKS, REDUCE_P2L_VALS, out); count_launch();
+cudaError_t launch_transform_final(const float4* in, float4* out, int n, const IcpState* st, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  k_transform_final<<<(n + 255) / 256, 256, 0, s>>>(in, out, n, st); count_launch();
   return cudaGetLastError();
 }
 

@@ -39,29 +39,70 @@ cudaError_t launch_gather_sorted(const float4* pts, const uint32_t* perm, int n,
 // start[c] = first sorted position with key >= c, for c in [0, 1 << 3*bits].
 cudaError_t launch_cell_table(const uint32_t* sorted_keys, int n, int bits, uint32_t* start, cudaStream_t s);
 
+// occ[mc] = 1 iff any cell of the 3x3x3 neighbourhood of coarse cell mc (coarse = fine >> shift per axis)
+// holds a point; occ has 1 << 3*(bits-shift) entries.
+cudaError_t launch_build_occupancy(const uint32_t* start, int bits, int shift, uint8_t* occ, cudaStream_t s);
+
 // ---- nn.cu ---------------------------------------------------------------------------------
 // Exact 1-NN of each query in the index.  q_has_index: queries carry their original index in .w
 // (results are written at that index) or are in caller order.  max_d2 gates the SEARCH only (points
 // farther than the gate may be reported as -1); pass +inf for un-gated.
-cudaError_t launch_nn_query(const float4* q, int nq, IndexDev ix, float max_d2, int32_t* out_idx, float* out_d2,
-                            cudaStream_t s);
+cudaError_t launch_nn_query(const float4* q, int nq, bool q_has_index, IndexDev ix, float max_d2, int32_t* out_idx,
+                            float* out_d2, cudaStream_t s);
+
+// ---- bin.cu --------------------------------------------------------------------------------
+// Counting sort of a (moving) cloud by grid cell: see bin.cu.  counters has cells+1 entries (the last
+// one collects non-finite points) and must be zero on entry (k_scan_cells re-zeroes it); start gets
+// cells+2 entries.  d_delta (nullable): device float[16] applied in place before binning.  d_done
+// (nullable): device flag, non-zero turns the launch into a no-op.
+cudaError_t launch_transform_bin(float4* pts, int n, const float* d_delta, const int* d_done, GridDev g, uint32_t* keys,
+                                 uint32_t* rank, uint32_t* counters, cudaStream_t s);
+int scan_num_tiles(size_t len);
+cudaError_t launch_scan_cells(uint32_t* counters, uint32_t* start, size_t len, unsigned long long* tile_state, uint32_t epoch,
+                              const int* d_done, cudaStream_t s);
+cudaError_t launch_bin_scatter(const float4* pts, int n, const uint32_t* keys, const uint32_t* rank, const uint32_t* start,
+                               const int* d_done, float4* sorted, cudaStream_t s);
 
 // ---- icp.cu --------------------------------------------------------------------------------
-// Forward (+ optional reciprocal) correspondence search.  Queries are the Morton-sorted source
-// (src.pts, .w = original index) when reciprocal, else `q` in caller order.  Output is indexed by the
-// query's ORIGINAL index: corr_j[i] = matched target original index or -1, corr_d2[i] = float d2.
-cudaError_t launch_correspond(const float4* q, int nq, bool q_has_index, IndexDev tgt, const float4* tgt_orig,
-                              IndexDev src, bool reciprocal, double max_dist2, float max_d2f, int32_t* corr_j,
-                              float* corr_d2, cudaStream_t s);
+enum { REDUCE_P2P_VALS = 18, REDUCE_P2L_VALS = 30, REDUCE_MAX_VALS = 32, REDUCE_BLOCKS = 296, ICP_MAX_LOG = 1024 };
 
-// Sums over kept correspondences for the point-to-point estimator (18 doubles, see icp.cu) or the
-// point-to-plane one (30 doubles).  partials: blocks x REDUCE_MAX_VALS doubles; out: REDUCE_MAX_VALS doubles.
-enum { REDUCE_P2P_VALS = 18, REDUCE_P2L_VALS = 30, REDUCE_MAX_VALS = 32, REDUCE_BLOCKS = 296 };
-cudaError_t launch_reduce_p2p(const float4* src_cur, int n, const int32_t* corr_j, const float* corr_d2,
-                              const float4* tgt_orig, double3 origin, double* partials, double* out, cudaStream_t s);
-cudaError_t launch_reduce_p2l(const float4* src_cur, int n, const int32_t* corr_j, const float* corr_d2,
-                              const float4* tgt_orig, const float4* tgt_normals, double3 origin, double* partials,
-                              double* out, cudaStream_t s);
+// Per-iteration record kept on the device (mirrors mvr_icp_iteration of the C ABI).
+struct IterRec {
+  int iteration;
+  int n_corr;
+  double mse;
+  float delta[16];
+};
+
+// Device-resident state of one align: the loop of pcl::IterativeClosestPoint::computeTransformation
+//  advances entirely on the GPU; k_reduce_* 's last block solves for the increment,
+// applies DefaultConvergenceCriteria (A8) and raises `done`, after which queued launches are no-ops.
+struct IcpState {
+  float delta[16];        // increment to apply at the start of the next iteration (the guess at first)
+  double fin[16];         // accumulated transform, column-major
+  double sums[REDUCE_MAX_VALS];
+  double prev_mse, cur_mse;
+  double rot_thr, trans_thr, fit_eps;   // criteria thresholds
+  double ox, oy, oz;      // origin the sums are taken about
+  unsigned long long queries;
+  int iter, done, reason, status, n_corr;
+  int max_iter, fixed, min_corr, p2l, recip, n_src;
+  unsigned int ticket;    // blocks of the running reduction that have finished
+};
+
+// Forward (+ optional reciprocal) correspondence search over the cell-sorted source `q` (.w = original
+// index).  Output is indexed by the query's ORIGINAL index: corr_j[i] = matched target original index,
+// -1 = none, -2-j = passed the gate but failed the reciprocal test; corr_d2[i] = float d2.
+cudaError_t launch_correspond(const float4* q, int nq, IndexDev tgt, IndexDev src, bool reciprocal, double max_dist2,
+                              float max_d2f, int32_t* corr_j, float* corr_d2, const int* d_done, cudaStream_t s);
+
+// Sums over kept correspondences in original-index order, then (last block) the solve + criteria:
+// advances st (delta, fin, iter, done, ...) and appends to log.  partials: REDUCE_BLOCKS x REDUCE_MAX_VALS.
+cudaError_t launch_reduce_solve(const float4* src_cur, int n, const int32_t* corr_j, const float* corr_d2,
+                                const float4* tgt_orig, const float4* tgt_normals, double* partials, IcpState* st,
+                                IterRec* log, bool p2l, cudaStream_t s);
+// out = float(st->fin) * in   (the aligned cloud icp.align returns)
+cudaError_t launch_transform_final(const float4* in, float4* out, int n, const IcpState* st, cudaStream_t s);
 // sum and count of d2[i] with idx[i] >= 0 and d2 <= max_range  (getFitnessScore); out[0]=sum, out[1]=count
 cudaError_t launch_reduce_fitness(const int32_t* idx, const float* d2, int n, double max_range, double* partials,
                                   double* out, cudaStream_t s);

@@ -151,6 +151,41 @@ def test_nn_exact_for_any_grid_resolution(ctx, orc, synth, bits, cell):
     assert np.array_equal(d2.view(np.uint32), od.view(np.uint32))
 
 
+@pytest.mark.gpu
+def test_nn_exact_when_points_and_queries_clamp_to_the_grid_boundary(ctx, orc):
+    """An explicit grid that covers only the middle of the cloud: points outside it are filed in clamped
+    boundary cells and queries outside it start from a clamped cell; the search must stay exact."""
+    rng = np.random.default_rng(21)
+    tgt = random_cloud(rng, 20_000, scale=30.0)
+    q = random_cloud(rng, 4000, scale=60.0)
+    ctx.set_target(tgt)
+    for bits, cell in ((4, 2.0), (6, 0.5), (3, 10.0)):
+        half = 0.5 * cell * (1 << bits)
+        grid = dict(origin=np.array([0.0 - half, 0.0 - half, 900.0 - half], dtype=np.float32),
+                    inv_cell=np.float32(1.0 / cell), cell=np.float32(cell), bits=bits)
+        ctx.index_build(0, grid)
+        idx, d2 = ctx.nn_query(q)
+        oi, od = orc.nn_kdtree(tgt, q)
+        assert np.array_equal(idx, oi)
+        assert np.array_equal(d2.view(np.uint32), od.view(np.uint32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_dist", [1.0, 4.0, 25.0, 400.0])
+def test_correspondences_far_apart_clouds(ctx, orc, max_dist):
+    """Source mostly outside the gate of the target (exercises the gate prefilter and empty cells)."""
+    rng = np.random.default_rng(22)
+    tgt = random_cloud(rng, 15_000, scale=10.0)
+    src = random_cloud(rng, 15_000, scale=10.0, center=(18.0, 0.0, 900.0))
+    ctx.set_target(tgt)
+    ctx.set_source(src)
+    for reciprocal in (False, True):
+        q, m, d = ctx.correspondences(len(src), max_dist, reciprocal)
+        oq, om, od = orc.correspondences(src, tgt, max_dist, reciprocal)
+        assert np.array_equal(q, oq) and np.array_equal(m, om)
+        assert np.array_equal(d.view(np.uint32), od.view(np.uint32))
+
+
 # ---- correspondences -------------------------------------------------------------------------------
 @pytest.mark.parametrize("reciprocal", [False, True])
 @pytest.mark.parametrize("max_dist", [0.5, 4.0, 1e9])
