@@ -115,6 +115,8 @@ int mvr_ctx_synchronize(mvr_ctx* ctx);
 const char* mvr_last_error(mvr_ctx* ctx);
 int mvr_ctx_set_profiling(mvr_ctx* ctx, int on);
 int mvr_ctx_get_kernel_stats(mvr_ctx* ctx, mvr_kernel_stat* out /* [MVR_K_COUNT] */, int reset);
+/* Diagnostics of the last align (development aid): k = 0 clock cycles in the serial per-iteration solve, 1 solves. */
+double mvr_debug_value(mvr_ctx* ctx, int k);
 /* Tuning knobs of the spatial index: cell edge (<= 0: automatic) and maximum bits per axis (1..10). */
 int mvr_ctx_set_index_options(mvr_ctx* ctx, float cell_edge, int max_bits);
 

@@ -118,6 +118,8 @@ def lib():
     L.mvr_last_error.restype = C.c_char_p
     L.mvr_ctx_set_profiling.argtypes = [vp, C.c_int]
     L.mvr_ctx_get_kernel_stats.argtypes = [vp, C.POINTER(KernelStat), C.c_int]
+    L.mvr_debug_value.argtypes = [vp, C.c_int]
+    L.mvr_debug_value.restype = C.c_double
     L.mvr_ctx_set_index_options.argtypes = [vp, C.c_float, C.c_int]
     for name in ("mvr_set_target", "mvr_set_source", "mvr_set_target_device", "mvr_set_source_device", "mvr_set_target_normals"):
         getattr(L, name).argtypes = [vp, vp, C.c_size_t]
@@ -219,6 +221,9 @@ class Context:
         self._ck(lib().mvr_ctx_get_kernel_stats(self._h, arr, int(bool(reset))))
         return {K_NAMES[i]: dict(launches=int(arr[i].launches), ms=arr[i].ms, bytes=arr[i].bytes, units=arr[i].units)
                 for i in range(K_COUNT)}
+
+    def debug_value(self, k):
+        return float(lib().mvr_debug_value(self._h, int(k)))
 
     def set_index_options(self, cell_edge=0.0, max_bits=8):
         self._ck(lib().mvr_ctx_set_index_options(self._h, C.c_float(cell_edge), int(max_bits)))

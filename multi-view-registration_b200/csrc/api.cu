@@ -59,21 +59,22 @@ struct Cloud {
   uint64_t index_gen = 0;
   mvr_grid grid{};
   GridDev gd{};
-  DevBuf keys, vals, keys_alt, vals_alt, hist, counters, sorted, table, occ;
+  DevBuf keys, vals, keys_alt, vals_alt, hist, counters, sorted, table, bricks, brick_cnt;
   uint32_t* sorted_keys = nullptr;
   uint32_t* perm = nullptr;
-  bool has_occ = false;          // gate prefilter built for this index (IndexDev::occ)
-  int occ_shift = 0;
-  float occ_gate2 = 0.f;
+  // occupied-brick list of the current index (search.cu): bricks[0 .. *brick_count())
+  int cnt_par = 0;               // which of the two counters the NEXT list launch fills
+  bool has_bricks = false;
+  const uint32_t* brick_count() const { return brick_cnt.as<uint32_t>() + (cnt_par ^ 1); }
   IndexDev dev() const {
     IndexDev ix;
     ix.pts = sorted.as<float4>(); ix.start = table.as<uint32_t>(); ix.g = gd; ix.n_valid = n - n_bad;
-    ix.occ = has_occ ? occ.as<uint8_t>() : nullptr; ix.occ_shift = occ_shift; ix.occ_gate2 = occ_gate2;
     return ix;
   }
+  QueryDev qdev(int shift) const { return QueryDev{sorted.as<float4>(), table.as<uint32_t>(), shift}; }
   void release() {
     own.release(); keys.release(); vals.release(); keys_alt.release(); vals_alt.release(); hist.release();
-    counters.release(); sorted.release(); table.release(); occ.release();
+    counters.release(); sorted.release(); table.release(); bricks.release(); brick_cnt.release();
   }
 };
 
@@ -87,7 +88,7 @@ struct mvr_ctx {
   bool own_stream = false;
   Cloud tgt, src, qry;          // qry: scratch cloud used to present queries in cell order
   DevBuf normals; bool has_normals = false;
-  DevBuf cur, corr_j, corr_d2, partials, sums, out_cloud, qtmp, itmp, ftmp, scratch, misc, tiles, state, log;
+  DevBuf cur, corr_p, corr_j, corr_d2, rmin, rnn, partials, sums, out_cloud, qtmp, itmp, ftmp, scratch, misc, tiles, state, log;
   uint32_t scan_epoch = 1;
   IcpState* h_state = nullptr;   // pinned staging copy of the device IcpState
   IterRec* h_log = nullptr;      // pinned, ICP_MAX_LOG records
@@ -102,7 +103,6 @@ struct mvr_ctx {
   bool have_out = false;         // out_cloud holds transform(source, final) of the last align
   float cell_edge_opt = 0.f;
   int max_bits_opt = 8;
-  bool presort_queries = true;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
 };
 
@@ -172,9 +172,9 @@ mvr_grid make_grid(const float lo[3], const float hi[3], double cell, int max_bi
   for (int a = 0; a < 3; ++a) ext = std::max(ext, (double)hi[a] - (double)lo[a]);
   if (!(ext > 0) || !std::isfinite(ext)) ext = 1.0;
   if (!(cell > 0) || !std::isfinite(cell)) cell = ext;
-  if (max_bits < 1) max_bits = 1;
   if (max_bits > 10) max_bits = 10;
-  int bits = 1;
+  if (max_bits < 3) max_bits = 3;   // the brick search works on 4 x 4 x 4-cell bricks with a 2-cell halo
+  int bits = 3;
   while (bits < max_bits && cell * (double)(1 << bits) < ext * 1.0001) ++bits;
   if (cell * (double)(1 << bits) < ext * 1.0001) cell = ext * 1.0001 / (double)(1 << bits);
   for (int a = 0; a < 3; ++a) g.origin[a] = lo[a];
@@ -262,7 +262,7 @@ int build_index(mvr_ctx* ctx, Cloud& c, const float4* pts, const mvr_grid& g) {
   }
   c.index_valid = true;
   c.exportable = true;
-  c.has_occ = false;
+  c.has_bricks = false;
   c.index_gen = c.gen;
   return MVR_OK;
 }
@@ -305,46 +305,72 @@ int bin_index(mvr_ctx* ctx, Cloud& c, float4* pts, const mvr_grid& g, const floa
   }
   c.index_valid = true;
   c.exportable = false;
-  c.has_occ = false;
+  c.has_bricks = false;
   c.index_gen = c.gen;
   return MVR_OK;
 }
 
+// List the occupied bricks of c's current index (table granularity `shift`: 6 = cell table, 0 = brick
+// table; fine_bits = bits of the grid the bricks belong to).
+int list_bricks(mvr_ctx* ctx, Cloud& c, int fine_bits, int shift, const int* d_done) {
+  const size_t nb = (size_t)1 << (3 * (fine_bits - 2));
+  CK(c.bricks.ensure((std::min(nb, (size_t)std::max(c.n, 1)) + 1) * sizeof(uint32_t)));
+  if (!c.brick_cnt.p) {
+    CK(c.brick_cnt.ensure(2 * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(c.brick_cnt.p, 0, c.brick_cnt.cap, ctx->stream));
+    c.cnt_par = 0;
+  }
+  uint32_t* cnt = c.brick_cnt.as<uint32_t>();
+  CK(launch_list_bricks(c.table.as<uint32_t>(), fine_bits, shift, c.bricks.as<uint32_t>(), cnt + c.cnt_par, cnt + (c.cnt_par ^ 1), d_done,
+                        ctx->stream));
+  c.cnt_par ^= 1;
+  c.has_bricks = true;
+  return MVR_OK;
+}
+
 mvr_grid auto_grid(mvr_ctx* ctx, const Cloud& c) {
-  double e = ctx->cell_edge_opt > 0 ? ctx->cell_edge_opt : density_cell_edge(c.lo, c.hi, c.n - c.n_bad, 4.0);
+  double e = ctx->cell_edge_opt > 0 ? ctx->cell_edge_opt : density_cell_edge(c.lo, c.hi, c.n - c.n_bad, 6.0);
   return make_grid(c.lo, c.hi, e, ctx->max_bits_opt);
 }
 
+// Target index usable by the brick search: counting-sorted in grid `want` (or an automatic one), with
+// its occupied-brick list.
 int ensure_target_index(mvr_ctx* ctx, const mvr_grid* want) {
   Cloud& t = ctx->tgt;
-  if (t.index_valid && t.index_gen == t.gen && (!want || same_grid(*want, t.grid))) return MVR_OK;
+  if (t.index_valid && t.index_gen == t.gen && t.grid.bits >= 3 && (!want || same_grid(*want, t.grid))) {
+    // also true for an index the caller built with mvr_index_build: same layout, only the brick list is missing
+    return t.has_bricks ? MVR_OK : list_bricks(ctx, t, t.grid.bits, 6, nullptr);
+  }
   mvr_grid g = want ? *want : auto_grid(ctx, t);
-  return bin_index(ctx, t, const_cast<float4*>(t.pts), g, nullptr, nullptr);
+  int rc = bin_index(ctx, t, const_cast<float4*>(t.pts), g, nullptr, nullptr);
+  if (rc) return rc;
+  return list_bricks(ctx, t, g.bits, 6, nullptr);
 }
 
-// Present `n` query points (device) in the cell order of the target grid: fills ctx->qry.
+// Present `n` query points (device) brick by brick of the target grid: fills ctx->qry (brick table).
 int sort_queries(mvr_ctx* ctx, const float4* q, int n) {
   Cloud& c = ctx->qry;
   c.pts = q; c.n = n; c.n_bad = 0; c.gen++;
-  // the order only has to be coherent, so a coarse (<= 64^3) version of the target grid is enough and
-  // keeps the counting sort's table small; coarse Morton order is a prefix of the fine one
+  // a grid of 4x larger cells with the same origin bins exactly like (fine cell >> 2): scaling by a
+  // power of two commutes with the float rounding of grid_t()
   mvr_grid g = ctx->tgt.grid;
-  while (g.bits > 6) { g.bits -= 1; g.inv_cell *= 0.5f; g.cell *= 2.0f; }
-  return bin_index(ctx, c, const_cast<float4*>(q), g, nullptr, nullptr);
+  g.bits -= 2; g.inv_cell *= 0.25f; g.cell *= 4.0f;
+  int rc = bin_index(ctx, c, const_cast<float4*>(q), g, nullptr, nullptr);
+  if (rc) return rc;
+  return list_bricks(ctx, c, ctx->tgt.grid.bits, 0, nullptr);
+}
+
+// Exact un-gated NN of n device points in the target index; results at the queries' original index.
+int nn_pass(mvr_ctx* ctx, const float4* q, int n, int32_t* d_idx, float* d_d2) {
+  int rc = sort_queries(ctx, q, n);
+  if (rc) return rc;
+  const Cloud& t = ctx->tgt;
+  ProfScope ps(ctx, MVR_K_NN, 24.0 * n + 16.0 * t.n, (double)n);
+  CK(launch_brick_nn(ctx->qry.qdev(0), n, t.dev(), ctx->qry.bricks.as<uint32_t>(), ctx->qry.brick_count(), d_idx, d_d2, ctx->stream));
+  return MVR_OK;
 }
 
 void mat_identity(float* m) { for (int k = 0; k < 16; ++k) m[k] = (k % 5 == 0) ? 1.f : 0.f; }
-
-void matmul4d(const double* A, const double* B, double* C) {
-  double t[16];
-  for (int c = 0; c < 4; ++c)
-    for (int r = 0; r < 4; ++r) {
-      double s = 0;
-      for (int k = 0; k < 4; ++k) s += A[k * 4 + r] * B[c * 4 + k];
-      t[c * 4 + r] = s;
-    }
-  std::memcpy(C, t, sizeof(t));
-}
 
 float gate_float(double max_dist) {
   double m2 = max_dist * max_dist;
@@ -354,15 +380,15 @@ float gate_float(double max_dist) {
   return std::nextafterf(f, INFINITY);
 }
 
-// Grids for an align / correspondence pass, both covering the target and the (guess-transformed)
-// source boxes so that clamping at the grid boundary stays rare:
-//   target grid: fine cells (~4 points per occupied cell) -- built once per align, searched 30 x n times;
-//   source grid: coarse cells (~16 points per cell) -- rebuilt every iteration, and the reciprocal
-//                search into it is seeded with a tight radius, so the cheap table matters more.
-void pair_grids(mvr_ctx* ctx, const float* G, mvr_grid* gt, mvr_grid* gs) {
+// The ONE grid both clouds of an align / correspondence pass are binned in.  It covers the target box
+// and the (guess-transformed) source box, so clamping at the grid boundary stays rare.  Cell edge:
+// gate / 2 when the point density allows (then the brick search's two-cell halo covers the gate and a
+// gated search never leaves shared memory), otherwise bounded to 2 .. 12 points per occupied cell.
+mvr_grid pair_grid(mvr_ctx* ctx, const float* G, double max_dist) {
   const Cloud &t = ctx->tgt, &s = ctx->src;
   float lo[3], hi[3];
   for (int a = 0; a < 3; ++a) { lo[a] = t.lo[a]; hi[a] = t.hi[a]; }
+  if (t.n - t.n_bad <= 0) for (int a = 0; a < 3; ++a) { lo[a] = INFINITY; hi[a] = -INFINITY; }
   if (s.n - s.n_bad > 0) {
     for (int corner = 0; corner < 8; ++corner) {
       double p[3] = {(corner & 1) ? s.hi[0] : s.lo[0], (corner & 2) ? s.hi[1] : s.lo[1], (corner & 4) ? s.hi[2] : s.lo[2]};
@@ -372,29 +398,20 @@ void pair_grids(mvr_ctx* ctx, const float* G, mvr_grid* gt, mvr_grid* gs) {
       }
     }
   }
-  double et = ctx->cell_edge_opt > 0 ? ctx->cell_edge_opt : density_cell_edge(t.lo, t.hi, t.n - t.n_bad, 4.0);
-  double es = ctx->cell_edge_opt > 0 ? ctx->cell_edge_opt : density_cell_edge(s.lo, s.hi, s.n - s.n_bad, 16.0);
-  float lt[3], ht[3], ls[3], hs[3];
-  for (int a = 0; a < 3; ++a) { lt[a] = lo[a] - (float)et; ht[a] = hi[a] + (float)et; ls[a] = lo[a] - (float)es; hs[a] = hi[a] + (float)es; }
-  *gt = make_grid(lt, ht, et, std::min(ctx->max_bits_opt, 7));
-  *gs = make_grid(ls, hs, es, std::min(ctx->max_bits_opt, 6));
-}
-
-// Gate prefilter of the target index for gates up to max_dist (no-op for an infinite gate).
-int ensure_target_occupancy(mvr_ctx* ctx, double max_dist) {
-  Cloud& t = ctx->tgt;
-  const double m2 = max_dist * max_dist;
-  if (!(m2 < 1e30) || t.n - t.n_bad <= 0) { t.has_occ = false; return MVR_OK; }
-  const double edge = 1.0 / (double)t.grid.inv_cell;
-  int shift = 0;
-  while (shift < t.grid.bits && edge * (double)(1 << shift) < 1.01 * max_dist) ++shift;
-  if (edge * (double)(1 << shift) < 1.01 * max_dist) { t.has_occ = false; return MVR_OK; }   // gate wider than the grid
-  const float g2 = gate_float(max_dist);
-  if (t.has_occ && t.occ_shift == shift && t.occ_gate2 >= g2) return MVR_OK;
-  CK(t.occ.ensure((size_t)1 << (3 * (t.grid.bits - shift))));
-  CK(launch_build_occupancy(t.table.as<uint32_t>(), t.grid.bits, shift, t.occ.as<uint8_t>(), ctx->stream));
-  t.has_occ = true; t.occ_shift = shift; t.occ_gate2 = g2;
-  return MVR_OK;
+  for (int a = 0; a < 3; ++a) if (!(lo[a] <= hi[a])) { lo[a] = 0.f; hi[a] = 0.f; }
+  double e;
+  if (ctx->cell_edge_opt > 0) {
+    e = ctx->cell_edge_opt;
+  } else {
+    const Cloud& d = (t.n - t.n_bad > 0) ? t : s;
+    const double e_lo = density_cell_edge(d.lo, d.hi, d.n - d.n_bad, 2.0), e_hi = density_cell_edge(d.lo, d.hi, d.n - d.n_bad, 12.0);
+    const double m2 = max_dist * max_dist;
+    e = (m2 < 1e30) ? std::min(std::max(0.5 * max_dist * 1.002, e_lo), e_hi) : density_cell_edge(d.lo, d.hi, d.n - d.n_bad, 6.0);
+  }
+  float l[3], h[3];
+  for (int a = 0; a < 3; ++a) { l[a] = lo[a] - (float)e; h[a] = hi[a] + (float)e; }
+  const int cap = (ctx->cell_edge_opt > 0) ? 10 : ((std::max(t.n, s.n) > 1500000) ? 8 : 7);   // per-iteration table scan: 2 M (16 M) entries
+  return make_grid(l, h, e, std::min(ctx->max_bits_opt, cap));
 }
 
 int ensure_pinned(mvr_ctx* ctx) {
@@ -405,28 +422,46 @@ int ensure_pinned(mvr_ctx* ctx) {
   return MVR_OK;
 }
 
-// Algorithmic bytes of one correspondence launch: each query read once (16 B) and
-// its result written once (8 B), each target point once (16 B); the reciprocal test reads each source
-// point once more (16 B).  Cell-table entries are NOT counted (conservative).
+// Algorithmic bytes of one iteration's correspondence search: each query read once
+// (16 B) and its result written once (8 B), each target point once (16 B); the reciprocal half reads
+// each source point once more as a candidate (16 B).  Cell-table entries are NOT counted (conservative).
 double corr_bytes(int n, int m, bool reciprocal) { return 24.0 * n + 16.0 * m + (reciprocal ? 16.0 * n : 0.0); }
 
+// Per-align search state: target indexed in grid g, reciprocal scratch armed.
+int prepare_pair(mvr_ctx* ctx, const mvr_grid& g, bool reciprocal) {
+  int rc = ensure_target_index(ctx, &g);
+  if (rc) return rc;
+  const size_t n = (size_t)std::max(ctx->src.n, 1), m = (size_t)std::max(ctx->tgt.n, 1);
+  CK(ctx->corr_p.ensure(n * sizeof(int32_t)));
+  CK(ctx->corr_d2.ensure(n * sizeof(float)));
+  if (reciprocal) {
+    CK(ctx->rmin.ensure(m * sizeof(uint32_t)));
+    CK(ctx->rnn.ensure(m * sizeof(int32_t)));
+    CK(launch_fill_u32(ctx->rmin.as<uint32_t>(), m, 0x7f800000u, ctx->stream));   // +inf: "chosen by nobody"
+  }
+  return MVR_OK;
+}
+
 // One ICP iteration's search half on the current source coordinates `cur`: apply the pending delta
-// in place, re-index the source in the pair grid (PCL rebuilds the source kd-tree every iteration; we
-// also use the cell order to keep neighbouring threads on neighbouring queries), then search.
-int correspond_pass(mvr_ctx* ctx, float4* cur, const mvr_grid& gs, bool reciprocal, double max_dist, const float* d_delta,
+// in place, re-index the source in the pair grid (PCL rebuilds the source kd-tree every iteration when
+// reciprocal; the cell order also gives every brick its queries as one run), forward search
+// source -> target with the gate, then, if reciprocal, the nearest source point of every chosen target.
+int correspond_pass(mvr_ctx* ctx, float4* cur, const mvr_grid& g, bool reciprocal, double max_dist, const float* d_delta,
                     const int* d_done) {
-  Cloud& s = ctx->src;
+  Cloud &s = ctx->src, &t = ctx->tgt;
   const int n = s.n;
   const double max2 = max_dist * max_dist;
   const float max_d2f = gate_float(max_dist);
-  CK(ctx->corr_j.ensure((size_t)std::max(n, 1) * sizeof(int32_t)));
-  CK(ctx->corr_d2.ensure((size_t)std::max(n, 1) * sizeof(float)));
-  int rc = bin_index(ctx, s, cur, gs, d_delta, d_done);
+  int rc = bin_index(ctx, s, cur, g, d_delta, d_done);
   if (rc) return rc;
   s.index_valid = false;   // the index describes `cur`, not the caller's source cloud
-  ProfScope ps(ctx, MVR_K_CORR, corr_bytes(n, ctx->tgt.n, reciprocal), (double)n);
-  CK(launch_correspond(s.sorted.as<float4>(), n, ctx->tgt.dev(), s.dev(), reciprocal, max2, max_d2f, ctx->corr_j.as<int32_t>(),
-                       ctx->corr_d2.as<float>(), d_done, ctx->stream));
+  if ((rc = list_bricks(ctx, s, g.bits, 6, d_done))) return rc;
+  ProfScope ps(ctx, MVR_K_CORR, corr_bytes(n, t.n, reciprocal), (double)n);
+  CK(launch_brick_forward(s.qdev(6), n, t.dev(), s.bricks.as<uint32_t>(), s.brick_count(), max2, max_d2f, ctx->corr_p.as<int32_t>(),
+                          ctx->corr_d2.as<float>(), reciprocal ? ctx->rmin.as<uint32_t>() : nullptr, d_done, ctx->stream));
+  if (reciprocal)
+    CK(launch_brick_reverse(t.qdev(6), t.n, s.dev(), t.bricks.as<uint32_t>(), t.brick_count(), ctx->rmin.as<uint32_t>(),
+                            ctx->rnn.as<int32_t>(), d_done, ctx->stream));
   return MVR_OK;
 }
 
@@ -490,7 +525,7 @@ int mvr_ctx_destroy(mvr_ctx* ctx) {
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   ctx->tgt.release(); ctx->src.release(); ctx->qry.release(); ctx->normals.release();
-  DevBuf* bufs[] = {&ctx->cur, &ctx->corr_j, &ctx->corr_d2, &ctx->partials, &ctx->sums, &ctx->out_cloud, &ctx->qtmp,
+  DevBuf* bufs[] = {&ctx->cur, &ctx->corr_p, &ctx->rmin, &ctx->rnn, &ctx->corr_j, &ctx->corr_d2, &ctx->partials, &ctx->sums, &ctx->out_cloud, &ctx->qtmp,
                     &ctx->itmp, &ctx->ftmp, &ctx->scratch, &ctx->misc, &ctx->tiles, &ctx->state, &ctx->log};
   for (DevBuf* b : bufs) b->release();
   if (ctx->h_sums) cudaFreeHost(ctx->h_sums);
@@ -618,16 +653,7 @@ int mvr_nn_query_device(mvr_ctx* ctx, const float* d_q, size_t n, int32_t* d_idx
   int rc = ensure_target_index(ctx, nullptr);
   if (rc) return rc;
   if (n == 0) return MVR_OK;
-  const Cloud& t = ctx->tgt;
-  const float4* q = (const float4*)d_q;
-  if (ctx->presort_queries) {
-    // queries arrive in caller order; walking them in cell order keeps a warp inside a few cells
-    if ((rc = sort_queries(ctx, q, (int)n))) return rc;
-    q = ctx->qry.sorted.as<float4>();
-  }
-  ProfScope ps(ctx, MVR_K_NN, 24.0 * n + 16.0 * t.n, (double)n);
-  CK(launch_nn_query(q, (int)n, ctx->presort_queries, t.dev(), INFINITY, d_idx, d_d2, ctx->stream));
-  return MVR_OK;
+  return nn_pass(ctx, (const float4*)d_q, (int)n, d_idx, d_d2);
 }
 
 int mvr_nn_query(mvr_ctx* ctx, const float* q, size_t n, int32_t* idx, float* d2) {
@@ -658,19 +684,20 @@ int mvr_correspondences(mvr_ctx* ctx, double max_dist, int reciprocal, int32_t* 
   if (!iq || !im || !dist) return MVR_ERR_BAD_ARG;
   float I[16];
   mat_identity(I);
-  mvr_grid gt, gs;
-  pair_grids(ctx, I, &gt, &gs);
-  int rc = ensure_target_index(ctx, &gt);
+  const mvr_grid g = pair_grid(ctx, I, max_dist);
+  int rc = prepare_pair(ctx, g, reciprocal != 0);
   if (rc) return rc;
-  if ((rc = ensure_target_occupancy(ctx, max_dist))) return rc;
-  rc = correspond_pass(ctx, const_cast<float4*>(ctx->src.pts), gs, reciprocal != 0, max_dist, nullptr, nullptr);
+  rc = correspond_pass(ctx, const_cast<float4*>(ctx->src.pts), g, reciprocal != 0, max_dist, nullptr, nullptr);
   if (rc) return rc;
+  CK(ctx->corr_j.ensure((size_t)n * sizeof(int32_t)));
   CK(ctx->scratch.ensure(compact_scratch_elems(n) * sizeof(uint32_t) + 64));
   CK(ctx->itmp.ensure((size_t)2 * n * sizeof(int32_t)));
   CK(ctx->ftmp.ensure((size_t)n * sizeof(float)));
   CK(ctx->misc.ensure(64));
   int32_t* dq = ctx->itmp.as<int32_t>();
   int32_t* dm = dq + n;
+  CK(launch_resolve_corr(ctx->corr_p.as<int32_t>(), reciprocal ? ctx->rnn.as<int32_t>() : nullptr, ctx->tgt.sorted.as<float4>(), n,
+                         ctx->corr_j.as<int32_t>(), ctx->stream));
   CK(launch_compact_corr(ctx->corr_j.as<int32_t>(), ctx->corr_d2.as<float>(), n, ctx->scratch.as<uint32_t>(), dq, dm,
                          ctx->ftmp.as<float>(), ctx->misc.as<uint32_t>(), ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_small, ctx->misc.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -703,11 +730,9 @@ int mvr_icp_align(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, f
   const double max_dist = prm->max_correspondence_distance;
   const bool p2l = prm->estimator == MVR_POINT_TO_PLANE;
 
-  mvr_grid gt, gs;
-  pair_grids(ctx, G, &gt, &gs);
-  int rc = ensure_target_index(ctx, &gt);
+  const mvr_grid gp = pair_grid(ctx, G, max_dist);
+  int rc = prepare_pair(ctx, gp, reciprocal);
   if (rc) return rc;
-  if ((rc = ensure_target_occupancy(ctx, max_dist))) return rc;
   CK(ctx->cur.ensure((size_t)n * sizeof(float4)));
   CK(ctx->partials.ensure((size_t)REDUCE_BLOCKS * REDUCE_MAX_VALS * sizeof(double)));
   CK(ctx->out_cloud.ensure((size_t)n * sizeof(float4)));
@@ -751,10 +776,11 @@ int mvr_icp_align(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, f
   while (!done) {
     int todo = std::min(batch, std::max(prm->max_iterations - enqueued, 1));
     for (int it = 0; it < todo; ++it) {
-      rc = correspond_pass(ctx, cur, gs, reciprocal, max_dist, d_delta, d_done);
+      rc = correspond_pass(ctx, cur, gp, reciprocal, max_dist, d_delta, d_done);
       if (rc) return rc;
       ProfScope ps(ctx, MVR_K_REDUCE, 36.0 * n, n);
-      CK(launch_reduce_solve(cur, n, ctx->corr_j.as<int32_t>(), ctx->corr_d2.as<float>(), ctx->tgt.pts,
+      CK(launch_reduce_solve(cur, n, ctx->corr_p.as<int32_t>(), ctx->corr_d2.as<float>(),
+                             reciprocal ? ctx->rnn.as<int32_t>() : nullptr, ctx->tgt.sorted.as<float4>(),
                              p2l ? ctx->normals.as<float4>() : nullptr, ctx->partials.as<double>(), d_st, d_log, p2l, ctx->stream));
     }
     enqueued += todo;
@@ -791,6 +817,11 @@ int mvr_icp_align(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, f
   return h.status;
 }
 
+double mvr_debug_value(mvr_ctx* ctx, int k) {
+  if (!ctx || !ctx->h_state || k < 0 || k >= 4) return 0.0;
+  return (double)ctx->h_state->dbg[k];
+}
+
 int mvr_icp_get_iterations(mvr_ctx* ctx, mvr_icp_iteration* out, int max_records, int* count) {
   if (!ctx || !count) return MVR_ERR_BAD_ARG;
   int c = (int)ctx->iters.size();
@@ -818,12 +849,7 @@ int mvr_fitness_score(mvr_ctx* ctx, double max_range, double* score) {
   CK(ctx->ftmp.ensure((size_t)n * sizeof(float)));
   CK(ctx->partials.ensure((size_t)REDUCE_BLOCKS * REDUCE_MAX_VALS * sizeof(double)));
   CK(ctx->sums.ensure(REDUCE_MAX_VALS * sizeof(double)));
-  const Cloud& t = ctx->tgt;
-  if ((rc = sort_queries(ctx, cloud, n))) return rc;
-  {
-    ProfScope ps(ctx, MVR_K_NN, 24.0 * n + 16.0 * t.n, (double)n);
-    CK(launch_nn_query(ctx->qry.sorted.as<float4>(), n, true, t.dev(), INFINITY, ctx->itmp.as<int32_t>(), ctx->ftmp.as<float>(), ctx->stream));
-  }
+  if ((rc = nn_pass(ctx, cloud, n, ctx->itmp.as<int32_t>(), ctx->ftmp.as<float>()))) return rc;
   CK(launch_reduce_fitness(ctx->itmp.as<int32_t>(), ctx->ftmp.as<float>(), n, max_range, ctx->partials.as<double>(),
                            ctx->sums.as<double>(), ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_sums, ctx->sums.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

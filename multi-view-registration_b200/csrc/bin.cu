@@ -156,40 +156,6 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const float4* __restrict__ 
   sorted[__ldg(start + __ldg(keys + i)) + __ldg(rank + i)] = p;
 }
 
-// Gate prefilter (see IndexDev::occ): one thread per coarse cell looks at the 27 coarse neighbours, each
-// of which is one contiguous range of the Morton-sorted array.
-__global__ void __launch_bounds__(256) k_build_occupancy(const uint32_t* __restrict__ start, int cbits, int shift3,
-                                                         uint8_t* __restrict__ occ) {
-  const uint32_t mc = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t Cc = 1u << (3 * cbits);
-  if (mc >= Cc) return;
-  // decode the coarse Morton code
-  uint32_t x = 0, y = 0, z = 0;
-  for (int b = 0; b < cbits; ++b) {
-    x |= ((mc >> (3 * b)) & 1u) << b;
-    y |= ((mc >> (3 * b + 1)) & 1u) << b;
-    z |= ((mc >> (3 * b + 2)) & 1u) << b;
-  }
-  const int Gc = 1 << cbits;
-  bool any = false;
-  for (int dz = -1; dz <= 1 && !any; ++dz)
-    for (int dy = -1; dy <= 1 && !any; ++dy)
-      for (int dx = -1; dx <= 1 && !any; ++dx) {
-        const int X = (int)x + dx, Y = (int)y + dy, Z = (int)z + dz;
-        if (X < 0 || Y < 0 || Z < 0 || X >= Gc || Y >= Gc || Z >= Gc) continue;
-        const uint32_t m = morton3((uint32_t)X, (uint32_t)Y, (uint32_t)Z);
-        any = __ldg(start + ((size_t)m << shift3)) != __ldg(start + ((size_t)(m + 1) << shift3));
-      }
-  occ[mc] = any ? 1 : 0;
-}
-
-cudaError_t launch_build_occupancy(const uint32_t* start, int bits, int shift, uint8_t* occ, cudaStream_t s) {
-  const int cbits = bits - shift;
-  const uint32_t Cc = 1u << (3 * cbits);
-  k_build_occupancy<<<(Cc + 255) / 256, 256, 0, s>>>(start, cbits, 3 * shift, occ); count_launch();
-  return cudaGetLastError();
-}
-
 cudaError_t launch_transform_bin(float4* pts, int n, const float* d_delta, const int* d_done, GridDev g, uint32_t* keys,
                                  uint32_t* rank, uint32_t* counters, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;

@@ -26,12 +26,15 @@ struct IndexDev {
   const uint32_t* start;
   GridDev g;
   int n_valid;   // finite points (they occupy sorted positions [0, n_valid))
-  // Optional gate prefilter: occ[morton(cell >> occ_shift)] != 0 iff some indexed point lies in the
-  // 3x3x3 neighbourhood of that coarse cell.  Coarse edge >= 1.01 * sqrt(occ_gate2), so a query whose
-  // coarse cell reads 0 has no point within any gate <= occ_gate2.  nullptr: no prefilter.
-  const uint8_t* occ;
-  int occ_shift;
-  float occ_gate2;
+};
+
+// Query points sorted by cell (shift = 6: `start` is a full cell table) or only by 4 x 4 x 4-cell brick
+// (shift = 0: `start` has one entry per brick); pts[k].w = bits(original index).  Same grid as the
+// candidate index it is searched against.
+struct QueryDev {
+  const float4* pts;
+  const uint32_t* start;
+  int shift;
 };
 
 struct Mat4f { float m[16]; };  // column-major

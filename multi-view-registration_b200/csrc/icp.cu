@@ -1,5 +1,4 @@
-// icp.cu -- per-iteration ICP kernels: correspondence search with gate + reciprocal test (K4+K5),
-// estimator sums (K6 point-to-point 3x3 cross-covariance, K9 point-to-plane 6x6 normal equations)
+// icp.cu -- per-iteration ICP kernels (the search itself is in search.cu): estimator sums (K6 point-to-point 3x3 cross-covariance, K9 point-to-plane 6x6 normal equations)
 // with the solve and the convergence test in the reduction's last block, fitness reduction (K8) and
 // order-preserving correspondence compaction.
 //
@@ -10,57 +9,9 @@
 // The whole loop state lives in an IcpState on the device, so an align needs no host round trip per
 // iteration: the host only enqueues iterations and reads the state back when a batch has run.
 #include "launch.h"
-#include "nn_search.cuh"
 #include "small_solve.h"
 
 namespace mvr {
-
-// ---------------------------------------------------------------------------------------------
-// correspondences: source point i -> nearest target j, gate, optional reciprocal test
-// ---------------------------------------------------------------------------------------------
-template <bool RECIP>
-__global__ void __launch_bounds__(128) k_correspond(const float4* __restrict__ q, int nq, IndexDev tgt, IndexDev src, double max2,
-                                                    float max_d2f, int32_t* __restrict__ corr_j, float* __restrict__ corr_d2,
-                                                    const int* __restrict__ done) {
-  if (done && *done) return;
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= nq) return;
-  float4 p = __ldg(q + k);
-  const int i = __float_as_int(p.w);
-  int j = -1;
-  float d2 = MVR_INF;
-  if (finite3(p)) {
-    NnBest b{MVR_INF, 0x7fffffff, -1};
-    nn_search(tgt, p.x, p.y, p.z, max_d2f, b);
-    if (b.idx != 0x7fffffff && !((double)b.d2 > max2)) {   // PCL: if (distance > max_dist_sqr) continue;
-      bool keep = true;
-      if (RECIP) {
-        // nearest source point of the matched target point; seeded with (d2, i), which is exactly
-        // what the search would compute for source point i (fsub(a,b) == -fsub(b,a)), so the result
-        // is i iff no other source point is lexicographically closer.
-        float4 t = __ldg(tgt.pts + b.pos);
-        NnBest rb{b.d2, i, -1};
-        nn_search(src, t.x, t.y, t.z, b.d2, rb);
-        keep = (rb.idx == i);
-      }
-      // -2-j marks "passed the gate, failed the reciprocal test" (counted as an answered query)
-      j = keep ? b.idx : -2 - b.idx;
-      d2 = b.d2;
-    }
-  }
-  corr_j[i] = j;
-  corr_d2[i] = d2;
-}
-
-cudaError_t launch_correspond(const float4* q, int nq, IndexDev tgt, IndexDev src, bool reciprocal, double max_dist2,
-                              float max_d2f, int32_t* corr_j, float* corr_d2, const int* d_done, cudaStream_t s) {
-  if (nq <= 0) return cudaSuccess;
-  dim3 grid((nq + 127) / 128), block(128);
-  if (reciprocal) k_correspond<true><<<grid, block, 0, s>>>(q, nq, tgt, src, max_dist2, max_d2f, corr_j, corr_d2, d_done);
-  else k_correspond<false><<<grid, block, 0, s>>>(q, nq, tgt, src, max_dist2, max_d2f, corr_j, corr_d2, d_done);
-  count_launch();
-  return cudaGetLastError();
-}
 
 // ---------------------------------------------------------------------------------------------
 // estimator sums: fixed topology (thread grid-stride over ORIGINAL indices -> warp shuffle tree ->
@@ -130,14 +81,22 @@ __device__ __forceinline__ void ordered_total(const double* __restrict__ partial
 // The tail of one ICP iteration, run by one thread: estimate the increment from the sums, compose it
 // into the accumulated transform, log, and evaluate DefaultConvergenceCriteria.
 __device__ __noinline__ void icp_finish_iteration(IcpState* st, IterRec* log) {
-  const double* S = st->sums;
+  // everything the step needs, fetched up front so the loads overlap (st lives in global memory)
+  double S[REDUCE_MAX_VALS], F0[16];
+#pragma unroll
+  for (int k = 0; k < REDUCE_MAX_VALS; ++k) S[k] = st->sums[k];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) F0[k] = st->fin[k];
   const bool p2l = st->p2l != 0;
+  const double ox = st->ox, oy = st->oy, oz = st->oz;
+  const int min_corr = st->min_corr, max_iter = st->max_iter, fixed = st->fixed, iter0 = st->iter;
+  const double prev_mse = st->prev_mse, rot_thr = st->rot_thr, trans_thr = st->trans_thr, fit_eps = st->fit_eps;
   const double cnt = p2l ? S[27] : S[0];
   const double d2sum = p2l ? S[28] : S[16];
   st->queries += (unsigned long long)st->n_src + (st->recip ? (unsigned long long)(p2l ? S[29] : S[17]) : 0ull);
   const int n_corr = (int)cnt;
   st->n_corr = n_corr;
-  if (n_corr < st->min_corr) { st->reason = 5; st->status = 2; st->done = 1; return; }  // "Not enough correspondences"
+  if (n_corr < min_corr) { st->reason = 5; st->status = 2; st->done = 1; return; }  // "Not enough correspondences"
   double T[16];
   if (p2l) {
     double A[36], b[6], x[6];
@@ -148,41 +107,52 @@ __device__ __noinline__ void icp_finish_iteration(IcpState* st, IterRec* log) {
     if (!cholesky_solve6(A, b, x)) { st->reason = 5; st->status = 5; st->done = 1; return; }
     pose_from_6(x, T);
   } else {
-    double mu_a[3] = {S[1] / cnt, S[2] / cnt, S[3] / cnt}, mu_b[3] = {S[4] / cnt, S[5] / cnt, S[6] / cnt};
+    const double inv = 1.0 / cnt;
+    const double mu_a[3] = {S[1] * inv, S[2] * inv, S[3] * inv}, mu_b[3] = {S[4] * inv, S[5] * inv, S[6] * inv};
     double Sg[9];
+#pragma unroll
     for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) Sg[r * 3 + c] = S[7 + r * 3 + c] / cnt - mu_b[r] * mu_a[c];
-    double mu_s[3] = {mu_a[0] + st->ox, mu_a[1] + st->oy, mu_a[2] + st->oz};
-    double mu_d[3] = {mu_b[0] + st->ox, mu_b[1] + st->oy, mu_b[2] + st->oz};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) Sg[r * 3 + c] = S[7 + r * 3 + c] * inv - mu_b[r] * mu_a[c];
+    const double mu_s[3] = {mu_a[0] + ox, mu_a[1] + oy, mu_a[2] + oz};
+    const double mu_d[3] = {mu_b[0] + ox, mu_b[1] + oy, mu_b[2] + oz};
     umeyama_rigid(mu_s, mu_d, Sg, T);
   }
   float Tf[16];
+#pragma unroll
   for (int k = 0; k < 16; ++k) Tf[k] = (float)T[k];
   Tf[3] = Tf[7] = Tf[11] = 0.f; Tf[15] = 1.f;
   double Td[16], F[16];
+#pragma unroll
   for (int k = 0; k < 16; ++k) Td[k] = Tf[k];
+#pragma unroll
   for (int c = 0; c < 4; ++c)
+#pragma unroll
     for (int r = 0; r < 4; ++r) {
       double x = 0;
-      for (int k = 0; k < 4; ++k) x += Td[k * 4 + r] * st->fin[c * 4 + k];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x += Td[k * 4 + r] * F0[c * 4 + k];
       F[c * 4 + r] = x;
     }
+#pragma unroll
   for (int k = 0; k < 16; ++k) { st->fin[k] = F[k]; st->delta[k] = Tf[k]; }
-  const int iter = ++st->iter;
+  const int iter = iter0 + 1;
+  st->iter = iter;
   const double cur_mse = d2sum / cnt;
   st->cur_mse = cur_mse;
   if (iter <= ICP_MAX_LOG) {
     IterRec& r = log[iter - 1];
     r.iteration = iter; r.n_corr = n_corr; r.mse = cur_mse;
+#pragma unroll
     for (int k = 0; k < 16; ++k) r.delta[k] = Tf[k];
   }
-  if (iter >= st->max_iter) { st->done = 1; st->reason = 1; return; }
-  if (!st->fixed) {
+  if (iter >= max_iter) { st->done = 1; st->reason = 1; return; }
+  if (!fixed) {
     const double cos_angle = 0.5 * (Td[0] + Td[5] + Td[10] - 1.0);
     const double t2 = Td[12] * Td[12] + Td[13] * Td[13] + Td[14] * Td[14];
-    if (cos_angle >= st->rot_thr && t2 <= st->trans_thr) { st->done = 1; st->reason = 2; return; }
-    if (fabs(cur_mse - st->prev_mse) < 1e-12) { st->done = 1; st->reason = 3; return; }
-    if (fabs(cur_mse - st->prev_mse) / st->prev_mse < st->fit_eps) { st->done = 1; st->reason = 4; return; }
+    if (cos_angle >= rot_thr && t2 <= trans_thr) { st->done = 1; st->reason = 2; return; }
+    if (fabs(cur_mse - prev_mse) < 1e-12) { st->done = 1; st->reason = 3; return; }
+    if (fabs(cur_mse - prev_mse) / prev_mse < fit_eps) { st->done = 1; st->reason = 4; return; }
     st->prev_mse = cur_mse;
   }
 }
@@ -190,21 +160,22 @@ __device__ __noinline__ void icp_finish_iteration(IcpState* st, IterRec* log) {
 // Point-to-point sums about the origin o (a = s - o, b = t - o, exact in double):
 // [0] n, [1..3] sum a, [4..6] sum b, [7..15] sum b_r * a_c (row r, col c), [16] sum d2,
 // [17] number of source points that passed the distance gate (= reciprocal queries when enabled).
-__global__ void __launch_bounds__(256) k_reduce_p2p(const float4* __restrict__ src, int n, const int32_t* __restrict__ corr_j,
-                                                    const float* __restrict__ corr_d2, const float4* __restrict__ tgt,
-                                                    double* __restrict__ partials, IcpState* __restrict__ st, IterRec* __restrict__ log) {
+__global__ void __launch_bounds__(256) k_reduce_p2p(const float4* __restrict__ src, int n, const int32_t* __restrict__ corr_p,
+                                                    const float* __restrict__ corr_d2, const int32_t* __restrict__ rnn,
+                                                    const float4* __restrict__ tgt, double* __restrict__ partials,
+                                                    IcpState* __restrict__ st, IterRec* __restrict__ log) {
   if (st->done) return;
   const double ox = st->ox, oy = st->oy, oz = st->oz;
   double v[REDUCE_P2P_VALS];
 #pragma unroll
   for (int a = 0; a < REDUCE_P2P_VALS; ++a) v[a] = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int j = __ldg(corr_j + i);
-    if (j < -1) v[17] += 1.0;
-    if (j < 0) continue;
+    const int p = __ldg(corr_p + i);
+    if (p < 0) continue;
     v[17] += 1.0;
+    if (rnn && __ldg(rnn + p) != i) continue;   // reciprocal test: the matched point's nearest source point is not i
     const float4 s = __ldg(src + i);
-    const float4 t = __ldg(tgt + j);
+    const float4 t = __ldg(tgt + p);
     double ax = (double)s.x - ox, ay = (double)s.y - oy, az = (double)s.z - oz;
     double bx = (double)t.x - ox, by = (double)t.y - oy, bz = (double)t.z - oz;
     v[0] += 1.0;
@@ -218,26 +189,30 @@ __global__ void __launch_bounds__(256) k_reduce_p2p(const float4* __restrict__ s
   block_reduce_store<REDUCE_P2P_VALS>(v, partials);
   if (!last_block_done(&st->ticket)) return;
   ordered_total<REDUCE_P2P_VALS>(partials, gridDim.x, st->sums);
-  if (threadIdx.x == 0) icp_finish_iteration(st, log);
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    icp_finish_iteration(st, log);
+    st->dbg[0] += clock64() - t0; st->dbg[1] += 1;
+  }
 }
 
 // Point-to-plane normal equations: J = [cross(s, n), n], r = n.(d - s).
 // [0..20] upper triangle of J^T J row-major, [21..26] J^T r, [27] n, [28] sum d2, [29] gate-passing count.
-__global__ void __launch_bounds__(256) k_reduce_p2l(const float4* __restrict__ src, int n, const int32_t* __restrict__ corr_j,
-                                                    const float* __restrict__ corr_d2, const float4* __restrict__ tgt,
-                                                    const float4* __restrict__ nrm, double* __restrict__ partials,
-                                                    IcpState* __restrict__ st, IterRec* __restrict__ log) {
+__global__ void __launch_bounds__(256) k_reduce_p2l(const float4* __restrict__ src, int n, const int32_t* __restrict__ corr_p,
+                                                    const float* __restrict__ corr_d2, const int32_t* __restrict__ rnn,
+                                                    const float4* __restrict__ tgt, const float4* __restrict__ nrm,
+                                                    double* __restrict__ partials, IcpState* __restrict__ st, IterRec* __restrict__ log) {
   if (st->done) return;
   double v[REDUCE_P2L_VALS];
 #pragma unroll
   for (int a = 0; a < REDUCE_P2L_VALS; ++a) v[a] = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int j = __ldg(corr_j + i);
-    if (j < -1) v[29] += 1.0;
-    if (j < 0) continue;
+    const int p = __ldg(corr_p + i);
+    if (p < 0) continue;
     v[29] += 1.0;
+    if (rnn && __ldg(rnn + p) != i) continue;
     const float4 s = __ldg(src + i);
-    const float4 t = __ldg(tgt + j), nn = __ldg(nrm + j);
+    const float4 t = __ldg(tgt + p), nn = __ldg(nrm + __float_as_int(t.w));
     double sx = s.x, sy = s.y, sz = s.z, nx = nn.x, ny = nn.y, nz = nn.z;
     double J[6] = {nz * sy - ny * sz, nx * sz - nz * sx, ny * sx - nx * sy, nx, ny, nz};
     double r = nx * ((double)t.x - sx) + ny * ((double)t.y - sy) + nz * ((double)t.z - sz);
@@ -254,7 +229,11 @@ __global__ void __launch_bounds__(256) k_reduce_p2l(const float4* __restrict__ s
   block_reduce_store<REDUCE_P2L_VALS>(v, partials);
   if (!last_block_done(&st->ticket)) return;
   ordered_total<REDUCE_P2L_VALS>(partials, gridDim.x, st->sums);
-  if (threadIdx.x == 0) icp_finish_iteration(st, log);
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    icp_finish_iteration(st, log);
+    st->dbg[0] += clock64() - t0; st->dbg[1] += 1;
+  }
 }
 
 __global__ void k_reduce_final(const double* __restrict__ partials, int nblk, int nv, double* __restrict__ out) {
@@ -287,11 +266,11 @@ __global__ void __launch_bounds__(256) k_transform_final(const float4* __restric
   out[i] = finite3(p) ? xform_pinned(M, p) : p;
 }
 
-cudaError_t launch_reduce_solve(const float4* src_cur, int n, const int32_t* corr_j, const float* corr_d2,
-                                const float4* tgt_orig, const float4* tgt_normals, double* partials, IcpState* st,
+cudaError_t launch_reduce_solve(const float4* src_cur, int n, const int32_t* corr_p, const float* corr_d2, const int32_t* rnn,
+                                const float4* tgt_sorted, const float4* tgt_normals, double* partials, IcpState* st,
                                 IterRec* log, bool p2l, cudaStream_t s) {
-  if (p2l) k_reduce_p2l<<<REDUCE_BLOCKS, 256, 0, s>>>(src_cur, n, corr_j, corr_d2, tgt_orig, tgt_normals, partials, st, log);
-  else k_reduce_p2p<<<REDUCE_BLOCKS, 256, 0, s>>>(src_cur, n, corr_j, corr_d2, tgt_orig, partials, st, log);
+  if (p2l) k_reduce_p2l<<<REDUCE_BLOCKS, 256, 0, s>>>(src_cur, n, corr_p, corr_d2, rnn, tgt_sorted, tgt_normals, partials, st, log);
+  else k_reduce_p2p<<<REDUCE_BLOCKS, 256, 0, s>>>(src_cur, n, corr_p, corr_d2, rnn, tgt_sorted, partials, st, log);
   count_launch();
   return cudaGetLastError();
 }
@@ -306,6 +285,26 @@ cudaError_t launch_reduce_fitness(const int32_t* idx, const float* d2, int n, do
                                   double* out, cudaStream_t s) {
   k_reduce_fitness<<<REDUCE_BLOCKS, 256, 0, s>>>(idx, d2, n, max_range, partials); count_launch();
   k_reduce_final<<<1, 32, 0, s>>>(partials, REDUCE_BLOCKS, 2, out); count_launch();
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) k_resolve_corr(const int32_t* __restrict__ corr_p, const int32_t* __restrict__ rnn,
+                                                      const float4* __restrict__ tgt, int n, int32_t* __restrict__ corr_j) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int p = __ldg(corr_p + i);
+  int j = -1;
+  if (p >= 0) {
+    j = __float_as_int(__ldg(tgt + p).w);
+    if (rnn && __ldg(rnn + p) != i) j = -2 - j;
+  }
+  corr_j[i] = j;
+}
+
+cudaError_t launch_resolve_corr(const int32_t* corr_p, const int32_t* rnn, const float4* tgt_sorted, int n, int32_t* corr_j,
+                                cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  k_resolve_corr<<<(n + 255) / 256, 256, 0, s>>>(corr_p, rnn, tgt_sorted, n, corr_j); count_launch();
   return cudaGetLastError();
 }
 

@@ -39,16 +39,24 @@ cudaError_t launch_gather_sorted(const float4* pts, const uint32_t* perm, int n,
 // start[c] = first sorted position with key >= c, for c in [0, 1 << 3*bits].
 cudaError_t launch_cell_table(const uint32_t* sorted_keys, int n, int bits, uint32_t* start, cudaStream_t s);
 
-// occ[mc] = 1 iff any cell of the 3x3x3 neighbourhood of coarse cell mc (coarse = fine >> shift per axis)
-// holds a point; occ has 1 << 3*(bits-shift) entries.
-cudaError_t launch_build_occupancy(const uint32_t* start, int bits, int shift, uint8_t* occ, cudaStream_t s);
-
-// ---- nn.cu ---------------------------------------------------------------------------------
-// Exact 1-NN of each query in the index.  q_has_index: queries carry their original index in .w
-// (results are written at that index) or are in caller order.  max_d2 gates the SEARCH only (points
-// farther than the gate may be reported as -1); pass +inf for un-gated.
-cudaError_t launch_nn_query(const float4* q, int nq, bool q_has_index, IndexDev ix, float max_d2, int32_t* out_idx,
+// ---- search.cu -----------------------------------------------------------------------------
+// Brick-tiled search (see search.cu).  Queries and candidates are binned in the SAME grid (bits >= 3).
+// list_bricks: list[0..*count) = occupied 4x4x4-cell bricks of a sorted cloud; *next (nullable) is zeroed.
+cudaError_t launch_list_bricks(const uint32_t* start, int bits, int shift, uint32_t* list, uint32_t* count, uint32_t* next,
+                               const int* d_done, cudaStream_t s);
+cudaError_t launch_fill_u32(uint32_t* p, size_t n, uint32_t v, cudaStream_t s);
+// Exact un-gated 1-NN; results at the query's original index.
+cudaError_t launch_brick_nn(QueryDev q, int nq, IndexDev c, const uint32_t* bricks, const uint32_t* n_bricks, int32_t* out_idx,
                             float* out_d2, cudaStream_t s);
+// Forward correspondences source -> target with gate: corr_p[i] = sorted position of the matched target
+// point (-1 none), corr_d2[i] = float d2; rmin[p] (nullable) = min d2 bits over the source points that
+// chose target position p (must hold +inf bits on entry).
+cudaError_t launch_brick_forward(QueryDev q, int nq, IndexDev c, const uint32_t* bricks, const uint32_t* n_bricks, double max2,
+                                 float max_d2f, int32_t* corr_p, float* corr_d2, uint32_t* rmin, const int* d_done, cudaStream_t s);
+// Reciprocal half: for every target position p with rmin[p] < inf, rnn[p] = original index of the
+// nearest source point (lowest index on ties); rmin[p] is reset to +inf bits.
+cudaError_t launch_brick_reverse(QueryDev q, int nq, IndexDev c, const uint32_t* bricks, const uint32_t* n_bricks, uint32_t* rmin,
+                                 int32_t* rnn, const int* d_done, cudaStream_t s);
 
 // ---- bin.cu --------------------------------------------------------------------------------
 // Counting sort of a (moving) cloud by grid cell: see bin.cu.  counters has cells+1 entries (the last
@@ -88,19 +96,20 @@ struct IcpState {
   int iter, done, reason, status, n_corr;
   int max_iter, fixed, min_corr, p2l, recip, n_src;
   unsigned int ticket;    // blocks of the running reduction that have finished
+  long long dbg[4];       // diagnostics: [0] clock cycles spent in the serial solve, [1] solves
 };
-
-// Forward (+ optional reciprocal) correspondence search over the cell-sorted source `q` (.w = original
-// index).  Output is indexed by the query's ORIGINAL index: corr_j[i] = matched target original index,
-// -1 = none, -2-j = passed the gate but failed the reciprocal test; corr_d2[i] = float d2.
-cudaError_t launch_correspond(const float4* q, int nq, IndexDev tgt, IndexDev src, bool reciprocal, double max_dist2,
-                              float max_d2f, int32_t* corr_j, float* corr_d2, const int* d_done, cudaStream_t s);
 
 // Sums over kept correspondences in original-index order, then (last block) the solve + criteria:
 // advances st (delta, fin, iter, done, ...) and appends to log.  partials: REDUCE_BLOCKS x REDUCE_MAX_VALS.
-cudaError_t launch_reduce_solve(const float4* src_cur, int n, const int32_t* corr_j, const float* corr_d2,
-                                const float4* tgt_orig, const float4* tgt_normals, double* partials, IcpState* st,
+// corr_p / corr_d2 come from launch_brick_forward, rnn (nullable: not reciprocal) from launch_brick_reverse;
+// a pair (i, p) is kept iff corr_p[i] = p >= 0 and (rnn == nullptr or rnn[p] == i).
+cudaError_t launch_reduce_solve(const float4* src_cur, int n, const int32_t* corr_p, const float* corr_d2, const int32_t* rnn,
+                                const float4* tgt_sorted, const float4* tgt_normals, double* partials, IcpState* st,
                                 IterRec* log, bool p2l, cudaStream_t s);
+// corr_j[i] = original index of the matched target point, -1 = none, -2-j = passed the gate but failed
+// the reciprocal test (the layout launch_compact_corr consumes).
+cudaError_t launch_resolve_corr(const int32_t* corr_p, const int32_t* rnn, const float4* tgt_sorted, int n, int32_t* corr_j,
+                                cudaStream_t s);
 // out = float(st->fin) * in   (the aligned cloud icp.align returns)
 cudaError_t launch_transform_final(const float4* in, float4* out, int n, const IcpState* st, cudaStream_t s);
 // sum and count of d2[i] with idx[i] >= 0 and d2 <= max_range  (getFitnessScore); out[0]=sum, out[1]=count

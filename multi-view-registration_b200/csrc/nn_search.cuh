@@ -59,11 +59,6 @@ __device__ __forceinline__ void nn_search(const IndexDev& ix, float qx, float qy
   const float margin = MVR_CELL_MARGIN + 1.0e-6f * fmaxf(fabsf(tx), fmaxf(fabsf(ty), fabsf(tz)));
   const float cell2 = g.cell_lo * g.cell_lo * MVR_REL_SHRINK;
 
-  // 0. gate prefilter: nothing indexed within the gate of this query's coarse cell
-  if (ix.occ != nullptr && max_d2f <= ix.occ_gate2) {
-    const int sh = ix.occ_shift;
-    if (__ldg(ix.occ + morton3((uint32_t)(cx >> sh), (uint32_t)(cy >> sh), (uint32_t)(cz >> sh))) == 0) return;
-  }
   // 1. own cell
   {
     const uint32_t m = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);

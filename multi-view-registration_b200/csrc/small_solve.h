@@ -17,56 +17,95 @@
 
 namespace mvr {
 
+// One rotation of the one-sided Jacobi SVD on columns P, Q (compile-time indices keep B and W in
+// registers on the device).  Returns false when the two columns are already orthogonal.
+template <int P, int Q>
+MVR_HD inline bool svd3_rotate(double (&B)[3][3], double (&W)[3][3]) {
+  const double al = B[0][P] * B[0][P] + B[1][P] * B[1][P] + B[2][P] * B[2][P];
+  const double be = B[0][Q] * B[0][Q] + B[1][Q] * B[1][Q] + B[2][Q] * B[2][Q];
+  const double ga = B[0][P] * B[0][Q] + B[1][P] * B[1][Q] + B[2][P] * B[2][Q];
+  if (ga == 0.0 || ga * ga <= 1e-32 * (al * be)) return false;   // |cos angle| <= 1e-16: orthogonal to working precision
+  const double zeta = (be - al) / (2.0 * ga);
+  const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+  const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 3; ++k) {
+    const double bp = B[k][P], bq = B[k][Q];
+    B[k][P] = c * bp - sn * bq; B[k][Q] = sn * bp + c * bq;
+    const double wp = W[k][P], wq = W[k][Q];
+    W[k][P] = c * wp - sn * wq; W[k][Q] = sn * wp + c * wq;
+  }
+  return true;
+}
+
+// Exchange columns P and Q of B and W when column Q is the longer one (sorting network step).
+template <int P, int Q>
+MVR_HD inline void svd3_order(double (&B)[3][3], double (&W)[3][3], double (&nrm)[3]) {
+  if (nrm[Q] > nrm[P]) {
+    double t = nrm[P]; nrm[P] = nrm[Q]; nrm[Q] = t;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 3; ++k) {
+      t = B[k][P]; B[k][P] = B[k][Q]; B[k][Q] = t;
+      t = W[k][P]; W[k][P] = W[k][Q]; W[k][Q] = t;
+    }
+  }
+}
+
 // One-sided (Hestenes) Jacobi SVD of a 3x3 row-major matrix: A = U diag(s) V^T, s descending,
 // U and V orthogonal.  Works on the columns of A directly, so small singular values keep full
 // relative accuracy (no A^T A squaring).
 MVR_HD inline void svd3(const double* A, double* U, double* s, double* V) {
   double B[3][3], W[3][3];
-  for (int i = 0; i < 3; ++i)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 3; ++i) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
     for (int j = 0; j < 3; ++j) { B[i][j] = A[i * 3 + j]; W[i][j] = (i == j) ? 1.0 : 0.0; }
+  }
   for (int sweep = 0; sweep < 40; ++sweep) {
-    bool rotated = false;
-    for (int p = 0; p < 2; ++p)
-      for (int q = p + 1; q < 3; ++q) {
-        double al = 0, be = 0, ga = 0;
-        for (int k = 0; k < 3; ++k) { al += B[k][p] * B[k][p]; be += B[k][q] * B[k][q]; ga += B[k][p] * B[k][q]; }
-        if (ga == 0.0 || fabs(ga) <= 1e-17 * sqrt(al * be)) continue;
-        rotated = true;
-        double zeta = (be - al) / (2.0 * ga);
-        double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
-        for (int k = 0; k < 3; ++k) {
-          double bp = B[k][p], bq = B[k][q];
-          B[k][p] = c * bp - sn * bq; B[k][q] = sn * bp + c * bq;
-          double wp = W[k][p], wq = W[k][q];
-          W[k][p] = c * wp - sn * wq; W[k][q] = sn * wp + c * wq;
-        }
-      }
+    bool rotated = svd3_rotate<0, 1>(B, W);
+    rotated = svd3_rotate<0, 2>(B, W) || rotated;
+    rotated = svd3_rotate<1, 2>(B, W) || rotated;
     if (!rotated) break;
   }
   double nrm[3];
-  int ord[3] = {0, 1, 2};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
   for (int j = 0; j < 3; ++j) nrm[j] = sqrt(B[0][j] * B[0][j] + B[1][j] * B[1][j] + B[2][j] * B[2][j]);
-  for (int a = 0; a < 2; ++a)
-    for (int b = a + 1; b < 3; ++b)
-      if (nrm[ord[b]] > nrm[ord[a]]) { int t = ord[a]; ord[a] = ord[b]; ord[b] = t; }
+  svd3_order<0, 1>(B, W, nrm);
+  svd3_order<0, 2>(B, W, nrm);
+  svd3_order<1, 2>(B, W, nrm);
   double Uc[3][3];  // Uc[col][row]
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
   for (int c = 0; c < 3; ++c) {
-    int j = ord[c];
-    s[c] = nrm[j];
-    for (int r = 0; r < 3; ++r) { V[r * 3 + c] = W[r][j]; Uc[c][r] = B[r][j]; }
+    s[c] = nrm[c];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 3; ++r) { V[r * 3 + c] = W[r][c]; Uc[c][r] = B[r][c]; }
   }
   const double tiny = 1e-300 + 1e-14 * s[0];
   if (s[0] > tiny) { for (int r = 0; r < 3; ++r) Uc[0][r] /= s[0]; }
   else { Uc[0][0] = 1; Uc[0][1] = 0; Uc[0][2] = 0; }
   if (s[1] > tiny) { for (int r = 0; r < 3; ++r) Uc[1][r] /= s[1]; }
   else {
-    int m = 0;
-    if (fabs(Uc[0][1]) < fabs(Uc[0][m])) m = 1;
-    if (fabs(Uc[0][2]) < fabs(Uc[0][m])) m = 2;
+    // second direction: the coordinate axis least aligned with the first, orthogonalised
+    const double a0 = fabs(Uc[0][0]), a1 = fabs(Uc[0][1]), a2 = fabs(Uc[0][2]);
     double e[3] = {0, 0, 0};
-    e[m] = 1;
-    double d = Uc[0][m];
+    double d;
+    if (a2 < a0 && a2 < a1) { e[2] = 1; d = Uc[0][2]; }
+    else if (a1 < a0) { e[1] = 1; d = Uc[0][1]; }
+    else { e[0] = 1; d = Uc[0][0]; }
     double n2 = 0;
     for (int r = 0; r < 3; ++r) { Uc[1][r] = e[r] - d * Uc[0][r]; n2 += Uc[1][r] * Uc[1][r]; }
     n2 = sqrt(n2);
