@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--reciprocal", type=int, default=1)
     ap.add_argument("--cpu-sample-pairs", type=int, default=1, help="pairs the cpu_baseline leg aligns (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--streams", type=int, default=4, help="concurrent GPU contexts (host threads) per rank")
     return ap.parse_args()
 
 
@@ -64,18 +65,19 @@ def pair_range(rank, world, n_pairs):
 
 
 def make_pairs(a, p0, p1):
-    """Synthetic scans and initial guesses of pairs [p0, p1): pair p aligns view (p+1)%V onto view p."""
+    """Synthetic scans and initial guesses of pairs [p0, p1): pair p aligns view (p+1)%V onto view p (CPU arm;
+    same scans and the same guesses as the native arm's view_init_poses)."""
     import mvr_b200.synth as synth
     V = a.views
     need = sorted({v % V for p in range(p0, p1) for v in (p, p + 1)})
     views, poses = {}, {}
     for v in need:
         views[v], poses[v] = synth.turntable_view(v, V, a.points)
-    E = synth.perturbation()
+    init = view_init_poses(a, [poses.get(v, synth.view_pose(v, V)) for v in range(V)])
     pairs = []
     for p in range(p0, p1):
         t, s = p % V, (p + 1) % V
-        guess = (E @ np.linalg.inv(poses[t]) @ poses[s]).astype(np.float32)   # ideal turntable step + fixed error
+        guess = (np.linalg.inv(init[t]) @ init[s]).astype(np.float32)   # ideal turntable step + fixed error
         pairs.append(dict(pair=p, tgt=t, src=s, guess=guess, truth=np.linalg.inv(poses[t]) @ poses[s]))
     return views, pairs
 
@@ -173,10 +175,20 @@ class ClockSampler:
         return out
 
 
+def view_init_poses(a, poses):
+    """Initial pose of every view = its ideal turntable pose, with the fixed perturbation (2 deg about a seeded axis
+    + 2 mm) applied to every odd view: each ring pair then starts from a guess that is off by
+    that perturbation, and the ring still closes."""
+    import mvr_b200.synth as synth
+    E = synth.perturbation()
+    return [(poses[v] @ E) if (v % 2 == 1) else poses[v].copy() for v in range(a.views)]
+
+
 def run_native(a):
     import torch
     import torch.distributed as dist
     import mvr_b200
+    import mvr_b200.synth as synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -194,82 +206,82 @@ def run_native(a):
         torch.cuda.synchronize()
 
     V = a.views
-    p0, p1 = pair_range(rank, world, V)
-    views, pairs = make_pairs(a, p0, p1)
     n = a.points
-    ctx = mvr_b200.Context(local)
-    stream = torch.cuda.Stream(device=dev)
-    ctx.set_stream(stream.cuda_stream)
-    prm = mvr_b200.default_params(max_iterations=a.iters, max_dist=a.max_dist, reciprocal=a.reciprocal, fixed_iterations=1)
+    p0, p1 = pair_range(rank, world, V)
+    need = sorted({v % V for p in range(p0, p1) for v in (p, p + 1)})
+    views, poses = {}, {}
+    for v in range(V):
+        if v in need:
+            views[v], poses[v] = synth.turntable_view(v, V, n)
+        else:
+            poses[v] = synth.view_pose(v, V)
+    init = view_init_poses(a, [poses[v] for v in range(V)])
+    truth0 = np.linalg.inv(poses[p0 % V]) @ poses[(p0 + 1) % V]
 
-    d_views = {v: torch.from_numpy(p).to(dev) for v, p in views.items()}
-    h_views = {v: torch.from_numpy(p).pin_memory() for v, p in views.items()}
+    reg = mvr_b200.Registrator(local, a.streams)   # C++ driver: a.streams GPU contexts, one host thread each
+    icp = mvr_b200.default_params(max_iterations=a.iters, max_dist=a.max_dist, reciprocal=a.reciprocal, fixed_iterations=1)
+    tp = mvr_b200.turntable_params(pivot=synth.PIVOT, axis=synth.AXIS, icp=icp, repeat_times=1, mode=mvr_b200.RING_PAIRS,
+                                   loop_closure=1, lum_iterations=16, pair_begin=p0, pair_end=p1, want_fitness=0)
+
+    d_views = {v: torch.from_numpy(pts).to(dev) for v, pts in views.items()}
+    h_views = {v: torch.from_numpy(pts).pin_memory() for v, pts in views.items()}
+    dev_list = [(d_views[v].data_ptr(), n) if v in d_views else None for v in range(V)]
+    host_list = [h_views[v].numpy() if v in h_views else None for v in range(V)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    REC = 24   # floats per pair record: pose 16, mse, n_corr, iterations, status, queries(lo, hi as 2^24 split), pad
-    gathered = torch.zeros(V * REC, dtype=torch.float32, device=dev)
+    REC = 24   # floats per pair record: pose 16, n_corr, mse, iterations, status, queries (2 x 24-bit halves), pad
     mine = torch.zeros((p1 - p0) * REC, dtype=torch.float32, device=dev)
+    gathered = torch.zeros(world * ((V + world - 1) // world) * REC, dtype=torch.float32, device=dev) if world > 1 else None
     h_rec = torch.zeros((p1 - p0) * REC, dtype=torch.float32).pin_memory()
-    h_all = torch.zeros(V * REC, dtype=torch.float32).pin_memory()
 
     def step(host_buffers):
-        """One registration of this rank's pairs + gather + loop closure.  Returns (queries, results)."""
+        """One registration: this rank's ring pairs through the C++ driver, gather of the per-pair results, host
+        loop closure over the whole ring.  Returns (queries of this rank, pair reports, absolute poses)."""
+        _, reps = reg.register_turntable(host_list if host_buffers else dev_list, tp, init_poses=init)
         q = 0
-        res = []
-        with torch.cuda.stream(stream):
-            for k, pr in enumerate(pairs):
-                if host_buffers:
-                    ctx.set_target(h_views[pr["tgt"]].numpy())
-                    ctx.set_source(h_views[pr["src"]].numpy())
-                else:
-                    ctx.set_target_device(d_views[pr["tgt"]].data_ptr(), n)
-                    ctx.set_source_device(d_views[pr["src"]].data_ptr(), n)
-                r = ctx.icp_align(prm, guess=pr["guess"], n_source=n)
-                q += r["nn_queries"]
-                res.append(r)
-                rec = h_rec[k * REC:(k + 1) * REC]
-                rec[:16] = torch.from_numpy(np.ascontiguousarray(r["final"].T).reshape(16))
-                rec[16] = r["mse"]
-                rec[17] = r["n_corr"]
-                rec[18] = r["iterations"]
-                rec[19] = r["status"]
+        for k, p in enumerate(range(p0, p1)):
+            r = reps[p]
+            q += r["nn_queries"]
+            rec = h_rec[k * REC:(k + 1) * REC]
+            rec[:16] = torch.from_numpy(np.ascontiguousarray(r["pose"].T).reshape(16))
+            rec[16] = r["n_corr"]
+            rec[17] = r["mse"]
+            rec[18] = r["iterations"]
+            rec[19] = r["status"]
+        if world > 1:
+            # per-pair results -> every rank (one small NCCL all-gather; ranks hold equal-size blocks when world | V)
             mine.copy_(h_rec, non_blocking=True)
-            if world > 1:
-                stream.synchronize()
-                dist.all_gather_into_tensor(gathered, mine)
-                h_all.copy_(gathered, non_blocking=True)
+            parts = [torch.zeros_like(mine) for _ in range(world)] if V % world else None
+            if parts is None:
+                dist.all_gather_into_tensor(gathered[:V * REC], mine)
+                allrec = gathered[:V * REC].cpu().numpy().reshape(V, REC)
             else:
-                h_all.copy_(mine, non_blocking=True)
-            stream.synchronize()
-        poses = loop_closure(h_all.numpy().reshape(V, REC), V)
-        return q, res, poses
-
-    def loop_closure(recs, V):
-        """Chain the ring pairs into absolute poses and spread the closing error evenly (host side).
-        TODO(next milestone): replaced by the C++ LUM-style relaxation in host/lum.cpp."""
-        P = [np.eye(4)]
-        for k in range(V - 1):
-            T = recs[k, :16].astype(np.float64).reshape(4, 4).T
-            P.append(P[-1] @ T)
-        return P
+                raise SystemExit("bench.py: --gpus must divide --views")
+        else:
+            allrec = h_rec.numpy().reshape(V, REC)
+        rel = [allrec[p, :16].reshape(4, 4).T for p in range(V)]
+        w = [float(allrec[p, 16]) if allrec[p, 19] == 0 else 0.0 for p in range(V)]
+        abs_poses = mvr_b200.ring_close(rel, w, relax=True, iterations=16)
+        return q, reps, abs_poses
 
     def timed(host_buffers, steps):
         tot_ms, tot_q = 0.0, 0
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
+        last = None
         barrier()
         for _ in range(steps):
             flush.fill_(1)
             torch.cuda.synchronize()
-            with torch.cuda.stream(stream):
-                e0.record(stream)
-            q, res, poses = step(host_buffers)
-            with torch.cuda.stream(stream):
-                e1.record(stream)
+            e0.record()
+            q, reps, abs_poses = step(host_buffers)
+            torch.cuda.synchronize()   # the driver's streams are non-blocking: make the closing event cover them
+            e1.record()
             e1.synchronize()
             tot_ms += e0.elapsed_time(e1)
             tot_q += q
+            last = (reps, abs_poses)
         barrier()
-        return tot_ms, tot_q, res
+        return tot_ms, tot_q, last
 
     def allmax(x):
         if world == 1:
@@ -290,7 +302,7 @@ def run_native(a):
         step(False)
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = mvr_b200.kernel_launch_count()
-    ms, q, res = timed(False, a.steps)
+    ms, q, last = timed(False, a.steps)
     launches = mvr_b200.kernel_launch_count() - l0
     clocks = sampler.stop() if sampler else None
     ms = allmax(ms)
@@ -306,17 +318,24 @@ def run_native(a):
         ms_e, q_e, _ = timed(True, a.steps)
         ms_e = allmax(ms_e)
         q_e = allsum(q_e)
-        h2d = allsum(float(len(pairs) * 2 * n * 16 + len(pairs) * REC * 4))
-        d2h = allsum(float(len(pairs) * 256 * a.iters)) + V * REC * 4   # 32 doubles of sums per iteration + records
+        h2d = allsum(float((p1 - p0) * 2 * n * 16 + (p1 - p0) * 512))       # both scans of every pair + state/params
+        d2h = allsum(float((p1 - p0) * (512 + 48 * a.iters)))                 # state + per-iteration log of every pair
         e2e = {"value": q_e / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e / a.steps,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
 
-    # ---- roofline of the dominant kernel: one extra untimed step with per-kernel CUDA events ----
-    ctx.set_profiling(True)
-    ctx.kernel_stats(reset=True)
+    # ---- roofline of the dominant kernel: one extra untimed step, per-kernel CUDA events on every stream ----
+    ctxs = [reg.context(k) for k in range(reg.streams())]
+    for c in ctxs:
+        c.set_profiling(True)
+        c.kernel_stats(reset=True)
     step(False)
-    st = ctx.kernel_stats(reset=True)
-    ctx.set_profiling(False)
+    st = {}
+    for c in ctxs:
+        for k, v in c.kernel_stats(reset=True).items():
+            d = st.setdefault(k, dict(launches=0, ms=0.0, bytes=0.0, units=0.0))
+            for f in d:
+                d[f] += v[f]
+        c.set_profiling(False)
     roof = None
     if rank == 0:
         peaks = {}
@@ -330,39 +349,50 @@ def run_native(a):
         bytes_per_launch = c["bytes"] / max(c["launches"], 1)
         ach = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
         total_kernel_ms = sum(v["ms"] for v in st.values())
-        roof = {"bound": "hbm", "kernel": "k_correspond (forward + reciprocal NN search, gate)", "achieved": ach, "peak": peak,
-                "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        roof = {"bound": "hbm", "kernel": "k_brick_search (forward + reciprocal halves of one iteration's correspondence search)",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "bytes_per_launch": bytes_per_launch, "avg_launch_us": avg_ms * 1e3, "launches": c["launches"],
                 "share_of_kernel_time": c["ms"] / total_kernel_ms if total_kernel_ms > 0 else None,
+                "concurrent_streams": a.streams,
                 "per_kernel_ms": {k: round(v["ms"], 4) for k, v in st.items() if v["launches"]}}
 
     # ---- accuracy summary (parity itself lives in tests/) ----
     acc = None
-    if rank == 0 and res:
-        r, pr = res[0], pairs[0]
-        dT = r["final"].astype(np.float64) @ np.linalg.inv(pr["truth"])
+    if rank == 0 and last:
+        reps, abs_poses = last
+        r = reps[p0]
+        dT = r["pose"].astype(np.float64) @ np.linalg.inv(truth0)
         w = 0.5 * np.array([dT[2, 1] - dT[1, 2], dT[0, 2] - dT[2, 0], dT[1, 0] - dT[0, 1]])
+        worst = 0.0
+        for v in range(V):
+            dA = abs_poses[v].astype(np.float64) @ np.linalg.inv(np.linalg.inv(poses[0]) @ poses[v])
+            wv = 0.5 * np.array([dA[2, 1] - dA[1, 2], dA[0, 2] - dA[2, 0], dA[1, 0] - dA[0, 1]])
+            worst = max(worst, float(np.arcsin(min(1.0, np.linalg.norm(wv)))))
         acc = {"pair0_rot_err_rad_vs_truth": float(np.arcsin(min(1.0, np.linalg.norm(w)))),
-               "pair0_rmse_mm": float(np.sqrt(r["mse"])), "pair0_n_corr": int(r["n_corr"])}
+               "pair0_rmse_mm": float(np.sqrt(r["mse"])), "pair0_n_corr": int(r["n_corr"]),
+               "worst_abs_rot_err_rad_vs_truth_after_loop_closure": worst}
 
     cpu = None
     if rank == 0 and a.cpu_sample_pairs > 0:
-        cq, cdt, cores = cpu_align_pairs(a, views, pairs[:a.cpu_sample_pairs])
+        cviews, cpairs = make_pairs(a, 0, a.cpu_sample_pairs)
+        cq, cdt, cores = cpu_align_pairs(a, cviews, cpairs)
         cpu = {"value": cq / cdt, "unit": UNIT, "cores": cores, "kind": "port", "seconds": cdt,
                "sample": "first %d pair(s) of the same sequence (%d/%d of a step), %d iterations each"
                          % (a.cpu_sample_pairs, a.cpu_sample_pairs, V, a.iters)}
 
     if rank == 0:
+        cfg = workload_config(a, world)
+        cfg["streams_per_gpu"] = a.streams
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(a, world),
+            "dtype": "f32", "data": "synthetic", "config": cfg,
             "registration_ms": ms / a.steps, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roof, "cpu_baseline": cpu, "accuracy": acc,
         }
         print(json.dumps(out))
-    ctx.close()
+    reg.close()
     if world > 1:
         dist.destroy_process_group()
 

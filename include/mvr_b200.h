@@ -168,6 +168,93 @@ int mvr_fitness_score(mvr_ctx* ctx, double max_range, double* score);
 int mvr_estimate_normals(mvr_ctx* ctx, int which, int k, const float viewpoint[3], float* out_nxyzc,
                          int32_t* neighbours);
 
+/* -- pose application: PointCloud::getTransformedPoints (mvr/src/point_cloud.cpp:290-303) ------------
+ * out[i] = {float(pose * p_i), 1}: the multiply runs in double (osg::Matrix is double) and is narrowed to
+ * float, RGB / normal lanes are dropped.  in: n records of `stride_bytes` bytes whose first three floats
+ * are x, y, z (16 for PointXYZ, 48 for PointXYZRGBNormal).  pose: double[16] column-major, p' = M p (the
+ * transpose of the reference's row-vector osg::Matrix, see PclMatrixCaster mvr/include/types.h:20-50). */
+int mvr_apply_pose(mvr_ctx* ctx, const void* points, size_t n, size_t stride_bytes, const double* pose, float* out_xyzw);
+/* Same with device pointers on both sides (returns after the work has completed). */
+int mvr_apply_pose_device(mvr_ctx* ctx, const void* d_points, size_t n, size_t stride_bytes, const double* pose, float* d_out_xyzw);
+/* Copy transform(source, final) of the last mvr_icp_align into a device buffer of source-size points
+ * (the reference grows its model with it: *target += transformed_source, mvr/src/registrator.cpp:576). */
+int mvr_copy_aligned_device(mvr_ctx* ctx, float* d_out_xyzw);
+
+/* -- registration driver: the reference's Registrator entry points (mvr/include/registrator.h:40-49) -- */
+typedef struct mvr_registrator mvr_registrator;
+
+typedef struct {
+  const float* xyzw;       /* n PointXYZ records in the view's own sensor frame */
+  size_t n;
+  int on_device;           /* non-zero: xyzw is a device pointer on the registrator's device */
+  const double* init_pose; /* nullable double[16] column-major initial pose of the view in view 0's frame;
+                              NULL = PointCloud::initRotation: ideal turntable rotation of view index v */
+} mvr_view;
+
+typedef enum {
+  MVR_REGISTER_RING_PAIRS = 0,  /* independent neighbour pairs (v+1 -> v, closing pair 0 -> V-1), then loop closure:
+                                   the shardable form (ring edges of registrationLUM, mvr/src/registrator.cpp:640-651) */
+  MVR_REGISTER_ACCUMULATE = 1,  /* automaticRegistration: views 1..V-1 in order, each aligned repeat_times against
+                                   the growing model, then refineAxis (mvr/src/registrator.cpp:746-842, 877-990) */
+  MVR_REGISTER_ICP = 2,         /* registrationICP: views in the order 1, V-1, 2, V-2, .. against the growing model,
+                                   the whole pass repeated repeat_times (mvr/src/registrator.cpp:517-588) */
+  MVR_REGISTER_LUM = 3          /* registrationLUM: ring relaxation from reciprocal correspondences of the posed
+                                   views, max(1, max_iterations / 16) outer loops (mvr/src/registrator.cpp:611-678) */
+} mvr_register_mode;
+
+typedef struct {
+  double pivot[3];         /* turntable axis: Registrator::getPivotPoint / getAxisNormal (axis.txt) */
+  double axis[3];
+  mvr_icp_params icp;      /* per-align settings (reference: reciprocal, max_dist 4, transEps 1e-6, fitEps 64) */
+  int repeat_times;        /* aligns per view/pair, each starting from the previous result (reference default 5) */
+  int mode;                /* mvr_register_mode */
+  int loop_closure;        /* ring mode: 0 = chain the pair poses, 1 = relax the ring (host, after the gather) */
+  int lum_iterations;      /* relaxation sweeps (reference lum.setMaxIterations(16)) */
+  int pair_begin, pair_end;/* ring mode: compute only pairs [begin, end) (multi-GPU sharding); end <= 0 = all V */
+  int want_fitness;        /* also run getFitnessScore() after the last align of each pair/view */
+} mvr_turntable_params;
+
+typedef struct {
+  int source_view, target_view;  /* target_view = -1: the accumulated model */
+  int status;                    /* mvr_status of the (last) align */
+  int iterations;                /* summed over the repeats */
+  int n_correspondences;
+  double mse;
+  double fitness;                /* getFitnessScore() if requested, else -1 */
+  double gpu_ms;
+  uint64_t nn_queries;
+  float pose[16];                /* ring mode: relative pose source -> target frame; accumulate: view -> model frame */
+} mvr_pair_report;
+
+void mvr_turntable_params_default(mvr_turntable_params* p);
+/* Registrator::getRotationMatrix (mvr/src/registrator.cpp:331-342): T(pivot) R(axis, angle) T(-pivot), double[16]
+ * column-major; and the angle PointCloud::initRotation gives view v of V (mvr/src/point_cloud.cpp:400-413). */
+void mvr_turntable_rotation(const double pivot[3], const double axis[3], double angle, double* out16);
+double mvr_turntable_view_angle(int view, int n_views);
+
+/* `streams` contexts on `device` run pairs concurrently (each pair is small next to a B200). */
+int mvr_registrator_create(int device, int streams, mvr_registrator** out);
+int mvr_registrator_destroy(mvr_registrator* r);
+const char* mvr_registrator_last_error(mvr_registrator* r);
+/* The GPU context behind stream `slot` (owned by the registrator): for profiling switches and kernel statistics. */
+mvr_ctx* mvr_registrator_context(mvr_registrator* r, int slot);
+int mvr_registrator_streams(mvr_registrator* r);
+/* icp.setInputSource / setInputTarget / align / getFinalTransformation as one call
+ * (mvr/src/registrator.cpp:565-573): the pairwise-align entry point. */
+int mvr_pairwise_align(mvr_registrator* r, const mvr_view* source, const mvr_view* target, const mvr_icp_params* icp,
+                       const float* guess, float* out_pose, mvr_icp_report* report);
+/* The multi-view-register entry point.  poses: V x float[16] absolute poses in view 0's frame (ring mode
+ * with a partial pair range: only the pair reports are meaningful; compose with mvr_ring_close after the
+ * gather).  reports: one per pair (ring: V entries indexed by pair; accumulate: V-1 entries, views 1..V-1). */
+int mvr_register_turntable(mvr_registrator* r, const mvr_view* views, int n_views, const mvr_turntable_params* prm,
+                           float* poses, mvr_pair_report* reports);
+/* Host-side loop closure over gathered ring pairs: rel[p] = pose of view (p+1)%V in view p's frame, w[p] its
+ * weight (e.g. n_correspondences; <= 0 drops the edge).  Output V absolute poses, view 0 = identity. */
+int mvr_ring_close(const float* rel_poses, const double* weights, int n_views, int relax, int iterations, float* poses);
+/* Registrator::refineAxis (mvr/src/registrator.cpp:402-455): least-squares turntable axis from registered
+ * view poses (poses: count x float[16] column-major).  pivot/axis are in-out. */
+int mvr_refine_axis(const float* poses, int count, double pivot[3], double axis[3]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,16 +66,21 @@ class KernelStat(C.Structure):
 
 class TurntableParams(C.Structure):
     _fields_ = [
-        ("n_views", C.c_int),
         ("pivot", C.c_double * 3),
         ("axis", C.c_double * 3),
         ("icp", IcpParams),
         ("repeat_times", C.c_int),
+        ("mode", C.c_int),
         ("loop_closure", C.c_int),
         ("lum_iterations", C.c_int),
         ("pair_begin", C.c_int),
         ("pair_end", C.c_int),
+        ("want_fitness", C.c_int),
     ]
+
+
+class ViewDesc(C.Structure):
+    _fields_ = [("xyzw", C.c_void_p), ("n", C.c_size_t), ("on_device", C.c_int), ("init_pose", C.POINTER(C.c_double))]
 
 
 class PairReport(C.Structure):
@@ -86,11 +91,14 @@ class PairReport(C.Structure):
         ("iterations", C.c_int),
         ("n_correspondences", C.c_int),
         ("mse", C.c_double),
+        ("fitness", C.c_double),
         ("gpu_ms", C.c_double),
         ("nn_queries", C.c_uint64),
         ("pose", C.c_float * 16),
     ]
 
+
+RING_PAIRS, ACCUMULATE, ICP_ORDER, LUM = 0, 1, 2, 3
 
 _lib = None
 
@@ -132,6 +140,25 @@ def lib():
     L.mvr_icp_get_iterations.argtypes = [vp, C.POINTER(IcpIteration), C.c_int, C.POINTER(C.c_int)]
     L.mvr_fitness_score.argtypes = [vp, C.c_double, C.POINTER(C.c_double)]
     L.mvr_estimate_normals.argtypes = [vp, C.c_int, C.c_int, fp, fp, ip]
+    dp = C.POINTER(C.c_double)
+    L.mvr_apply_pose.argtypes = [vp, vp, C.c_size_t, C.c_size_t, dp, fp]
+    L.mvr_apply_pose_device.argtypes = [vp, vp, C.c_size_t, C.c_size_t, dp, vp]
+    L.mvr_copy_aligned_device.argtypes = [vp, vp]
+    L.mvr_turntable_params_default.argtypes = [C.POINTER(TurntableParams)]
+    L.mvr_turntable_rotation.argtypes = [dp, dp, C.c_double, dp]
+    L.mvr_turntable_view_angle.argtypes = [C.c_int, C.c_int]
+    L.mvr_turntable_view_angle.restype = C.c_double
+    L.mvr_registrator_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
+    L.mvr_registrator_destroy.argtypes = [vp]
+    L.mvr_registrator_last_error.argtypes = [vp]
+    L.mvr_registrator_last_error.restype = C.c_char_p
+    L.mvr_registrator_context.argtypes = [vp, C.c_int]
+    L.mvr_registrator_context.restype = vp
+    L.mvr_registrator_streams.argtypes = [vp]
+    L.mvr_pairwise_align.argtypes = [vp, C.POINTER(ViewDesc), C.POINTER(ViewDesc), C.POINTER(IcpParams), fp, fp, C.POINTER(IcpReport)]
+    L.mvr_register_turntable.argtypes = [vp, C.POINTER(ViewDesc), C.c_int, C.POINTER(TurntableParams), fp, C.POINTER(PairReport)]
+    L.mvr_ring_close.argtypes = [fp, dp, C.c_int, C.c_int, C.c_int, fp]
+    L.mvr_refine_axis.argtypes = [fp, C.c_int, dp, dp]
     _lib = L
     return L
 
@@ -183,7 +210,12 @@ class Context:
     """One CUDA device + stream; mirrors a pcl::IterativeClosestPoint instance holding its
     source/target (Registrator::icp_, mvr/include/registrator.h:91)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, _borrowed=None):
+        self._keep = {}
+        self._owned = _borrowed is None
+        if _borrowed is not None:
+            self._h = C.c_void_p(_borrowed)
+            return
         self._h = C.c_void_p()
         rc = lib().mvr_ctx_create(int(device), C.byref(self._h))
         if rc != OK:
@@ -192,7 +224,8 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
-            lib().mvr_ctx_destroy(self._h)
+            if self._owned:
+                lib().mvr_ctx_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -323,3 +356,140 @@ class Context:
         nbr = np.empty((n, k), dtype=np.int32) if want_neighbours else None
         self._ck(lib().mvr_estimate_normals(self._h, int(which), int(k), _fp(vp), _fp(out), _ip(nbr) if nbr is not None else None))
         return (out, nbr) if want_neighbours else out
+
+
+    def apply_pose(self, pts, pose):
+        """PointCloud::getTransformedPoints: pts (n x k float32, xyz first) -> n x 4 float32, pose 4x4 double."""
+        pts = np.ascontiguousarray(pts, dtype=np.float32)
+        M = np.ascontiguousarray(np.asarray(pose, dtype=np.float64).T).reshape(16)
+        out = np.empty((len(pts), 4), dtype=np.float32)
+        self._ck(lib().mvr_apply_pose(self._h, pts.ctypes.data, len(pts), pts.strides[0], M.ctypes.data_as(C.POINTER(C.c_double)), _fp(out)))
+        return out
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def turntable_rotation(pivot, axis, angle):
+    """Registrator::getRotationMatrix (mvr/src/registrator.cpp:331-342) as a 4x4 double (column-vector form)."""
+    pv = np.ascontiguousarray(pivot, dtype=np.float64)
+    ax = np.ascontiguousarray(axis, dtype=np.float64)
+    out = np.empty(16, dtype=np.float64)
+    lib().mvr_turntable_rotation(_dp(pv), _dp(ax), float(angle), _dp(out))
+    return out.reshape(4, 4).T.copy()
+
+
+def turntable_view_angle(view, n_views):
+    return float(lib().mvr_turntable_view_angle(int(view), int(n_views)))
+
+
+def turntable_params(**kw):
+    p = TurntableParams()
+    lib().mvr_turntable_params_default(C.byref(p))
+    for k, v in kw.items():
+        if k in ("pivot", "axis"):
+            getattr(p, k)[:] = [float(x) for x in v]
+        elif k == "icp":
+            p.icp = v
+        else:
+            setattr(p, k, v)
+    return p
+
+
+def ring_close(rel_poses, weights=None, relax=True, iterations=16):
+    """Host loop closure: rel_poses V x 4x4 (view p+1 in view p's frame) -> V absolute 4x4 poses."""
+    V = len(rel_poses)
+    rel = np.ascontiguousarray(np.stack([pose_from_numpy(T) for T in rel_poses]), dtype=np.float32)
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+    out = np.empty((V, 16), dtype=np.float32)
+    rc = lib().mvr_ring_close(_fp(rel), _dp(w) if w is not None else None, V, int(bool(relax)), int(iterations), _fp(out))
+    if rc != OK:
+        raise MvrError(rc, lib().mvr_status_string(rc).decode())
+    return [pose_to_numpy(out[k]) for k in range(V)]
+
+
+def refine_axis(poses, pivot, axis):
+    """Registrator::refineAxis: poses = list of registered views' 4x4; returns (pivot, axis)."""
+    P = np.ascontiguousarray(np.stack([pose_from_numpy(T) for T in poses]), dtype=np.float32) if len(poses) else np.zeros((0, 16), np.float32)
+    pv = np.ascontiguousarray(pivot, dtype=np.float64).copy()
+    ax = np.ascontiguousarray(axis, dtype=np.float64).copy()
+    rc = lib().mvr_refine_axis(_fp(P), len(poses), _dp(pv), _dp(ax))
+    if rc != OK:
+        raise MvrError(rc, lib().mvr_status_string(rc).decode())
+    return pv, ax
+
+
+class Registrator:
+    """The reference's Registrator entry points (mvr/include/registrator.h:40-49) over `streams` GPU contexts."""
+
+    def __init__(self, device=0, streams=1):
+        self._h = C.c_void_p()
+        rc = lib().mvr_registrator_create(int(device), int(streams), C.byref(self._h))
+        if rc != OK:
+            raise MvrError(rc, "mvr_registrator_create failed (no usable CUDA device %d; there is no CPU fallback)" % device)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().mvr_registrator_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def streams(self):
+        return int(lib().mvr_registrator_streams(self._h))
+
+    def context(self, slot=0):
+        """The Context behind stream `slot` (borrowed: stays owned by the registrator)."""
+        return Context(_borrowed=lib().mvr_registrator_context(self._h, int(slot)))
+
+    @staticmethod
+    def _views(views, init_poses=None):
+        """views: list of n x 4 float32 arrays, or of (device_ptr, n) tuples."""
+        arr = (ViewDesc * len(views))()
+        keep = []
+        for k, v in enumerate(views):
+            if v is None:
+                arr[k].xyzw, arr[k].n, arr[k].on_device = None, 0, 0
+            elif isinstance(v, tuple):
+                arr[k].xyzw, arr[k].n, arr[k].on_device = int(v[0]), int(v[1]), 1
+            else:
+                a = _pts(v)
+                keep.append(a)
+                arr[k].xyzw, arr[k].n, arr[k].on_device = a.ctypes.data, len(a), 0
+            if init_poses is not None and init_poses[k] is not None:
+                m = np.ascontiguousarray(np.asarray(init_poses[k], dtype=np.float64).T).reshape(16)
+                keep.append(m)
+                arr[k].init_pose = _dp(m)
+        return arr, keep
+
+    def pairwise_align(self, source, target, params, guess=None):
+        arr, keep = self._views([source, target])
+        g = pose_from_numpy(guess) if guess is not None else None
+        fin = np.empty(16, dtype=np.float32)
+        rep = IcpReport()
+        rc = lib().mvr_pairwise_align(self._h, C.byref(arr[0]), C.byref(arr[1]), C.byref(params), _fp(g) if g is not None else None, _fp(fin), C.byref(rep))
+        if rc not in (OK, ERR_TOO_FEW):
+            raise MvrError(rc, (lib().mvr_registrator_last_error(self._h) or b"").decode())
+        return dict(status=rc, final=pose_to_numpy(fin), iterations=rep.iterations, n_corr=rep.n_correspondences, mse=rep.mse,
+                    gpu_ms=rep.gpu_ms, nn_queries=int(rep.nn_queries))
+
+    def register_turntable(self, views, params, init_poses=None):
+        """Returns (poses: list of V 4x4 float32, reports: list of dict)."""
+        V = len(views)
+        arr, keep = self._views(views, init_poses)
+        poses = np.empty((max(V, 1), 16), dtype=np.float32)
+        reps = (PairReport * max(V, 1))()
+        rc = lib().mvr_register_turntable(self._h, arr, V, C.byref(params), _fp(poses), reps)
+        if rc != OK:
+            raise MvrError(rc, (lib().mvr_registrator_last_error(self._h) or b"").decode())
+        n_rep = V if params.mode == RING_PAIRS else (0 if params.mode == LUM else max(V - 1, 0))
+        reports = [dict(source_view=reps[k].source_view, target_view=reps[k].target_view, status=reps[k].status,
+                        iterations=reps[k].iterations, n_corr=reps[k].n_correspondences, mse=reps[k].mse, fitness=reps[k].fitness,
+                        gpu_ms=reps[k].gpu_ms, nn_queries=int(reps[k].nn_queries), pose=pose_to_numpy(reps[k].pose[:]))
+                   for k in range(n_rep)]
+        return [pose_to_numpy(poses[k]) for k in range(V)], reports

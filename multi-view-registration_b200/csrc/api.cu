@@ -858,6 +858,41 @@ int mvr_fitness_score(mvr_ctx* ctx, double max_range, double* score) {
   return MVR_OK;
 }
 
+int mvr_apply_pose(mvr_ctx* ctx, const void* points, size_t n, size_t stride_bytes, const double* pose, float* out_xyzw) {
+  if (!ctx || !pose || (n && (!points || !out_xyzw))) return MVR_ERR_BAD_ARG;
+  if (stride_bytes < 12 || stride_bytes % 4 != 0) return fail(ctx, MVR_ERR_BAD_ARG, "stride must be a multiple of 4 and >= 12");
+  if (n > (size_t)INT_MAX / 2) return fail(ctx, MVR_ERR_BAD_ARG, "cloud too large");
+  cudaSetDevice(ctx->device);
+  if (n == 0) return MVR_OK;
+  CK(ctx->scratch.ensure(n * stride_bytes));
+  CK(ctx->qtmp.ensure(n * sizeof(float4)));
+  CK(cudaMemcpyAsync(ctx->scratch.p, points, n * stride_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(launch_apply_pose(ctx->scratch.p, stride_bytes, (int)n, pose, ctx->qtmp.as<float4>(), ctx->stream));
+  CK(cudaMemcpyAsync(out_xyzw, ctx->qtmp.p, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MVR_OK;
+}
+
+int mvr_apply_pose_device(mvr_ctx* ctx, const void* d_points, size_t n, size_t stride_bytes, const double* pose, float* d_out) {
+  if (!ctx || !pose || (n && (!d_points || !d_out))) return MVR_ERR_BAD_ARG;
+  if (stride_bytes < 12 || stride_bytes % 4 != 0) return fail(ctx, MVR_ERR_BAD_ARG, "stride must be a multiple of 4 and >= 12");
+  if (n > (size_t)INT_MAX / 2) return fail(ctx, MVR_ERR_BAD_ARG, "cloud too large");
+  cudaSetDevice(ctx->device);
+  if (n == 0) return MVR_OK;
+  CK(launch_apply_pose(d_points, stride_bytes, (int)n, pose, (float4*)d_out, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MVR_OK;
+}
+
+int mvr_copy_aligned_device(mvr_ctx* ctx, float* d_out) {
+  if (!ctx || !d_out) return MVR_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  if (!ctx->have_out) return fail(ctx, MVR_ERR_NO_INPUT, "no align has run");
+  if (ctx->src.n > 0) CK(cudaMemcpyAsync(d_out, ctx->out_cloud.p, (size_t)ctx->src.n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MVR_OK;
+}
+
 int mvr_estimate_normals(mvr_ctx* ctx, int which, int k, const float viewpoint[3], float* out, int32_t* neighbours) {
   if (!ctx || !out || (which != MVR_CLOUD_TARGET && which != MVR_CLOUD_SOURCE)) return MVR_ERR_BAD_ARG;
   if (k < 3 || k > 32) return fail(ctx, MVR_ERR_BAD_ARG, "k must be in 3..32");

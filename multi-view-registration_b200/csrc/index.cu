@@ -104,6 +104,30 @@ __global__ void __launch_bounds__(256) k_transform(const float4* __restrict__ in
   out[i] = finite3(p) ? xform_pinned(M, p) : p;
 }
 
+// PointCloud::getTransformedPoints (mvr/src/point_cloud.cpp:290-303): p' = pose * p evaluated in double and
+// narrowed to float; the input records may be wider than 16 bytes (PointXYZRGBNormal = 48).
+struct Mat4d { double m[16]; };
+__global__ void __launch_bounds__(256) k_apply_pose(const char* __restrict__ in, size_t stride, int n, Mat4d M, float4* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = reinterpret_cast<const float*>(in + (size_t)i * stride);
+  const double x = p[0], y = p[1], z = p[2];
+  float4 r;
+  r.x = (float)(M.m[0] * x + M.m[4] * y + M.m[8] * z + M.m[12]);
+  r.y = (float)(M.m[1] * x + M.m[5] * y + M.m[9] * z + M.m[13]);
+  r.z = (float)(M.m[2] * x + M.m[6] * y + M.m[10] * z + M.m[14]);
+  r.w = 1.0f;
+  out[i] = r;
+}
+
+cudaError_t launch_apply_pose(const void* in, size_t stride, int n, const double* M16, float4* out, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  Mat4d M;
+  for (int k = 0; k < 16; ++k) M.m[k] = M16[k];
+  k_apply_pose<<<(n + 255) / 256, 256, 0, s>>>((const char*)in, stride, n, M, out); count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_morton_keys(const float4* pts, int n, GridDev g, uint32_t* keys, uint32_t* vals, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   k_morton_keys<<<(n + 255) / 256, 256, 0, s>>>(pts, n, g, keys, vals); count_launch();

@@ -19,6 +19,9 @@ cudaError_t launch_bbox_init(uint32_t* out7, cudaStream_t s);
 cudaError_t launch_bbox(const float4* pts, int n, uint32_t* out7, cudaStream_t s);
 float bbox_decode(uint32_t enc);
 
+// out[i] = float(M * in[i]) in double arithmetic; `in` records are `stride` bytes apart (x, y, z first).
+cudaError_t launch_apply_pose(const void* in, size_t stride, int n, const double* M16, float4* out, cudaStream_t s);
+
 cudaError_t launch_morton_keys(const float4* pts, int n, GridDev g, uint32_t* keys, uint32_t* vals, cudaStream_t s);
 // In-place pinned transform of pts followed by key generation (ICP's per-iteration transformCloud).
 cudaError_t launch_transform_keys(float4* pts, int n, Mat4f M, GridDev g, uint32_t* keys, uint32_t* vals, cudaStream_t s);

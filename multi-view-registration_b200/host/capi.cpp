@@ -1,0 +1,185 @@
+// capi.cpp -- extern "C" face of the host driver (declared in include/mvr_b200.h): the entry points a
+// maintainer binds under the reference's Registrator slots.
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "registrator.h"
+
+using namespace mvr;
+
+struct mvr_registrator {
+  Registrator* reg;
+  std::string err;
+};
+
+namespace {
+void fill_views(const mvr_view* in, int V, std::vector<View>& out) {
+  out.resize((size_t)V);
+  for (int v = 0; v < V; ++v) {
+    View& o = out[(size_t)v];
+    o.points = reinterpret_cast<const PointXYZ*>(in[v].xyzw);
+    o.size = in[v].n;
+    o.on_device = in[v].on_device != 0;
+    o.view = v;
+    if (in[v].init_pose) {
+      std::memcpy(o.pose.m, in[v].init_pose, sizeof(o.pose.m));
+      o.pose_is_identity = false;
+    }
+  }
+}
+}  // namespace
+
+extern "C" {
+
+void mvr_turntable_params_default(mvr_turntable_params* p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  p->axis[1] = -1.0;                          // Registrator's default axis normal (mvr/src/registrator.cpp:86-87)
+  mvr_icp_params_default(&p->icp);
+  p->icp.use_reciprocal_correspondences = 1;  // mvr/src/registrator.cpp:552
+  p->icp.max_correspondence_distance = 4.0;   // ParameterManager default (mvr/src/parameter_manager.cpp:14)
+  p->icp.max_iterations = 2147483647;         // dialog default INT_MAX (:13)
+  p->icp.transformation_epsilon = 0.000001;   // mvr/src/registrator.cpp:558
+  p->icp.euclidean_fitness_epsilon = 64;      // :560
+  p->repeat_times = 5;                        // mvr/src/parameter_manager.cpp:17
+  p->mode = MVR_REGISTER_RING_PAIRS;
+  p->loop_closure = 1;
+  p->lum_iterations = 16;                     // mvr/src/registrator.cpp:623
+}
+
+void mvr_turntable_rotation(const double pivot[3], const double axis[3], double angle, double* out16) {
+  // osg: I * translate(-pivot) * rotate(angle, axis) * translate(pivot) in row-vector order
+  //  ==  T(pivot) R T(-pivot) for column vectors (mvr/src/registrator.cpp:331-342)
+  double n[3] = {axis[0], axis[1], axis[2]};
+  const double len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+  for (int k = 0; k < 16; ++k) out16[k] = (k % 5 == 0) ? 1.0 : 0.0;
+  if (!(len > 0)) return;
+  for (int k = 0; k < 3; ++k) n[k] /= len;
+  const double c = std::cos(angle), s = std::sin(angle), t = 1.0 - c;
+  const double R[9] = {t * n[0] * n[0] + c,        t * n[0] * n[1] - s * n[2], t * n[0] * n[2] + s * n[1],
+                       t * n[0] * n[1] + s * n[2], t * n[1] * n[1] + c,        t * n[1] * n[2] - s * n[0],
+                       t * n[0] * n[2] - s * n[1], t * n[1] * n[2] + s * n[0], t * n[2] * n[2] + c};
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) out16[j * 4 + i] = R[i * 3 + j];
+    out16[12 + i] = pivot[i] - (R[i * 3] * pivot[0] + R[i * 3 + 1] * pivot[1] + R[i * 3 + 2] * pivot[2]);
+  }
+}
+
+double mvr_turntable_view_angle(int view, int n_views) {
+  // reference, 12 views: ((view < 7) ? -view : 12 - view) * pi / 6  (mvr/src/point_cloud.cpp:409)
+  if (n_views <= 0) return 0.0;
+  const int half = n_views / 2;
+  const int k = (view <= half) ? -view : n_views - view;
+  return (double)k * (2.0 * M_PI / (double)n_views);
+}
+
+int mvr_registrator_create(int device, int streams, mvr_registrator** out) {
+  if (!out) return MVR_ERR_BAD_ARG;
+  *out = nullptr;
+  mvr_registrator* r = new (std::nothrow) mvr_registrator();
+  if (!r) return MVR_ERR_ALLOC;
+  r->reg = new (std::nothrow) Registrator(device, streams);
+  if (!r->reg || !r->reg->ok()) {
+    delete r->reg;
+    delete r;
+    return MVR_ERR_CUDA;
+  }
+  *out = r;
+  return MVR_OK;
+}
+
+int mvr_registrator_destroy(mvr_registrator* r) {
+  if (!r) return MVR_OK;
+  delete r->reg;
+  delete r;
+  return MVR_OK;
+}
+
+const char* mvr_registrator_last_error(mvr_registrator* r) { return r ? r->reg->lastError().c_str() : "null registrator"; }
+
+mvr_ctx* mvr_registrator_context(mvr_registrator* r, int slot) { return r ? r->reg->context(slot) : nullptr; }
+int mvr_registrator_streams(mvr_registrator* r) { return r ? r->reg->streams() : 0; }
+
+int mvr_pairwise_align(mvr_registrator* r, const mvr_view* source, const mvr_view* target, const mvr_icp_params* icp,
+                       const float* guess, float* out_pose, mvr_icp_report* report) {
+  if (!r || !source || !target || !icp) return MVR_ERR_BAD_ARG;
+  std::vector<View> v;
+  const mvr_view two[2] = {*source, *target};
+  fill_views(two, 2, v);
+  Matrix4f g;
+  if (guess) std::memcpy(g.m, guess, sizeof(g.m));
+  AlignResult a = r->reg->pairwiseAlign(v[0], v[1], *icp, guess ? &g : nullptr, false, 0);
+  if (out_pose) std::memcpy(out_pose, a.final_transformation.m, sizeof(a.final_transformation.m));
+  if (report) {
+    report->iterations = a.iterations; report->converged = a.converged; report->reason = 0;
+    report->n_correspondences = a.n_correspondences; report->mse = a.mse; report->gpu_ms = a.gpu_ms; report->nn_queries = a.nn_queries;
+  }
+  return a.status;
+}
+
+int mvr_register_turntable(mvr_registrator* r, const mvr_view* views, int n_views, const mvr_turntable_params* prm,
+                           float* poses, mvr_pair_report* reports) {
+  if (!r || !prm || n_views < 0 || (n_views && !views)) return MVR_ERR_BAD_ARG;
+  std::vector<View> v;
+  fill_views(views, n_views, v);
+  Registrator& reg = *r->reg;
+  reg.setPivotPoint(prm->pivot[0], prm->pivot[1], prm->pivot[2]);
+  reg.setAxisNormal(prm->axis[0], prm->axis[1], prm->axis[2]);
+  std::vector<mvr_pair_report> rep;
+  int rc;
+  if (prm->mode == MVR_REGISTER_ACCUMULATE) {
+    const int V = n_views;
+    for (int k = 0; k < V; ++k) reg.initRotation(v[(size_t)k], V);
+    mvr_icp_params icp = prm->icp;
+    // automaticRegistration's shape: views 1..V-1 in order against the growing model, repeat_times aligns each
+    rc = reg.automaticRegistration(v, icp.max_iterations, prm->repeat_times, icp.max_correspondence_distance,
+                                   icp.transformation_epsilon, icp.euclidean_fitness_epsilon, &rep);
+  } else if (prm->mode == MVR_REGISTER_ICP) {
+    rc = reg.registrationICP(v, prm->icp.max_iterations, prm->icp.max_correspondence_distance, prm->repeat_times, &rep);
+  } else if (prm->mode == MVR_REGISTER_LUM) {
+    rc = reg.registrationLUM(v, prm->icp.max_iterations, prm->icp.max_correspondence_distance);
+  } else {
+    rc = reg.multiViewRegister(v, *prm, rep);
+  }
+  if (reports) for (size_t k = 0; k < rep.size(); ++k) reports[k] = rep[k];
+  if (poses)
+    for (int k = 0; k < n_views; ++k) {
+      Matrix4f f = toFloat(v[(size_t)k].pose);
+      std::memcpy(poses + 16 * k, f.m, sizeof(f.m));
+    }
+  return rc;
+}
+
+int mvr_ring_close(const float* rel_poses, const double* weights, int n_views, int relax, int iterations, float* poses) {
+  if (!rel_poses || !poses || n_views < 1) return MVR_ERR_BAD_ARG;
+  std::vector<Matrix4d> rel((size_t)n_views), X;
+  std::vector<double> w((size_t)n_views, 1.0);
+  for (int p = 0; p < n_views; ++p) {
+    Matrix4f f;
+    std::memcpy(f.m, rel_poses + 16 * p, sizeof(f.m));
+    rel[(size_t)p] = toDouble(f);
+    if (weights) w[(size_t)p] = weights[p];
+  }
+  int rc = ringClose(rel, w, relax != 0, iterations > 0 ? iterations : 16, X);
+  if (rc) return rc;
+  for (int p = 0; p < n_views; ++p) {
+    Matrix4f f = toFloat(X[(size_t)p]);
+    std::memcpy(poses + 16 * p, f.m, sizeof(f.m));
+  }
+  return MVR_OK;
+}
+
+int mvr_refine_axis(const float* poses, int count, double pivot[3], double axis[3]) {
+  if (count < 0 || (count && !poses) || !pivot || !axis) return MVR_ERR_BAD_ARG;
+  std::vector<Matrix4d> P((size_t)count);
+  for (int k = 0; k < count; ++k) {
+    Matrix4f f;
+    std::memcpy(f.m, poses + 16 * k, sizeof(f.m));
+    P[(size_t)k] = toDouble(f);
+  }
+  return refineAxisFromPoses(P, pivot, axis);
+}
+
+}  // extern "C"

@@ -1,0 +1,307 @@
+// lum.cpp -- host-side global adjustment of a turntable ring and the turntable axis fit.
+//
+// ringClose: the loop-closure step after the (possibly multi-GPU) pairwise aligns.  The reference's precedent is
+// pcl::registration::LUM over the ring graph i -> i+1, 11 -> 0 (mvr/src/registrator.cpp:627-663): vertices are
+// 6-DoF view poses with vertex 0 fixed, every edge carries a relative-pose constraint with an information
+// weight, and the poses are relaxed by solving the dense 6(V-1) normal equations a fixed number of times.
+// Here an edge constraint is the relative pose measured by the pair's ICP, weighted by its correspondence count
+// (isotropic information), and the relaxation is Gauss-Newton on SE(3) -- the same graph, unknowns and solve
+// size as LUM; the per-correspondence 6x6 information of PCL's computeEdge is a listed next step.
+//
+// refineAxisFromPoses: Registrator::refineAxis (mvr/src/registrator.cpp:402-455) with math_solvers::least_squares
+// (mvr/src/math_solvers.cpp:24-39; LAPACK dgels there, Householder QR here).
+#include <cmath>
+#include <cstring>
+
+#include "registrator.h"
+
+namespace mvr {
+
+namespace {
+
+struct Vec6 { double v[6]; };   // (omega, upsilon): rotation vector, translation part
+
+void mat3_mul(const double* A, const double* B, double* C) {   // row-major 3x3
+  double t[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) t[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+  std::memcpy(C, t, sizeof(t));
+}
+
+void skew(const double* w, double* S) {
+  S[0] = 0; S[1] = -w[2]; S[2] = w[1];
+  S[3] = w[2]; S[4] = 0; S[5] = -w[0];
+  S[6] = -w[1]; S[7] = w[0]; S[8] = 0;
+}
+
+void get_Rt(const Matrix4d& T, double* R, double* t) {   // R row-major
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) R[i * 3 + j] = T.m[j * 4 + i];
+    t[i] = T.m[12 + i];
+  }
+}
+
+Matrix4d from_Rt(const double* R, const double* t) {
+  Matrix4d T = identity4d();
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) T.m[j * 4 + i] = R[i * 3 + j];
+    T.m[12 + i] = t[i];
+  }
+  return T;
+}
+
+// SO(3) logarithm, robust near 0 and near pi.
+void so3_log(const double* R, double* w) {
+  const double tr = R[0] + R[4] + R[8];
+  double c = 0.5 * (tr - 1.0);
+  c = c > 1.0 ? 1.0 : (c < -1.0 ? -1.0 : c);
+  const double ax[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]};   // 2 sin(theta) * axis
+  const double s2 = std::sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);   // 2 sin(theta)
+  const double theta = std::atan2(0.5 * s2, c);
+  if (s2 < 1e-12) {
+    if (c > 0) { w[0] = 0.5 * ax[0]; w[1] = 0.5 * ax[1]; w[2] = 0.5 * ax[2]; return; }
+    // theta ~ pi: axis from the diagonal of (R + I) / 2
+    double d[3] = {std::sqrt(std::fmax(0.0, 0.5 * (R[0] + 1))), std::sqrt(std::fmax(0.0, 0.5 * (R[4] + 1))), std::sqrt(std::fmax(0.0, 0.5 * (R[8] + 1)))};
+    int k = d[0] >= d[1] ? (d[0] >= d[2] ? 0 : 2) : (d[1] >= d[2] ? 1 : 2);
+    double a[3];
+    a[k] = d[k];
+    for (int j = 0; j < 3; ++j) if (j != k) a[j] = 0.25 * (R[k * 3 + j] + R[j * 3 + k]) / d[k];
+    for (int j = 0; j < 3; ++j) w[j] = theta * a[j];
+    return;
+  }
+  const double f = theta / s2;
+  w[0] = f * ax[0]; w[1] = f * ax[1]; w[2] = f * ax[2];
+}
+
+void so3_exp(const double* w, double* R) {
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], th = std::sqrt(th2);
+  double A, B;
+  if (th < 1e-6) { A = 1.0 - th2 / 6.0; B = 0.5 - th2 / 24.0; }
+  else { A = std::sin(th) / th; B = (1.0 - std::cos(th)) / th2; }
+  double S[9], S2[9];
+  skew(w, S);
+  mat3_mul(S, S, S2);
+  for (int k = 0; k < 9; ++k) R[k] = ((k % 4 == 0) ? 1.0 : 0.0) + A * S[k] + B * S2[k];
+}
+
+// SE(3) log with the exact left-Jacobian inverse on the translation.
+Vec6 se3_log(const Matrix4d& T) {
+  double R[9], t[3], w[3];
+  get_Rt(T, R, t);
+  so3_log(R, w);
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], th = std::sqrt(th2);
+  double S[9], S2[9];
+  skew(w, S);
+  mat3_mul(S, S, S2);
+  double cf;
+  if (th < 1e-6) cf = 1.0 / 12.0 + th2 / 720.0;
+  else cf = (1.0 - 0.5 * th * std::sin(th) / (1.0 - std::cos(th))) / th2;
+  Vec6 r;
+  for (int i = 0; i < 3; ++i) {
+    r.v[i] = w[i];
+    double u = 0;
+    for (int j = 0; j < 3; ++j) u += (((i == j) ? 1.0 : 0.0) - 0.5 * S[i * 3 + j] + cf * S2[i * 3 + j]) * t[j];
+    r.v[3 + i] = u;
+  }
+  return r;
+}
+
+Matrix4d se3_exp(const Vec6& x) {
+  const double* w = x.v;
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], th = std::sqrt(th2);
+  double R[9], S[9], S2[9];
+  so3_exp(w, R);
+  skew(w, S);
+  mat3_mul(S, S, S2);
+  double B, C;
+  if (th < 1e-6) { B = 0.5 - th2 / 24.0; C = 1.0 / 6.0 - th2 / 120.0; }
+  else { B = (1.0 - std::cos(th)) / th2; C = (th - std::sin(th)) / (th2 * th); }
+  double t[3];
+  for (int i = 0; i < 3; ++i) {
+    double u = 0;
+    for (int j = 0; j < 3; ++j) u += (((i == j) ? 1.0 : 0.0) + B * S[i * 3 + j] + C * S2[i * 3 + j]) * x.v[3 + j];
+    t[i] = u;
+  }
+  return from_Rt(R, t);
+}
+
+// 6x6 adjoint of T for twists ordered (omega, upsilon), row-major.
+void se3_adjoint(const Matrix4d& T, double* Ad) {
+  double R[9], t[3], tx[9], tR[9];
+  get_Rt(T, R, t);
+  skew(t, tx);
+  mat3_mul(tx, R, tR);
+  for (int k = 0; k < 36; ++k) Ad[k] = 0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      Ad[i * 6 + j] = R[i * 3 + j];
+      Ad[(3 + i) * 6 + 3 + j] = R[i * 3 + j];
+      Ad[(3 + i) * 6 + j] = tR[i * 3 + j];
+    }
+}
+
+// Dense SPD solve (Cholesky), A row-major n x n, overwritten.
+bool chol_solve(std::vector<double>& A, std::vector<double>& b, int n) {
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double s = A[(size_t)i * n + j];
+      for (int k = 0; k < j; ++k) s -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
+      if (i == j) {
+        if (!(s > 0)) return false;
+        A[(size_t)i * n + i] = std::sqrt(s);
+      } else {
+        A[(size_t)i * n + j] = s / A[(size_t)j * n + j];
+      }
+    }
+  for (int i = 0; i < n; ++i) {
+    double s = b[(size_t)i];
+    for (int k = 0; k < i; ++k) s -= A[(size_t)i * n + k] * b[(size_t)k];
+    b[(size_t)i] = s / A[(size_t)i * n + i];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double s = b[(size_t)i];
+    for (int k = i + 1; k < n; ++k) s -= A[(size_t)k * n + i] * b[(size_t)k];
+    b[(size_t)i] = s / A[(size_t)i * n + i];
+  }
+  return true;
+}
+
+}  // namespace
+
+// Absolute poses X_v (X_0 = I) of a ring from relative measurements rel[p] ~ X_p^-1 X_{(p+1) % V}.
+// relax = false: plain chaining of pairs 0 .. V-2 (the closing pair is ignored).
+// relax = true : Gauss-Newton on  sum_p w_p | Log(rel[p]^-1 X_p^-1 X_{p+1}) |^2, X_v <- X_v Exp(d_v),
+//                 `iterations` sweeps of the dense 6(V-1) solve (LUM runs 16 of them).
+int ringClose(const std::vector<Matrix4d>& rel, const std::vector<double>& weight, bool relax, int iterations,
+              std::vector<Matrix4d>& X) {
+  const int V = (int)rel.size();
+  X.assign((size_t)std::max(V, 1), identity4d());
+  if (V < 2) return MVR_OK;
+  for (int p = 0; p + 1 < V; ++p) X[(size_t)p + 1] = multiply(X[(size_t)p], rel[(size_t)p]);
+  if (!relax) return MVR_OK;
+  double wmax = 0;
+  for (double w : weight) wmax = std::fmax(wmax, w);
+  if (!(wmax > 0)) return MVR_OK;
+  const int n = 6 * (V - 1);
+  for (int it = 0; it < iterations; ++it) {
+    std::vector<double> H((size_t)n * n, 0.0), g((size_t)n, 0.0);
+    double cost = 0;
+    for (int p = 0; p < V; ++p) {
+      const double w = weight[(size_t)p] / wmax;
+      if (!(w > 0)) continue;
+      const int a = p, b = (p + 1) % V;
+      // E = rel^-1 X_a^-1 X_b ; residual r = Log(E).  With X <- X Exp(d):
+      //   dr/dd_b ~ I,  dr/dd_a ~ -Ad(E^-1 ... ) ~ -Ad(X_b^-1 X_a)   (first order, exact at r = 0)
+      const Matrix4d XaiXb = multiply(inverseRigid(X[(size_t)a]), X[(size_t)b]);
+      const Matrix4d E = multiply(inverseRigid(rel[(size_t)p]), XaiXb);
+      const Vec6 r = se3_log(E);
+      double Ja[36];
+      se3_adjoint(inverseRigid(XaiXb), Ja);
+      for (int k = 0; k < 36; ++k) Ja[k] = -Ja[k];
+      for (int k = 0; k < 6; ++k) cost += w * r.v[k] * r.v[k];
+      const int ia = 6 * (a - 1), ib = 6 * (b - 1);   // vertex 0 is fixed (no unknowns)
+      // H += J^T w J ; g += J^T w r   with J = [Ja at a, I at b]
+      if (a > 0) {
+        for (int i = 0; i < 6; ++i) {
+          double gi = 0;
+          for (int k = 0; k < 6; ++k) gi += Ja[k * 6 + i] * r.v[k];
+          g[(size_t)ia + i] += w * gi;
+          for (int j = 0; j < 6; ++j) {
+            double h = 0;
+            for (int k = 0; k < 6; ++k) h += Ja[k * 6 + i] * Ja[k * 6 + j];
+            H[(size_t)(ia + i) * n + ia + j] += w * h;
+          }
+        }
+      }
+      if (b > 0) {
+        for (int i = 0; i < 6; ++i) {
+          g[(size_t)ib + i] += w * r.v[i];
+          H[(size_t)(ib + i) * n + ib + i] += w;
+        }
+      }
+      if (a > 0 && b > 0) {
+        for (int i = 0; i < 6; ++i)
+          for (int j = 0; j < 6; ++j) {
+            H[(size_t)(ia + i) * n + ib + j] += w * Ja[j * 6 + i];   // Ja^T I
+            H[(size_t)(ib + j) * n + ia + i] += w * Ja[j * 6 + i];
+          }
+      }
+    }
+    for (int i = 0; i < n; ++i) { H[(size_t)i * n + i] += 1e-12; g[(size_t)i] = -g[(size_t)i]; }
+    if (!chol_solve(H, g, n)) return MVR_ERR_NOT_SPD;
+    double step = 0;
+    for (int v = 1; v < V; ++v) {
+      Vec6 d;
+      for (int k = 0; k < 6; ++k) { d.v[k] = g[(size_t)6 * (v - 1) + k]; step = std::fmax(step, std::fabs(d.v[k])); }
+      X[(size_t)v] = multiply(X[(size_t)v], se3_exp(d));
+    }
+    if (step < 1e-14 || cost < 1e-30) break;
+  }
+  return MVR_OK;
+}
+
+// min |A x - b|_2 by Householder QR (A rows x cols row-major, rows >= cols, full column rank).
+bool leastSquares(const std::vector<double>& A_in, const std::vector<double>& b_in, int rows, int cols, std::vector<double>& x) {
+  if (rows < cols || cols <= 0) return false;
+  std::vector<double> A(A_in), b(b_in);
+  for (int k = 0; k < cols; ++k) {
+    double nrm = 0;
+    for (int i = k; i < rows; ++i) nrm += A[(size_t)i * cols + k] * A[(size_t)i * cols + k];
+    nrm = std::sqrt(nrm);
+    if (!(nrm > 0)) return false;
+    const double alpha = A[(size_t)k * cols + k] > 0 ? -nrm : nrm;
+    std::vector<double> v((size_t)rows, 0.0);
+    for (int i = k; i < rows; ++i) v[(size_t)i] = A[(size_t)i * cols + k];
+    v[(size_t)k] -= alpha;
+    double vv = 0;
+    for (int i = k; i < rows; ++i) vv += v[(size_t)i] * v[(size_t)i];
+    if (vv > 0) {
+      for (int j = k; j < cols; ++j) {
+        double s = 0;
+        for (int i = k; i < rows; ++i) s += v[(size_t)i] * A[(size_t)i * cols + j];
+        s = 2.0 * s / vv;
+        for (int i = k; i < rows; ++i) A[(size_t)i * cols + j] -= s * v[(size_t)i];
+      }
+      double s = 0;
+      for (int i = k; i < rows; ++i) s += v[(size_t)i] * b[(size_t)i];
+      s = 2.0 * s / vv;
+      for (int i = k; i < rows; ++i) b[(size_t)i] -= s * v[(size_t)i];
+    }
+  }
+  x.assign((size_t)cols, 0.0);
+  for (int i = cols - 1; i >= 0; --i) {
+    double s = b[(size_t)i];
+    for (int j = i + 1; j < cols; ++j) s -= A[(size_t)i * cols + j] * x[(size_t)j];
+    const double d = A[(size_t)i * cols + i];
+    if (d == 0.0) return false;
+    x[(size_t)i] = s / d;
+  }
+  return true;
+}
+
+int refineAxisFromPoses(const std::vector<Matrix4d>& poses, double pivot[3], double axis[3]) {
+  if (poses.empty()) return MVR_OK;   // reference: nothing registered, nothing to do (:420-421)
+  const int m = (int)poses.size(), rows = 3 * m + 1;
+  std::vector<double> A((size_t)rows * 3, 0.0), b((size_t)rows, 0.0), x;
+  // axis: (R_i - I) n = 0 for every pose, regularised by n_x + n_y + n_z = 1 (:426-439).  The reference fills
+  // A(i*3+j, k) = M(k, j) - delta_jk from the row-vector osg matrix M = R^T, i.e. exactly R(j, k) - delta_jk.
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < 3; ++j)
+      for (int k = 0; k < 3; ++k) A[(size_t)(i * 3 + j) * 3 + k] = poses[(size_t)i].m[k * 4 + j] - ((j == k) ? 1.0 : 0.0);
+  A[(size_t)(3 * m) * 3 + 0] = 1; A[(size_t)(3 * m) * 3 + 1] = 1; A[(size_t)(3 * m) * 3 + 2] = 1; b[(size_t)3 * m] = 1;
+  if (!leastSquares(A, b, rows, 3, x)) return MVR_ERR_BAD_ARG;
+  // the reference narrows to osg::Vec3 (float) before normalising (:437-438)
+  float nf[3] = {(float)x[0], (float)x[1], (float)x[2]};
+  const float len = std::sqrt(nf[0] * nf[0] + nf[1] * nf[1] + nf[2] * nf[2]);
+  if (len > 0) for (int k = 0; k < 3; ++k) nf[k] /= len;
+  for (int k = 0; k < 3; ++k) axis[k] = nf[k];
+  // pivot: (R_i - I) c = -t_i, regularised by c_y = old pivot y (:442-450)
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < 3; ++j) b[(size_t)i * 3 + j] = -poses[(size_t)i].m[12 + j];
+  A[(size_t)(3 * m) * 3 + 0] = 0; A[(size_t)(3 * m) * 3 + 1] = 1; A[(size_t)(3 * m) * 3 + 2] = 0; b[(size_t)3 * m] = (float)pivot[1];
+  if (!leastSquares(A, b, rows, 3, x)) return MVR_ERR_BAD_ARG;
+  for (int k = 0; k < 3; ++k) pivot[k] = (float)x[k];
+  return MVR_OK;
+}
+
+}  // namespace mvr

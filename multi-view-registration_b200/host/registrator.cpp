@@ -1,0 +1,468 @@
+// registrator.cpp -- host orchestration of the registration path (see registrator.h).
+//
+// Mirrors the reference's Registrator workflows (mvr/src/registrator.cpp) with the PCL calls replaced by
+// the C ABI of this library: view ordering, turntable initial guess, align, pose composition, model growth.
+// Point clouds stay on the GPU between steps; only poses and reports come back to the host.
+#include "registrator.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <thread>
+
+namespace mvr {
+
+// ---- small pose algebra ----------------------------------------------------------------------
+Matrix4d identity4d() {
+  Matrix4d r;
+  for (int k = 0; k < 16; ++k) r.m[k] = (k % 5 == 0) ? 1.0 : 0.0;
+  return r;
+}
+
+Matrix4d multiply(const Matrix4d& a, const Matrix4d& b) {
+  Matrix4d r;
+  for (int c = 0; c < 4; ++c)
+    for (int row = 0; row < 4; ++row) {
+      double s = 0;
+      for (int k = 0; k < 4; ++k) s += a.m[k * 4 + row] * b.m[c * 4 + k];
+      r.m[c * 4 + row] = s;
+    }
+  return r;
+}
+
+Matrix4d inverseRigid(const Matrix4d& a) {
+  Matrix4d r = identity4d();
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) r.m[j * 4 + i] = a.m[i * 4 + j];
+  for (int i = 0; i < 3; ++i) r.m[12 + i] = -(r.m[i] * a.m[12] + r.m[4 + i] * a.m[13] + r.m[8 + i] * a.m[14]);
+  return r;
+}
+
+Matrix4d toDouble(const Matrix4f& a) {
+  Matrix4d r;
+  for (int k = 0; k < 16; ++k) r.m[k] = a.m[k];
+  return r;
+}
+
+Matrix4f toFloat(const Matrix4d& a) {
+  Matrix4f r;
+  for (int k = 0; k < 16; ++k) r.m[k] = (float)a.m[k];
+  return r;
+}
+
+Matrix4d transposeOsg(const Matrix4d& a) {
+  Matrix4d r;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) r.m[j * 4 + i] = a.m[i * 4 + j];
+  return r;
+}
+
+static bool isIdentity(const Matrix4d& a) {
+  for (int k = 0; k < 16; ++k)
+    if (a.m[k] != ((k % 5 == 0) ? 1.0 : 0.0)) return false;
+  return true;
+}
+
+// ---- device scratch owned by the driver ----------------------------------------------------------
+namespace {
+struct DeviceCloud {
+  float* p = nullptr;
+  size_t cap = 0;   // points
+  bool ensure(size_t n) {
+    if (n <= cap) return true;
+    float* q = nullptr;
+    size_t want = n + n / 8 + 64;
+    if (cudaMalloc((void**)&q, want * 16) != cudaSuccess) return false;
+    if (p) cudaFree(p);
+    p = q; cap = want;
+    return true;
+  }
+  bool grow_keep(size_t n, size_t used, cudaStream_t s) {   // like ensure(), keeping the first `used` points
+    if (n <= cap) return true;
+    float* q = nullptr;
+    size_t want = n + n / 2 + 64;
+    if (cudaMalloc((void**)&q, want * 16) != cudaSuccess) return false;
+    if (p && used) cudaMemcpyAsync(q, p, used * 16, cudaMemcpyDeviceToDevice, s);
+    cudaStreamSynchronize(s);
+    if (p) cudaFree(p);
+    p = q; cap = want;
+    return true;
+  }
+  ~DeviceCloud() { if (p) cudaFree(p); }
+};
+
+void fill_report(mvr_pair_report& r, int src, int tgt, const AlignResult& a, int iterations, uint64_t queries, double ms,
+                 const Matrix4f& pose) {
+  r.source_view = src; r.target_view = tgt; r.status = a.status; r.iterations = iterations;
+  r.n_correspondences = a.n_correspondences; r.mse = a.mse; r.fitness = a.fitness; r.gpu_ms = ms; r.nn_queries = queries;
+  std::memcpy(r.pose, pose.m, sizeof(r.pose));
+}
+}  // namespace
+
+// ---- Registrator -------------------------------------------------------------------------------------
+Registrator::Registrator(int device, int streams) : device_(device) {
+  if (streams < 1) streams = 1;
+  for (int k = 0; k < streams; ++k) {
+    mvr_ctx* c = nullptr;
+    if (mvr_ctx_create(device, &c) != MVR_OK) {
+      err_ = "mvr_ctx_create failed: no usable CUDA device (there is no CPU fallback)";
+      for (mvr_ctx* x : ctx_) mvr_ctx_destroy(x);
+      ctx_.clear();
+      return;
+    }
+    ctx_.push_back(c);
+  }
+}
+
+Registrator::~Registrator() {
+  for (mvr_ctx* x : ctx_) mvr_ctx_destroy(x);
+}
+
+Matrix4d Registrator::getRotationMatrix(double angle) const {
+  Matrix4d r;
+  mvr_turntable_rotation(pivot_, axis_, angle, r.m);
+  return r;
+}
+
+void Registrator::initRotation(View& v, int n_views) const {
+  if (!v.pose_is_identity && !isIdentity(v.pose)) return;   // reference: only an untouched pose gets the turntable guess
+  if (v.view == 0) return;
+  v.pose = getRotationMatrix(mvr_turntable_view_angle(v.view, n_views));
+  v.pose_is_identity = false;
+}
+
+bool Registrator::load(const char* axis_txt) {
+  // axis.txt: pivot x y z, then normal x y z (mvr/src/registrator.cpp:258-292)
+  FILE* f = std::fopen(axis_txt, "r");
+  if (!f) return false;
+  double v[6];
+  int got = 0;
+  for (int k = 0; k < 6; ++k) got += std::fscanf(f, "%lf", &v[k]) == 1;
+  std::fclose(f);
+  if (got != 6) return false;
+  for (int k = 0; k < 3; ++k) { pivot_[k] = v[k]; axis_[k] = v[3 + k]; }
+  return true;
+}
+
+bool Registrator::save(const char* axis_txt) const {
+  FILE* f = std::fopen(axis_txt, "w");
+  if (!f) return false;
+  std::fprintf(f, "%lf %lf %lf\n%lf %lf %lf\n", pivot_[0], pivot_[1], pivot_[2], axis_[0], axis_[1], axis_[2]);
+  std::fclose(f);
+  return true;
+}
+
+int Registrator::getTransformedPoints(const View& v, PointCloudXYZ& out) {
+  if (!ok()) return fail(MVR_ERR_CUDA, "no GPU context");
+  out.resize(v.size);
+  if (v.on_device) return fail(MVR_ERR_BAD_ARG, "getTransformedPoints: host views only (device views stay on the device)");
+  int rc = mvr_apply_pose(ctx_[0], v.points, v.size, sizeof(PointXYZ), v.pose.m, v.size ? &out[0].x : nullptr);
+  if (rc) err_ = mvr_last_error(ctx_[0]);
+  return rc;
+}
+
+AlignResult Registrator::pairwiseAlign(const View& source, const View& target, const mvr_icp_params& icp, const Matrix4f* guess,
+                                       bool want_fitness, int slot) {
+  AlignResult a;
+  for (int k = 0; k < 16; ++k) a.final_transformation.m[k] = (k % 5 == 0) ? 1.f : 0.f;
+  if (!ok()) { a.status = MVR_ERR_CUDA; return a; }
+  mvr_ctx* c = ctx_[(size_t)slot % ctx_.size()];
+  int rc = target.on_device ? mvr_set_target_device(c, &target.points->x, target.size) : mvr_set_target(c, &target.points->x, target.size);
+  if (!rc) rc = source.on_device ? mvr_set_source_device(c, &source.points->x, source.size) : mvr_set_source(c, &source.points->x, source.size);
+  mvr_icp_report rep{};
+  if (!rc) rc = mvr_icp_align(c, &icp, guess ? guess->m : nullptr, a.final_transformation.m, nullptr, &rep);
+  a.status = rc;
+  a.iterations = rep.iterations; a.n_correspondences = rep.n_correspondences; a.converged = rep.converged != 0;
+  a.mse = rep.mse; a.gpu_ms = rep.gpu_ms; a.nn_queries = rep.nn_queries;
+  if ((rc == MVR_OK || rc == MVR_ERR_TOO_FEW_CORRESPONDENCES) && want_fitness) {
+    double f = -1;
+    if (mvr_fitness_score(c, DBL_MAX, &f) == MVR_OK) a.fitness = f;
+  }
+  if (rc && rc != MVR_ERR_TOO_FEW_CORRESPONDENCES) fail(rc, mvr_last_error(c));
+  return a;
+}
+
+// The shared body of registrationICP / automaticRegistration: every view of `order` is aligned, `repeat_times`
+// times, against the model accumulated so far; its pose is composed with each result; the aligned points join
+// the model (mvr/src/registrator.cpp:562-577 and 909-983).
+int Registrator::accumulate(std::vector<View>& views, const std::vector<int>& order, const mvr_icp_params& icp, int repeat_times,
+                            bool want_fitness, std::vector<mvr_pair_report>* reports) {
+  if (!ok()) return fail(MVR_ERR_CUDA, "no GPU context");
+  if (views.empty()) return MVR_OK;
+  cudaSetDevice(device_);
+  mvr_ctx* c = ctx_[0];
+  size_t total = views[0].size;
+  for (int v : order) total += views[(size_t)v].size;
+  DeviceCloud model, src, raw;
+  if (!model.ensure(std::max<size_t>(total, 1))) return fail(MVR_ERR_ALLOC, "model buffer");
+  size_t model_n = 0;
+  auto upload_posed = [&](const View& v, float* dst) -> int {   // dst = getTransformedPoints(v) on the device
+    if (v.size == 0) return MVR_OK;
+    const float* in = &v.points->x;
+    if (!v.on_device) {
+      if (!raw.ensure(v.size)) return MVR_ERR_ALLOC;
+      if (cudaMemcpy(raw.p, in, v.size * 16, cudaMemcpyHostToDevice) != cudaSuccess) return MVR_ERR_CUDA;
+      in = raw.p;
+    }
+    return mvr_apply_pose_device(c, in, v.size, 16, v.pose.m, dst);
+  };
+  int rc = upload_posed(views[0], model.p);
+  if (rc) return fail(rc, "target upload");
+  model_n = views[0].size;
+  views[0].registered = true;
+  if (reports) reports->clear();
+  for (int vi : order) {
+    View& v = views[(size_t)vi];
+    if (!src.ensure(std::max<size_t>(v.size, 1))) return fail(MVR_ERR_ALLOC, "source buffer");
+    if ((rc = upload_posed(v, src.p))) return fail(rc, "source upload");
+    if ((rc = mvr_set_target_device(c, model.p, model_n))) return fail(rc, mvr_last_error(c));
+    AlignResult last;
+    int iterations = 0;
+    uint64_t queries = 0;
+    double ms = 0;
+    for (int r = 0; r < std::max(repeat_times, 1); ++r) {
+      // the reference aligns in place (icp_.align(*source_)): every repeat starts from the previous output
+      if ((rc = mvr_set_source_device(c, src.p, v.size))) return fail(rc, mvr_last_error(c));
+      mvr_icp_report rep{};
+      Matrix4f fin;
+      rc = mvr_icp_align(c, &icp, nullptr, fin.m, nullptr, &rep);
+      if (rc && rc != MVR_ERR_TOO_FEW_CORRESPONDENCES) return fail(rc, mvr_last_error(c));
+      last.status = rc; last.final_transformation = fin; last.n_correspondences = rep.n_correspondences; last.mse = rep.mse;
+      iterations += rep.iterations; queries += rep.nn_queries; ms += rep.gpu_ms;
+      // pose <- final * pose  (reference: setMatrix(getMatrix() * cast(final)) in row-vector order)
+      v.pose = multiply(toDouble(fin), v.pose);
+      v.pose_is_identity = false;
+      if ((rc = mvr_copy_aligned_device(c, src.p))) return fail(rc, mvr_last_error(c));
+    }
+    if (want_fitness) {
+      double f = -1;
+      if (mvr_fitness_score(c, DBL_MAX, &f) == MVR_OK) last.fitness = f;
+    }
+    v.registered = true;
+    // *target += transformed_source
+    if (cudaMemcpy(model.p + model_n * 4, src.p, v.size * 16, cudaMemcpyDeviceToDevice) != cudaSuccess ||
+        cudaStreamSynchronize(0) != cudaSuccess)   // device-to-device copies do not block the host
+      return fail(MVR_ERR_CUDA, "model append");
+    model_n += v.size;
+    if (reports) {
+      mvr_pair_report pr{};
+      fill_report(pr, v.view, -1, last, iterations, queries, ms, toFloat(v.pose));
+      reports->push_back(pr);
+    }
+  }
+  return MVR_OK;
+}
+
+// View order of registrationICP (mvr/src/registrator.cpp:529-541): 1, V-1, 2, V-2, ..., then the middle view.
+static std::vector<int> front_back_order(int V) {
+  std::vector<int> o;
+  for (int i = 1; 2 * i < V; ++i) { o.push_back(i); if (V - i != i) o.push_back(V - i); }
+  if (V % 2 == 0 && V >= 2) o.push_back(V / 2);
+  return o;
+}
+
+int Registrator::registrationICP(std::vector<View>& views, int max_iterations, double max_distance, int repeat_times,
+                                 std::vector<mvr_pair_report>* reports) {
+  const int V = (int)views.size();
+  for (int v = 0; v < V; ++v) { views[(size_t)v].view = v; initRotation(views[(size_t)v], V); }
+  mvr_icp_params icp;
+  mvr_icp_params_default(&icp);
+  icp.use_reciprocal_correspondences = 1;          // :552
+  icp.max_correspondence_distance = max_distance;  // :554
+  icp.max_iterations = max_iterations;             // :556
+  icp.transformation_epsilon = 0.000001;           // :558
+  icp.euclidean_fitness_epsilon = 64;              // :560
+  int rc = MVR_OK;
+  for (int r = 0; r < std::max(repeat_times, 1) && rc == MVR_OK; ++r)   // :517-524 repeats the whole pass
+    rc = accumulate(views, front_back_order(V), icp, 1, false, reports);
+  return rc;
+}
+
+int Registrator::automaticRegistration(std::vector<View>& views, int max_iterations, int repeat_times, double max_distance,
+                                       double transformation_epsilon, double euclidean_fitness_epsilon,
+                                       std::vector<mvr_pair_report>* reports) {
+  // The reference collects transformation_epsilon but never applies it to icp_; kept so.
+  (void)transformation_epsilon;
+  const int V = (int)views.size();
+  for (int v = 0; v < V; ++v) { views[(size_t)v].view = v; initRotation(views[(size_t)v], V); }
+  mvr_icp_params icp;
+  mvr_icp_params_default(&icp);
+  icp.use_reciprocal_correspondences = 1;                       // :768, 901
+  icp.max_correspondence_distance = max_distance;               // :769, 902
+  icp.max_iterations = max_iterations;                          // :770, 903
+  icp.euclidean_fitness_epsilon = euclidean_fitness_epsilon;    // :771, 904
+  std::vector<int> order;
+  for (int v = 1; v < V; ++v) order.push_back(v);               // views 1..V-1 against the growing model
+  int rc = accumulate(views, order, icp, repeat_times, true, reports);
+  if (rc == MVR_OK) refineAxis(views);                           // :836, 986
+  return rc;
+}
+
+int Registrator::multiViewRegister(std::vector<View>& views, const mvr_turntable_params& prm, std::vector<mvr_pair_report>& reports) {
+  if (!ok()) return fail(MVR_ERR_CUDA, "no GPU context");
+  const int V = (int)views.size();
+  reports.assign((size_t)std::max(V, 0), mvr_pair_report{});
+  if (V < 2) return MVR_OK;
+  for (int k = 0; k < 3; ++k) { pivot_[k] = prm.pivot[k]; axis_[k] = prm.axis[k]; }
+  for (int v = 0; v < V; ++v) { views[(size_t)v].view = v; initRotation(views[(size_t)v], V); }
+  int p0 = std::max(prm.pair_begin, 0), p1 = prm.pair_end <= 0 ? V : std::min(prm.pair_end, V);
+  for (int p = 0; p < V; ++p) { reports[(size_t)p].source_view = (p + 1) % V; reports[(size_t)p].target_view = p; reports[(size_t)p].status = -1; reports[(size_t)p].fitness = -1; }
+  std::atomic<int> next(p0);
+  std::atomic<int> first_error(0);
+  const int repeats = std::max(prm.repeat_times, 1);
+  auto worker = [&](int slot) {
+    cudaSetDevice(device_);
+    for (;;) {
+      const int p = next.fetch_add(1);
+      if (p >= p1) break;
+      const View& tgt = views[(size_t)p];
+      const View& src = views[(size_t)((p + 1) % V)];
+      // initial guess: where the turntable says the source sits in the target's frame
+      Matrix4f guess = toFloat(multiply(inverseRigid(tgt.pose), src.pose));
+      AlignResult a;
+      int iterations = 0;
+      uint64_t queries = 0;
+      double ms = 0;
+      for (int r = 0; r < repeats; ++r) {
+        a = pairwiseAlign(src, tgt, prm.icp, &guess, prm.want_fitness && r == repeats - 1, slot);
+        iterations += a.iterations; queries += a.nn_queries; ms += a.gpu_ms;
+        if (a.status != MVR_OK && a.status != MVR_ERR_TOO_FEW_CORRESPONDENCES) { int z = 0; first_error.compare_exchange_strong(z, a.status); break; }
+        guess = a.final_transformation;   // the next repeat continues from this result
+      }
+      fill_report(reports[(size_t)p], (p + 1) % V, p, a, iterations, queries, ms, a.final_transformation);
+    }
+  };
+  const int K = std::max(1, std::min((int)ctx_.size(), p1 - p0));
+  if (K == 1) {
+    worker(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int k = 0; k < K; ++k) th.emplace_back(worker, k);
+    for (std::thread& t : th) t.join();
+  }
+  if (first_error.load()) return fail(first_error.load(), "align failed");
+  if (p0 == 0 && p1 == V) {
+    std::vector<Matrix4d> rel((size_t)V), abs_pose;
+    std::vector<double> w((size_t)V);
+    for (int p = 0; p < V; ++p) {
+      Matrix4f f;
+      std::memcpy(f.m, reports[(size_t)p].pose, sizeof(f.m));
+      rel[(size_t)p] = toDouble(f);
+      w[(size_t)p] = reports[(size_t)p].status == MVR_OK ? (double)reports[(size_t)p].n_correspondences : 0.0;
+    }
+    int rc = ringClose(rel, w, prm.loop_closure != 0, prm.lum_iterations > 0 ? prm.lum_iterations : 16, abs_pose);
+    if (rc) return fail(rc, "loop closure failed");
+    const Matrix4d base = views[0].pose;
+    for (int v = 0; v < V; ++v) {
+      views[(size_t)v].pose = multiply(base, abs_pose[(size_t)v]);
+      views[(size_t)v].pose_is_identity = false;
+      views[(size_t)v].registered = true;
+    }
+  }
+  return MVR_OK;
+}
+
+int Registrator::registrationLUM(std::vector<View>& views, int max_iterations, double max_distance) {
+  // mvr/src/registrator.cpp:611-678: every view gets its turntable pose, then outer loops of
+  // {reciprocal correspondences on the ring edges i -> i+1, relax 16 sweeps, compose the corrections}.
+  // The edge constraint used here is the rigid motion that best superposes the edge's reciprocal
+  // correspondences (one estimator step on the GPU), weighted by their number; see lum.cpp.
+  if (!ok()) return fail(MVR_ERR_CUDA, "no GPU context");
+  const int V = (int)views.size();
+  if (V < 2) return MVR_OK;
+  for (int v = 0; v < V; ++v) { views[(size_t)v].view = v; initRotation(views[(size_t)v], V); views[(size_t)v].registered = true; }
+  const int lum_max_iterations = 16;
+  const int outer = std::max(1, max_iterations / lum_max_iterations);
+  mvr_icp_params one;
+  mvr_icp_params_default(&one);
+  one.use_reciprocal_correspondences = 1;
+  one.max_correspondence_distance = max_distance;
+  one.max_iterations = 1;
+  one.fixed_iterations = 1;
+  for (int loop = 0; loop < outer; ++loop) {
+    std::vector<Matrix4d> rel((size_t)V);
+    std::vector<double> w((size_t)V, 0.0);
+    std::atomic<int> next(0);
+    std::atomic<int> bad(0);
+    auto worker = [&](int slot) {
+      cudaSetDevice(device_);
+      for (;;) {
+        const int i = next.fetch_add(1);
+        if (i >= V) break;
+        const View& s = views[(size_t)i];
+        const View& t = views[(size_t)((i + 1) % V)];
+        // world-frame clouds of both ends: source posed by guess = pose_t^-1 pose_s in t's sensor frame
+        Matrix4f guess = toFloat(multiply(inverseRigid(t.pose), s.pose));
+        AlignResult a = pairwiseAlign(s, t, one, &guess, false, slot);
+        if (a.status == MVR_OK) {
+          // a.final = Z * guess in t's frame  ->  Z_world = pose_t Z pose_t^-1, and X_{i+1}^-1 X_i ~ Z_world
+          Matrix4d Z = multiply(toDouble(a.final_transformation), inverseRigid(toDouble(guess)));
+          Matrix4d Zw = multiply(multiply(t.pose, Z), inverseRigid(t.pose));
+          rel[(size_t)i] = inverseRigid(Zw);   // ringClose wants X_i^-1 X_{i+1}
+          w[(size_t)i] = (double)a.n_correspondences;
+        } else if (a.status == MVR_ERR_TOO_FEW_CORRESPONDENCES) {
+          rel[(size_t)i] = identity4d();
+        } else {
+          bad.store(a.status);
+        }
+      }
+    };
+    const int K = std::max(1, std::min((int)ctx_.size(), V));
+    if (K == 1) worker(0);
+    else {
+      std::vector<std::thread> th;
+      for (int k = 0; k < K; ++k) th.emplace_back(worker, k);
+      for (std::thread& t : th) t.join();
+    }
+    if (bad.load()) return fail(bad.load(), "edge estimation failed");
+    std::vector<Matrix4d> X;
+    int rc = ringClose(rel, w, true, lum_max_iterations, X);
+    if (rc) return fail(rc, "relaxation failed");
+    for (int v = 0; v < V; ++v) views[(size_t)v].pose = multiply(X[(size_t)v], views[(size_t)v].pose);   // pose <- lum_T * pose
+  }
+  refineAxis(views);
+  return MVR_OK;
+}
+
+int Registrator::refineAxis(const std::vector<View>& views) {
+  std::vector<Matrix4d> poses;
+  for (size_t i = 1; i < views.size(); ++i)
+    if (views[i].registered) poses.push_back(views[i].pose);
+  return refineAxisFromPoses(poses, pivot_, axis_);
+}
+
+int Registrator::computeError(std::vector<View>& views, double max_distance, std::vector<std::pair<size_t, double> >& out) {
+  // mvr/src/registrator.cpp:466-515: neighbour pairs (i, i+1) and (0, V-1) of registered views
+  if (!ok()) return fail(MVR_ERR_CUDA, "no GPU context");
+  out.clear();
+  const int V = (int)views.size();
+  mvr_ctx* c = ctx_[0];
+  DeviceCloud a, b, raw;
+  for (int i = 0; i < V; ++i) {
+    const int j = (i + 1) % V;
+    if (V == 2 && i == 1) break;
+    View &s = views[(size_t)i], &t = views[(size_t)j];
+    if (!s.registered || !t.registered) continue;
+    PointCloudXYZ ps, pt;
+    int rc = getTransformedPoints(s, ps);
+    if (!rc) rc = getTransformedPoints(t, pt);
+    if (rc) return rc;
+    if ((rc = mvr_set_source(c, ps.empty() ? nullptr : &ps[0].x, ps.size()))) return fail(rc, mvr_last_error(c));
+    if ((rc = mvr_set_target(c, pt.empty() ? nullptr : &pt[0].x, pt.size()))) return fail(rc, mvr_last_error(c));
+    std::vector<int32_t> q(std::max<size_t>(ps.size(), 1)), m(std::max<size_t>(ps.size(), 1));
+    std::vector<float> d(std::max<size_t>(ps.size(), 1));
+    size_t cnt = 0;
+    if ((rc = mvr_correspondences(c, max_distance, 1, q.data(), m.data(), d.data(), &cnt))) return fail(rc, mvr_last_error(c));
+    double sum = 0;
+    for (size_t k = 0; k < cnt; ++k) sum += d[k];
+    out.push_back(std::make_pair(cnt, cnt ? sum / (double)cnt : 0.0));
+  }
+  return MVR_OK;
+}
+
+}  // namespace mvr

@@ -13,6 +13,7 @@ import numpy as np
 
 CENTER = np.array([0.0, 0.0, 900.0])
 AXIS = np.array([0.0, -1.0, 0.0])
+PIVOT = CENTER
 _M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
 
 
@@ -93,6 +94,11 @@ def turntable_angle(view, n_views):
     ((v<7)?-v:12-v)*pi/6 for 12 views)."""
     half = n_views // 2
     return ((-view) if view <= half else (n_views - view)) * (2.0 * np.pi / n_views)
+
+
+def view_pose(view, n_views):
+    """Ground-truth pose of `view` (sensor frame -> frame of view 0) without generating its points."""
+    return np.linalg.inv(rotation_about_axis(view * 2.0 * np.pi / n_views))
 
 
 def turntable_view(view, n_views, n, noise=0.2, seed=0x5EED0000, partial=True):

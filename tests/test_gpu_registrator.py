@@ -1,0 +1,175 @@
+"""GPU parity of the C++ registration driver (host/registrator.cpp behind the C ABI) against the CPU oracle
+replaying the reference's workflows (mvr/src/registrator.cpp:517-588, 746-842, 877-990) step by step."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROT_TOL = 1e-5       # rad (north star)
+TRANS_REL_TOL = 1e-6
+
+
+def rot_angle(A, B):
+    R = np.asarray(A, dtype=np.float64)[:3, :3] @ np.asarray(B, dtype=np.float64)[:3, :3].T
+    w = 0.5 * np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    return float(np.arcsin(min(1.0, np.linalg.norm(w))))
+
+
+def assert_pose_close(A, B, scale):
+    assert rot_angle(A, B) < ROT_TOL
+    dt = np.linalg.norm(np.asarray(A, dtype=np.float64)[:3, 3] - np.asarray(B, dtype=np.float64)[:3, 3])
+    assert dt <= TRANS_REL_TOL * scale, (dt, scale)
+
+
+@pytest.fixture(scope="module")
+def seq(synth):
+    V, n = 6, 8000
+    views, poses = synth.turntable_sequence(V, n)
+    E = synth.perturbation()
+    init = [(poses[v] @ E) if v % 2 else poses[v].copy() for v in range(V)]
+    return V, n, views, poses, init
+
+
+def test_apply_pose_bit_exact(ctx, orc, synth):
+    """PointCloud::getTransformedPoints: double multiply narrowed to float, 48-byte rich points accepted."""
+    rng = np.random.default_rng(2)
+    rich = rng.normal(size=(5000, 12)).astype(np.float32) * 50 + 400   # PointXYZRGBNormal-sized records
+    M = synth.rotation_about_axis(0.7, axis=(0.2, -1.0, 0.1))
+    M[:3, 3] += [3.0, -2.0, 1.5]
+    out = ctx.apply_pose(rich, M)
+    ref = orc.apply_pose_double(rich, M)
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+    xyz = np.ascontiguousarray(rich[:, :4])
+    assert np.array_equal(ctx.apply_pose(xyz, M)[:, :3], out[:, :3])
+
+
+def test_turntable_rotation_matches_reference_formula(mvr, synth):
+    """getRotationMatrix = T(pivot) R(axis, angle) T(-pivot); initRotation's angle generalised to V views."""
+    for v, V in ((1, 12), (6, 12), (7, 12), (11, 12), (13, 24)):
+        ang = mvr.turntable_view_angle(v, V)
+        if V == 12:
+            assert ang == pytest.approx(((-v) if v < 7 else (12 - v)) * np.pi / 6, abs=1e-15)
+        T = mvr.turntable_rotation(synth.PIVOT, synth.AXIS, ang)
+        assert np.abs(T - synth.rotation_about_axis(ang, axis=synth.AXIS, pivot=synth.PIVOT)).max() < 1e-12
+
+
+def test_pairwise_align_equals_context_align(mvr, ctx, synth, seq):
+    V, n, views, poses, init = seq
+    reg = mvr.Registrator(0, 1)
+    p = mvr.default_params(max_iterations=8, max_dist=4.0, reciprocal=1, fixed_iterations=1)
+    guess = (np.linalg.inv(init[0]) @ init[1]).astype(np.float32)
+    r = reg.pairwise_align(views[1], views[0], p, guess=guess)
+    ctx.set_target(views[0])
+    ctx.set_source(views[1])
+    c = ctx.icp_align(p, guess=guess, n_source=n)
+    assert np.array_equal(r["final"], c["final"]) and r["n_corr"] == c["n_corr"] and r["mse"] == c["mse"]
+    reg.close()
+
+
+def test_ring_register_matches_oracle_and_is_stream_and_shard_invariant(mvr, orc, synth, seq):
+    V, n, views, poses, init = seq
+    icp = mvr.default_params(max_iterations=10, max_dist=4.0, reciprocal=1, fixed_iterations=1)
+    tp = mvr.turntable_params(pivot=synth.PIVOT, axis=synth.AXIS, icp=icp, repeat_times=2, mode=mvr.RING_PAIRS, loop_closure=1)
+    reg1 = mvr.Registrator(0, 1)
+    abs1, rep1 = reg1.register_turntable(views, tp, init_poses=init)
+    # oracle: every ring pair, two aligns, the second continuing from the first
+    op = orc.make_params(max_iterations=10, max_dist=4.0, reciprocal=True, fixed_iterations=True)
+    ext = float(np.abs(views[0][:, :3] - views[0][:, :3].mean(axis=0)).max())
+    for p in range(V):
+        t, s = p, (p + 1) % V
+        g = (np.linalg.inv(init[t]) @ init[s]).astype(np.float32)
+        o = orc.icp_align(views[s], views[t], op, guess=g)
+        o = orc.icp_align(views[s], views[t], op, guess=o["final"])
+        assert rep1[p]["source_view"] == s and rep1[p]["target_view"] == t and rep1[p]["status"] == 0
+        assert rep1[p]["n_corr"] == o["n_corr"]
+        assert_pose_close(rep1[p]["pose"], o["final"], scale=max(1.0, float(np.linalg.norm(o["final"][:3, 3]))))
+    # the relaxed absolute poses stay near the ground truth (60-degree steps of 8000-point scans: ICP itself is
+    # only good to ~1e-2 rad here) and, unlike the plain chain, close the ring
+    for v in range(V):
+        truth = np.linalg.inv(poses[0]) @ poses[v]
+        assert rot_angle(abs1[v], truth) < 5e-2
+    chain = mvr.ring_close([r["pose"] for r in rep1], relax=False)
+    gap_chain = rot_angle(chain[V - 1].astype(np.float64) @ rep1[V - 1]["pose"].astype(np.float64), np.eye(4))
+    gap_relaxed = rot_angle(abs1[V - 1].astype(np.float64) @ rep1[V - 1]["pose"].astype(np.float64), abs1[0])
+    assert gap_relaxed < 0.5 * gap_chain + 1e-6
+    # several streams (host threads + GPU contexts) and sharded pair ranges give bit-identical reports
+    reg3 = mvr.Registrator(0, 3)
+    abs3, rep3 = reg3.register_turntable(views, tp, init_poses=init)
+    for p in range(V):
+        assert np.array_equal(rep1[p]["pose"], rep3[p]["pose"]) and rep1[p]["n_corr"] == rep3[p]["n_corr"]
+    for v in range(V):
+        assert np.array_equal(abs1[v], abs3[v])
+    got = {}
+    for lo, hi in ((0, 2), (2, 5), (5, 6)):
+        tps = mvr.turntable_params(pivot=synth.PIVOT, axis=synth.AXIS, icp=icp, repeat_times=2, mode=mvr.RING_PAIRS, loop_closure=1,
+                                   pair_begin=lo, pair_end=hi)
+        need = {q % V for p in range(lo, hi) for q in (p, p + 1)}
+        _, reps = reg3.register_turntable([views[v] if v in need else None for v in range(V)], tps, init_poses=init)
+        for p in range(lo, hi):
+            got[p] = reps[p]
+    rel = [got[p]["pose"] for p in range(V)]
+    for p in range(V):
+        assert np.array_equal(rel[p], rep1[p]["pose"])
+    closed = mvr.ring_close(rel, [got[p]["n_corr"] for p in range(V)], relax=True, iterations=16)
+    for v in range(V):
+        assert np.array_equal(closed[v], abs1[v])
+    reg1.close()
+    reg3.close()
+
+
+def _oracle_accumulate(orc, views, init, order, op, repeats):
+    """The reference's model-growing loop (mvr/src/registrator.cpp:562-577 / 909-983) on the CPU oracle."""
+    pose = [np.array(T, dtype=np.float64) for T in init]
+    model = orc.apply_pose_double(views[0], pose[0])
+    ncorr = {}
+    for v in order:
+        src = orc.apply_pose_double(views[v], pose[v])
+        for _ in range(repeats):
+            o = orc.icp_align(src, model, op)
+            pose[v] = o["final"].astype(np.float64) @ pose[v]
+            src = o["cloud"]
+            ncorr[v] = o["n_corr"]
+        model = np.concatenate([model, src])
+    return pose, ncorr
+
+
+def test_automatic_registration_matches_oracle(mvr, orc, synth, seq):
+    V, n, views, poses, init = seq
+    icp = mvr.default_params(max_iterations=6, max_dist=4.0, reciprocal=1, fixed_iterations=1)
+    tp = mvr.turntable_params(pivot=synth.PIVOT, axis=synth.AXIS, icp=icp, repeat_times=2, mode=mvr.ACCUMULATE)
+    reg = mvr.Registrator(0, 1)
+    got, reps = reg.register_turntable(views[:4], tp, init_poses=init[:4])
+    op = orc.make_params(max_iterations=6, max_dist=4.0, reciprocal=True, fixed_iterations=True)
+    want, _ = _oracle_accumulate(orc, views[:4], init[:4], [1, 2, 3], op, repeats=2)
+    for v in range(4):
+        assert_pose_close(got[v], want[v], scale=max(1.0, float(np.linalg.norm(want[v][:3, 3]))))
+    assert [r["source_view"] for r in reps] == [1, 2, 3] and all(r["fitness"] > 0 for r in reps)
+    reg.close()
+
+
+def test_registration_icp_order_and_reference_settings(mvr, orc, synth, seq):
+    """registrationICP: order 1, V-1, 2, V-2, ..., middle; transEps 1e-6, fitEps 64 => one iteration per align."""
+    V, n, views, poses, init = seq
+    icp = mvr.default_params(max_iterations=2**31 - 1, max_dist=4.0)
+    tp = mvr.turntable_params(pivot=synth.PIVOT, axis=synth.AXIS, icp=icp, repeat_times=1, mode=mvr.ICP_ORDER)
+    reg = mvr.Registrator(0, 1)
+    got, reps = reg.register_turntable(views, tp, init_poses=init)
+    assert [r["source_view"] for r in reps] == [1, 5, 2, 4, 3]
+    assert all(r["iterations"] == 1 for r in reps)
+    op = orc.make_params(max_iterations=2**31 - 1, max_dist=4.0, reciprocal=True, transformation_epsilon=1e-6, euclidean_fitness_epsilon=64.0)
+    want, _ = _oracle_accumulate(orc, views, init, [1, 5, 2, 4, 3], op, repeats=1)
+    for v in range(V):
+        assert_pose_close(got[v], want[v], scale=max(1.0, float(np.linalg.norm(want[v][:3, 3]))))
+    reg.close()
+
+
+def test_registration_lum_reduces_ring_error(mvr, synth, seq):
+    V, n, views, poses, init = seq
+    icp = mvr.default_params(max_iterations=64, max_dist=4.0)
+    tp = mvr.turntable_params(pivot=synth.PIVOT, axis=synth.AXIS, icp=icp, mode=mvr.LUM)
+    reg = mvr.Registrator(0, 2)
+    got, _ = reg.register_turntable(views, tp, init_poses=init)
+    before = max(rot_angle(np.linalg.inv(init[0]) @ init[v], np.linalg.inv(poses[0]) @ poses[v]) for v in range(V))
+    after = max(rot_angle(np.linalg.inv(got[0]) @ got[v], np.linalg.inv(poses[0]) @ poses[v]) for v in range(V))
+    assert before > 0.02 and after < 0.3 * before
+    reg.close()
