@@ -36,7 +36,7 @@ UNIT = "queries/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--views", type=int, default=24)
@@ -61,7 +61,8 @@ def workload_config(a, world):
 
 
 def pair_range(rank, world, n_pairs):
-    return (rank * n_pairs) // world, ((rank + 1) * n_pairs) // world
+    import mvr_b200.ring as ring
+    return ring.pair_range(rank, world, n_pairs)
 
 
 def make_pairs(a, p0, p1):
@@ -129,7 +130,7 @@ def run_reference(a):
 # native arm
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
@@ -141,7 +142,9 @@ class ClockSampler:
         except OSError:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples taken between wall-clock times t0 and t1 (all samples when None)."""
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
@@ -156,15 +159,18 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
-            if len(c) < 8:
+            if len(c) < 9:
                 continue
             try:
-                sm.append(float(c[0]))
-                mx.append(float(c[1]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.05):
+                    continue
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
             except ValueError:
                 continue
             for k, nm in enumerate(names):
-                if c[4 + k].lower().startswith("active"):
+                if c[5 + k].lower().startswith("active"):
                     reasons.add(nm)
         try:
             os.unlink(self.f.name)
@@ -217,6 +223,8 @@ def run_native(a):
             poses[v] = synth.view_pose(v, V)
     init = view_init_poses(a, [poses[v] for v in range(V)])
     truth0 = np.linalg.inv(poses[p0 % V]) @ poses[(p0 + 1) % V]
+    some = views[need[0]][:, :3]
+    obj_radius = 0.5 * float((some.max(axis=0) - some.min(axis=0)).max())
 
     reg = mvr_b200.Registrator(local, a.streams)   # C++ driver: a.streams GPU contexts, one host thread each
     icp = mvr_b200.default_params(max_iterations=a.iters, max_dist=a.max_dist, reciprocal=a.reciprocal, fixed_iterations=1)
@@ -228,39 +236,15 @@ def run_native(a):
     dev_list = [(d_views[v].data_ptr(), n) if v in d_views else None for v in range(V)]
     host_list = [h_views[v].numpy() if v in h_views else None for v in range(V)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    REC = 24   # floats per pair record: pose 16, n_corr, mse, iterations, status, queries (2 x 24-bit halves), pad
-    mine = torch.zeros((p1 - p0) * REC, dtype=torch.float32, device=dev)
-    gathered = torch.zeros(world * ((V + world - 1) // world) * REC, dtype=torch.float32, device=dev) if world > 1 else None
-    h_rec = torch.zeros((p1 - p0) * REC, dtype=torch.float32).pin_memory()
+    import mvr_b200.ring as ring
 
     def step(host_buffers):
         """One registration: this rank's ring pairs through the C++ driver, gather of the per-pair results, host
         loop closure over the whole ring.  Returns (queries of this rank, pair reports, absolute poses)."""
         _, reps = reg.register_turntable(host_list if host_buffers else dev_list, tp, init_poses=init)
-        q = 0
-        for k, p in enumerate(range(p0, p1)):
-            r = reps[p]
-            q += r["nn_queries"]
-            rec = h_rec[k * REC:(k + 1) * REC]
-            rec[:16] = torch.from_numpy(np.ascontiguousarray(r["pose"].T).reshape(16))
-            rec[16] = r["n_corr"]
-            rec[17] = r["mse"]
-            rec[18] = r["iterations"]
-            rec[19] = r["status"]
-        if world > 1:
-            # per-pair results -> every rank (one small NCCL all-gather; ranks hold equal-size blocks when world | V)
-            mine.copy_(h_rec, non_blocking=True)
-            parts = [torch.zeros_like(mine) for _ in range(world)] if V % world else None
-            if parts is None:
-                dist.all_gather_into_tensor(gathered[:V * REC], mine)
-                allrec = gathered[:V * REC].cpu().numpy().reshape(V, REC)
-            else:
-                raise SystemExit("bench.py: --gpus must divide --views")
-        else:
-            allrec = h_rec.numpy().reshape(V, REC)
-        rel = [allrec[p, :16].reshape(4, 4).T for p in range(V)]
-        w = [float(allrec[p, 16]) if allrec[p, 19] == 0 else 0.0 for p in range(V)]
-        abs_poses = mvr_b200.ring_close(rel, w, relax=True, iterations=16)
+        q = sum(reps[p]["nn_queries"] for p in range(p0, p1))
+        allrec = ring.gather_records(ring.pack_reports(reps, p0, p1), rank, world, V, dist=dist if world > 1 else None, device=dev)
+        abs_poses = ring.close_ring(allrec, synth.PIVOT, obj_radius)
         return q, reps, abs_poses
 
     def timed(host_buffers, steps):
@@ -298,13 +282,15 @@ def run_native(a):
         return float(t.item())
 
     # ---- device-resident leg (value) ----
+    sampler = ClockSampler(local) if rank == 0 else None   # started before the warm-up: nvidia-smi takes a while to come up
     for _ in range(a.warmup):
         step(False)
-    sampler = ClockSampler(local) if rank == 0 else None
     l0 = mvr_b200.kernel_launch_count()
+    w0 = time.time()
     ms, q, last = timed(False, a.steps)
+    w1 = time.time()
     launches = mvr_b200.kernel_launch_count() - l0
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(w0, w1) if sampler else None
     ms = allmax(ms)
     q = allsum(q)
     launches = allsum(launches)
@@ -319,7 +305,7 @@ def run_native(a):
         ms_e = allmax(ms_e)
         q_e = allsum(q_e)
         h2d = allsum(float((p1 - p0) * 2 * n * 16 + (p1 - p0) * 512))       # both scans of every pair + state/params
-        d2h = allsum(float((p1 - p0) * (512 + 48 * a.iters)))                 # state + per-iteration log of every pair
+        d2h = allsum(float((p1 - p0) * (512 + 48 * a.iters + 4 * ring.REC)))  # state + per-iteration log + record of every pair
         e2e = {"value": q_e / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e / a.steps,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
 

@@ -112,6 +112,8 @@ int mvr_ctx_destroy(mvr_ctx* ctx);
 /* Run on a caller-owned stream (e.g. torch's current stream) instead of the context's own. */
 int mvr_ctx_set_stream(mvr_ctx* ctx, void* cuda_stream);
 int mvr_ctx_synchronize(mvr_ctx* ctx);
+/* The CUDA stream (cudaStream_t) the context enqueues on: callers that move data themselves order it here. */
+void* mvr_ctx_get_stream(mvr_ctx* ctx);
 const char* mvr_last_error(mvr_ctx* ctx);
 int mvr_ctx_set_profiling(mvr_ctx* ctx, int on);
 int mvr_ctx_get_kernel_stats(mvr_ctx* ctx, mvr_kernel_stat* out /* [MVR_K_COUNT] */, int reset);
@@ -249,8 +251,13 @@ int mvr_pairwise_align(mvr_registrator* r, const mvr_view* source, const mvr_vie
 int mvr_register_turntable(mvr_registrator* r, const mvr_view* views, int n_views, const mvr_turntable_params* prm,
                            float* poses, mvr_pair_report* reports);
 /* Host-side loop closure over gathered ring pairs: rel[p] = pose of view (p+1)%V in view p's frame, w[p] its
- * weight (e.g. n_correspondences; <= 0 drops the edge).  Output V absolute poses, view 0 = identity. */
-int mvr_ring_close(const float* rel_poses, const double* weights, int n_views, int relax, int iterations, float* poses);
+ * weight (e.g. n_correspondences; <= 0 drops the edge).  centre (nullable) = where the object sits in every
+ * view's frame (the turntable pivot), rot_scale = its radius: residuals are point displacements of such an
+ * object.  Output V absolute poses, view 0 = identity. */
+int mvr_ring_close(const float* rel_poses, const double* weights, int n_views, int relax, int iterations, const double* centre,
+                   double rot_scale, float* poses);
+/* Bounding box of the finite points of a cloud given to the context. */
+int mvr_get_bbox(mvr_ctx* ctx, int which, float lo[3], float hi[3]);
 /* Registrator::refineAxis (mvr/src/registrator.cpp:402-455): least-squares turntable axis from registered
  * view poses (poses: count x float[16] column-major).  pivot/axis are in-out. */
 int mvr_refine_axis(const float* poses, int count, double pivot[3], double axis[3]);

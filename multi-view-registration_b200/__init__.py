@@ -157,7 +157,8 @@ def lib():
     L.mvr_registrator_streams.argtypes = [vp]
     L.mvr_pairwise_align.argtypes = [vp, C.POINTER(ViewDesc), C.POINTER(ViewDesc), C.POINTER(IcpParams), fp, fp, C.POINTER(IcpReport)]
     L.mvr_register_turntable.argtypes = [vp, C.POINTER(ViewDesc), C.c_int, C.POINTER(TurntableParams), fp, C.POINTER(PairReport)]
-    L.mvr_ring_close.argtypes = [fp, dp, C.c_int, C.c_int, C.c_int, fp]
+    L.mvr_ring_close.argtypes = [fp, dp, C.c_int, C.c_int, C.c_int, dp, C.c_double, fp]
+    L.mvr_get_bbox.argtypes = [vp, C.c_int, fp, fp]
     L.mvr_refine_axis.argtypes = [fp, C.c_int, dp, dp]
     _lib = L
     return L
@@ -397,13 +398,16 @@ def turntable_params(**kw):
     return p
 
 
-def ring_close(rel_poses, weights=None, relax=True, iterations=16):
-    """Host loop closure: rel_poses V x 4x4 (view p+1 in view p's frame) -> V absolute 4x4 poses."""
+def ring_close(rel_poses, weights=None, relax=True, iterations=16, centre=None, rot_scale=1.0):
+    """Host loop closure: rel_poses V x 4x4 (view p+1 in view p's frame) -> V absolute 4x4 poses.
+    centre = the turntable pivot, rot_scale = the object's radius (residuals become point displacements)."""
     V = len(rel_poses)
     rel = np.ascontiguousarray(np.stack([pose_from_numpy(T) for T in rel_poses]), dtype=np.float32)
     w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
     out = np.empty((V, 16), dtype=np.float32)
-    rc = lib().mvr_ring_close(_fp(rel), _dp(w) if w is not None else None, V, int(bool(relax)), int(iterations), _fp(out))
+    cc = None if centre is None else np.ascontiguousarray(centre, dtype=np.float64)
+    rc = lib().mvr_ring_close(_fp(rel), _dp(w) if w is not None else None, V, int(bool(relax)), int(iterations),
+                              _dp(cc) if cc is not None else None, float(rot_scale), _fp(out))
     if rc != OK:
         raise MvrError(rc, lib().mvr_status_string(rc).decode())
     return [pose_to_numpy(out[k]) for k in range(V)]

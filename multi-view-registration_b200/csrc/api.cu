@@ -547,6 +547,8 @@ int mvr_ctx_set_stream(mvr_ctx* ctx, void* s) {
   return MVR_OK;
 }
 
+void* mvr_ctx_get_stream(mvr_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
 int mvr_ctx_synchronize(mvr_ctx* ctx) {
   if (!ctx) return MVR_ERR_BAD_ARG;
   CK(cudaStreamSynchronize(ctx->stream));
@@ -614,6 +616,14 @@ int mvr_set_target_normals(mvr_ctx* ctx, const float* nxyzc, size_t n) {
   CK(cudaMemcpyAsync(ctx->normals.p, nxyzc, n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->has_normals = true;
+  return MVR_OK;
+}
+
+int mvr_get_bbox(mvr_ctx* ctx, int which, float lo[3], float hi[3]) {
+  if (!ctx || !lo || !hi || (which != MVR_CLOUD_TARGET && which != MVR_CLOUD_SOURCE)) return MVR_ERR_BAD_ARG;
+  const Cloud& c = which == MVR_CLOUD_TARGET ? ctx->tgt : ctx->src;
+  if (c.gen == 0) return fail(ctx, MVR_ERR_NO_INPUT, "cloud not set");
+  for (int a = 0; a < 3; ++a) { lo[a] = c.lo[a]; hi[a] = c.hi[a]; }
   return MVR_OK;
 }
 

@@ -152,7 +152,8 @@ int mvr_register_turntable(mvr_registrator* r, const mvr_view* views, int n_view
   return rc;
 }
 
-int mvr_ring_close(const float* rel_poses, const double* weights, int n_views, int relax, int iterations, float* poses) {
+int mvr_ring_close(const float* rel_poses, const double* weights, int n_views, int relax, int iterations, const double* centre,
+                   double rot_scale, float* poses) {
   if (!rel_poses || !poses || n_views < 1) return MVR_ERR_BAD_ARG;
   std::vector<Matrix4d> rel((size_t)n_views), X;
   std::vector<double> w((size_t)n_views, 1.0);
@@ -162,7 +163,7 @@ int mvr_ring_close(const float* rel_poses, const double* weights, int n_views, i
     rel[(size_t)p] = toDouble(f);
     if (weights) w[(size_t)p] = weights[p];
   }
-  int rc = ringClose(rel, w, relax != 0, iterations > 0 ? iterations : 16, X);
+  int rc = ringClose(rel, w, relax != 0, iterations > 0 ? iterations : 16, centre, rot_scale, X);
   if (rc) return rc;
   for (int p = 0; p < n_views; ++p) {
     Matrix4f f = toFloat(X[(size_t)p]);

@@ -172,13 +172,28 @@ bool chol_solve(std::vector<double>& A, std::vector<double>& b, int n) {
 // relax = false: plain chaining of pairs 0 .. V-2 (the closing pair is ignored).
 // relax = true : Gauss-Newton on  sum_p w_p | Log(rel[p]^-1 X_p^-1 X_{p+1}) |^2, X_v <- X_v Exp(d_v),
 //                 `iterations` sweeps of the dense 6(V-1) solve (LUM runs 16 of them).
-int ringClose(const std::vector<Matrix4d>& rel, const std::vector<double>& weight, bool relax, int iterations,
-              std::vector<Matrix4d>& X) {
-  const int V = (int)rel.size();
+//                 The residual twist is taken about `centre` (the turntable pivot: the object sits there in every
+//                 view's frame, so the poses are nearly pure rotations about it) and its rotation part is scaled
+//                 by `rot_scale` (the object's radius), which makes the cost the mean squared displacement of the
+//                 object's points -- what LUM's per-correspondence information encodes -- instead of mixing
+//                 radians and millimetres measured at the sensor origin.
+int ringClose(const std::vector<Matrix4d>& rel_in, const std::vector<double>& weight, bool relax, int iterations,
+              const double* centre, double rot_scale, std::vector<Matrix4d>& X) {
+  const int V = (int)rel_in.size();
   X.assign((size_t)std::max(V, 1), identity4d());
   if (V < 2) return MVR_OK;
+  if (!relax) {
+    for (int p = 0; p + 1 < V; ++p) X[(size_t)p + 1] = multiply(X[(size_t)p], rel_in[(size_t)p]);
+    return MVR_OK;
+  }
+  // work in coordinates centred on the pivot: T' = S^-1 T S with S = translate(centre)
+  Matrix4d S = identity4d(), Si = identity4d();
+  if (centre) for (int k = 0; k < 3; ++k) { S.m[12 + k] = centre[k]; Si.m[12 + k] = -centre[k]; }
+  std::vector<Matrix4d> rel((size_t)V);
+  for (int p = 0; p < V; ++p) rel[(size_t)p] = multiply(multiply(Si, rel_in[(size_t)p]), S);
+  const double rho2 = (rot_scale > 0) ? rot_scale * rot_scale : 1.0;
+  const double Wd[6] = {rho2, rho2, rho2, 1.0, 1.0, 1.0};
   for (int p = 0; p + 1 < V; ++p) X[(size_t)p + 1] = multiply(X[(size_t)p], rel[(size_t)p]);
-  if (!relax) return MVR_OK;
   double wmax = 0;
   for (double w : weight) wmax = std::fmax(wmax, w);
   if (!(wmax > 0)) return MVR_OK;
@@ -198,32 +213,32 @@ int ringClose(const std::vector<Matrix4d>& rel, const std::vector<double>& weigh
       double Ja[36];
       se3_adjoint(inverseRigid(XaiXb), Ja);
       for (int k = 0; k < 36; ++k) Ja[k] = -Ja[k];
-      for (int k = 0; k < 6; ++k) cost += w * r.v[k] * r.v[k];
+      for (int k = 0; k < 6; ++k) cost += w * Wd[k] * r.v[k] * r.v[k];
       const int ia = 6 * (a - 1), ib = 6 * (b - 1);   // vertex 0 is fixed (no unknowns)
       // H += J^T w J ; g += J^T w r   with J = [Ja at a, I at b]
       if (a > 0) {
         for (int i = 0; i < 6; ++i) {
           double gi = 0;
-          for (int k = 0; k < 6; ++k) gi += Ja[k * 6 + i] * r.v[k];
+          for (int k = 0; k < 6; ++k) gi += Ja[k * 6 + i] * Wd[k] * r.v[k];
           g[(size_t)ia + i] += w * gi;
           for (int j = 0; j < 6; ++j) {
             double h = 0;
-            for (int k = 0; k < 6; ++k) h += Ja[k * 6 + i] * Ja[k * 6 + j];
+            for (int k = 0; k < 6; ++k) h += Ja[k * 6 + i] * Wd[k] * Ja[k * 6 + j];
             H[(size_t)(ia + i) * n + ia + j] += w * h;
           }
         }
       }
       if (b > 0) {
         for (int i = 0; i < 6; ++i) {
-          g[(size_t)ib + i] += w * r.v[i];
-          H[(size_t)(ib + i) * n + ib + i] += w;
+          g[(size_t)ib + i] += w * Wd[i] * r.v[i];
+          H[(size_t)(ib + i) * n + ib + i] += w * Wd[i];
         }
       }
       if (a > 0 && b > 0) {
         for (int i = 0; i < 6; ++i)
           for (int j = 0; j < 6; ++j) {
-            H[(size_t)(ia + i) * n + ib + j] += w * Ja[j * 6 + i];   // Ja^T I
-            H[(size_t)(ib + j) * n + ia + i] += w * Ja[j * 6 + i];
+            H[(size_t)(ia + i) * n + ib + j] += w * Wd[j] * Ja[j * 6 + i];   // Ja^T W I
+            H[(size_t)(ib + j) * n + ia + i] += w * Wd[j] * Ja[j * 6 + i];
           }
       }
     }
@@ -237,6 +252,7 @@ int ringClose(const std::vector<Matrix4d>& rel, const std::vector<double>& weigh
     }
     if (step < 1e-14 || cost < 1e-30) break;
   }
+  for (int v = 0; v < V; ++v) X[(size_t)v] = multiply(multiply(S, X[(size_t)v]), Si);
   return MVR_OK;
 }
 

@@ -123,6 +123,15 @@ Registrator::~Registrator() {
   for (mvr_ctx* x : ctx_) mvr_ctx_destroy(x);
 }
 
+double Registrator::objectRadius(int slot) const {
+  float lo[3], hi[3];
+  mvr_ctx* c = context(slot);
+  if (!c || mvr_get_bbox(c, MVR_CLOUD_TARGET, lo, hi) != MVR_OK) return 1.0;
+  double e = 0;
+  for (int k = 0; k < 3; ++k) e = std::max(e, (double)hi[k] - (double)lo[k]);
+  return e > 0 ? 0.5 * e : 1.0;
+}
+
 Matrix4d Registrator::getRotationMatrix(double angle) const {
   Matrix4d r;
   mvr_turntable_rotation(pivot_, axis_, angle, r.m);
@@ -179,6 +188,7 @@ AlignResult Registrator::pairwiseAlign(const View& source, const View& target, c
   a.status = rc;
   a.iterations = rep.iterations; a.n_correspondences = rep.n_correspondences; a.converged = rep.converged != 0;
   a.mse = rep.mse; a.gpu_ms = rep.gpu_ms; a.nn_queries = rep.nn_queries;
+  a.target_radius = objectRadius((int)((size_t)slot % ctx_.size()));
   if ((rc == MVR_OK || rc == MVR_ERR_TOO_FEW_CORRESPONDENCES) && want_fitness) {
     double f = -1;
     if (mvr_fitness_score(c, DBL_MAX, &f) == MVR_OK) a.fitness = f;
@@ -196,6 +206,9 @@ int Registrator::accumulate(std::vector<View>& views, const std::vector<int>& or
   if (views.empty()) return MVR_OK;
   cudaSetDevice(device_);
   mvr_ctx* c = ctx_[0];
+  // every copy the driver makes is ordered on the context's own (non-blocking) stream: the legacy stream
+  // would not be ordered against the context's kernels
+  cudaStream_t st = (cudaStream_t)mvr_ctx_get_stream(c);
   size_t total = views[0].size;
   for (int v : order) total += views[(size_t)v].size;
   DeviceCloud model, src, raw;
@@ -206,7 +219,7 @@ int Registrator::accumulate(std::vector<View>& views, const std::vector<int>& or
     const float* in = &v.points->x;
     if (!v.on_device) {
       if (!raw.ensure(v.size)) return MVR_ERR_ALLOC;
-      if (cudaMemcpy(raw.p, in, v.size * 16, cudaMemcpyHostToDevice) != cudaSuccess) return MVR_ERR_CUDA;
+      if (cudaMemcpyAsync(raw.p, in, v.size * 16, cudaMemcpyHostToDevice, st) != cudaSuccess) return MVR_ERR_CUDA;
       in = raw.p;
     }
     return mvr_apply_pose_device(c, in, v.size, 16, v.pose.m, dst);
@@ -245,8 +258,7 @@ int Registrator::accumulate(std::vector<View>& views, const std::vector<int>& or
     }
     v.registered = true;
     // *target += transformed_source
-    if (cudaMemcpy(model.p + model_n * 4, src.p, v.size * 16, cudaMemcpyDeviceToDevice) != cudaSuccess ||
-        cudaStreamSynchronize(0) != cudaSuccess)   // device-to-device copies do not block the host
+    if (cudaMemcpyAsync(model.p + model_n * 4, src.p, v.size * 16, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
       return fail(MVR_ERR_CUDA, "model append");
     model_n += v.size;
     if (reports) {
@@ -314,6 +326,7 @@ int Registrator::multiViewRegister(std::vector<View>& views, const mvr_turntable
   for (int p = 0; p < V; ++p) { reports[(size_t)p].source_view = (p + 1) % V; reports[(size_t)p].target_view = p; reports[(size_t)p].status = -1; reports[(size_t)p].fitness = -1; }
   std::atomic<int> next(p0);
   std::atomic<int> first_error(0);
+  std::vector<double> radius((size_t)V, 1.0);
   const int repeats = std::max(prm.repeat_times, 1);
   auto worker = [&](int slot) {
     cudaSetDevice(device_);
@@ -335,6 +348,7 @@ int Registrator::multiViewRegister(std::vector<View>& views, const mvr_turntable
         guess = a.final_transformation;   // the next repeat continues from this result
       }
       fill_report(reports[(size_t)p], (p + 1) % V, p, a, iterations, queries, ms, a.final_transformation);
+      radius[(size_t)p] = a.target_radius;
     }
   };
   const int K = std::max(1, std::min((int)ctx_.size(), p1 - p0));
@@ -355,7 +369,7 @@ int Registrator::multiViewRegister(std::vector<View>& views, const mvr_turntable
       rel[(size_t)p] = toDouble(f);
       w[(size_t)p] = reports[(size_t)p].status == MVR_OK ? (double)reports[(size_t)p].n_correspondences : 0.0;
     }
-    int rc = ringClose(rel, w, prm.loop_closure != 0, prm.lum_iterations > 0 ? prm.lum_iterations : 16, abs_pose);
+    int rc = ringClose(rel, w, prm.loop_closure != 0, prm.lum_iterations > 0 ? prm.lum_iterations : 16, pivot_, radius[0], abs_pose);   // radius of view 0: the same whatever the stream count
     if (rc) return fail(rc, "loop closure failed");
     const Matrix4d base = views[0].pose;
     for (int v = 0; v < V; ++v) {
@@ -389,6 +403,7 @@ int Registrator::registrationLUM(std::vector<View>& views, int max_iterations, d
     std::vector<double> w((size_t)V, 0.0);
     std::atomic<int> next(0);
     std::atomic<int> bad(0);
+    std::vector<double> radius((size_t)V, 1.0);
     auto worker = [&](int slot) {
       cudaSetDevice(device_);
       for (;;) {
@@ -399,6 +414,7 @@ int Registrator::registrationLUM(std::vector<View>& views, int max_iterations, d
         // world-frame clouds of both ends: source posed by guess = pose_t^-1 pose_s in t's sensor frame
         Matrix4f guess = toFloat(multiply(inverseRigid(t.pose), s.pose));
         AlignResult a = pairwiseAlign(s, t, one, &guess, false, slot);
+        radius[(size_t)i] = a.target_radius;
         if (a.status == MVR_OK) {
           // a.final = Z * guess in t's frame  ->  Z_world = pose_t Z pose_t^-1, and X_{i+1}^-1 X_i ~ Z_world
           Matrix4d Z = multiply(toDouble(a.final_transformation), inverseRigid(toDouble(guess)));
@@ -421,7 +437,10 @@ int Registrator::registrationLUM(std::vector<View>& views, int max_iterations, d
     }
     if (bad.load()) return fail(bad.load(), "edge estimation failed");
     std::vector<Matrix4d> X;
-    int rc = ringClose(rel, w, true, lum_max_iterations, X);
+    // world frame = view 0's frame posed by views[0].pose: the object sits at pose_0 * pivot
+    double cw[3];
+    for (int k = 0; k < 3; ++k) cw[k] = views[0].pose.m[k] * pivot_[0] + views[0].pose.m[4 + k] * pivot_[1] + views[0].pose.m[8 + k] * pivot_[2] + views[0].pose.m[12 + k];
+    int rc = ringClose(rel, w, true, lum_max_iterations, cw, radius[0], X);
     if (rc) return fail(rc, "relaxation failed");
     for (int v = 0; v < V; ++v) views[(size_t)v].pose = multiply(X[(size_t)v], views[(size_t)v].pose);   // pose <- lum_T * pose
   }

@@ -62,6 +62,7 @@ struct AlignResult {
   int n_correspondences = 0;
   bool converged = false;
   double mse = 0, fitness = -1, gpu_ms = 0;
+  double target_radius = 1.0;         // half the largest extent of the target cloud
   uint64_t nn_queries = 0;
 };
 
@@ -116,6 +117,7 @@ class Registrator {
  private:
   int accumulate(std::vector<View>& views, const std::vector<int>& order, const mvr_icp_params& icp, int repeat_times,
                  bool want_fitness, std::vector<mvr_pair_report>* reports);
+  double objectRadius(int slot) const;   // half the largest extent of the target cloud last given to context `slot`
   int fail(int code, const std::string& msg) { std::lock_guard<std::mutex> g(err_mu_); err_ = msg; return code; }
   std::mutex err_mu_;
   std::vector<mvr_ctx*> ctx_;
@@ -127,7 +129,7 @@ class Registrator {
 
 // Ring loop closure (host): see lum.cpp.
 int ringClose(const std::vector<Matrix4d>& rel, const std::vector<double>& weight, bool relax, int iterations,
-              std::vector<Matrix4d>& abs_out);
+              const double* centre, double rot_scale, std::vector<Matrix4d>& abs_out);
 // least squares min |A x - b| for a tall dense A (rows x cols, row-major): math_solvers::least_squares
 // (mvr/src/math_solvers.cpp:24-39, LAPACK dgels there; Householder QR here).
 bool leastSquares(const std::vector<double>& A, const std::vector<double>& b, int rows, int cols, std::vector<double>& x);
