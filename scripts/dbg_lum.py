@@ -12,7 +12,7 @@ P = [(poses[v] @ E) if v % 2 else poses[v].copy() for v in range(V)]
 reg = mvr.Registrator(0, 1)
 one = mvr.default_params(max_iterations=1, max_dist=4.0, reciprocal=1, fixed_iterations=1)
 c = np.array([0, 0, 900.0])
-for loop in range(4):
+for loop in range(8):
     rel, w = [], []
     for i in range(V):
         s, t = i, (i + 1) % V
@@ -22,9 +22,9 @@ for loop in range(4):
         Zw = P[t] @ Z @ np.linalg.inv(P[t])
         # displacement of the object centre (world) by Zw
         cw = P[t] @ np.append(c, 1.0)
-        print("loop", loop, "edge", i, "ncorr", r["n_corr"], "mse", round(r["mse"], 3), "Z rot", round(rot_angle(Z, np.eye(4)), 5), "centre shift", round(float(np.linalg.norm((Zw @ cw - cw)[:3])), 3))
+        if loop < 0: print("loop", loop, "edge", i, "ncorr", r["n_corr"], "mse", round(r["mse"], 3), "Z rot", round(rot_angle(Z, np.eye(4)), 5), "centre shift", round(float(np.linalg.norm((Zw @ cw - cw)[:3])), 3))
         rel.append(np.linalg.inv(Zw)); w.append(r["n_corr"])
-    X = mvr.ring_close(rel, w, relax=True, iterations=16)
+    X = mvr.ring_close(rel, w, relax=True, iterations=16, centre=(P[0] @ np.append(c, 1.0))[:3], rot_scale=100.0)
     print("  X rot", [round(rot_angle(x, np.eye(4)), 4) for x in X])
     P = [X[v].astype(np.float64) @ P[v] for v in range(V)]
     print("  err vs truth", [round(rot_angle(np.linalg.inv(P[0]) @ P[v], np.linalg.inv(poses[0]) @ poses[v]), 4) for v in range(V)])
