@@ -90,6 +90,11 @@ def cpu_align_pairs(a, views, pairs):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle
     oracle.build()
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would cripple the CPU arm)
+    try:
+        oracle.set_num_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        oracle.set_num_threads(os.cpu_count() or 1)
     prm = oracle.make_params(max_iterations=a.iters, max_dist=a.max_dist, reciprocal=bool(a.reciprocal), fixed_iterations=True)
     t0 = time.perf_counter()
     q = 0

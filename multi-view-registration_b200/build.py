@@ -57,7 +57,8 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-shared", "-o", LIB, "-x", "cu"] + sources()
+    extra = os.environ.get("MVR_NVCC_DEFS", "").split()   # development: e.g. MVR_NVCC_DEFS="-DMVR_BS_THREADS=64"
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-shared", "-o", LIB, "-x", "cu"] + sources()
     if verbose:
         cmd += ["-Xptxas", "-v"]
         print(" ".join(cmd))

@@ -29,8 +29,17 @@
 
 namespace mvr {
 
-constexpr int BS_THREADS = 256;
-constexpr int BS_CAP = 2048;   // staged candidate points per brick (32 KB)
+#ifndef MVR_BS_THREADS
+#define MVR_BS_THREADS 128
+#endif
+#ifndef MVR_BS_CAP
+#define MVR_BS_CAP 1536
+#endif
+#ifndef MVR_BS_CTAS_PER_SM
+#define MVR_BS_CTAS_PER_SM 7
+#endif
+constexpr int BS_THREADS = MVR_BS_THREADS;   // a brick holds ~100 queries: 4 warps keep the lanes busy, more CTAs per SM hide its barriers
+constexpr int BS_CAP = MVR_BS_CAP;           // staged candidate points per brick (16 B each); bigger regions fall back to global memory
 constexpr int BS_RUNS = 64;    // 4 x 4 x 4 sub-bricks of 2 x 2 x 2 cells
 constexpr int BS_REGION = 8;   // staged region edge, cells
 constexpr int BS_HALO = 2;     // cells around the brick
@@ -98,6 +107,16 @@ __device__ __forceinline__ bool range_nonempty(uint32_t w) { return ((w ^ (w >> 
 // Per-axis parts of a cell's index into LocalIx::cell (they add up to run * 8 + inner).
 __device__ __forceinline__ int cell_part(int l, int axis) { return ((l >> 1) << (3 + 2 * axis)) + ((l & 1) << axis); }
 
+__device__ __forceinline__ void fold(const float4 p, int pos, float qx, float qy, float qz, NnBest& b) {
+  const float d2 = d2_pinned(qx, qy, qz, p.x, p.y, p.z);
+  const int id = __float_as_int(p.w);
+  if (lex_less(d2, id, b.d2, b.idx)) { b.d2 = d2; b.idx = id; b.pos = pos; }
+}
+
+// One loop over all points of the listed ranges, four points per trip: the four shared-memory loads and
+// distance evaluations are independent, which is what hides their latency (a warp has few peers to
+// overlap with).  Slots past the end of a range are clamped to its last point -- folding a point twice
+// changes nothing, the comparison is strict.
 __device__ __forceinline__ void flat_scan(const LocalIx& L, int cnt, float qx, float qy, float qz, NnBest& b) {
   int li = 0, dk = 0;
   uint32_t k = 0, e = 0;
@@ -106,13 +125,16 @@ __device__ __forceinline__ void flat_scan(const LocalIx& L, int cnt, float qx, f
       if (li >= cnt) break;
       const uint32_t w = L.list[li * BS_THREADS];
       ++li;
-      k = w & 0xfffu; e = (w >> 12) & 0xfffu; dk = L.delta[w >> 24];
+      k = w & 0xfffu; e = (w >> 12) & 0xfffu; dk = L.delta[w >> 24];   // BS_CAP <= 2048 keeps slots in 12 bits
     }
-    const float4 p = L.pts[k];
-    const float d2 = d2_pinned(qx, qy, qz, p.x, p.y, p.z);
-    const int id = __float_as_int(p.w);
-    if (lex_less(d2, id, b.d2, b.idx)) { b.d2 = d2; b.idx = id; b.pos = (int)k + dk; }
-    ++k;
+    const uint32_t last = e - 1u;
+    const uint32_t k1 = min(k + 1u, last), k2 = min(k + 2u, last), k3 = min(k + 3u, last);
+    const float4 p0 = L.pts[k], p1 = L.pts[k1], p2 = L.pts[k2], p3 = L.pts[k3];
+    fold(p0, (int)k + dk, qx, qy, qz, b);
+    fold(p1, (int)k1 + dk, qx, qy, qz, b);
+    fold(p2, (int)k2 + dk, qx, qy, qz, b);
+    fold(p3, (int)k3 + dk, qx, qy, qz, b);
+    k += 4u;
   }
 }
 
@@ -384,7 +406,7 @@ cudaError_t launch_list_bricks(const uint32_t* start, int bits, int shift, uint3
 
 static int brick_grid(int n_queries) {
   // persistent CTAs: enough to fill the machine, no more than there can be bricks with work
-  const int want = 148 * 6;
+  const int want = 148 * MVR_BS_CTAS_PER_SM;
   return std::max(1, std::min(want, (n_queries + 15) / 16));
 }
 

@@ -242,8 +242,18 @@ int ringClose(const std::vector<Matrix4d>& rel_in, const std::vector<double>& we
           }
       }
     }
-    for (int i = 0; i < n; ++i) { H[(size_t)i * n + i] += 1e-12; g[(size_t)i] = -g[(size_t)i]; }
-    if (!chol_solve(H, g, n)) return MVR_ERR_NOT_SPD;
+    // Levenberg damping, raised only if the plain system is not numerically positive definite (edges dropped for
+    // lack of correspondences can leave a vertex without information: it then simply keeps its pose).
+    double dmax = 0;
+    for (int i = 0; i < n; ++i) { dmax = std::fmax(dmax, H[(size_t)i * n + i]); g[(size_t)i] = -g[(size_t)i]; }
+    if (!(dmax > 0) || !std::isfinite(dmax)) break;
+    bool solved = false;
+    for (double lambda = 1e-12 * dmax; lambda <= 1e3 * dmax; lambda *= 1e3) {
+      std::vector<double> Hd(H), gd(g);
+      for (int i = 0; i < n; ++i) Hd[(size_t)i * n + i] += lambda;
+      if (chol_solve(Hd, gd, n)) { g.swap(gd); solved = true; break; }
+    }
+    if (!solved) return MVR_ERR_NOT_SPD;
     double step = 0;
     for (int v = 1; v < V; ++v) {
       Vec6 d;

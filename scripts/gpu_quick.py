@@ -21,17 +21,10 @@ for recip in (1, 0):
     print("   serial solve: %.0f cycles/iteration (%d solves)" % (ctx.debug_value(0) / max(ctx.debug_value(1), 1), ctx.debug_value(1)))
     for k, v in st.items():
         if v["launches"]: print("   %-10s launches %4d  total %.3f ms  avg %.1f us  GB/s(alg) %.1f" % (k, v["launches"], v["ms"], 1e3*v["ms"]/v["launches"], v["bytes"]/max(v["ms"],1e-9)/1e6))
-for cell in (1.0, 1.5, 2.0, 3.0):
-    ctx.set_index_options(cell, 9)
-    p = mvr_b200.default_params(max_iterations=30, max_dist=4.0, reciprocal=1, fixed_iterations=1)
-    for rep in range(2):
-        ctx.kernel_stats(reset=True); r = ctx.icp_align(p, guess=guess, n_source=n); st = ctx.kernel_stats(reset=True)
-    print("cell %.1f: gpu %.2f ms  corr %.1f us  table %.1f us  sort %.1f us  ncorr %d" % (cell, r["gpu_ms"], 1e3*st["corr"]["ms"]/30, 1e3*st["table"]["ms"]/30, 1e3*st["sort"]["ms"]/30, r["n_corr"]))
-ctx.set_index_options(0.0, 8)
 t0 = time.time(); f = ctx.fitness_score(); print("fitness %.4f in %.2f ms" % (f, (time.time()-t0)*1e3))
 # NN sweep
 import torch
-for m, nq in ((1_000_000, 1_000_000), (1_000_000, 16_000_000)):
+for m, nq in ((1_000_000, 16_000_000),):
     tgt, q = synth.nn_sweep_case(m, nq, order="random")
     for order in ("random", "morton"):
         if order == "morton":

@@ -34,7 +34,7 @@ for k in range(n):
     a[0] += int(rows[k][i_i]); a[1] += int(rows[k][i_t]); a[2] += int(rows[k][i_s])
 ti = sum(a[0] for a in agg.values()); ts = sum(a[2] for a in agg.values())
 src = {}
-for (f, l), a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+for (f, l), a in sorted(agg.items(), key=lambda kv: -kv[1][2 if os.environ.get("BY_SAMPLES") else 0])[:top]:
     if f not in src:
         for d in ('multi-view-registration_b200/csrc', '.'):
             pth = os.path.join(d, f)
