@@ -164,6 +164,21 @@ int mvr_icp_get_iterations(mvr_ctx* ctx, mvr_icp_iteration* out, int max_records
  * un-gated NN distance of the last align's output cloud (or of the source if no align ran). */
 int mvr_fitness_score(mvr_ctx* ctx, double max_range, double* score);
 
+/* -- edge statistics of the LUM relaxation: what pcl::registration::LUM::computeEdge derives from the
+ *    correspondences the reference hands it (lum.setCorrespondences, mvr/src/registrator.cpp:640-651).
+ *    One correspondence pass source -> target (guess applied to the source first), gate d2 <= max_dist^2,
+ *    reciprocal or not; over the kept pairs (a = posed source point, b = target point), about `origin`:
+ *    every quantity a rigid least-squares cost  sum |X_a a - X_b b|^2  needs, for ANY rigid X_a, X_b. */
+typedef struct {
+  double n;               /* number of correspondences (0: the edge carries no information) */
+  double origin[3];       /* the sums below are over a - origin, b - origin (target frame) */
+  double sa[3], sb[3];    /* sum a, sum b */
+  double sba[9];          /* sum b a^T, row-major (row = component of b) */
+  double saa[6], sbb[6];  /* sum a a^T, sum b b^T: xx xy xz yy yz zz */
+  double d2;              /* sum of the float32 squared distances */
+} mvr_pair_moments;
+int mvr_pair_moments_compute(mvr_ctx* ctx, double max_dist, int reciprocal, const float* guess, mvr_pair_moments* out);
+
 /* -- extensions named by the north star (no reference call site) -------------------------------- */
 /* pcl::NormalEstimation semantics: kNN(k) PCA normals of a cloud, flipped towards viewpoint.
  * out: n x {nx, ny, nz, curvature}.  neighbours (nullable): n x k int32, ascending (d2, index). */
@@ -256,6 +271,16 @@ int mvr_register_turntable(mvr_registrator* r, const mvr_view* views, int n_view
  * object.  Output V absolute poses, view 0 = identity. */
 int mvr_ring_close(const float* rel_poses, const double* weights, int n_views, int relax, int iterations, const double* centre,
                    double rot_scale, float* poses);
+/* pcl::registration::LUM::compute() for a pose graph whose edges are mvr_pair_moments in ONE common (world)
+ * frame: minimises  sum_edges sum_k |X_s a_k - X_t b_k|^2  over rigid corrections X_v, X_0 = identity, by
+ * `iterations` Gauss-Newton sweeps (LUM: setMaxIterations(16), mvr/src/registrator.cpp:630) of the dense
+ * 6 (V - 1) normal equations.  edges[e] joins views src[e] -> tgt[e]; its sums must already be expressed
+ * in the world frame (mvr_pair_moments_transform).  poses: V x double[16] column-major corrections. */
+int mvr_lum_relax(const mvr_pair_moments* edges, const int* src, const int* tgt, int n_edges, int n_views, int iterations,
+                  double* poses);
+/* Re-express moments under the rigid map p -> pose * p (double[16] column-major); the new origin is
+ * new_origin (nullable: keep pose * old origin). */
+void mvr_pair_moments_transform(const mvr_pair_moments* in, const double* pose, const double* new_origin, mvr_pair_moments* out);
 /* Bounding box of the finite points of a cloud given to the context. */
 int mvr_get_bbox(mvr_ctx* ctx, int which, float lo[3], float hi[3]);
 /* Registrator::refineAxis (mvr/src/registrator.cpp:402-455): least-squares turntable axis from registered

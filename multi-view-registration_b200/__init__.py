@@ -79,6 +79,35 @@ class TurntableParams(C.Structure):
     ]
 
 
+class PairMoments(C.Structure):
+    """mvr_pair_moments: first and second moments of one edge's correspondence pairs (a = source, b = target)."""
+    _fields_ = [("n", C.c_double), ("origin", C.c_double * 3), ("sa", C.c_double * 3), ("sb", C.c_double * 3),
+                ("sba", C.c_double * 9), ("saa", C.c_double * 6), ("sbb", C.c_double * 6), ("d2", C.c_double)]
+
+    @classmethod
+    def from_pairs(cls, a, b, origin=None):
+        """Moments of explicit pairs (n x 3 arrays), numpy double: what the GPU reduction returns for them."""
+        a = np.asarray(a, dtype=np.float64).reshape(-1, 3)
+        b = np.asarray(b, dtype=np.float64).reshape(-1, 3)
+        o = np.zeros(3) if origin is None else np.asarray(origin, dtype=np.float64)
+        m = cls()
+        m.n = float(len(a))
+        m.origin[:] = o.tolist()
+        if len(a):
+            x, y = a - o, b - o
+            m.sa[:] = x.sum(0).tolist(); m.sb[:] = y.sum(0).tolist()
+            m.sba[:] = (y.T @ x).reshape(9).tolist()
+            xx, yy = x.T @ x, y.T @ y
+            m.saa[:] = [xx[0, 0], xx[0, 1], xx[0, 2], xx[1, 1], xx[1, 2], xx[2, 2]]
+            m.sbb[:] = [yy[0, 0], yy[0, 1], yy[0, 2], yy[1, 1], yy[1, 2], yy[2, 2]]
+            m.d2 = float(((a - b) ** 2).sum())
+        return m
+
+    def as_dict(self):
+        return dict(n=self.n, origin=np.array(self.origin[:]), sa=np.array(self.sa[:]), sb=np.array(self.sb[:]),
+                    sba=np.array(self.sba[:]).reshape(3, 3), saa=np.array(self.saa[:]), sbb=np.array(self.sbb[:]), d2=self.d2)
+
+
 class ViewDesc(C.Structure):
     _fields_ = [("xyzw", C.c_void_p), ("n", C.c_size_t), ("on_device", C.c_int), ("init_pose", C.POINTER(C.c_double))]
 
@@ -160,6 +189,10 @@ def lib():
     L.mvr_ring_close.argtypes = [fp, dp, C.c_int, C.c_int, C.c_int, dp, C.c_double, fp]
     L.mvr_get_bbox.argtypes = [vp, C.c_int, fp, fp]
     L.mvr_refine_axis.argtypes = [fp, C.c_int, dp, dp]
+    L.mvr_pair_moments_compute.argtypes = [vp, C.c_double, C.c_int, fp, C.POINTER(PairMoments)]
+    L.mvr_lum_relax.argtypes = [C.POINTER(PairMoments), ip, ip, C.c_int, C.c_int, C.c_int, dp]
+    L.mvr_pair_moments_transform.argtypes = [C.POINTER(PairMoments), dp, dp, C.POINTER(PairMoments)]
+    L.mvr_pair_moments_transform.restype = None
     _lib = L
     return L
 
@@ -345,6 +378,13 @@ class Context:
                     reason=rep.reason, n_corr=rep.n_correspondences, mse=rep.mse, gpu_ms=rep.gpu_ms,
                     nn_queries=int(rep.nn_queries), log=log)
 
+    def pair_moments(self, max_dist, reciprocal=True, guess=None):
+        """Moments of the (reciprocal) correspondences source -> target under `guess` (target frame)."""
+        g = pose_from_numpy(guess) if guess is not None else None
+        m = PairMoments()
+        self._ck(lib().mvr_pair_moments_compute(self._h, float(max_dist), int(bool(reciprocal)), _fp(g) if g is not None else None, C.byref(m)))
+        return m
+
     def fitness_score(self, max_range=None):
         import sys
         s = C.c_double(0)
@@ -411,6 +451,28 @@ def ring_close(rel_poses, weights=None, relax=True, iterations=16, centre=None, 
     if rc != OK:
         raise MvrError(rc, lib().mvr_status_string(rc).decode())
     return [pose_to_numpy(out[k]) for k in range(V)]
+
+
+def pair_moments_transform(m, pose, new_origin=None):
+    """Moments of the pairs after the rigid map p -> pose * p (4x4), about new_origin (default pose * origin)."""
+    P = np.ascontiguousarray(np.asarray(pose, dtype=np.float64).T).reshape(16)
+    o = None if new_origin is None else np.ascontiguousarray(new_origin, dtype=np.float64)
+    out = PairMoments()
+    lib().mvr_pair_moments_transform(C.byref(m), _dp(P), _dp(o) if o is not None else None, C.byref(out))
+    return out
+
+
+def lum_relax(edges, src, tgt, n_views, iterations=16):
+    """pcl::registration::LUM::compute on correspondence moments (world frame): V rigid corrections, X[0] = I (float64)."""
+    E = len(edges)
+    arr = (PairMoments * max(E, 1))(*edges)
+    s = np.ascontiguousarray(src, dtype=np.int32)
+    t = np.ascontiguousarray(tgt, dtype=np.int32)
+    out = np.empty((max(n_views, 1), 16), dtype=np.float64)
+    rc = lib().mvr_lum_relax(arr, _ip(s), _ip(t), E, int(n_views), int(iterations), _dp(out))
+    if rc != OK:
+        raise MvrError(rc, lib().mvr_status_string(rc).decode())
+    return [out[k].reshape(4, 4).T.copy() for k in range(n_views)]
 
 
 def refine_axis(poses, pivot, axis):

@@ -80,6 +80,17 @@ struct Cloud {
 
 struct ProfRec { int kind; cudaEvent_t a, b; double bytes, units; };
 
+// Per-align row-major index of one cloud (pair_index.cu).
+struct PairIndex {
+  DevBuf sorted, start, s0;   // points by cell (the source's move in place), cell table, source binning-time copy
+  PairGrid g{};
+  uint32_t cells = 0;
+  int n_valid = 0;
+  uint64_t gen = 0;
+  bool valid = false;
+  void release() { sorted.release(); start.release(); s0.release(); valid = false; }
+};
+
 }  // namespace
 
 struct mvr_ctx {
@@ -89,6 +100,8 @@ struct mvr_ctx {
   Cloud tgt, src, qry;          // qry: scratch cloud used to present queries in cell order
   DevBuf normals; bool has_normals = false;
   DevBuf cur, corr_p, corr_j, corr_d2, rmin, rnn, partials, sums, out_cloud, qtmp, itmp, ftmp, scratch, misc, tiles, state, log;
+  PairIndex pt, ps;              // target / source index of the running align
+  DevBuf pkeys, pvals, pkeys_alt, pvals_alt, phist, pmoved;
   uint32_t scan_epoch = 1;
   IcpState* h_state = nullptr;   // pinned staging copy of the device IcpState
   IterRec* h_log = nullptr;      // pinned, ICP_MAX_LOG records
@@ -414,6 +427,77 @@ mvr_grid pair_grid(mvr_ctx* ctx, const float* G, double max_dist) {
   return make_grid(l, h, e, std::min(ctx->max_bits_opt, cap));
 }
 
+// ---- per-align row-major index (pair_index.cu) ---------------------------------------------------
+// Cell edge of a cloud's pair grid: gate / 2 when the point density allows (a settled alignment then
+// looks at 1-2 cells per axis), otherwise bounded to 2 .. 12 points per occupied cell.
+double pair_cell_edge(mvr_ctx* ctx, const Cloud& c, double max_dist) {
+  if (ctx->cell_edge_opt > 0) return ctx->cell_edge_opt;
+  const int nv = c.n - c.n_bad;
+  const double e_lo = density_cell_edge(c.lo, c.hi, nv, 2.0), e_hi = density_cell_edge(c.lo, c.hi, nv, 12.0);
+  const double m2 = max_dist * max_dist;
+  return (m2 < 1e30) ? std::min(std::max(0.5 * max_dist * 1.002, e_lo), e_hi) : density_cell_edge(c.lo, c.hi, nv, 6.0);
+}
+
+// Grid over the box [lo, hi] padded by one cell; the edge grows until the table fits max_cells.
+PairGrid make_pair_grid(const float lo[3], const float hi[3], double e, uint32_t* cells_out) {
+  const double max_cells = 16.0 * 1024 * 1024;
+  double ext[3];
+  for (int a = 0; a < 3; ++a) {
+    ext[a] = (double)hi[a] - (double)lo[a];
+    if (!(ext[a] >= 0) || !std::isfinite(ext[a])) ext[a] = 0;
+  }
+  if (!(e > 0) || !std::isfinite(e)) e = std::max(1e-3, std::max(ext[0], std::max(ext[1], ext[2])));
+  int n[3];
+  for (;;) {
+    double tot = 1;
+    for (int a = 0; a < 3; ++a) { n[a] = (int)std::min(4096.0, std::floor(ext[a] / e) + 3.0); tot *= n[a]; }
+    if (tot <= max_cells) break;
+    e *= 1.25;
+  }
+  PairGrid g;
+  g.ox = lo[0] - (float)e; g.oy = lo[1] - (float)e; g.oz = lo[2] - (float)e;
+  if (!std::isfinite(g.ox)) g.ox = 0.f;
+  if (!std::isfinite(g.oy)) g.oy = 0.f;
+  if (!std::isfinite(g.oz)) g.oz = 0.f;
+  g.inv_cell = (float)(1.0 / e);
+  g.cell_lo = std::nextafterf((float)((1.0 / (double)g.inv_cell) * (1.0 - 1e-6)), 0.0f);
+  g.nx = n[0]; g.ny = n[1]; g.nz = n[2];
+  *cells_out = (uint32_t)n[0] * (uint32_t)n[1] * (uint32_t)n[2];
+  return g;
+}
+
+bool same_pair_grid(const PairGrid& a, const PairGrid& b) { return std::memcmp(&a, &b, sizeof(PairGrid)) == 0; }
+
+// Index `n` points (n_bad of them non-finite) in grid g; guess (nullable) is applied first (pinned float
+// transform); keep_s0: also keep a copy of the sorted binning-time coordinates.
+int build_pair_index(mvr_ctx* ctx, PairIndex& ix, const float4* pts, int n, int n_bad, const Mat4f* guess, const PairGrid& g,
+                     uint32_t cells, bool keep_s0) {
+  const size_t nn = (size_t)std::max(n, 1);
+  CK(ctx->pkeys.ensure(nn * sizeof(uint32_t)));
+  CK(ctx->pvals.ensure(nn * sizeof(uint32_t)));
+  CK(ctx->pkeys_alt.ensure(nn * sizeof(uint32_t)));
+  CK(ctx->pvals_alt.ensure(nn * sizeof(uint32_t)));
+  CK(ctx->phist.ensure((size_t)256 * radix_num_blocks(n) * sizeof(uint32_t)));
+  if (guess) CK(ctx->pmoved.ensure(nn * sizeof(float4)));
+  CK(ix.sorted.ensure(nn * sizeof(float4)));
+  CK(ix.start.ensure(((size_t)cells + 2) * sizeof(uint32_t)));
+  if (keep_s0) CK(ix.s0.ensure(nn * sizeof(float4)));
+  ix.valid = false;
+  ProfScope ps(ctx, MVR_K_SORT, (keep_s0 ? 48.0 : 32.0) * n + 4.0 * cells, n);
+  CK(launch_pair_keys(pts, n, guess, g, cells, guess ? ctx->pmoved.as<float4>() : nullptr, ctx->pkeys.as<uint32_t>(),
+                      ctx->pvals.as<uint32_t>(), ctx->stream));
+  int key_bits = 1;
+  while (((uint64_t)1 << key_bits) <= (uint64_t)cells) ++key_bits;   // the sentinel key `cells` must sort last
+  SortScratch sc{ctx->pkeys_alt.as<uint32_t>(), ctx->pvals_alt.as<uint32_t>(), ctx->phist.as<uint32_t>()};
+  uint32_t *sk = nullptr, *perm = nullptr;
+  CK(launch_radix_sort(ctx->pkeys.as<uint32_t>(), ctx->pvals.as<uint32_t>(), n, key_bits, sc, &sk, &perm, ctx->stream));
+  CK(launch_pair_gather(guess ? ctx->pmoved.as<float4>() : pts, perm, n, ix.sorted.as<float4>(), keep_s0 ? ix.s0.as<float4>() : nullptr,
+                        ctx->stream));
+  CK(launch_cell_table_n(sk, n, cells, ix.start.as<uint32_t>(), ctx->stream));
+  ix.g = g; ix.cells = cells; ix.n_valid = n - n_bad; ix.valid = true;
+  return MVR_OK;
+}
+
 int ensure_pinned(mvr_ctx* ctx) {
   if (!ctx->h_sums) CK(cudaMallocHost((void**)&ctx->h_sums, REDUCE_MAX_VALS * sizeof(double)));
   if (!ctx->h_small) CK(cudaMallocHost((void**)&ctx->h_small, 64 * sizeof(uint32_t)));
@@ -525,6 +609,8 @@ int mvr_ctx_destroy(mvr_ctx* ctx) {
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   ctx->tgt.release(); ctx->src.release(); ctx->qry.release(); ctx->normals.release();
+  ctx->pt.release(); ctx->ps.release();
+  ctx->pkeys.release(); ctx->pvals.release(); ctx->pkeys_alt.release(); ctx->pvals_alt.release(); ctx->phist.release(); ctx->pmoved.release();
   DevBuf* bufs[] = {&ctx->cur, &ctx->corr_p, &ctx->rmin, &ctx->rnn, &ctx->corr_j, &ctx->corr_d2, &ctx->partials, &ctx->sums, &ctx->out_cloud, &ctx->qtmp,
                     &ctx->itmp, &ctx->ftmp, &ctx->scratch, &ctx->misc, &ctx->tiles, &ctx->state, &ctx->log};
   for (DevBuf* b : bufs) b->release();
@@ -723,8 +809,10 @@ int mvr_correspondences(mvr_ctx* ctx, double max_dist, int reciprocal, int32_t* 
   return MVR_OK;
 }
 
-int mvr_icp_align(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, float* out_pose, float* out_xyzw,
-                  mvr_icp_report* report) {
+// The align behind mvr_icp_align and mvr_pair_moments_compute.  est = EST_MOM accumulates second moments
+// next to the point-to-point sums; they are those of the LAST iteration's correspondence set.
+static int icp_align_impl(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, float* out_pose, float* out_xyzw,
+                          mvr_icp_report* report, bool moments) {
   if (!ctx || !prm) return MVR_ERR_BAD_ARG;
   cudaSetDevice(ctx->device);
   if (ctx->tgt.gen == 0 || ctx->src.gen == 0) return fail(ctx, MVR_ERR_NO_INPUT, "source/target not set");
@@ -739,25 +827,61 @@ int mvr_icp_align(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, f
   const bool reciprocal = prm->use_reciprocal_correspondences != 0;
   const double max_dist = prm->max_correspondence_distance;
   const bool p2l = prm->estimator == MVR_POINT_TO_PLANE;
+  if (moments && p2l) return fail(ctx, MVR_ERR_BAD_ARG, "pair moments are point-to-point statistics");
+  const int est = p2l ? EST_P2L : (moments ? EST_MOM : EST_P2P);
 
-  const mvr_grid gp = pair_grid(ctx, G, max_dist);
-  int rc = prepare_pair(ctx, gp, reciprocal);
-  if (rc) return rc;
-  CK(ctx->cur.ensure((size_t)n * sizeof(float4)));
-  CK(ctx->partials.ensure((size_t)REDUCE_BLOCKS * REDUCE_MAX_VALS * sizeof(double)));
+  // ---- per-align indices: target over its own box (reused while the target and the grid stay the same),
+  //      source over the box of the guessed source
+  const int m = ctx->tgt.n;
+  int rc = MVR_OK;
+  {
+    uint32_t cells = 0;
+    const PairGrid gt = make_pair_grid(ctx->tgt.lo, ctx->tgt.hi, pair_cell_edge(ctx, ctx->tgt, max_dist), &cells);
+    PairIndex& pt = ctx->pt;
+    if (!(pt.valid && pt.gen == ctx->tgt.gen && same_pair_grid(pt.g, gt))) {
+      if ((rc = build_pair_index(ctx, pt, ctx->tgt.pts, m, ctx->tgt.n_bad, nullptr, gt, cells, false))) return rc;
+      pt.gen = ctx->tgt.gen;
+    }
+  }
+  {
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (s.n - s.n_bad > 0) {
+      for (int corner = 0; corner < 8; ++corner) {
+        const double p[3] = {(corner & 1) ? s.hi[0] : s.lo[0], (corner & 2) ? s.hi[1] : s.lo[1], (corner & 4) ? s.hi[2] : s.lo[2]};
+        for (int a = 0; a < 3; ++a) {
+          const double v = G[a] * p[0] + G[4 + a] * p[1] + G[8 + a] * p[2] + G[12 + a];
+          if (std::isfinite(v)) { lo[a] = std::min(lo[a], (float)v); hi[a] = std::max(hi[a], (float)v); }
+        }
+      }
+    }
+    for (int a = 0; a < 3; ++a) if (!(lo[a] <= hi[a])) { lo[a] = 0.f; hi[a] = 0.f; }
+    uint32_t cells = 0;
+    // the cell edge follows the source's own density (its box as given: a rigid guess keeps the surface area)
+    const PairGrid gs = make_pair_grid(lo, hi, pair_cell_edge(ctx, s, max_dist), &cells);
+    Mat4f Gm;
+    std::memcpy(Gm.m, G, sizeof(Gm.m));
+    if ((rc = build_pair_index(ctx, ctx->ps, s.pts, n, s.n_bad, &Gm, gs, cells, reciprocal))) return rc;
+  }
+  const PairIndex &pt = ctx->pt, &psx = ctx->ps;
+  CK(ctx->corr_p.ensure((size_t)std::max(n, 1) * sizeof(int32_t)));
+  CK(cudaMemsetAsync(ctx->corr_p.p, 0xff, (size_t)std::max(n, 1) * sizeof(int32_t), ctx->stream));   // -1: no seed yet
+  if (reciprocal) {
+    CK(ctx->rmin.ensure((size_t)std::max(m, 1) * sizeof(uint32_t)));
+    CK(launch_fill_u32(ctx->rmin.as<uint32_t>(), (size_t)std::max(m, 1), 0x7f800000u, ctx->stream));   // +inf: "chosen by nobody"
+  }
+  CK(ctx->partials.ensure((size_t)FUSED_BLOCKS * REDUCE_MAX_VALS * sizeof(double)));
   CK(ctx->out_cloud.ensure((size_t)n * sizeof(float4)));
   CK(ctx->state.ensure(sizeof(IcpState)));
   CK(ctx->log.ensure((size_t)ICP_MAX_LOG * sizeof(IterRec)));
-  float4* cur = ctx->cur.as<float4>();
   IcpState* d_st = ctx->state.as<IcpState>();
   IterRec* d_log = ctx->log.as<IterRec>();
-  const float* d_delta = (const float*)((const char*)d_st + offsetof(IcpState, delta));
-  const int* d_done = (const int*)((const char*)d_st + offsetof(IcpState, done));
 
-  // initial state: the guess is the first "delta" (ICP transforms the input by the guess, then iterates)
+  // initial state: the guess has been applied while binning the source; it is the start of `fin`
   IcpState& h = *ctx->h_state;
   std::memset(&h, 0, sizeof(h));
-  for (int k = 0; k < 16; ++k) { h.delta[k] = G[k]; h.fin[k] = G[k]; }
+  for (int k = 0; k < 16; ++k) { h.delta[k] = (k % 5 == 0) ? 1.f : 0.f; h.fin[k] = G[k]; h.cum[k] = (k % 5 == 0) ? 1.0 : 0.0; }
+  for (int k = 0; k < 12; ++k) h.cinv[k] = (k % 5 == 0) ? 1.0 : 0.0;
+  h.stretch = 1.0f;
   h.prev_mse = DBL_MAX;
   h.rot_thr = 1.0 - prm->transformation_epsilon;
   h.trans_thr = prm->transformation_epsilon;
@@ -774,9 +898,19 @@ int mvr_icp_align(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, f
 
   CK(cudaEventRecord(ctx->ev_a, ctx->stream));
   CK(cudaMemcpyAsync(d_st, &h, sizeof(IcpState), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(cur, s.pts, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
   ctx->iters.clear();
   ctx->have_out = false;
+
+  FwdArgs fa{};
+  fa.cur = psx.sorted.as<float4>(); fa.s0 = reciprocal ? psx.s0.as<float4>() : nullptr; fa.n_valid = psx.n_valid;
+  fa.tgt = pt.sorted.as<float4>(); fa.tstart = pt.start.as<uint32_t>(); fa.gt = pt.g; fa.m_valid = pt.n_valid;
+  fa.corr_p = ctx->corr_p.as<int32_t>(); fa.rmin = reciprocal ? ctx->rmin.as<uint32_t>() : nullptr;
+  fa.max2 = max_dist * max_dist; fa.max_d2f = gate_float(max_dist);
+  fa.nrm = p2l ? ctx->normals.as<float4>() : nullptr;
+  fa.partials = ctx->partials.as<double>(); fa.st = d_st; fa.log = d_log; fa.first = 1;
+  RevArgs ra{};
+  ra.tgt = fa.tgt; ra.m_valid = pt.n_valid; ra.rmin = fa.rmin; ra.cur = fa.cur; ra.sstart = psx.start.as<uint32_t>(); ra.gs = psx.g;
+  ra.n_valid = psx.n_valid; ra.corr_p = fa.corr_p; ra.nrm = fa.nrm; ra.partials = fa.partials; ra.st = d_st; ra.log = d_log;
 
   // Enqueue iterations in batches; after each batch read the state back.  Once the device raises
   // `done` the remaining launches of a batch return immediately.
@@ -786,12 +920,11 @@ int mvr_icp_align(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, f
   while (!done) {
     int todo = std::min(batch, std::max(prm->max_iterations - enqueued, 1));
     for (int it = 0; it < todo; ++it) {
-      rc = correspond_pass(ctx, cur, gp, reciprocal, max_dist, d_delta, d_done);
-      if (rc) return rc;
-      ProfScope ps(ctx, MVR_K_REDUCE, 36.0 * n, n);
-      CK(launch_reduce_solve(cur, n, ctx->corr_p.as<int32_t>(), ctx->corr_d2.as<float>(),
-                             reciprocal ? ctx->rnn.as<int32_t>() : nullptr, ctx->tgt.sorted.as<float4>(),
-                             p2l ? ctx->normals.as<float4>() : nullptr, ctx->partials.as<double>(), d_st, d_log, p2l, ctx->stream));
+      // one scope = one iteration: forward search (+ transform), reciprocal search (+ sums, solve, criteria)
+      ProfScope ps(ctx, MVR_K_CORR, corr_bytes(n, m, reciprocal), (double)n);
+      CK(launch_icp_forward(fa, reciprocal, est, ctx->stream));
+      fa.first = 0;
+      if (reciprocal) CK(launch_icp_reverse(ra, est, ctx->stream));
     }
     enqueued += todo;
     CK(cudaMemcpyAsync(&h, d_st, sizeof(IcpState), cudaMemcpyDeviceToHost, ctx->stream));
@@ -799,6 +932,7 @@ int mvr_icp_align(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, f
     done = h.done != 0;
     batch = std::min(batch * 2, 64);
   }
+  if (h.dbg[2] != 0) return fail(ctx, MVR_ERR_CUDA, "internal error: a reciprocal search lost its chooser (search bound violated)");
   {
     ProfScope ps(ctx, MVR_K_TRANSFORM, 32.0 * n, n);
     CK(launch_transform_final(s.pts, ctx->out_cloud.as<float4>(), n, d_st, ctx->stream));
@@ -825,6 +959,35 @@ int mvr_icp_align(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, f
   if (h.status == MVR_ERR_TOO_FEW_CORRESPONDENCES) ctx->err = "not enough correspondences";
   if (h.status == MVR_ERR_NOT_SPD) ctx->err = "point-to-plane normal equations not positive definite";
   return h.status;
+}
+
+int mvr_icp_align(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, float* out_pose, float* out_xyzw,
+                  mvr_icp_report* report) {
+  return icp_align_impl(ctx, prm, guess, out_pose, out_xyzw, report, false);
+}
+
+int mvr_pair_moments_compute(mvr_ctx* ctx, double max_dist, int reciprocal, const float* guess, mvr_pair_moments* out) {
+  if (!ctx || !out) return MVR_ERR_BAD_ARG;
+  std::memset(out, 0, sizeof(*out));
+  mvr_icp_params one;
+  mvr_icp_params_default(&one);
+  one.max_iterations = 1; one.fixed_iterations = 1;
+  one.use_reciprocal_correspondences = reciprocal ? 1 : 0;
+  one.max_correspondence_distance = max_dist;
+  one.min_correspondences = 1;
+  mvr_icp_report rep{};
+  const int rc = icp_align_impl(ctx, &one, guess, nullptr, nullptr, &rep, true);
+  if (rc != MVR_OK && rc != MVR_ERR_TOO_FEW_CORRESPONDENCES) return rc;
+  const IcpState& h = *ctx->h_state;
+  out->origin[0] = h.ox; out->origin[1] = h.oy; out->origin[2] = h.oz;
+  if (rc == MVR_OK) {
+    out->n = h.sums[0];
+    for (int k = 0; k < 3; ++k) { out->sa[k] = h.sums[1 + k]; out->sb[k] = h.sums[4 + k]; }
+    for (int k = 0; k < 9; ++k) out->sba[k] = h.sums[7 + k];
+    out->d2 = h.sums[16];
+    for (int k = 0; k < 6; ++k) { out->saa[k] = h.sums[17 + k]; out->sbb[k] = h.sums[23 + k]; }
+  }
+  return MVR_OK;
 }
 
 double mvr_debug_value(mvr_ctx* ctx, int k) {

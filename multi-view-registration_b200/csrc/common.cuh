@@ -37,6 +37,15 @@ struct QueryDev {
   int shift;
 };
 
+// Row-major uniform grid of the per-align index (pair_index.cu): nx x ny x nz cells, x fastest,
+// cell_a = clamp(floor((p_a - o_a) * inv_cell), 0, n_a - 1).
+struct PairGrid {
+  float ox, oy, oz;
+  float inv_cell;
+  float cell_lo;   // a float strictly below the true cell edge
+  int nx, ny, nz;
+};
+
 struct Mat4f { float m[16]; };  // column-major
 
 #define MVR_INF __int_as_float(0x7f800000)

@@ -9,6 +9,7 @@
 // The whole loop state lives in an IcpState on the device, so an align needs no host round trip per
 // iteration: the host only enqueues iterations and reads the state back when a batch has run.
 #include "launch.h"
+#include "pair_search.cuh"
 #include "small_solve.h"
 
 namespace mvr {
@@ -78,6 +79,54 @@ __device__ __forceinline__ void ordered_total(const double* __restrict__ partial
   __syncthreads();
 }
 
+// The source index is kept in the frame the source was binned in (pair_index.cu).  cum = the increments
+// applied since then (including the one the next iteration will apply), cinv its affine inverse, stretch
+// an upper bound of ||A^-1||_2 for its linear part A (1 for an exact rotation; float-rounded rotations
+// drift by ~1e-7 per iteration).  With eta = ||A^T A - I||_F: lambda_min(A^T A) >= 1 - eta.
+__device__ __forceinline__ void icp_advance_frame(IcpState* st, const double (&Td)[16]) {
+  double C0[16], C[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) C0[k] = st->cum[k];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      double x = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x += Td[k * 4 + r] * C0[c * 4 + k];
+      C[c * 4 + r] = x;
+    }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) st->cum[k] = C[k];
+  // A(r, c) = C[c * 4 + r]
+  const double a00 = C[0], a10 = C[1], a20 = C[2], a01 = C[4], a11 = C[5], a21 = C[6], a02 = C[8], a12 = C[9], a22 = C[10];
+  const double c00 = a11 * a22 - a12 * a21, c01 = a12 * a20 - a10 * a22, c02 = a10 * a21 - a11 * a20;
+  const double det = a00 * c00 + a01 * c01 + a02 * c02;
+  const double id = 1.0 / det;
+  double I[9];   // row-major inverse
+  I[0] = c00 * id; I[1] = (a02 * a21 - a01 * a22) * id; I[2] = (a01 * a12 - a02 * a11) * id;
+  I[3] = c01 * id; I[4] = (a00 * a22 - a02 * a20) * id; I[5] = (a02 * a10 - a00 * a12) * id;
+  I[6] = c02 * id; I[7] = (a01 * a20 - a00 * a21) * id; I[8] = (a00 * a11 - a01 * a10) * id;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    st->cinv[r * 4 + 0] = I[r * 3 + 0]; st->cinv[r * 4 + 1] = I[r * 3 + 1]; st->cinv[r * 4 + 2] = I[r * 3 + 2];
+    st->cinv[r * 4 + 3] = -(I[r * 3 + 0] * C[12] + I[r * 3 + 1] * C[13] + I[r * 3 + 2] * C[14]);
+  }
+  double eta2 = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double g = C[i * 4 + 0] * C[j * 4 + 0] + C[i * 4 + 1] * C[j * 4 + 1] + C[i * 4 + 2] * C[j * 4 + 2] - ((i == j) ? 1.0 : 0.0);
+      eta2 += g * g;
+    }
+  const double eta = sqrt(eta2);
+  // not a rigid motion any more (cannot happen with the estimators here): make every bound vacuous
+  st->stretch = (eta < 0.5 && det > 0) ? (float)(1.0 / sqrt(1.0 - eta)) * 1.000001f + 1.0e-7f : 1.0e6f;
+  st->dev_bits = 0u;
+  st->n_gate = 0u;
+}
+
 // The tail of one ICP iteration, run by one thread: estimate the increment from the sums, compose it
 // into the accumulated transform, log, and evaluate DefaultConvergenceCriteria.
 __device__ __noinline__ void icp_finish_iteration(IcpState* st, IterRec* log) {
@@ -93,7 +142,7 @@ __device__ __noinline__ void icp_finish_iteration(IcpState* st, IterRec* log) {
   const double prev_mse = st->prev_mse, rot_thr = st->rot_thr, trans_thr = st->trans_thr, fit_eps = st->fit_eps;
   const double cnt = p2l ? S[27] : S[0];
   const double d2sum = p2l ? S[28] : S[16];
-  st->queries += (unsigned long long)st->n_src + (st->recip ? (unsigned long long)(p2l ? S[29] : S[17]) : 0ull);
+  st->queries += (unsigned long long)st->n_src + (st->recip ? (unsigned long long)st->n_gate : 0ull);
   const int n_corr = (int)cnt;
   st->n_corr = n_corr;
   if (n_corr < min_corr) { st->reason = 5; st->status = 2; st->done = 1; return; }  // "Not enough correspondences"
@@ -136,6 +185,7 @@ __device__ __noinline__ void icp_finish_iteration(IcpState* st, IterRec* log) {
     }
 #pragma unroll
   for (int k = 0; k < 16; ++k) { st->fin[k] = F[k]; st->delta[k] = Tf[k]; }
+  icp_advance_frame(st, Td);
   const int iter = iter0 + 1;
   st->iter = iter;
   const double cur_mse = d2sum / cnt;
@@ -157,38 +207,72 @@ __device__ __noinline__ void icp_finish_iteration(IcpState* st, IterRec* log) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The fused iteration.  Per iteration of pcl::IterativeClosestPoint::computeTransformation:
+//   k_icp_forward : transformCloud (the pending increment, in place) + determineCorrespondences
+//                   (exact 1-NN in the target, gate) for every source point; without reciprocal
+//                   correspondences also the estimator sums, the solve and the criteria;
+//   k_icp_reverse : the reciprocal half of determineReciprocalCorrespondences (A5) -- for every target
+//                   point some source point chose, its nearest source point -- fused with the estimator
+//                   sums over the mutual pairs, the solve and the criteria.
+// Two launches per iteration, no host round trip.  Both kernels walk SORTED positions with a fixed
+// grid, and sorted positions are reproducible (pair_index.cu), so the sums are identical run to run.
+// ---------------------------------------------------------------------------------------------
+
 // Point-to-point sums about the origin o (a = s - o, b = t - o, exact in double):
-// [0] n, [1..3] sum a, [4..6] sum b, [7..15] sum b_r * a_c (row r, col c), [16] sum d2,
-// [17] number of source points that passed the distance gate (= reciprocal queries when enabled).
-__global__ void __launch_bounds__(256) k_reduce_p2p(const float4* __restrict__ src, int n, const int32_t* __restrict__ corr_p,
-                                                    const float* __restrict__ corr_d2, const int32_t* __restrict__ rnn,
-                                                    const float4* __restrict__ tgt, double* __restrict__ partials,
-                                                    IcpState* __restrict__ st, IterRec* __restrict__ log) {
-  if (st->done) return;
-  const double ox = st->ox, oy = st->oy, oz = st->oz;
-  double v[REDUCE_P2P_VALS];
+// [0] n, [1..3] sum a, [4..6] sum b, [7..15] sum b_r * a_c (row r, col c), [16] sum d2.
+__device__ __forceinline__ void acc_p2p(double (&v)[REDUCE_P2P_VALS], float4 s, float4 t, float d2, double ox, double oy, double oz) {
+  const double ax = (double)s.x - ox, ay = (double)s.y - oy, az = (double)s.z - oz;
+  const double bx = (double)t.x - ox, by = (double)t.y - oy, bz = (double)t.z - oz;
+  v[0] += 1.0;
+  v[1] += ax; v[2] += ay; v[3] += az;
+  v[4] += bx; v[5] += by; v[6] += bz;
+  v[7] += bx * ax; v[8] += bx * ay; v[9] += bx * az;
+  v[10] += by * ax; v[11] += by * ay; v[12] += by * az;
+  v[13] += bz * ax; v[14] += bz * ay; v[15] += bz * az;
+  v[16] += (double)d2;
+}
+
+// Second moments on top of the point-to-point sums (the edge statistics of the LUM relaxation, lum.cpp):
+// [17..22] sum a a^T (xx, xy, xz, yy, yz, zz), [23..28] sum b b^T.
+__device__ __forceinline__ void acc_mom(double (&v)[REDUCE_MOM_VALS], float4 s, float4 t, float d2, double ox, double oy, double oz) {
+  const double ax = (double)s.x - ox, ay = (double)s.y - oy, az = (double)s.z - oz;
+  const double bx = (double)t.x - ox, by = (double)t.y - oy, bz = (double)t.z - oz;
+  v[0] += 1.0;
+  v[1] += ax; v[2] += ay; v[3] += az;
+  v[4] += bx; v[5] += by; v[6] += bz;
+  v[7] += bx * ax; v[8] += bx * ay; v[9] += bx * az;
+  v[10] += by * ax; v[11] += by * ay; v[12] += by * az;
+  v[13] += bz * ax; v[14] += bz * ay; v[15] += bz * az;
+  v[16] += (double)d2;
+  v[17] += ax * ax; v[18] += ax * ay; v[19] += ax * az; v[20] += ay * ay; v[21] += ay * az; v[22] += az * az;
+  v[23] += bx * bx; v[24] += bx * by; v[25] += bx * bz; v[26] += by * by; v[27] += by * bz; v[28] += bz * bz;
+}
+
+// Point-to-plane normal equations (SURVEY.md A12): J = [cross(s, n), n], r = n.(d - s).
+// [0..20] upper triangle of J^T J row-major, [21..26] J^T r, [27] n, [28] sum d2.
+__device__ __forceinline__ void acc_p2l(double (&v)[REDUCE_P2L_VALS], float4 s, float4 t, float4 nn, float d2) {
+  const double sx = s.x, sy = s.y, sz = s.z, nx = nn.x, ny = nn.y, nz = nn.z;
+  const double J[6] = {nz * sy - ny * sz, nx * sz - nz * sx, ny * sx - nx * sy, nx, ny, nz};
+  const double r = nx * ((double)t.x - sx) + ny * ((double)t.y - sy) + nz * ((double)t.z - sz);
+  int k = 0;
 #pragma unroll
-  for (int a = 0; a < REDUCE_P2P_VALS; ++a) v[a] = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int p = __ldg(corr_p + i);
-    if (p < 0) continue;
-    v[17] += 1.0;
-    if (rnn && __ldg(rnn + p) != i) continue;   // reciprocal test: the matched point's nearest source point is not i
-    const float4 s = __ldg(src + i);
-    const float4 t = __ldg(tgt + p);
-    double ax = (double)s.x - ox, ay = (double)s.y - oy, az = (double)s.z - oz;
-    double bx = (double)t.x - ox, by = (double)t.y - oy, bz = (double)t.z - oz;
-    v[0] += 1.0;
-    v[1] += ax; v[2] += ay; v[3] += az;
-    v[4] += bx; v[5] += by; v[6] += bz;
-    v[7] += bx * ax; v[8] += bx * ay; v[9] += bx * az;
-    v[10] += by * ax; v[11] += by * ay; v[12] += by * az;
-    v[13] += bz * ax; v[14] += bz * ay; v[15] += bz * az;
-    v[16] += (double)__ldg(corr_d2 + i);
-  }
-  block_reduce_store<REDUCE_P2P_VALS>(v, partials);
+  for (int a = 0; a < 6; ++a)
+#pragma unroll
+    for (int b = a; b < 6; ++b) v[k++] += J[a] * J[b];
+#pragma unroll
+  for (int a = 0; a < 6; ++a) v[21 + a] += J[a] * r;
+  v[27] += 1.0;
+  v[28] += (double)d2;
+}
+
+// Block partials -> (last block) ordered total -> solve, compose, criteria.
+template <int NV>
+__device__ __forceinline__ void reduce_and_finish(double (&v)[NV], double* __restrict__ partials, IcpState* __restrict__ st,
+                                                  IterRec* __restrict__ log) {
+  block_reduce_store<NV>(v, partials);
   if (!last_block_done(&st->ticket)) return;
-  ordered_total<REDUCE_P2P_VALS>(partials, gridDim.x, st->sums);
+  ordered_total<NV>(partials, gridDim.x, st->sums);
   if (threadIdx.x == 0) {
     const long long t0 = clock64();
     icp_finish_iteration(st, log);
@@ -196,44 +280,144 @@ __global__ void __launch_bounds__(256) k_reduce_p2p(const float4* __restrict__ s
   }
 }
 
-// Point-to-plane normal equations (SURVEY.md A12): J = [cross(s, n), n], r = n.(d - s).
-// [0..20] upper triangle of J^T J row-major, [21..26] J^T r, [27] n, [28] sum d2, [29] gate-passing count.
-__global__ void __launch_bounds__(256) k_reduce_p2l(const float4* __restrict__ src, int n, const int32_t* __restrict__ corr_p,
-                                                    const float* __restrict__ corr_d2, const int32_t* __restrict__ rnn,
-                                                    const float4* __restrict__ tgt, const float4* __restrict__ nrm,
-                                                    double* __restrict__ partials, IcpState* __restrict__ st, IterRec* __restrict__ log) {
+template <int EST> struct EstVals { static constexpr int value = EST == EST_P2L ? (int)REDUCE_P2L_VALS : (EST == EST_MOM ? (int)REDUCE_MOM_VALS : (int)REDUCE_P2P_VALS); };
+
+template <int EST, int NV>
+__device__ __forceinline__ void acc_pair(double (&v)[NV], float4 s, float4 t, const float4* __restrict__ nrm, float d2, double ox, double oy, double oz) {
+  if constexpr (EST == EST_P2L) acc_p2l(v, s, t, __ldg(nrm + __float_as_int(t.w)), d2);
+  else if constexpr (EST == EST_MOM) acc_mom(v, s, t, d2, ox, oy, oz);
+  else acc_p2p(v, s, t, d2, ox, oy, oz);
+}
+
+template <bool RECIP, int EST>
+__global__ void __launch_bounds__(FUSED_THREADS) k_icp_forward(FwdArgs a) {
+  IcpState* __restrict__ st = a.st;
   if (st->done) return;
-  double v[REDUCE_P2L_VALS];
+  Mat4f M;
+  if (!a.first) {
 #pragma unroll
-  for (int a = 0; a < REDUCE_P2L_VALS; ++a) v[a] = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int p = __ldg(corr_p + i);
-    if (p < 0) continue;
-    v[29] += 1.0;
-    if (rnn && __ldg(rnn + p) != i) continue;
-    const float4 s = __ldg(src + i);
-    const float4 t = __ldg(tgt + p), nn = __ldg(nrm + __float_as_int(t.w));
-    double sx = s.x, sy = s.y, sz = s.z, nx = nn.x, ny = nn.y, nz = nn.z;
-    double J[6] = {nz * sy - ny * sz, nx * sz - nz * sx, ny * sx - nx * sy, nx, ny, nz};
-    double r = nx * ((double)t.x - sx) + ny * ((double)t.y - sy) + nz * ((double)t.z - sz);
-    int k = 0;
-#pragma unroll
-    for (int a = 0; a < 6; ++a)
-#pragma unroll
-      for (int b = a; b < 6; ++b) v[k++] += J[a] * J[b];
-#pragma unroll
-    for (int a = 0; a < 6; ++a) v[21 + a] += J[a] * r;
-    v[27] += 1.0;
-    v[28] += (double)__ldg(corr_d2 + i);
+    for (int k = 0; k < 16; ++k) M.m[k] = st->delta[k];
   }
-  block_reduce_store<REDUCE_P2L_VALS>(v, partials);
-  if (!last_block_done(&st->ticket)) return;
-  ordered_total<REDUCE_P2L_VALS>(partials, gridDim.x, st->sums);
-  if (threadIdx.x == 0) {
-    const long long t0 = clock64();
-    icp_finish_iteration(st, log);
-    st->dbg[0] += clock64() - t0; st->dbg[1] += 1;
+  double C[12];   // rows of cum: ref = C * s0
+  if (RECIP) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) C[r * 4 + c] = st->cum[c * 4 + r];
   }
+  const double ox = st->ox, oy = st->oy, oz = st->oz;
+  constexpr int NV = EstVals<EST>::value;
+  double v[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = 0.0;
+  float devmax = 0.0f;
+  unsigned int ngate = 0;
+  for (int i = blockIdx.x * FUSED_THREADS + threadIdx.x; i < a.n_valid; i += gridDim.x * FUSED_THREADS) {
+    float4 p = a.cur[i];
+    if (!a.first) {
+      const float w = p.w;
+      p = xform_pinned(M, p);
+      p.w = w;
+      a.cur[i] = p;
+    }
+    if (RECIP) {
+      // how far the float chain of in-place transforms has drifted from cum * (binning-time position)
+      const float4 s = __ldg(a.s0 + i);
+      const double ex = C[0] * s.x + C[1] * s.y + C[2] * s.z + C[3] - (double)p.x;
+      const double ey = C[4] * s.x + C[5] * s.y + C[6] * s.z + C[7] - (double)p.y;
+      const double ez = C[8] * s.x + C[9] * s.y + C[10] * s.z + C[11] - (double)p.z;
+      devmax = fmaxf(devmax, (float)sqrt(ex * ex + ey * ey + ez * ez) * 1.000001f);
+    }
+    NnBest b{MVR_INF, 0x7fffffff, -1};
+    const int j0 = a.corr_p[i];
+    if (j0 >= 0) {   // seed: last iteration's neighbour is a real candidate and usually still the answer
+      const float4 t = __ldg(a.tgt + j0);
+      b.d2 = d2_pinned(p.x, p.y, p.z, t.x, t.y, t.z); b.idx = __float_as_int(t.w); b.pos = j0;
+    }
+    pg_search(a.gt, a.tstart, a.tgt, a.m_valid, p.x, p.y, p.z, p.x, p.y, p.z, 0.0f, 1.0f, a.max_d2f, b);
+    const bool keep = b.pos >= 0 && !((double)b.d2 > a.max2);   // PCL: if (distance > max_dist_sqr) continue;
+    a.corr_p[i] = keep ? b.pos : -1;
+    if (keep) {
+      ++ngate;
+      if (RECIP) {
+        atomicMin(a.rmin + b.pos, __float_as_uint(b.d2));
+      } else {
+        acc_pair<EST>(v, p, __ldg(a.tgt + b.pos), a.nrm, b.d2, ox, oy, oz);
+      }
+    }
+  }
+  if (RECIP) {
+    __shared__ unsigned int s_dev, s_gate;
+    if (threadIdx.x == 0) { s_dev = 0u; s_gate = 0u; }
+    __syncthreads();
+    const unsigned int wd = __reduce_max_sync(0xffffffffu, __float_as_uint(devmax));   // non-negative floats order like their bits
+    const unsigned int wg = __reduce_add_sync(0xffffffffu, ngate);
+    if ((threadIdx.x & 31) == 0) { atomicMax(&s_dev, wd); atomicAdd(&s_gate, wg); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (s_dev) atomicMax(&st->dev_bits, s_dev);
+      if (s_gate) atomicAdd(&st->n_gate, s_gate);
+    }
+  } else {
+    reduce_and_finish<NV>(v, a.partials, st, a.log);
+  }
+}
+
+template <int EST>
+__global__ void __launch_bounds__(FUSED_THREADS) k_icp_reverse(RevArgs a) {
+  IcpState* __restrict__ st = a.st;
+  if (st->done) return;
+  double Ci[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) Ci[k] = st->cinv[k];
+  const float stretch = st->stretch;
+  const float dev0 = __uint_as_float(st->dev_bits) * 1.000001f;
+  const double ox = st->ox, oy = st->oy, oz = st->oz;
+  constexpr int NV = EstVals<EST>::value;
+  double v[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = 0.0;
+  unsigned int missed = 0;
+  for (int j = blockIdx.x * FUSED_THREADS + threadIdx.x; j < a.m_valid; j += gridDim.x * FUSED_THREADS) {
+    const uint32_t r = a.rmin[j];
+    if (r == 0x7f800000u) continue;   // no source point chose this target point
+    a.rmin[j] = 0x7f800000u;          // re-armed for the next iteration
+    const float4 t = __ldg(a.tgt + j);
+    // the query in the frame the source was binned in
+    const float ux = (float)(Ci[0] * t.x + Ci[1] * t.y + Ci[2] * t.z + Ci[3]);
+    const float uy = (float)(Ci[4] * t.x + Ci[5] * t.y + Ci[6] * t.z + Ci[7]);
+    const float uz = (float)(Ci[8] * t.x + Ci[9] * t.y + Ci[10] * t.z + Ci[11]);
+    const float dev = dev0 + 1.0e-6f * fmaxf(fabsf(ux), fmaxf(fabsf(uy), fabsf(uz)));
+    // a chooser sits at exactly this distance: the lexicographic minimum (d2, index) over all source points is found
+    NnBest b{__uint_as_float(r), 0x7fffffff, -1};
+    pg_search(a.gs, a.sstart, a.cur, a.n_valid, t.x, t.y, t.z, ux, uy, uz, dev, stretch, MVR_INF, b);
+    if (b.pos < 0) { ++missed; continue; }
+    if (__ldg(a.corr_p + b.pos) != j) continue;   // the nearest source point chose another target point
+    acc_pair<EST>(v, __ldg(a.cur + b.pos), t, a.nrm, b.d2, ox, oy, oz);
+  }
+  if (missed) atomicAdd((unsigned long long*)&st->dbg[2], (unsigned long long)missed);   // must stay 0: a chooser was not found again
+  reduce_and_finish<NV>(v, a.partials, st, a.log);
+}
+
+cudaError_t launch_icp_forward(const FwdArgs& a, bool reciprocal, int est, cudaStream_t s) {
+  if (reciprocal) {
+    // the reciprocal forward half accumulates nothing: one instantiation serves every estimator
+    k_icp_forward<true, EST_P2P><<<FUSED_BLOCKS, FUSED_THREADS, 0, s>>>(a);
+  } else {
+    if (est == EST_P2L) k_icp_forward<false, EST_P2L><<<FUSED_BLOCKS, FUSED_THREADS, 0, s>>>(a);
+    else if (est == EST_MOM) k_icp_forward<false, EST_MOM><<<FUSED_BLOCKS, FUSED_THREADS, 0, s>>>(a);
+    else k_icp_forward<false, EST_P2P><<<FUSED_BLOCKS, FUSED_THREADS, 0, s>>>(a);
+  }
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_icp_reverse(const RevArgs& a, int est, cudaStream_t s) {
+  if (est == EST_P2L) k_icp_reverse<EST_P2L><<<FUSED_BLOCKS, FUSED_THREADS, 0, s>>>(a);
+  else if (est == EST_MOM) k_icp_reverse<EST_MOM><<<FUSED_BLOCKS, FUSED_THREADS, 0, s>>>(a);
+  else k_icp_reverse<EST_P2P><<<FUSED_BLOCKS, FUSED_THREADS, 0, s>>>(a);
+  count_launch();
+  return cudaGetLastError();
 }
 
 __global__ void k_reduce_final(const double* __restrict__ partials, int nblk, int nv, double* __restrict__ out) {
@@ -264,15 +448,6 @@ __global__ void __launch_bounds__(256) k_transform_final(const float4* __restric
   for (int k = 0; k < 16; ++k) M.m[k] = (float)st->fin[k];
   float4 p = __ldg(in + i);
   out[i] = finite3(p) ? xform_pinned(M, p) : p;
-}
-
-cudaError_t launch_reduce_solve(const float4* src_cur, int n, const int32_t* corr_p, const float* corr_d2, const int32_t* rnn,
-                                const float4* tgt_sorted, const float4* tgt_normals, double* partials, IcpState* st,
-                                IterRec* log, bool p2l, cudaStream_t s) {
-  if (p2l) k_reduce_p2l<<<REDUCE_BLOCKS, 256, 0, s>>>(src_cur, n, corr_p, corr_d2, rnn, tgt_sorted, tgt_normals, partials, st, log);
-  else k_reduce_p2p<<<REDUCE_BLOCKS, 256, 0, s>>>(src_cur, n, corr_p, corr_d2, rnn, tgt_sorted, partials, st, log);
-  count_launch();
-  return cudaGetLastError();
 }
 
 cudaError_t launch_transform_final(const float4* in, float4* out, int n, const IcpState* st, cudaStream_t s) {

@@ -320,4 +320,11 @@ cudaError_t launch_cell_table(const uint32_t* sorted_keys, int n, int bits, uint
   return cudaGetLastError();
 }
 
+cudaError_t launch_cell_table_n(const uint32_t* sorted_keys, int n, uint32_t cells, uint32_t* start, cudaStream_t s) {
+  long long threads = (long long)n + 1;
+  int blocks = (int)((threads + 255) / 256);
+  k_cell_table<<<blocks, 256, 0, s>>>(sorted_keys, n, cells, start); count_launch();
+  return cudaGetLastError();
+}
+
 }  // namespace mvr

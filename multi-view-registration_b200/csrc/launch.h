@@ -75,7 +75,7 @@ cudaError_t launch_bin_scatter(const float4* pts, int n, const uint32_t* keys, c
                                const int* d_done, float4* sorted, cudaStream_t s);
 
 // ---- icp.cu --------------------------------------------------------------------------------
-enum { REDUCE_P2P_VALS = 18, REDUCE_P2L_VALS = 30, REDUCE_MAX_VALS = 32, REDUCE_BLOCKS = 296, ICP_MAX_LOG = 1024 };
+enum { REDUCE_P2P_VALS = 18, REDUCE_P2L_VALS = 30, REDUCE_MOM_VALS = 30, REDUCE_MAX_VALS = 32, REDUCE_BLOCKS = 592, ICP_MAX_LOG = 1024 };
 
 // Per-iteration record kept on the device (mirrors mvr_icp_iteration of the C ABI).
 struct IterRec {
@@ -99,16 +99,62 @@ struct IcpState {
   int iter, done, reason, status, n_corr;
   int max_iter, fixed, min_corr, p2l, recip, n_src;
   unsigned int ticket;    // blocks of the running reduction that have finished
-  long long dbg[4];       // diagnostics: [0] clock cycles spent in the serial solve, [1] solves
+  long long dbg[4];       // diagnostics: [0] clock cycles spent in the serial solve, [1] solves, [2] reciprocal searches that lost their chooser (must be 0)
+  // frame bookkeeping of the static source index (pair_index.cu / pair_search.cuh)
+  double cum[16];         // increments applied since the source was binned, incl. the pending `delta`, column-major
+  double cinv[12];        // its affine inverse, rows {A^-1 | -A^-1 b}
+  float stretch;          // >= ||A^-1||_2
+  unsigned int dev_bits;  // float bits of max |cur - cum * s0| over the source points, measured by k_icp_forward
+  unsigned int n_gate;    // forward matches that passed the gate in the running iteration
 };
 
-// Sums over kept correspondences in original-index order, then (last block) the solve + criteria:
-// advances st (delta, fin, iter, done, ...) and appends to log.  partials: REDUCE_BLOCKS x REDUCE_MAX_VALS.
-// corr_p / corr_d2 come from launch_brick_forward, rnn (nullable: not reciprocal) from launch_brick_reverse;
-// a pair (i, p) is kept iff corr_p[i] = p >= 0 and (rnn == nullptr or rnn[p] == i).
-cudaError_t launch_reduce_solve(const float4* src_cur, int n, const int32_t* corr_p, const float* corr_d2, const int32_t* rnn,
-                                const float4* tgt_sorted, const float4* tgt_normals, double* partials, IcpState* st,
-                                IterRec* log, bool p2l, cudaStream_t s);
+// ---- fused iteration (icp.cu) + per-align index (pair_index.cu) ---------------------------------
+enum { FUSED_THREADS = 256, FUSED_BLOCKS = 148 * 4 };
+
+// Row-major key of every point (after the optional pinned transform by *guess), `moved` (nullable) = the
+// transformed points; keys of non-finite points = cells.
+cudaError_t launch_pair_keys(const float4* in, int n, const Mat4f* guess, PairGrid g, uint32_t cells, float4* moved, uint32_t* keys,
+                             uint32_t* vals, cudaStream_t s);
+// sorted[k] = {pts[perm[k]].xyz, bits(perm[k])}; copy (nullable) gets the same.
+cudaError_t launch_pair_gather(const float4* pts, const uint32_t* perm, int n, float4* sorted, float4* copy, cudaStream_t s);
+cudaError_t launch_cell_table_n(const uint32_t* sorted_keys, int n, uint32_t cells, uint32_t* start, cudaStream_t s);
+
+struct FwdArgs {
+  float4* cur;             // source, sorted by binning cell, current coordinates (updated in place), .w = original index
+  const float4* s0;        // the same points at binning time (reciprocal only)
+  int n_valid;             // finite source points = sorted positions [0, n_valid)
+  const float4* tgt;       // target, sorted by cell
+  const uint32_t* tstart;
+  PairGrid gt;
+  int m_valid;
+  int32_t* corr_p;         // [source sorted position] matched target sorted position, -1 none (in: last iteration's = seed)
+  uint32_t* rmin;          // [target sorted position] min d2 bits over its choosers (reciprocal only; +inf bits on entry)
+  double max2;             // gate, exact (PCL compares in double)
+  float max_d2f;           // gate rounded up to float: bounds the search
+  const float4* nrm;       // target normals by ORIGINAL index (point-to-plane only)
+  double* partials;        // FUSED_BLOCKS x REDUCE_MAX_VALS
+  IcpState* st;
+  IterRec* log;
+  int first;               // first iteration of an align: the guess is already applied, no increment pending
+};
+struct RevArgs {
+  const float4* tgt;
+  int m_valid;
+  uint32_t* rmin;
+  const float4* cur;
+  const uint32_t* sstart;
+  PairGrid gs;
+  int n_valid;
+  const int32_t* corr_p;
+  const float4* nrm;
+  double* partials;
+  IcpState* st;
+  IterRec* log;
+};
+// est: which sums the iteration accumulates over its correspondences
+enum { EST_P2P = 0, EST_P2L = 1, EST_MOM = 2 /* point-to-point + second moments (LUM edge statistics) */ };
+cudaError_t launch_icp_forward(const FwdArgs& a, bool reciprocal, int est, cudaStream_t s);
+cudaError_t launch_icp_reverse(const RevArgs& a, int est, cudaStream_t s);
 // corr_j[i] = original index of the matched target point, -1 = none, -2-j = passed the gate but failed
 // the reciprocal test (the layout launch_compact_corr consumes).
 cudaError_t launch_resolve_corr(const int32_t* corr_p, const int32_t* rnn, const float4* tgt_sorted, int n, int32_t* corr_j,

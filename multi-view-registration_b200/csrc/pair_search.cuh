@@ -33,13 +33,6 @@
 
 namespace mvr {
 
-struct PairGrid {
-  float ox, oy, oz;
-  float inv_cell;
-  float cell_lo;   // a float strictly below the true cell edge
-  int nx, ny, nz;
-};
-
 __device__ __forceinline__ int pg_cell(float t, int n) { return (int)fminf(fmaxf(floorf(t), 0.0f), (float)(n - 1)); }
 
 // Row-major cell of a finite point.
@@ -81,6 +74,7 @@ __device__ __forceinline__ void pg_search(const PairGrid& g, const uint32_t* __r
   const int cx = pg_cell(tx, g.nx), cy = pg_cell(ty, g.ny), cz = pg_cell(tz, g.nz);
   const float margin = MVR_CELL_MARGIN + 1.0e-6f * fmaxf(fabsf(tx), fmaxf(fabsf(ty), fabsf(tz))) + dev * stretch * g.inv_cell * 1.000001f;
   const float cell2 = g.cell_lo * g.cell_lo * MVR_REL_SHRINK / (stretch * stretch * 1.000001f);
+  const float inv_cell2 = 1.000002f / cell2;
   const int rowlen = g.nx, slab = g.nx * g.ny;
 
   float lim = fminf(b.d2, gate);
@@ -122,7 +116,7 @@ __device__ __forceinline__ void pg_search(const PairGrid& g, const uint32_t* __r
       const float eyz = ez2 + ey * ey;
       if (eyz * cell2 > lim) continue;
       // x extent of the ball inside this row
-      const float rem = fmaxf(lim / cell2 - eyz, 0.0f);
+      const float rem = fmaxf(lim * inv_cell2 - eyz, 0.0f);
       const float rx = sqrtf(rem) * 1.000001f + margin + margin;
       const int xa = max(x0, (int)fminf(fmaxf(floorf(tx - rx), 0.0f), (float)(g.nx - 1)));
       const int xb = min(x1, (int)fminf(fmaxf(floorf(tx + rx), 0.0f), (float)(g.nx - 1)));

@@ -172,6 +172,26 @@ int mvr_ring_close(const float* rel_poses, const double* weights, int n_views, i
   return MVR_OK;
 }
 
+int mvr_lum_relax(const mvr_pair_moments* edges, const int* src, const int* tgt, int n_edges, int n_views, int iterations,
+                  double* poses) {
+  if (n_edges < 0 || n_views < 1 || !poses || (n_edges && (!edges || !src || !tgt))) return MVR_ERR_BAD_ARG;
+  std::vector<mvr_pair_moments> e(edges, edges + n_edges);
+  std::vector<Matrix4d> X;
+  int rc = lumRelax(e, src, tgt, n_views, iterations > 0 ? iterations : 16, X);
+  if (rc) return rc;
+  for (int v = 0; v < n_views; ++v) std::memcpy(poses + 16 * v, X[(size_t)v].m, sizeof(X[(size_t)v].m));
+  return MVR_OK;
+}
+
+void mvr_pair_moments_transform(const mvr_pair_moments* in, const double* pose, const double* new_origin, mvr_pair_moments* out) {
+  if (!in || !pose || !out) return;
+  Matrix4d P;
+  std::memcpy(P.m, pose, sizeof(P.m));
+  mvr_pair_moments tmp;
+  momentsTransform(*in, P, new_origin, tmp);
+  *out = tmp;
+}
+
 int mvr_refine_axis(const float* poses, int count, double pivot[3], double axis[3]) {
   if (count < 0 || (count && !poses) || !pivot || !axis) return MVR_ERR_BAD_ARG;
   std::vector<Matrix4d> P((size_t)count);

@@ -266,6 +266,211 @@ int ringClose(const std::vector<Matrix4d>& rel_in, const std::vector<double>& we
   return MVR_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// LUM relaxation on correspondence moments.
+//
+// pcl::registration::LUM (the reference's global adjustment, mvr/src/registrator.cpp:627-663) gives every edge
+// of the pose graph a 6x6 information matrix and a 6-vector built from the edge's point correspondences
+// (computeEdge: midpoints and differences of the pairs), then solves the dense 6 (V - 1) system `max_iterations`
+// times, re-deriving the edges from the SAME correspondences after every pose update.  The cost that procedure
+// descends is  sum_edges sum_k |X_s a_k - X_t b_k|^2.  For rigid X that cost -- and its Gauss-Newton model at any
+// X -- is a function of the pairs' first and second moments only (mvr_pair_moments, one GPU reduction per edge),
+// so the sweeps below run on 30 doubles per edge and never touch a point.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Sym3 { double xx, xy, xz, yy, yz, zz; };
+
+void sym_to_full(const double* s6, double* F) {   // xx xy xz yy yz zz -> row-major 3x3
+  F[0] = s6[0]; F[1] = s6[1]; F[2] = s6[2];
+  F[3] = s6[1]; F[4] = s6[3]; F[5] = s6[4];
+  F[6] = s6[2]; F[7] = s6[4]; F[8] = s6[5];
+}
+
+void full_to_sym(const double* F, double* s6) {
+  s6[0] = F[0]; s6[1] = 0.5 * (F[1] + F[3]); s6[2] = 0.5 * (F[2] + F[6]);
+  s6[3] = F[4]; s6[4] = 0.5 * (F[5] + F[7]); s6[5] = F[8];
+}
+
+void mat3_T(const double* A, double* At) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) At[i * 3 + j] = A[j * 3 + i];
+}
+
+// out = Ra S Rb^T + (Ra u) cb^T + ca (Rb v)^T + n ca cb^T   -- the second moment sum (Ra x + ca)(Rb y + cb)^T
+// given S = sum x y^T, u = sum x, v = sum y.
+void moment2(const double* Ra, const double* ca, const double* Rb, const double* cb, const double* S, const double* u,
+             const double* v, double n, double* out) {
+  double RbT[9], T[9];
+  mat3_T(Rb, RbT);
+  mat3_mul(Ra, S, T);
+  mat3_mul(T, RbT, out);
+  double Rau[3], Rbv[3];
+  for (int i = 0; i < 3; ++i) {
+    Rau[i] = Ra[i * 3] * u[0] + Ra[i * 3 + 1] * u[1] + Ra[i * 3 + 2] * u[2];
+    Rbv[i] = Rb[i * 3] * v[0] + Rb[i * 3 + 1] * v[1] + Rb[i * 3 + 2] * v[2];
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) out[i * 3 + j] += Rau[i] * cb[j] + ca[i] * Rbv[j] + n * ca[i] * cb[j];
+}
+
+// Moments of the pairs (Xa a, Xb b) about new_origin, from those of (a, b) about in.origin.
+void moments_apply(const mvr_pair_moments& in, const Matrix4d& Xa, const Matrix4d& Xb, const double* new_origin, mvr_pair_moments& out) {
+  double Ra[9], ta[3], Rb[9], tb[3], ca[3], cb[3];
+  get_Rt(Xa, Ra, ta);
+  get_Rt(Xb, Rb, tb);
+  for (int i = 0; i < 3; ++i) {
+    ca[i] = Ra[i * 3] * in.origin[0] + Ra[i * 3 + 1] * in.origin[1] + Ra[i * 3 + 2] * in.origin[2] + ta[i] - new_origin[i];
+    cb[i] = Rb[i * 3] * in.origin[0] + Rb[i * 3 + 1] * in.origin[1] + Rb[i * 3 + 2] * in.origin[2] + tb[i] - new_origin[i];
+  }
+  mvr_pair_moments o;
+  o.n = in.n;
+  for (int i = 0; i < 3; ++i) {
+    o.origin[i] = new_origin[i];
+    o.sa[i] = Ra[i * 3] * in.sa[0] + Ra[i * 3 + 1] * in.sa[1] + Ra[i * 3 + 2] * in.sa[2] + in.n * ca[i];
+    o.sb[i] = Rb[i * 3] * in.sb[0] + Rb[i * 3 + 1] * in.sb[1] + Rb[i * 3 + 2] * in.sb[2] + in.n * cb[i];
+  }
+  double Saa[9], Sbb[9], F[9];
+  sym_to_full(in.saa, Saa);
+  sym_to_full(in.sbb, Sbb);
+  moment2(Ra, ca, Ra, ca, Saa, in.sa, in.sa, in.n, F);
+  full_to_sym(F, o.saa);
+  moment2(Rb, cb, Rb, cb, Sbb, in.sb, in.sb, in.n, F);
+  full_to_sym(F, o.sbb);
+  moment2(Rb, cb, Ra, ca, in.sba, in.sb, in.sa, in.n, o.sba);
+  o.d2 = (o.saa[0] + o.saa[3] + o.saa[5]) + (o.sbb[0] + o.sbb[3] + o.sbb[5]) - 2.0 * (o.sba[0] + o.sba[4] + o.sba[8]);
+  out = o;
+}
+
+// Gauss-Newton model of one edge at the identity:  sum_k |delta_k + omega x m_k + upsilon|^2 = d^T M d + 2 v^T d + c
+// with m = (a + b) / 2, delta = a - b, d = (omega, upsilon) = d_source - d_target, twists about the moments' origin.
+void edge_model(const mvr_pair_moments& e, double* M /* 36 */, double* v /* 6 */) {
+  double Saa[9], Sbb[9], Smm[9];
+  sym_to_full(e.saa, Saa);
+  sym_to_full(e.sbb, Sbb);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) Smm[i * 3 + j] = 0.25 * (Saa[i * 3 + j] + Sbb[i * 3 + j] + e.sba[i * 3 + j] + e.sba[j * 3 + i]);
+  const double tr = Smm[0] + Smm[4] + Smm[8];
+  const double sm[3] = {0.5 * (e.sa[0] + e.sb[0]), 0.5 * (e.sa[1] + e.sb[1]), 0.5 * (e.sa[2] + e.sb[2])};
+  double K[9];
+  skew(sm, K);   // sum [m]x
+  for (int k = 0; k < 36; ++k) M[k] = 0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      M[i * 6 + j] = ((i == j) ? tr : 0.0) - Smm[i * 3 + j];   // sum |m|^2 I - m m^T
+      M[i * 6 + 3 + j] = K[i * 3 + j];                        // sum [m]x
+      M[(3 + i) * 6 + j] = -K[i * 3 + j];                     // its transpose
+      M[(3 + i) * 6 + 3 + j] = (i == j) ? e.n : 0.0;
+    }
+  // sum m x delta = sum b x a ; sum delta = sa - sb
+  v[0] = e.sba[1 * 3 + 2] - e.sba[2 * 3 + 1];
+  v[1] = e.sba[2 * 3 + 0] - e.sba[0 * 3 + 2];
+  v[2] = e.sba[0 * 3 + 1] - e.sba[1 * 3 + 0];
+  for (int i = 0; i < 3; ++i) v[3 + i] = e.sa[i] - e.sb[i];
+}
+
+double graph_cost(const std::vector<mvr_pair_moments>& base, const int* src, const int* tgt, const std::vector<Matrix4d>& X,
+                  const double* origin, std::vector<mvr_pair_moments>* moved) {
+  double c = 0;
+  if (moved) moved->resize(base.size());
+  for (size_t e = 0; e < base.size(); ++e) {
+    mvr_pair_moments m;
+    moments_apply(base[e], X[(size_t)src[e]], X[(size_t)tgt[e]], origin, m);
+    c += m.d2;
+    if (moved) (*moved)[e] = m;
+  }
+  return c;
+}
+
+}  // namespace
+
+void momentsTransform(const mvr_pair_moments& in, const Matrix4d& pose, const double* new_origin, mvr_pair_moments& out) {
+  double o[3];
+  if (new_origin) {
+    for (int i = 0; i < 3; ++i) o[i] = new_origin[i];
+  } else {
+    for (int i = 0; i < 3; ++i) o[i] = pose.m[i] * in.origin[0] + pose.m[4 + i] * in.origin[1] + pose.m[8 + i] * in.origin[2] + pose.m[12 + i];
+  }
+  moments_apply(in, pose, pose, o, out);
+  out.d2 = in.d2;   // a common rigid motion keeps every distance: carry the measured sum
+}
+
+int lumRelax(const std::vector<mvr_pair_moments>& edges_in, const int* src, const int* tgt, int V, int iterations, std::vector<Matrix4d>& X) {
+  X.assign((size_t)std::max(V, 1), identity4d());
+  const int E = (int)edges_in.size();
+  if (V < 2 || E == 0) return MVR_OK;
+  for (int e = 0; e < E; ++e)
+    if (src[e] < 0 || src[e] >= V || tgt[e] < 0 || tgt[e] >= V || src[e] == tgt[e]) return MVR_ERR_BAD_ARG;
+  // one common origin for every twist: the correspondence centroid of the whole graph
+  double origin[3] = {0, 0, 0}, ntot = 0;
+  for (const mvr_pair_moments& e : edges_in) {
+    if (!(e.n > 0)) continue;
+    for (int i = 0; i < 3; ++i) origin[i] += e.n * e.origin[i] + 0.5 * (e.sa[i] + e.sb[i]);
+    ntot += e.n;
+  }
+  if (!(ntot > 0)) return MVR_OK;
+  for (int i = 0; i < 3; ++i) origin[i] /= ntot;
+  std::vector<mvr_pair_moments> base;
+  std::vector<int> es, et;
+  for (int e = 0; e < E; ++e)
+    if (edges_in[(size_t)e].n > 0) { base.push_back(edges_in[(size_t)e]); es.push_back(src[e]); et.push_back(tgt[e]); }
+  Matrix4d S = identity4d(), Si = identity4d();
+  for (int k = 0; k < 3; ++k) { S.m[12 + k] = origin[k]; Si.m[12 + k] = -origin[k]; }
+  const int n = 6 * (V - 1);
+  std::vector<mvr_pair_moments> cur;
+  double cost = graph_cost(base, es.data(), et.data(), X, origin, &cur);
+  double lambda = 0.0;
+  for (int it = 0; it < iterations; ++it) {
+    std::vector<double> H((size_t)n * n, 0.0), g((size_t)n, 0.0);
+    for (size_t e = 0; e < cur.size(); ++e) {
+      double M[36], v[6];
+      edge_model(cur[e], M, v);
+      const int a = es[e], b = et[e];
+      const int ia = 6 * (a - 1), ib = 6 * (b - 1);   // vertex 0 is fixed (LUM: the first cloud is the reference)
+      for (int i = 0; i < 6; ++i) {
+        if (a > 0) g[(size_t)ia + i] += v[i];
+        if (b > 0) g[(size_t)ib + i] -= v[i];
+        for (int j = 0; j < 6; ++j) {
+          const double m = M[i * 6 + j];
+          if (a > 0) H[(size_t)(ia + i) * n + ia + j] += m;
+          if (b > 0) H[(size_t)(ib + i) * n + ib + j] += m;
+          if (a > 0 && b > 0) { H[(size_t)(ia + i) * n + ib + j] -= m; H[(size_t)(ib + i) * n + ia + j] -= m; }
+        }
+      }
+    }
+    double dmax = 0;
+    for (int i = 0; i < n; ++i) dmax = std::fmax(dmax, H[(size_t)i * n + i]);
+    if (!(dmax > 0) || !std::isfinite(dmax)) break;
+    // Levenberg-Marquardt safeguard: the plain Gauss-Newton step (lambda = 0) is LUM's; damping is raised only when
+    // the system is not positive definite (a view without edges keeps its pose) or the true cost would grow.
+    bool accepted = false;
+    double step = 0;
+    for (int attempt = 0; attempt < 12 && !accepted; ++attempt) {
+      std::vector<double> Hd(H), x(g);
+      for (int i = 0; i < n; ++i) { Hd[(size_t)i * n + i] += lambda * std::fmax(H[(size_t)i * n + i], 1e-12 * dmax) + 1e-14 * dmax; x[(size_t)i] = -x[(size_t)i]; }
+      if (!chol_solve(Hd, x, n)) { lambda = lambda > 0 ? lambda * 10.0 : 1e-6; continue; }
+      std::vector<Matrix4d> Xn(X);
+      step = 0;
+      for (int v = 1; v < V; ++v) {
+        Vec6 d;
+        for (int k = 0; k < 6; ++k) { d.v[k] = x[(size_t)6 * (v - 1) + k]; step = std::fmax(step, std::fabs(d.v[k])); }
+        Xn[(size_t)v] = multiply(multiply(multiply(S, se3_exp(d)), Si), X[(size_t)v]);   // twist about the common origin
+      }
+      std::vector<mvr_pair_moments> moved;
+      const double c2 = graph_cost(base, es.data(), et.data(), Xn, origin, &moved);
+      if (c2 <= cost * (1.0 + 1e-12) || !(step > 1e-14)) {
+        X.swap(Xn); cur.swap(moved); cost = c2; accepted = true;
+        lambda *= 0.1;
+        if (lambda < 1e-9) lambda = 0.0;
+      } else {
+        lambda = lambda > 0 ? lambda * 10.0 : 1e-6;
+      }
+    }
+    if (!accepted || step < 1e-13) break;
+  }
+  return MVR_OK;
+}
+
 // min |A x - b|_2 by Householder QR (A rows x cols row-major, rows >= cols, full column rank).
 bool leastSquares(const std::vector<double>& A_in, const std::vector<double>& b_in, int rows, int cols, std::vector<double>& x) {
   if (rows < cols || cols <= 0) return false;

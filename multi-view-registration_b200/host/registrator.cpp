@@ -12,6 +12,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -381,66 +382,65 @@ int Registrator::multiViewRegister(std::vector<View>& views, const mvr_turntable
   return MVR_OK;
 }
 
+int Registrator::edgeMoments(const View& source, const View& target, double max_distance, const Matrix4f& guess, int slot,
+                             mvr_pair_moments& out) {
+  if (!ok()) return fail(MVR_ERR_CUDA, "no GPU context");
+  mvr_ctx* c = ctx_[(size_t)slot % ctx_.size()];
+  int rc = target.on_device ? mvr_set_target_device(c, &target.points->x, target.size) : mvr_set_target(c, &target.points->x, target.size);
+  if (!rc) rc = source.on_device ? mvr_set_source_device(c, &source.points->x, source.size) : mvr_set_source(c, &source.points->x, source.size);
+  if (!rc) rc = mvr_pair_moments_compute(c, max_distance, 1, guess.m, &out);
+  if (rc) fail(rc, mvr_last_error(c));
+  return rc;
+}
+
 int Registrator::registrationLUM(std::vector<View>& views, int max_iterations, double max_distance) {
-  // mvr/src/registrator.cpp:611-678: every view gets its turntable pose, then outer loops of
-  // {reciprocal correspondences on the ring edges i -> i+1, relax 16 sweeps, compose the corrections}.
-  // The edge constraint used here is the rigid motion that best superposes the edge's reciprocal
-  // correspondences (one estimator step on the GPU), weighted by their number; see lum.cpp.
+  // mvr/src/registrator.cpp:611-678: every view gets its turntable pose, then max(1, max_iterations / 16) outer
+  // loops of { reciprocal correspondences on the ring edges i -> (i + 1) % V (:640-651), lum.compute() with 16
+  // sweeps (:630, 653), pose <- lum_T * pose (:655-661) }.  The correspondences of an edge are reduced on the GPU
+  // to their moments (mvr_pair_moments_compute); the relaxation itself is host work on 30 doubles per edge (lum.cpp).
   if (!ok()) return fail(MVR_ERR_CUDA, "no GPU context");
   const int V = (int)views.size();
   if (V < 2) return MVR_OK;
   for (int v = 0; v < V; ++v) { views[(size_t)v].view = v; initRotation(views[(size_t)v], V); views[(size_t)v].registered = true; }
   const int lum_max_iterations = 16;
   const int outer = std::max(1, max_iterations / lum_max_iterations);
-  mvr_icp_params one;
-  mvr_icp_params_default(&one);
-  one.use_reciprocal_correspondences = 1;
-  one.max_correspondence_distance = max_distance;
-  one.max_iterations = 1;
-  one.fixed_iterations = 1;
+  const int E = (V == 2) ? 1 : V;   // two views: one edge, not the same pair twice
+  std::vector<int> es((size_t)E), et((size_t)E);
+  for (int i = 0; i < E; ++i) { es[(size_t)i] = i; et[(size_t)i] = (i + 1) % V; }
   for (int loop = 0; loop < outer; ++loop) {
-    std::vector<Matrix4d> rel((size_t)V);
-    std::vector<double> w((size_t)V, 0.0);
+    std::vector<mvr_pair_moments> edges((size_t)E);
     std::atomic<int> next(0);
     std::atomic<int> bad(0);
-    std::vector<double> radius((size_t)V, 1.0);
     auto worker = [&](int slot) {
       cudaSetDevice(device_);
       for (;;) {
         const int i = next.fetch_add(1);
-        if (i >= V) break;
-        const View& s = views[(size_t)i];
-        const View& t = views[(size_t)((i + 1) % V)];
-        // world-frame clouds of both ends: source posed by guess = pose_t^-1 pose_s in t's sensor frame
-        Matrix4f guess = toFloat(multiply(inverseRigid(t.pose), s.pose));
-        AlignResult a = pairwiseAlign(s, t, one, &guess, false, slot);
-        radius[(size_t)i] = a.target_radius;
-        if (a.status == MVR_OK) {
-          // a.final = Z * guess in t's frame  ->  Z_world = pose_t Z pose_t^-1, and X_{i+1}^-1 X_i ~ Z_world
-          Matrix4d Z = multiply(toDouble(a.final_transformation), inverseRigid(toDouble(guess)));
-          Matrix4d Zw = multiply(multiply(t.pose, Z), inverseRigid(t.pose));
-          rel[(size_t)i] = inverseRigid(Zw);   // ringClose wants X_i^-1 X_{i+1}
-          w[(size_t)i] = (double)a.n_correspondences;
-        } else if (a.status == MVR_ERR_TOO_FEW_CORRESPONDENCES) {
-          rel[(size_t)i] = identity4d();
-        } else {
-          bad.store(a.status);
-        }
+        if (i >= E) break;
+        const View& s = views[(size_t)es[(size_t)i]];
+        const View& t = views[(size_t)et[(size_t)i]];
+        // the source posed into t's sensor frame; the moments come back in that frame and move to the world with pose_t
+        const Matrix4f guess = toFloat(multiply(inverseRigid(t.pose), s.pose));
+        mvr_pair_moments m;
+        const int rc = edgeMoments(s, t, max_distance, guess, slot, m);
+        if (rc) { bad.store(rc); continue; }
+        momentsTransform(m, t.pose, nullptr, edges[(size_t)i]);
       }
     };
-    const int K = std::max(1, std::min((int)ctx_.size(), V));
+    const int K = std::max(1, std::min((int)ctx_.size(), E));
     if (K == 1) worker(0);
     else {
       std::vector<std::thread> th;
       for (int k = 0; k < K; ++k) th.emplace_back(worker, k);
       for (std::thread& t : th) t.join();
     }
-    if (bad.load()) return fail(bad.load(), "edge estimation failed");
+    if (bad.load()) return bad.load();
     std::vector<Matrix4d> X;
-    // world frame = view 0's frame posed by views[0].pose: the object sits at pose_0 * pivot
-    double cw[3];
-    for (int k = 0; k < 3; ++k) cw[k] = views[0].pose.m[k] * pivot_[0] + views[0].pose.m[4 + k] * pivot_[1] + views[0].pose.m[8 + k] * pivot_[2] + views[0].pose.m[12 + k];
-    int rc = ringClose(rel, w, true, lum_max_iterations, cw, radius[0], X);
+    const int rc = lumRelax(edges, es.data(), et.data(), V, lum_max_iterations, X);
+    if (std::getenv("MVR_DEBUG_LUM")) {
+      double c = 0, n = 0;
+      for (const mvr_pair_moments& e : edges) { c += e.d2; n += e.n; }
+      std::fprintf(stderr, "[lum] loop %d rc %d pairs %.0f mean d2 %.6f\n", loop, rc, n, n > 0 ? c / n : 0.0);
+    }
     if (rc) return fail(rc, "relaxation failed");
     for (int v = 0; v < V; ++v) views[(size_t)v].pose = multiply(X[(size_t)v], views[(size_t)v].pose);   // pose <- lum_T * pose
   }

@@ -105,6 +105,9 @@ class Registrator {
                             double transformation_epsilon, double euclidean_fitness_epsilon,
                             std::vector<mvr_pair_report>* reports = nullptr);
   int registrationLUM(std::vector<View>& views, int max_iterations, double max_distance);
+  // One LUM edge: reciprocal correspondences source -> target under `guess` (source in the target's frame),
+  // reduced on the GPU to their moments (target frame).
+  int edgeMoments(const View& source, const View& target, double max_distance, const Matrix4f& guess, int slot, mvr_pair_moments& out);
   int refineAxis(const std::vector<View>& views);
   // computeError (mvr/src/registrator.cpp:466-515): reciprocal correspondences of neighbouring registered views;
   // returns per pair (count, mean squared distance).
@@ -130,6 +133,11 @@ class Registrator {
 // Ring loop closure (host): see lum.cpp.
 int ringClose(const std::vector<Matrix4d>& rel, const std::vector<double>& weight, bool relax, int iterations,
               const double* centre, double rot_scale, std::vector<Matrix4d>& abs_out);
+// LUM relaxation on correspondence moments (host): see lum.cpp.  edges[e] joins views src[e] -> tgt[e], sums in
+// the common world frame; X = rigid corrections, X[0] = identity.
+void momentsTransform(const mvr_pair_moments& in, const Matrix4d& pose, const double* new_origin, mvr_pair_moments& out);
+int lumRelax(const std::vector<mvr_pair_moments>& edges, const int* src, const int* tgt, int n_views, int iterations,
+             std::vector<Matrix4d>& X);
 // least squares min |A x - b| for a tall dense A (rows x cols, row-major): math_solvers::least_squares
 // (mvr/src/math_solvers.cpp:24-39, LAPACK dgels there; Householder QR here).
 bool leastSquares(const std::vector<double>& A, const std::vector<double>& b, int rows, int cols, std::vector<double>& x);

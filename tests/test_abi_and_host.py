@@ -179,3 +179,132 @@ def test_sharded_ring_over_gloo_world_size_2_equals_single_process(tmp_path, mvr
                  nn_queries=12345 + p) for p in range(V)]
     one = ring.close_ring(ring.gather_records(ring.pack_reports(reps, 0, V), 0, 1, V), c, 100.0)
     assert np.array_equal(np.stack(one), a)
+
+
+# ---- LUM relaxation on correspondence moments (lum.cpp lumRelax; reference mvr/src/registrator.cpp:627-663) ----------
+def _rigid(rng, rot, trans):
+    w = rot * rng.standard_normal(3)
+    th = np.linalg.norm(w)
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    R = np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * (K @ K)
+    T = np.eye(4)
+    T[:3, :3] = R
+    T[:3, 3] = trans * rng.standard_normal(3)
+    return T
+
+
+def _apply(T, p):
+    return p @ T[:3, :3].T + T[:3, 3]
+
+
+def test_pair_moments_transform_matches_moments_of_transformed_pairs(mvr):
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((500, 3)) * 40 + [0, 0, 900]
+    b = a + rng.standard_normal((500, 3))
+    T = _rigid(rng, 0.7, 50.0)
+    m = mvr.PairMoments.from_pairs(a, b, origin=[1, 2, 880])
+    got = mvr.pair_moments_transform(m, T, new_origin=[5, -3, 20]).as_dict()
+    want = mvr.PairMoments.from_pairs(_apply(T, a), _apply(T, b), origin=[5, -3, 20]).as_dict()
+    for k in ("n", "sa", "sb", "sba", "saa", "sbb", "d2"):
+        np.testing.assert_allclose(got[k], want[k], rtol=1e-10, atol=1e-6)
+    keep = mvr.pair_moments_transform(m, T).as_dict()   # default origin: pose * old origin
+    np.testing.assert_allclose(keep["origin"], _apply(T, np.array([[1.0, 2.0, 880.0]]))[0], atol=1e-9)
+
+
+def test_lum_relax_recovers_known_corrections_from_exact_pairs(mvr):
+    """Same surface points seen by both ends of every ring edge, views displaced rigidly: the relaxation must undo it."""
+    rng = np.random.default_rng(11)
+    V = 5
+    truth = [np.eye(4)] + [_rigid(rng, 0.01, 0.8) for _ in range(V - 1)]   # displacement D_v of view v (world frame)
+    edges, src, tgt = [], [], []
+    for i in range(V):
+        s, t = i, (i + 1) % V
+        p = rng.standard_normal((300, 3)) * 60 + [0, 0, 900]
+        edges.append(mvr.PairMoments.from_pairs(_apply(truth[s], p), _apply(truth[t], p), origin=[0, 0, 900]))
+        src.append(s); tgt.append(t)
+    X = mvr.lum_relax(edges, src, tgt, V, 16)
+    np.testing.assert_allclose(X[0], np.eye(4), atol=0)
+    for v in range(1, V):
+        np.testing.assert_allclose(X[v] @ truth[v], np.eye(4), atol=1e-8)   # X_v = D_v^-1 (D_0 = I fixes the gauge)
+
+
+def test_lum_relax_minimises_the_pair_cost_like_a_generic_solver(mvr):
+    from scipy.optimize import least_squares
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(5)
+    V = 4
+    disp = [np.eye(4)] + [_rigid(rng, 0.02, 1.0) for _ in range(V - 1)]
+    pairs, edges, src, tgt = [], [], [], []
+    for (s, t) in [(0, 1), (1, 2), (2, 3), (3, 0), (0, 2)]:          # a ring plus a chord: any graph is allowed
+        p = rng.standard_normal((200, 3)) * 50 + [0, 0, 900]
+        a = _apply(disp[s], p) + 0.3 * rng.standard_normal(p.shape)   # noisy: the optimum has a non-zero residual
+        b = _apply(disp[t], p) + 0.3 * rng.standard_normal(p.shape)
+        pairs.append((s, t, a, b))
+        edges.append(mvr.PairMoments.from_pairs(a, b, origin=[0, 0, 900]))
+        src.append(s); tgt.append(t)
+
+    def pose(x6):
+        T = np.eye(4)
+        T[:3, :3] = Rotation.from_rotvec(x6[:3]).as_matrix()
+        T[:3, 3] = x6[3:]
+        return T
+
+    def resid(x):
+        Xs = [np.eye(4)] + [pose(x[6 * k:6 * k + 6]) for k in range(V - 1)]
+        return np.concatenate([(_apply(Xs[s], a) - _apply(Xs[t], b)).ravel() for (s, t, a, b) in pairs])
+
+    sol = least_squares(resid, np.zeros(6 * (V - 1)), xtol=1e-14, ftol=1e-14, gtol=1e-14)
+    X = mvr.lum_relax(edges, src, tgt, V, 16)
+    cost = lambda Xs: sum(((_apply(Xs[s], a) - _apply(Xs[t], b)) ** 2).sum() for (s, t, a, b) in pairs)
+    c_lum, c_ref, c_0 = cost(X), 2.0 * sol.cost, cost([np.eye(4)] * V)
+    assert c_lum < 0.5 * c_0 and abs(c_lum - c_ref) <= 1e-9 * c_ref
+    for v in range(1, V):
+        np.testing.assert_allclose(X[v], pose(sol.x[6 * (v - 1):6 * v]), atol=1e-6)
+
+
+def test_lum_relax_edge_cases(mvr):
+    X = mvr.lum_relax([], [], [], 3, 16)                       # no edges: nothing moves
+    assert all(np.array_equal(x, np.eye(4)) for x in X)
+    empty = mvr.PairMoments()                                  # an edge without correspondences carries no information
+    rng = np.random.default_rng(2)
+    p = rng.standard_normal((50, 3)) * 30
+    D = _rigid(rng, 0.01, 0.5)
+    e01 = mvr.PairMoments.from_pairs(p, _apply(D, p))
+    X = mvr.lum_relax([e01, empty], [0, 1], [1, 2], 3, 16)
+    np.testing.assert_allclose(X[1] @ D, np.eye(4), atol=1e-8)  # view 1 follows its only edge
+    np.testing.assert_allclose(X[2], np.eye(4), atol=1e-12)     # view 2 is unconstrained: stays
+    with pytest.raises(mvr.MvrError):
+        mvr.lum_relax([e01], [0], [3], 3, 16)                   # view index out of range
+
+
+def test_lum_outer_loops_descend_steadily_on_oracle_correspondences(mvr, orc, synth):
+    """registrationLUM's loop (reciprocal correspondences -> moments -> 16 sweeps -> pose update), with the oracle's
+    correspondences: the mean pair distance and the pose error fall loop after loop (the former pose-graph
+    approximation of the edges diverged here after five loops)."""
+    V, n = 6, 4000
+    views, poses = synth.turntable_sequence(V, n)
+    E = synth.perturbation()
+    P = [(poses[v] @ E) if v % 2 else poses[v].copy() for v in range(V)]
+
+    def rot_err(Pv):
+        out = []
+        for v in range(V):
+            R = (np.linalg.inv(Pv[0]) @ Pv[v])[:3, :3] @ (np.linalg.inv(poses[0]) @ poses[v])[:3, :3].T
+            out.append(np.arcsin(min(1.0, 0.5 * np.linalg.norm([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]]))))
+        return max(out)
+
+    e0, msd = rot_err(P), []
+    for loop in range(10):
+        edges = []
+        for i in range(V):
+            s, t = i, (i + 1) % V
+            guess = (np.linalg.inv(P[t]) @ P[s]).astype(np.float32)
+            a = orc.transform(views[s], guess)
+            q, m, _ = orc.correspondences(a, views[t], 6.0, True)
+            mom = mvr.PairMoments.from_pairs(a[q, :3], views[t][m, :3], origin=synth.PIVOT)
+            edges.append(mvr.pair_moments_transform(mom, P[t]))
+        msd.append(sum(e.d2 for e in edges) / sum(e.n for e in edges))
+        X = mvr.lum_relax(edges, list(range(V)), [(i + 1) % V for i in range(V)], V, 16)
+        P = [X[v] @ P[v] for v in range(V)]
+    assert e0 > 0.02 and rot_err(P) < 0.75 * e0
+    assert all(b < a * 1.01 for a, b in zip(msd, msd[1:])) and msd[-1] < 0.7 * msd[0]

@@ -213,6 +213,30 @@ def test_correspondences_empty_and_tiny(ctx, orc):
     assert len(q) == 0
 
 
+# ---- LUM edge statistics: moments of the correspondence pairs ------------------------------------------
+@pytest.mark.parametrize("reciprocal", [True, False])
+def test_pair_moments_match_numpy_sums_over_oracle_correspondences(ctx, orc, mvr, synth, reciprocal):
+    src, tgt, guess, _ = _pair(synth, 30_000, n_views=12)
+    ctx.set_target(tgt)
+    ctx.set_source(src)
+    got = ctx.pair_moments(4.0, reciprocal, guess).as_dict()
+    a = orc.transform(src, guess)
+    q, m, d2 = orc.correspondences(a, tgt, 4.0, reciprocal)
+    want = mvr.PairMoments.from_pairs(a[q, :3], tgt[m, :3], origin=got["origin"]).as_dict()
+    assert got["n"] == len(q) > 1000
+    for k in ("sa", "sb", "sba", "saa", "sbb"):
+        np.testing.assert_allclose(got[k], want[k], rtol=1e-11, atol=1e-7 * len(q))
+    assert abs(got["d2"] - float(d2.astype(np.float64).sum())) <= 1e-12 * got["d2"]
+
+
+def test_pair_moments_without_correspondences(ctx, mvr):
+    rng = np.random.default_rng(4)
+    ctx.set_target(random_cloud(rng, 500, scale=5.0))
+    ctx.set_source(random_cloud(rng, 300, scale=5.0) + np.float32([1000, 0, 0, 0]))
+    m = ctx.pair_moments(2.0, True, None)
+    assert m.n == 0 and m.d2 == 0
+
+
 # ---- ICP -------------------------------------------------------------------------------------------
 def _pair(synth, n, n_views=24):
     tgt, Tt = synth.turntable_view(0, n_views, n)
