@@ -130,6 +130,10 @@ int mvr_set_target(mvr_ctx* ctx, const float* xyzw, size_t n);
 int mvr_set_source(mvr_ctx* ctx, const float* xyzw, size_t n);
 int mvr_set_target_device(mvr_ctx* ctx, const float* d_xyzw, size_t n);
 int mvr_set_source_device(mvr_ctx* ctx, const float* d_xyzw, size_t n);
+/* Give `dst` the cloud another context of the same device already holds (same device pointer, same bounding box:
+ * nothing is copied or recomputed).  The points must stay alive and unchanged while `dst` uses them -- a view of a
+ * turntable ring is the target of one pair and the source of the next. */
+int mvr_cloud_share(mvr_ctx* dst, int which_dst /* mvr_cloud */, mvr_ctx* src, int which_src);
 /* Optional per-target-point normals (n x {nx,ny,nz,curvature}) for point-to-plane ICP. */
 int mvr_set_target_normals(mvr_ctx* ctx, const float* nxyzc, size_t n);
 
@@ -158,6 +162,16 @@ int mvr_correspondences(mvr_ctx* ctx, double max_dist, int reciprocal, int32_t* 
  *    logged "Not enough correspondences"; out_pose then holds the transform accumulated so far. */
 int mvr_icp_align(mvr_ctx* ctx, const mvr_icp_params* params, const float* guess, float* out_pose, float* out_xyzw,
                   mvr_icp_report* report);
+/* `count` aligns in lock-step: context k holds pair k's source and target, every pair advances one iteration per
+ * kernel launch (one launch serves the whole batch -- a single scan pair does not fill a B200).  Results are those of
+ * `count` separate mvr_icp_align calls.  guesses: count x float[16] (nullable: identities), out_poses: count x
+ * float[16], statuses: count x mvr_status of the individual aligns; the return value reports batch-level failures.
+ * All contexts must live on one device; the work runs on the first context's stream. */
+int mvr_icp_align_batch(mvr_ctx* const* ctxs, int count, const mvr_icp_params* params, const float* guesses, float* out_poses,
+                        mvr_icp_report* reports, int* statuses);
+/* Pairs per kernel launch of the batches this context leads (1..8, default 8): a group of pairs runs all its
+ * iterations before the next group starts, so that its working set stays in L2. */
+int mvr_ctx_set_batch_group(mvr_ctx* ctx, int pairs);
 /* Per-iteration records of the last align (n_correspondences, mse, delta). */
 int mvr_icp_get_iterations(mvr_ctx* ctx, mvr_icp_iteration* out, int max_records, int* count);
 /* Registration::getFitnessScore(max_range) (mvr/src/registrator.cpp:572, 923, 1015): mean squared

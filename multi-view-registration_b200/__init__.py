@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmvr_b200.so")
+LIB_PATH = os.environ.get("MVR_B200_LIB") or os.path.join(_HERE, "libmvr_b200.so")   # the override is a development aid (A/B builds)
 
 K_NAMES = ["morton", "sort", "table", "nn", "corr", "reduce", "transform", "normals"]
 K_COUNT = 8
@@ -158,6 +158,7 @@ def lib():
     L.mvr_debug_value.argtypes = [vp, C.c_int]
     L.mvr_debug_value.restype = C.c_double
     L.mvr_ctx_set_index_options.argtypes = [vp, C.c_float, C.c_int]
+    L.mvr_ctx_set_batch_group.argtypes = [vp, C.c_int]
     for name in ("mvr_set_target", "mvr_set_source", "mvr_set_target_device", "mvr_set_source_device", "mvr_set_target_normals"):
         getattr(L, name).argtypes = [vp, vp, C.c_size_t]
     L.mvr_index_build.argtypes = [vp, C.c_int, C.POINTER(Grid)]
@@ -166,6 +167,7 @@ def lib():
     L.mvr_nn_query_device.argtypes = [vp, vp, C.c_size_t, vp, vp]
     L.mvr_correspondences.argtypes = [vp, C.c_double, C.c_int, ip, ip, fp, C.POINTER(C.c_size_t)]
     L.mvr_icp_align.argtypes = [vp, C.POINTER(IcpParams), fp, fp, vp, C.POINTER(IcpReport)]
+    L.mvr_icp_align_batch.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(IcpParams), fp, fp, C.POINTER(IcpReport), ip]
     L.mvr_icp_get_iterations.argtypes = [vp, C.POINTER(IcpIteration), C.c_int, C.POINTER(C.c_int)]
     L.mvr_fitness_score.argtypes = [vp, C.c_double, C.POINTER(C.c_double)]
     L.mvr_estimate_normals.argtypes = [vp, C.c_int, C.c_int, fp, fp, ip]
@@ -296,6 +298,10 @@ class Context:
         self._ck(lib().mvr_ctx_set_index_options(self._h, C.c_float(cell_edge), int(max_bits)))
 
     # -- inputs --------------------------------------------------------------------------------
+    def set_batch_group(self, pairs):
+        """Pairs per kernel launch of the batches this context leads (1..8)."""
+        self._ck(lib().mvr_ctx_set_batch_group(self._h, int(pairs)))
+
     def set_target(self, pts):
         pts = _pts(pts)
         self._ck(lib().mvr_set_target(self._h, pts.ctypes.data, len(pts)))
@@ -451,6 +457,25 @@ def ring_close(rel_poses, weights=None, relax=True, iterations=16, centre=None, 
     if rc != OK:
         raise MvrError(rc, lib().mvr_status_string(rc).decode())
     return [pose_to_numpy(out[k]) for k in range(V)]
+
+
+def icp_align_batch(contexts, params, guesses=None):
+    """mvr_icp_align_batch: the aligns of `contexts` (each with its own source/target) in lock-step, one kernel launch
+    per iteration half for all of them.  Returns a list of dicts like Context.icp_align."""
+    n = len(contexts)
+    hs = (C.c_void_p * max(n, 1))(*[c._h for c in contexts])
+    g = None
+    if guesses is not None:
+        g = np.ascontiguousarray(np.stack([pose_from_numpy(T) for T in guesses]), dtype=np.float32)
+    fin = np.empty((max(n, 1), 16), dtype=np.float32)
+    reps = (IcpReport * max(n, 1))()
+    st = np.zeros(max(n, 1), dtype=np.int32)
+    rc = lib().mvr_icp_align_batch(hs, n, C.byref(params), _fp(g) if g is not None else None, _fp(fin), reps, _ip(st))
+    if rc != OK:
+        raise MvrError(rc, (lib().mvr_last_error(contexts[0]._h) or b"").decode() if n else "bad batch")
+    return [dict(status=int(st[k]), final=pose_to_numpy(fin[k]), iterations=reps[k].iterations, converged=bool(reps[k].converged),
+                 reason=reps[k].reason, n_corr=reps[k].n_correspondences, mse=reps[k].mse, gpu_ms=reps[k].gpu_ms,
+                 nn_queries=int(reps[k].nn_queries)) for k in range(n)]
 
 
 def pair_moments_transform(m, pose, new_origin=None):

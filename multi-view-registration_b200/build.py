@@ -54,11 +54,11 @@ def stale():
     return any(os.path.getmtime(p) > t for p in deps())
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, out=None):
+    if out is None and not force and not stale():
         return LIB
     extra = os.environ.get("MVR_NVCC_DEFS", "").split()   # development: e.g. MVR_NVCC_DEFS="-DMVR_BS_THREADS=64"
-    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-shared", "-o", LIB, "-x", "cu"] + sources()
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-shared", "-o", out or LIB, "-x", "cu"] + sources()
     if verbose:
         cmd += ["-Xptxas", "-v"]
         print(" ".join(cmd))
@@ -69,7 +69,7 @@ def build(force=False, verbose=False):
         sys.stderr.write(res.stdout)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libmvr_b200.so")
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

@@ -101,7 +101,9 @@ struct mvr_ctx {
   DevBuf normals; bool has_normals = false;
   DevBuf cur, corr_p, corr_j, corr_d2, rmin, rnn, partials, sums, out_cloud, qtmp, itmp, ftmp, scratch, misc, tiles, state, log;
   PairIndex pt, ps;              // target / source index of the running align
-  DevBuf pkeys, pvals, pkeys_alt, pvals_alt, phist, pmoved;
+  FwdArgs fa{}; RevArgs ra{};    // kernel arguments of the prepared align
+  int group_pairs = 8;           // pairs per launch of a batch led by this context (mvr_ctx_set_batch_group)
+  DevBuf pkeys, pvals, pmoved, pcount;   // build scratch of the per-align indices: keys, arrival ranks, arrival-order records, cell counters
   uint32_t scan_epoch = 1;
   IcpState* h_state = nullptr;   // pinned staging copy of the device IcpState
   IterRec* h_log = nullptr;      // pinned, ICP_MAX_LOG records
@@ -475,25 +477,29 @@ int build_pair_index(mvr_ctx* ctx, PairIndex& ix, const float4* pts, int n, int 
   const size_t nn = (size_t)std::max(n, 1);
   CK(ctx->pkeys.ensure(nn * sizeof(uint32_t)));
   CK(ctx->pvals.ensure(nn * sizeof(uint32_t)));
-  CK(ctx->pkeys_alt.ensure(nn * sizeof(uint32_t)));
-  CK(ctx->pvals_alt.ensure(nn * sizeof(uint32_t)));
-  CK(ctx->phist.ensure((size_t)256 * radix_num_blocks(n) * sizeof(uint32_t)));
-  if (guess) CK(ctx->pmoved.ensure(nn * sizeof(float4)));
+  CK(ctx->pmoved.ensure(nn * sizeof(float4)));
   CK(ix.sorted.ensure(nn * sizeof(float4)));
   CK(ix.start.ensure(((size_t)cells + 2) * sizeof(uint32_t)));
   if (keep_s0) CK(ix.s0.ensure(nn * sizeof(float4)));
+  if (((size_t)cells + 1) * sizeof(uint32_t) > ctx->pcount.cap) {
+    CK(ctx->pcount.ensure(((size_t)cells + 1) * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(ctx->pcount.p, 0, ctx->pcount.cap, ctx->stream));   // k_scan_cells keeps the counters zero afterwards
+  }
+  const size_t tiles = (size_t)scan_num_tiles((size_t)cells + 1);
+  if (tiles * sizeof(unsigned long long) > ctx->tiles.cap) {
+    CK(ctx->tiles.ensure(tiles * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(ctx->tiles.p, 0, ctx->tiles.cap, ctx->stream));
+  }
   ix.valid = false;
-  ProfScope ps(ctx, MVR_K_SORT, (keep_s0 ? 48.0 : 32.0) * n + 4.0 * cells, n);
-  CK(launch_pair_keys(pts, n, guess, g, cells, guess ? ctx->pmoved.as<float4>() : nullptr, ctx->pkeys.as<uint32_t>(),
-                      ctx->pvals.as<uint32_t>(), ctx->stream));
-  int key_bits = 1;
-  while (((uint64_t)1 << key_bits) <= (uint64_t)cells) ++key_bits;   // the sentinel key `cells` must sort last
-  SortScratch sc{ctx->pkeys_alt.as<uint32_t>(), ctx->pvals_alt.as<uint32_t>(), ctx->phist.as<uint32_t>()};
-  uint32_t *sk = nullptr, *perm = nullptr;
-  CK(launch_radix_sort(ctx->pkeys.as<uint32_t>(), ctx->pvals.as<uint32_t>(), n, key_bits, sc, &sk, &perm, ctx->stream));
-  CK(launch_pair_gather(guess ? ctx->pmoved.as<float4>() : pts, perm, n, ix.sorted.as<float4>(), keep_s0 ? ix.s0.as<float4>() : nullptr,
-                        ctx->stream));
-  CK(launch_cell_table_n(sk, n, cells, ix.start.as<uint32_t>(), ctx->stream));
+  ProfScope ps(ctx, MVR_K_SORT, (keep_s0 ? 48.0 : 32.0) * n + 8.0 * cells, n);
+  CK(launch_pair_count(pts, n, guess, g, cells, ctx->pkeys.as<uint32_t>(), ctx->pvals.as<uint32_t>(), ctx->pcount.as<uint32_t>(), ctx->stream));
+  CK(launch_scan_cells(ctx->pcount.as<uint32_t>(), ix.start.as<uint32_t>(), (size_t)cells + 1, ctx->tiles.as<unsigned long long>(),
+                       ctx->scan_epoch, nullptr, ctx->stream));
+  ctx->scan_epoch = (ctx->scan_epoch % 0x3fffffffu) + 1;
+  CK(launch_pair_scatter(pts, n, guess, ctx->pkeys.as<uint32_t>(), ctx->pvals.as<uint32_t>(), ix.start.as<uint32_t>(),
+                         ctx->pmoved.as<float4>(), ctx->stream));
+  CK(launch_pair_rerank(ctx->pmoved.as<float4>(), n, ctx->pkeys.as<uint32_t>(), ix.start.as<uint32_t>(), ix.sorted.as<float4>(),
+                        keep_s0 ? ix.s0.as<float4>() : nullptr, ctx->stream));
   ix.g = g; ix.cells = cells; ix.n_valid = n - n_bad; ix.valid = true;
   return MVR_OK;
 }
@@ -610,7 +616,7 @@ int mvr_ctx_destroy(mvr_ctx* ctx) {
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   ctx->tgt.release(); ctx->src.release(); ctx->qry.release(); ctx->normals.release();
   ctx->pt.release(); ctx->ps.release();
-  ctx->pkeys.release(); ctx->pvals.release(); ctx->pkeys_alt.release(); ctx->pvals_alt.release(); ctx->phist.release(); ctx->pmoved.release();
+  ctx->pkeys.release(); ctx->pvals.release(); ctx->pmoved.release(); ctx->pcount.release();
   DevBuf* bufs[] = {&ctx->cur, &ctx->corr_p, &ctx->rmin, &ctx->rnn, &ctx->corr_j, &ctx->corr_d2, &ctx->partials, &ctx->sums, &ctx->out_cloud, &ctx->qtmp,
                     &ctx->itmp, &ctx->ftmp, &ctx->scratch, &ctx->misc, &ctx->tiles, &ctx->state, &ctx->log};
   for (DevBuf* b : bufs) b->release();
@@ -669,6 +675,12 @@ int mvr_ctx_set_index_options(mvr_ctx* ctx, float cell_edge, int max_bits) {
   return MVR_OK;
 }
 
+int mvr_ctx_set_batch_group(mvr_ctx* ctx, int pairs) {
+  if (!ctx || pairs < 1 || pairs > (int)FUSED_MAX_PAIRS) return MVR_ERR_BAD_ARG;
+  ctx->group_pairs = pairs;
+  return MVR_OK;
+}
+
 int mvr_set_target(mvr_ctx* ctx, const float* xyzw, size_t n) {
   if (!ctx) return MVR_ERR_BAD_ARG;
   cudaSetDevice(ctx->device);
@@ -692,6 +704,22 @@ int mvr_set_source_device(mvr_ctx* ctx, const float* d, size_t n) {
   cudaSetDevice(ctx->device);
   ctx->have_out = false;
   return cloud_set(ctx, ctx->src, d, n, true);
+}
+
+int mvr_cloud_share(mvr_ctx* dst, int which_dst, mvr_ctx* src, int which_src) {
+  if (!dst || !src || (which_dst != MVR_CLOUD_TARGET && which_dst != MVR_CLOUD_SOURCE) ||
+      (which_src != MVR_CLOUD_TARGET && which_src != MVR_CLOUD_SOURCE)) return MVR_ERR_BAD_ARG;
+  if (dst->device != src->device) return fail(dst, MVR_ERR_BAD_ARG, "contexts on different devices");
+  const Cloud& s = which_src == MVR_CLOUD_TARGET ? src->tgt : src->src;
+  Cloud& d = which_dst == MVR_CLOUD_TARGET ? dst->tgt : dst->src;
+  if (s.gen == 0) return fail(dst, MVR_ERR_NO_INPUT, "cloud not set");
+  if (&s == &d) return MVR_OK;
+  d.index_valid = false;
+  d.gen++;
+  d.pts = s.pts; d.n = s.n; d.n_bad = s.n_bad;
+  for (int a = 0; a < 3; ++a) { d.lo[a] = s.lo[a]; d.hi[a] = s.hi[a]; }
+  if (which_dst == MVR_CLOUD_TARGET) dst->has_normals = false; else dst->have_out = false;
+  return MVR_OK;
 }
 
 int mvr_set_target_normals(mvr_ctx* ctx, const float* nxyzc, size_t n) {
@@ -809,11 +837,14 @@ int mvr_correspondences(mvr_ctx* ctx, double max_dist, int reciprocal, int32_t* 
   return MVR_OK;
 }
 
-// The align behind mvr_icp_align and mvr_pair_moments_compute.  est = EST_MOM accumulates second moments
-// next to the point-to-point sums; they are those of the LAST iteration's correspondence set.
-static int icp_align_impl(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, float* out_pose, float* out_xyzw,
-                          mvr_icp_report* report, bool moments) {
-  if (!ctx || !prm) return MVR_ERR_BAD_ARG;
+// ---- the align behind mvr_icp_align, mvr_icp_align_batch and mvr_pair_moments_compute ------------------------------
+// An align is split in three so that many of them can advance in lock-step, ONE launch per iteration half for the
+// whole batch (a single 200k-point pair fills a fraction of a B200):
+//   align_prepare : per context, on its own stream -- per-align indices, initial state, kernel arguments;
+//   align_run     : the iterations of every context of the batch, on the first context's stream;
+//   align_finish  : per context -- aligned cloud, iteration log, report.
+// est = EST_MOM accumulates second moments next to the point-to-point sums (those of the LAST iteration's pairs).
+static int align_prepare(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, int est) {
   cudaSetDevice(ctx->device);
   if (ctx->tgt.gen == 0 || ctx->src.gen == 0) return fail(ctx, MVR_ERR_NO_INPUT, "source/target not set");
   Cloud& s = ctx->src;
@@ -826,9 +857,7 @@ static int icp_align_impl(mvr_ctx* ctx, const mvr_icp_params* prm, const float* 
   if (guess) std::memcpy(G, guess, sizeof(G)); else mat_identity(G);
   const bool reciprocal = prm->use_reciprocal_correspondences != 0;
   const double max_dist = prm->max_correspondence_distance;
-  const bool p2l = prm->estimator == MVR_POINT_TO_PLANE;
-  if (moments && p2l) return fail(ctx, MVR_ERR_BAD_ARG, "pair moments are point-to-point statistics");
-  const int est = p2l ? EST_P2L : (moments ? EST_MOM : EST_P2P);
+  const bool p2l = est == EST_P2L;
 
   // ---- per-align indices: target over its own box (reused while the target and the grid stay the same),
   //      source over the box of the guessed source
@@ -868,8 +897,9 @@ static int icp_align_impl(mvr_ctx* ctx, const mvr_icp_params* prm, const float* 
   if (reciprocal) {
     CK(ctx->rmin.ensure((size_t)std::max(m, 1) * sizeof(uint32_t)));
     CK(launch_fill_u32(ctx->rmin.as<uint32_t>(), (size_t)std::max(m, 1), 0x7f800000u, ctx->stream));   // +inf: "chosen by nobody"
+    CK(ctx->rnn.ensure((size_t)std::max(m, 1) * sizeof(int32_t)));
   }
-  CK(ctx->partials.ensure((size_t)FUSED_BLOCKS * REDUCE_MAX_VALS * sizeof(double)));
+  CK(ctx->partials.ensure((size_t)FUSED_MAX_BLOCKS * REDUCE_MAX_VALS * sizeof(double)));
   CK(ctx->out_cloud.ensure((size_t)n * sizeof(float4)));
   CK(ctx->state.ensure(sizeof(IcpState)));
   CK(ctx->log.ensure((size_t)ICP_MAX_LOG * sizeof(IterRec)));
@@ -895,53 +925,104 @@ static int icp_align_impl(mvr_ctx* ctx, const mvr_icp_params* prm, const float* 
   h.min_corr = prm->min_correspondences > 0 ? prm->min_correspondences : 3;
   h.p2l = p2l; h.recip = reciprocal; h.n_src = n;
   if (prm->max_iterations <= 0) { h.done = 1; h.reason = MVR_REASON_ITERATIONS; }
-
-  CK(cudaEventRecord(ctx->ev_a, ctx->stream));
   CK(cudaMemcpyAsync(d_st, &h, sizeof(IcpState), cudaMemcpyHostToDevice, ctx->stream));
   ctx->iters.clear();
   ctx->have_out = false;
 
-  FwdArgs fa{};
+  FwdArgs& fa = ctx->fa;
+  fa = FwdArgs{};
   fa.cur = psx.sorted.as<float4>(); fa.s0 = reciprocal ? psx.s0.as<float4>() : nullptr; fa.n_valid = psx.n_valid;
   fa.tgt = pt.sorted.as<float4>(); fa.tstart = pt.start.as<uint32_t>(); fa.gt = pt.g; fa.m_valid = pt.n_valid;
   fa.corr_p = ctx->corr_p.as<int32_t>(); fa.rmin = reciprocal ? ctx->rmin.as<uint32_t>() : nullptr;
   fa.max2 = max_dist * max_dist; fa.max_d2f = gate_float(max_dist);
   fa.nrm = p2l ? ctx->normals.as<float4>() : nullptr;
-  fa.partials = ctx->partials.as<double>(); fa.st = d_st; fa.log = d_log; fa.first = 1;
-  RevArgs ra{};
+  fa.partials = ctx->partials.as<double>(); fa.st = d_st; fa.log = d_log; fa.grid = fused_grid(psx.n_valid);
+  RevArgs& ra = ctx->ra;
+  ra = RevArgs{};
   ra.tgt = fa.tgt; ra.m_valid = pt.n_valid; ra.rmin = fa.rmin; ra.cur = fa.cur; ra.sstart = psx.start.as<uint32_t>(); ra.gs = psx.g;
-  ra.n_valid = psx.n_valid; ra.corr_p = fa.corr_p; ra.nrm = fa.nrm; ra.partials = fa.partials; ra.st = d_st; ra.log = d_log;
+  ra.n_valid = psx.n_valid; ra.corr_p = fa.corr_p; ra.rnn = reciprocal ? ctx->rnn.as<int32_t>() : nullptr; ra.nrm = fa.nrm;
+  ra.partials = fa.partials; ra.st = d_st; ra.log = d_log; ra.grid = fused_grid(pt.n_valid);
+  return MVR_OK;
+}
 
-  // Enqueue iterations in batches; after each batch read the state back.  Once the device raises
-  // `done` the remaining launches of a batch return immediately.
-  int enqueued = 0;
-  int batch = h.fixed ? 64 : 2;
-  bool done = h.done != 0;
-  while (!done) {
-    int todo = std::min(batch, std::max(prm->max_iterations - enqueued, 1));
-    for (int it = 0; it < todo; ++it) {
-      // one scope = one iteration: forward search (+ transform), reciprocal search (+ sums, solve, criteria)
-      ProfScope ps(ctx, MVR_K_CORR, corr_bytes(n, m, reciprocal), (double)n);
-      CK(launch_icp_forward(fa, reciprocal, est, ctx->stream));
-      fa.first = 0;
-      if (reciprocal) CK(launch_icp_reverse(ra, est, ctx->stream));
-    }
-    enqueued += todo;
-    CK(cudaMemcpyAsync(&h, d_st, sizeof(IcpState), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    done = h.done != 0;
-    batch = std::min(batch * 2, 64);
+// The iterations of `count` prepared contexts (same device, same params) on the first one's stream.  The pairs
+// advance in lock-step in groups of ctx->group_pairs (<= FUSED_MAX_PAIRS): a group runs to completion before the next
+// one starts, so that its working set (~20 MB per 200k-point pair) stays in the 126 MB L2 across its iterations.
+static int align_run(mvr_ctx* const* ctxs, int count, const mvr_icp_params* prm, int est) {
+  mvr_ctx* ctx = ctxs[0];   // the lead: its stream carries the batch, CK() reports into it
+  cudaSetDevice(ctx->device);
+  const bool reciprocal = prm->use_reciprocal_correspondences != 0;
+  for (int k = 1; k < count; ++k) {   // the lead stream continues after every context's preparation
+    CK(cudaEventRecord(ctxs[k]->ev_b, ctxs[k]->stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctxs[k]->ev_b, 0));
   }
-  if (h.dbg[2] != 0) return fail(ctx, MVR_ERR_CUDA, "internal error: a reciprocal search lost its chooser (search bound violated)");
-  {
-    ProfScope ps(ctx, MVR_K_TRANSFORM, 32.0 * n, n);
-    CK(launch_transform_final(s.pts, ctx->out_cloud.as<float4>(), n, d_st, ctx->stream));
+  CK(cudaEventRecord(ctx->ev_a, ctx->stream));
+  const int gsz = std::max(1, std::min(ctx->group_pairs, (int)FUSED_MAX_PAIRS));
+  for (int g0 = 0; g0 < count; g0 += gsz) {
+    const int gn = std::min(gsz, count - g0);
+    FwdBatch fb{};
+    RevBatch rb{};
+    int gf = 1, gr = 1;
+    bool done = true;
+    long long n_tot = 0, m_tot = 0;
+    for (int k = 0; k < gn; ++k) {
+      mvr_ctx* c = ctxs[g0 + k];
+      fb.a[k] = c->fa; rb.a[k] = c->ra;
+      gf = std::max(gf, c->fa.grid); gr = std::max(gr, c->ra.grid);
+      if (!c->h_state->done) done = false;
+      n_tot += c->src.n; m_tot += c->tgt.n;
+    }
+    // Enqueue iterations in batches; after each batch read the states back.  Once a pair raises `done` its
+    // blocks of the remaining launches return immediately.
+    int enqueued = 0;
+    int batch = prm->fixed_iterations ? 64 : 2;
+    int first = 1;
+    while (!done) {
+      const int todo = std::min(batch, std::max(prm->max_iterations - enqueued, 1));
+      for (int it = 0; it < todo; ++it) {
+        // one scope = one iteration: forward search (+ transform), reciprocal search (+ sums, solve, criteria)
+        ProfScope ps(ctx, MVR_K_CORR, 24.0 * n_tot + 16.0 * m_tot + (reciprocal ? 16.0 * n_tot : 0.0), (double)n_tot);
+        CK(launch_icp_forward(fb, gn, gf, first, reciprocal, est, ctx->stream));
+        first = 0;
+        if (reciprocal) CK(launch_icp_reverse(rb, gn, gr, est, ctx->stream));
+      }
+      enqueued += todo;
+      for (int k = 0; k < gn; ++k)
+        CK(cudaMemcpyAsync(ctxs[g0 + k]->h_state, ctxs[g0 + k]->state.p, sizeof(IcpState), cudaMemcpyDeviceToHost, ctx->stream));
+      if (g0 + gn >= count || !prm->fixed_iterations) CK(cudaStreamSynchronize(ctx->stream));
+      done = true;
+      if (!prm->fixed_iterations)
+        for (int k = 0; k < gn; ++k) if (!ctxs[g0 + k]->h_state->done) done = false;
+      batch = std::min(batch * 2, 64);
+      if (prm->fixed_iterations && enqueued < prm->max_iterations) done = false;
+    }
   }
   CK(cudaEventRecord(ctx->ev_b, ctx->stream));
-  const int n_log = std::min(h.iter, (int)ICP_MAX_LOG);
-  if (n_log > 0) CK(cudaMemcpyAsync(ctx->h_log, d_log, (size_t)n_log * sizeof(IterRec), cudaMemcpyDeviceToHost, ctx->stream));
-  if (out_xyzw) CK(cudaMemcpyAsync(out_xyzw, ctx->out_cloud.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return MVR_OK;
+}
+
+// lead: the context whose stream ran the batch (its ev_a .. ev_b bracket the iterations).  Split in two so that a
+// batch enqueues the tails of all its aligns before it waits once.
+static int align_finish_enqueue(mvr_ctx* ctx, mvr_ctx* lead, float* out_xyzw) {
+  const IcpState& h = *ctx->h_state;
+  const int n = ctx->src.n;
+  cudaStream_t st = lead->stream;
+  if (h.dbg[2] != 0) return fail(ctx, MVR_ERR_CUDA, "internal error: a reciprocal search lost its chooser (search bound violated)");
+  {
+    ProfScope ps(lead, MVR_K_TRANSFORM, 32.0 * n, n);
+    CK(launch_transform_final(ctx->src.pts, ctx->out_cloud.as<float4>(), n, ctx->state.as<IcpState>(), st));
+  }
+  const int n_log = std::min(h.iter, (int)ICP_MAX_LOG);
+  if (n_log > 0) CK(cudaMemcpyAsync(ctx->h_log, ctx->log.p, (size_t)n_log * sizeof(IterRec), cudaMemcpyDeviceToHost, st));
+  if (out_xyzw) CK(cudaMemcpyAsync(out_xyzw, ctx->out_cloud.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, st));
+  return MVR_OK;
+}
+
+// After the lead stream has been synchronised.
+static int align_finish_collect(mvr_ctx* ctx, mvr_ctx* lead, float* out_pose, mvr_icp_report* report) {
+  const IcpState& h = *ctx->h_state;
+  const int n_log = std::min(h.iter, (int)ICP_MAX_LOG);
   ctx->have_out = true;
   for (int k = 0; k < n_log; ++k) {
     mvr_icp_iteration rec;
@@ -952,7 +1033,7 @@ static int icp_align_impl(mvr_ctx* ctx, const mvr_icp_params* prm, const float* 
   if (out_pose) for (int k = 0; k < 16; ++k) out_pose[k] = (float)h.fin[k];
   if (report) {
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
+    cudaEventElapsedTime(&ms, lead->ev_a, lead->ev_b);
     report->iterations = h.iter; report->converged = (h.done && h.status == 0) ? 1 : 0; report->reason = h.reason;
     report->n_correspondences = h.n_corr; report->mse = h.cur_mse; report->gpu_ms = ms; report->nn_queries = h.queries;
   }
@@ -961,9 +1042,56 @@ static int icp_align_impl(mvr_ctx* ctx, const mvr_icp_params* prm, const float* 
   return h.status;
 }
 
+static int align_finish(mvr_ctx* ctx, mvr_ctx* lead, float* out_pose, float* out_xyzw, mvr_icp_report* report) {
+  int rc = align_finish_enqueue(ctx, lead, out_xyzw);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(lead->stream));
+  return align_finish_collect(ctx, lead, out_pose, report);
+}
+
+static int icp_align_impl(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, float* out_pose, float* out_xyzw,
+                          mvr_icp_report* report, bool moments) {
+  if (!ctx || !prm) return MVR_ERR_BAD_ARG;
+  const bool p2l = prm->estimator == MVR_POINT_TO_PLANE;
+  if (moments && p2l) return fail(ctx, MVR_ERR_BAD_ARG, "pair moments are point-to-point statistics");
+  const int est = p2l ? EST_P2L : (moments ? EST_MOM : EST_P2P);
+  int rc = align_prepare(ctx, prm, guess, est);
+  if (rc) return rc;
+  if ((rc = align_run(&ctx, 1, prm, est))) return rc;
+  return align_finish(ctx, ctx, out_pose, out_xyzw, report);
+}
+
 int mvr_icp_align(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, float* out_pose, float* out_xyzw,
                   mvr_icp_report* report) {
   return icp_align_impl(ctx, prm, guess, out_pose, out_xyzw, report, false);
+}
+
+int mvr_icp_align_batch(mvr_ctx* const* ctxs, int count, const mvr_icp_params* prm, const float* guesses, float* out_poses,
+                        mvr_icp_report* reports, int* statuses) {
+  if (count < 0 || (count && (!ctxs || !statuses)) || !prm) return MVR_ERR_BAD_ARG;
+  if (count == 0) return MVR_OK;
+  for (int k = 0; k < count; ++k) {
+    if (!ctxs[k]) return MVR_ERR_BAD_ARG;
+    for (int j = 0; j < k; ++j) if (ctxs[j] == ctxs[k]) return fail(ctxs[0], MVR_ERR_BAD_ARG, "a context appears twice in the batch");
+    if (ctxs[k]->device != ctxs[0]->device) return fail(ctxs[0], MVR_ERR_BAD_ARG, "the contexts of a batch must share a device");
+  }
+  const int est = prm->estimator == MVR_POINT_TO_PLANE ? EST_P2L : EST_P2P;
+  std::vector<mvr_ctx*> ok;
+  std::vector<int> slot;
+  for (int k = 0; k < count; ++k) {
+    statuses[k] = align_prepare(ctxs[k], prm, guesses ? guesses + 16 * k : nullptr, est);
+    if (statuses[k] == MVR_OK) { ok.push_back(ctxs[k]); slot.push_back(k); }
+  }
+  if (ok.empty()) return MVR_OK;
+  int rc = align_run(ok.data(), (int)ok.size(), prm, est);
+  if (rc) { if (ok[0] != ctxs[0]) ctxs[0]->err = ok[0]->err; return rc; }
+  for (size_t j = 0; j < ok.size(); ++j) statuses[slot[j]] = align_finish_enqueue(ok[j], ok[0], nullptr);
+  if (cudaStreamSynchronize(ok[0]->stream) != cudaSuccess) return fail(ctxs[0], MVR_ERR_CUDA, "batch tail failed");
+  for (size_t j = 0; j < ok.size(); ++j) {
+    const int k = slot[j];
+    if (statuses[k] == MVR_OK) statuses[k] = align_finish_collect(ok[j], ok[0], out_poses ? out_poses + 16 * k : nullptr, reports ? reports + k : nullptr);
+  }
+  return MVR_OK;
 }
 
 int mvr_pair_moments_compute(mvr_ctx* ctx, double max_dist, int reciprocal, const float* guess, mvr_pair_moments* out) {

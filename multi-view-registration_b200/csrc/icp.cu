@@ -12,6 +12,11 @@
 #include "pair_search.cuh"
 #include "small_solve.h"
 
+// candidates evaluated per trip of the flat scan = independent 16-byte loads in flight per thread (measured: 8 > 4 > 2)
+#ifndef MVR_PG_UNROLL
+#define MVR_PG_UNROLL 8
+#endif
+
 namespace mvr {
 
 // ---------------------------------------------------------------------------------------------
@@ -19,9 +24,10 @@ namespace mvr {
 // 8 warps in order -> REDUCE_BLOCKS partials summed in block order by the last block to finish), so
 // results are identical run to run and do not depend on the order of points inside grid cells.
 // ---------------------------------------------------------------------------------------------
-template <int NV>
+// WARPS = warps of the calling block (8 for the 256-thread utility kernels, FUSED_WARPS for the fused iteration).
+template <int NV, int WARPS = 8>
 __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* __restrict__ partials) {
-  __shared__ double sm[8][NV];
+  __shared__ double sm[WARPS][NV];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int a = 0; a < NV; ++a) {
@@ -34,20 +40,20 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* __re
   if (threadIdx.x < NV) {
     double x = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) x += sm[w][threadIdx.x];
+    for (int w = 0; w < WARPS; ++w) x += sm[w][threadIdx.x];
     partials[(size_t)blockIdx.x * REDUCE_MAX_VALS + threadIdx.x] = x;
   }
 }
 
 // True in exactly one block per launch: the one that finished last.  On return in that block every
 // block's partials are visible.
-__device__ __forceinline__ bool last_block_done(unsigned int* ticket) {
+__device__ __forceinline__ bool last_block_done(unsigned int* ticket, unsigned int nblk) {
   __shared__ bool is_last;
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned int t = atomicAdd(ticket, 1u);
-    is_last = (t == gridDim.x - 1);
+    is_last = (t == nblk - 1);
     if (is_last) *ticket = 0;
   }
   __syncthreads();
@@ -55,25 +61,32 @@ __device__ __forceinline__ bool last_block_done(unsigned int* ticket) {
   return is_last;
 }
 
-// Ordered sum of the blocks' partials: 8 chunks of consecutive blocks summed in parallel (each in
-// block order), then the 8 chunk sums in chunk order.  Called by all 256 threads of the last block.
+// Ordered sum of the blocks' partials: FUSED_WARPS chunks of consecutive blocks summed in parallel (each in block
+// order, 8 loads in flight), then the chunk sums in chunk order.  Called by all threads of the last block.
 template <int NV>
 __device__ __forceinline__ void ordered_total(const double* __restrict__ partials, int nblk, double* __restrict__ out) {
-  __shared__ double ch[8][REDUCE_MAX_VALS];
+  __shared__ double ch[FUSED_WARPS][REDUCE_MAX_VALS];
   const int a = threadIdx.x & 31, c = threadIdx.x >> 5;
-  const int per = (nblk + 7) / 8;
+  const int per = (nblk + FUSED_WARPS - 1) / FUSED_WARPS;
   if (a < NV) {
     const int b0 = c * per, b1 = min(b0 + per, nblk);
     double x = 0;
-#pragma unroll 8
-    for (int b = b0; b < b1; ++b) x += __ldcg(partials + (size_t)b * REDUCE_MAX_VALS + a);
+    int b = b0;
+    for (; b + 8 <= b1; b += 8) {
+      double t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = __ldcg(partials + (size_t)(b + u) * REDUCE_MAX_VALS + a);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) x += t[u];
+    }
+    for (; b < b1; ++b) x += __ldcg(partials + (size_t)b * REDUCE_MAX_VALS + a);
     ch[c][a] = x;
   }
   __syncthreads();
   if (threadIdx.x < NV) {
     double x = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) x += ch[k][threadIdx.x];
+    for (int k = 0; k < FUSED_WARPS; ++k) x += ch[k][threadIdx.x];
     out[threadIdx.x] = x;
   }
   __syncthreads();
@@ -269,10 +282,10 @@ __device__ __forceinline__ void acc_p2l(double (&v)[REDUCE_P2L_VALS], float4 s, 
 // Block partials -> (last block) ordered total -> solve, compose, criteria.
 template <int NV>
 __device__ __forceinline__ void reduce_and_finish(double (&v)[NV], double* __restrict__ partials, IcpState* __restrict__ st,
-                                                  IterRec* __restrict__ log) {
-  block_reduce_store<NV>(v, partials);
-  if (!last_block_done(&st->ticket)) return;
-  ordered_total<NV>(partials, gridDim.x, st->sums);
+                                                  IterRec* __restrict__ log, int nblk) {
+  block_reduce_store<NV, FUSED_WARPS>(v, partials);
+  if (!last_block_done(&st->ticket, (unsigned int)nblk)) return;
+  ordered_total<NV>(partials, nblk, st->sums);
   if (threadIdx.x == 0) {
     const long long t0 = clock64();
     icp_finish_iteration(st, log);
@@ -289,32 +302,34 @@ __device__ __forceinline__ void acc_pair(double (&v)[NV], float4 s, float4 t, co
   else acc_p2p(v, s, t, d2, ox, oy, oz);
 }
 
+// Phase A of both kernels is the search (registers: the query, the running best, grid geometry); phase B
+// re-reads the matches the block found and accumulates the estimator sums (registers: 18-30 doubles).  The
+// two never overlap, so the kernel's register budget is the larger of the two, not their sum.
 template <bool RECIP, int EST>
-__global__ void __launch_bounds__(FUSED_THREADS) k_icp_forward(FwdArgs a) {
+__global__ void __launch_bounds__(FUSED_THREADS, (RECIP ? 4 : 3) * (256 / FUSED_THREADS)) k_icp_forward(const __grid_constant__ FwdBatch batch, int first) {
+  // this pair's arguments: parameter space -> shared memory (a dynamically indexed parameter would be copied to
+  // local memory and pin registers)
+  __shared__ FwdArgs s_args;
+  static_assert(sizeof(FwdArgs) % 4 == 0 && sizeof(FwdArgs) / 4 <= FUSED_THREADS, "argument block");
+  if (threadIdx.x < sizeof(FwdArgs) / 4) ((uint32_t*)&s_args)[threadIdx.x] = ((const uint32_t*)&batch.a[blockIdx.y])[threadIdx.x];
+  __syncthreads();
+  const FwdArgs& a = s_args;
+  if ((int)blockIdx.x >= a.grid) return;
   IcpState* __restrict__ st = a.st;
   if (st->done) return;
+  const int stride = a.grid * FUSED_THREADS;
+  __shared__ uint2 s_seg[PG_SEGS * PG_STRIDE];
+  uint2* seg = s_seg + threadIdx.x;
   Mat4f M;
-  if (!a.first) {
+  if (!first) {
 #pragma unroll
     for (int k = 0; k < 16; ++k) M.m[k] = st->delta[k];
   }
-  double C[12];   // rows of cum: ref = C * s0
-  if (RECIP) {
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) C[r * 4 + c] = st->cum[c * 4 + r];
-  }
-  const double ox = st->ox, oy = st->oy, oz = st->oz;
-  constexpr int NV = EstVals<EST>::value;
-  double v[NV];
-#pragma unroll
-  for (int k = 0; k < NV; ++k) v[k] = 0.0;
   float devmax = 0.0f;
   unsigned int ngate = 0;
-  for (int i = blockIdx.x * FUSED_THREADS + threadIdx.x; i < a.n_valid; i += gridDim.x * FUSED_THREADS) {
+  for (int i = blockIdx.x * FUSED_THREADS + threadIdx.x; i < a.n_valid; i += stride) {
     float4 p = a.cur[i];
-    if (!a.first) {
+    if (!first) {
       const float w = p.w;
       p = xform_pinned(M, p);
       p.w = w;
@@ -323,9 +338,9 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_icp_forward(FwdArgs a) {
     if (RECIP) {
       // how far the float chain of in-place transforms has drifted from cum * (binning-time position)
       const float4 s = __ldg(a.s0 + i);
-      const double ex = C[0] * s.x + C[1] * s.y + C[2] * s.z + C[3] - (double)p.x;
-      const double ey = C[4] * s.x + C[5] * s.y + C[6] * s.z + C[7] - (double)p.y;
-      const double ez = C[8] * s.x + C[9] * s.y + C[10] * s.z + C[11] - (double)p.z;
+      const double ex = st->cum[0] * s.x + st->cum[4] * s.y + st->cum[8] * s.z + st->cum[12] - (double)p.x;
+      const double ey = st->cum[1] * s.x + st->cum[5] * s.y + st->cum[9] * s.z + st->cum[13] - (double)p.y;
+      const double ez = st->cum[2] * s.x + st->cum[6] * s.y + st->cum[10] * s.z + st->cum[14] - (double)p.z;
       devmax = fmaxf(devmax, (float)sqrt(ex * ex + ey * ey + ez * ez) * 1.000001f);
     }
     NnBest b{MVR_INF, 0x7fffffff, -1};
@@ -334,88 +349,155 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_icp_forward(FwdArgs a) {
       const float4 t = __ldg(a.tgt + j0);
       b.d2 = d2_pinned(p.x, p.y, p.z, t.x, t.y, t.z); b.idx = __float_as_int(t.w); b.pos = j0;
     }
-    pg_search(a.gt, a.tstart, a.tgt, a.m_valid, p.x, p.y, p.z, p.x, p.y, p.z, 0.0f, 1.0f, a.max_d2f, b);
+    pg_search<MVR_PG_UNROLL>(a.gt, a.tstart, a.tgt, a.m_valid, p.x, p.y, p.z, p.x, p.y, p.z, 0.0f, 1.0f, a.max_d2f, b, seg);
     const bool keep = b.pos >= 0 && !((double)b.d2 > a.max2);   // PCL: if (distance > max_dist_sqr) continue;
     a.corr_p[i] = keep ? b.pos : -1;
     if (keep) {
       ++ngate;
-      if (RECIP) {
-        atomicMin(a.rmin + b.pos, __float_as_uint(b.d2));
-      } else {
-        acc_pair<EST>(v, p, __ldg(a.tgt + b.pos), a.nrm, b.d2, ox, oy, oz);
-      }
+      if (RECIP) atomicMin(a.rmin + b.pos, __float_as_uint(b.d2));
     }
   }
   if (RECIP) {
-    __shared__ unsigned int s_dev, s_gate;
-    if (threadIdx.x == 0) { s_dev = 0u; s_gate = 0u; }
-    __syncthreads();
+    // warp-level: no block barrier, a warp that is done is done
     const unsigned int wd = __reduce_max_sync(0xffffffffu, __float_as_uint(devmax));   // non-negative floats order like their bits
     const unsigned int wg = __reduce_add_sync(0xffffffffu, ngate);
-    if ((threadIdx.x & 31) == 0) { atomicMax(&s_dev, wd); atomicAdd(&s_gate, wg); }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      if (s_dev) atomicMax(&st->dev_bits, s_dev);
-      if (s_gate) atomicAdd(&st->n_gate, s_gate);
+    if ((threadIdx.x & 31) == 0) {
+      if (wd) atomicMax(&st->dev_bits, wd);
+      if (wg) atomicAdd(&st->n_gate, wg);
     }
   } else {
-    reduce_and_finish<NV>(v, a.partials, st, a.log);
+    // phase B: every thread revisits exactly the points it searched (its own writes, no barrier needed)
+    const double ox = st->ox, oy = st->oy, oz = st->oz;
+    constexpr int NV = EstVals<EST>::value;
+    double v[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = 0.0;
+    for (int i = blockIdx.x * FUSED_THREADS + threadIdx.x; i < a.n_valid; i += stride) {
+      const int j = a.corr_p[i];
+      if (j < 0) continue;
+      const float4 p = a.cur[i];
+      const float4 t = __ldg(a.tgt + j);
+      acc_pair<EST>(v, p, t, a.nrm, d2_pinned(p.x, p.y, p.z, t.x, t.y, t.z), ox, oy, oz);
+    }
+    reduce_and_finish<NV>(v, a.partials, st, a.log, a.grid);
   }
 }
 
+// Reciprocal half.  Only the target points some source point chose are searched; a block compacts them
+// (in order) into a queue so that every lane of every warp searches.  Results go to rnn[j] = sorted position
+// of the mutual partner, -1 otherwise; phase B sums over them.
 template <int EST>
-__global__ void __launch_bounds__(FUSED_THREADS) k_icp_reverse(RevArgs a) {
+__global__ void __launch_bounds__(FUSED_THREADS, 3 * (256 / FUSED_THREADS)) k_icp_reverse(const __grid_constant__ RevBatch batch) {
+  __shared__ RevArgs s_args;
+  static_assert(sizeof(RevArgs) % 4 == 0 && sizeof(RevArgs) / 4 <= FUSED_THREADS, "argument block");
+  if (threadIdx.x < sizeof(RevArgs) / 4) ((uint32_t*)&s_args)[threadIdx.x] = ((const uint32_t*)&batch.a[blockIdx.y])[threadIdx.x];
+  __syncthreads();
+  const RevArgs& a = s_args;
+  if ((int)blockIdx.x >= a.grid) return;
   IcpState* __restrict__ st = a.st;
   if (st->done) return;
-  double Ci[12];
-#pragma unroll
-  for (int k = 0; k < 12; ++k) Ci[k] = st->cinv[k];
+  __shared__ uint2 s_seg[PG_SEGS * PG_STRIDE];
+  __shared__ int s_q[2 * FUSED_THREADS];
+  __shared__ int s_wcnt[FUSED_THREADS / 32];
+  __shared__ int s_qn;
+  uint2* seg = s_seg + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float stretch = st->stretch;
   const float dev0 = __uint_as_float(st->dev_bits) * 1.000001f;
+  unsigned int missed = 0;
+  if (threadIdx.x == 0) s_qn = 0;
+  __syncthreads();
+
+  auto search_one = [&](int j) {
+    const uint32_t r = a.rmin[j];
+    a.rmin[j] = 0x7f800000u;          // re-armed for the next iteration
+    const float4 t = __ldg(a.tgt + j);
+    // the query in the frame the source was binned in
+    const float ux = (float)(st->cinv[0] * t.x + st->cinv[1] * t.y + st->cinv[2] * t.z + st->cinv[3]);
+    const float uy = (float)(st->cinv[4] * t.x + st->cinv[5] * t.y + st->cinv[6] * t.z + st->cinv[7]);
+    const float uz = (float)(st->cinv[8] * t.x + st->cinv[9] * t.y + st->cinv[10] * t.z + st->cinv[11]);
+    const float dev = dev0 + 1.0e-6f * fmaxf(fabsf(ux), fmaxf(fabsf(uy), fabsf(uz)));
+    // a chooser sits at exactly this distance: the lexicographic minimum (d2, index) over all source points is found
+    NnBest b{__uint_as_float(r), 0x7fffffff, -1};
+    pg_search<MVR_PG_UNROLL>(a.gs, a.sstart, a.cur, a.n_valid, t.x, t.y, t.z, ux, uy, uz, dev, stretch, MVR_INF, b, seg);
+    if (b.pos < 0) ++missed;
+    a.rnn[j] = (b.pos >= 0 && __ldg(a.corr_p + b.pos) == j) ? b.pos : -1;   // mutual, or the nearest source point chose another target
+  };
+
+  const int chunks = (a.m_valid + FUSED_THREADS - 1) / FUSED_THREADS;
+  for (int c = blockIdx.x; c < chunks; c += a.grid) {
+    const int j = c * FUSED_THREADS + threadIdx.x;
+    const bool chosen = j < a.m_valid && a.rmin[j] != 0x7f800000u;
+    if (j < a.m_valid && !chosen) a.rnn[j] = -1;
+    const unsigned int bal = __ballot_sync(0xffffffffu, chosen);
+    if (lane == 0) s_wcnt[warp] = __popc(bal);
+    __syncthreads();
+    int ofs = s_qn, tot = 0;
+#pragma unroll
+    for (int w = 0; w < FUSED_THREADS / 32; ++w) { const int n = s_wcnt[w]; if (w < warp) ofs += n; tot += n; }
+    if (chosen) s_q[ofs + __popc(bal & ((1u << lane) - 1u))] = j;
+    __syncthreads();
+    int qn = s_qn + tot;   // the same in every thread
+    if (qn >= FUSED_THREADS) {
+      search_one(s_q[threadIdx.x]);
+      __syncthreads();
+      const int rest = qn - FUSED_THREADS;
+      const int mv = threadIdx.x < rest ? s_q[FUSED_THREADS + threadIdx.x] : 0;
+      __syncthreads();
+      if (threadIdx.x < rest) s_q[threadIdx.x] = mv;
+      qn = rest;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_qn = qn;
+    __syncthreads();
+  }
+  if (threadIdx.x < s_qn) search_one(s_q[threadIdx.x]);
+  if (missed) atomicAdd((unsigned long long*)&st->dbg[2], (unsigned long long)missed);   // must stay 0: a chooser was not found again
+  __syncthreads();   // rnn of this block's chunks is complete (written by whichever thread drew the item)
+
   const double ox = st->ox, oy = st->oy, oz = st->oz;
   constexpr int NV = EstVals<EST>::value;
   double v[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) v[k] = 0.0;
-  unsigned int missed = 0;
-  for (int j = blockIdx.x * FUSED_THREADS + threadIdx.x; j < a.m_valid; j += gridDim.x * FUSED_THREADS) {
-    const uint32_t r = a.rmin[j];
-    if (r == 0x7f800000u) continue;   // no source point chose this target point
-    a.rmin[j] = 0x7f800000u;          // re-armed for the next iteration
+  for (int c = blockIdx.x; c < chunks; c += a.grid) {
+    const int j = c * FUSED_THREADS + threadIdx.x;
+    if (j >= a.m_valid) continue;
+    const int r = a.rnn[j];
+    if (r < 0) continue;
     const float4 t = __ldg(a.tgt + j);
-    // the query in the frame the source was binned in
-    const float ux = (float)(Ci[0] * t.x + Ci[1] * t.y + Ci[2] * t.z + Ci[3]);
-    const float uy = (float)(Ci[4] * t.x + Ci[5] * t.y + Ci[6] * t.z + Ci[7]);
-    const float uz = (float)(Ci[8] * t.x + Ci[9] * t.y + Ci[10] * t.z + Ci[11]);
-    const float dev = dev0 + 1.0e-6f * fmaxf(fabsf(ux), fmaxf(fabsf(uy), fabsf(uz)));
-    // a chooser sits at exactly this distance: the lexicographic minimum (d2, index) over all source points is found
-    NnBest b{__uint_as_float(r), 0x7fffffff, -1};
-    pg_search(a.gs, a.sstart, a.cur, a.n_valid, t.x, t.y, t.z, ux, uy, uz, dev, stretch, MVR_INF, b);
-    if (b.pos < 0) { ++missed; continue; }
-    if (__ldg(a.corr_p + b.pos) != j) continue;   // the nearest source point chose another target point
-    acc_pair<EST>(v, __ldg(a.cur + b.pos), t, a.nrm, b.d2, ox, oy, oz);
+    const float4 s = a.cur[r];
+    acc_pair<EST>(v, s, t, a.nrm, d2_pinned(t.x, t.y, t.z, s.x, s.y, s.z), ox, oy, oz);
   }
-  if (missed) atomicAdd((unsigned long long*)&st->dbg[2], (unsigned long long)missed);   // must stay 0: a chooser was not found again
-  reduce_and_finish<NV>(v, a.partials, st, a.log);
+  reduce_and_finish<NV>(v, a.partials, st, a.log, a.grid);
 }
 
-cudaError_t launch_icp_forward(const FwdArgs& a, bool reciprocal, int est, cudaStream_t s) {
+int fused_grid(int items) {
+  const int blocks = (items + FUSED_THREADS - 1) / FUSED_THREADS;
+  return blocks < 1 ? 1 : (blocks > FUSED_MAX_BLOCKS ? FUSED_MAX_BLOCKS : blocks);
+}
+
+cudaError_t launch_icp_forward(const FwdBatch& d_batch, int pairs, int max_grid, int first, bool reciprocal, int est, cudaStream_t s) {
+  if (pairs <= 0 || pairs > FUSED_MAX_PAIRS) return pairs <= 0 ? cudaSuccess : cudaErrorInvalidValue;
+  const dim3 grid((unsigned)max_grid, (unsigned)pairs);
   if (reciprocal) {
     // the reciprocal forward half accumulates nothing: one instantiation serves every estimator
-    k_icp_forward<true, EST_P2P><<<FUSED_BLOCKS, FUSED_THREADS, 0, s>>>(a);
+    k_icp_forward<true, EST_P2P><<<grid, FUSED_THREADS, 0, s>>>(d_batch, first);
   } else {
-    if (est == EST_P2L) k_icp_forward<false, EST_P2L><<<FUSED_BLOCKS, FUSED_THREADS, 0, s>>>(a);
-    else if (est == EST_MOM) k_icp_forward<false, EST_MOM><<<FUSED_BLOCKS, FUSED_THREADS, 0, s>>>(a);
-    else k_icp_forward<false, EST_P2P><<<FUSED_BLOCKS, FUSED_THREADS, 0, s>>>(a);
+    if (est == EST_P2L) k_icp_forward<false, EST_P2L><<<grid, FUSED_THREADS, 0, s>>>(d_batch, first);
+    else if (est == EST_MOM) k_icp_forward<false, EST_MOM><<<grid, FUSED_THREADS, 0, s>>>(d_batch, first);
+    else k_icp_forward<false, EST_P2P><<<grid, FUSED_THREADS, 0, s>>>(d_batch, first);
   }
   count_launch();
   return cudaGetLastError();
 }
 
-cudaError_t launch_icp_reverse(const RevArgs& a, int est, cudaStream_t s) {
-  if (est == EST_P2L) k_icp_reverse<EST_P2L><<<FUSED_BLOCKS, FUSED_THREADS, 0, s>>>(a);
-  else if (est == EST_MOM) k_icp_reverse<EST_MOM><<<FUSED_BLOCKS, FUSED_THREADS, 0, s>>>(a);
-  else k_icp_reverse<EST_P2P><<<FUSED_BLOCKS, FUSED_THREADS, 0, s>>>(a);
+cudaError_t launch_icp_reverse(const RevBatch& d_batch, int pairs, int max_grid, int est, cudaStream_t s) {
+  if (pairs <= 0 || pairs > FUSED_MAX_PAIRS) return pairs <= 0 ? cudaSuccess : cudaErrorInvalidValue;
+  const dim3 grid((unsigned)max_grid, (unsigned)pairs);
+  if (est == EST_P2L) k_icp_reverse<EST_P2L><<<grid, FUSED_THREADS, 0, s>>>(d_batch);
+  else if (est == EST_MOM) k_icp_reverse<EST_MOM><<<grid, FUSED_THREADS, 0, s>>>(d_batch);
+  else k_icp_reverse<EST_P2P><<<grid, FUSED_THREADS, 0, s>>>(d_batch);
   count_launch();
   return cudaGetLastError();
 }

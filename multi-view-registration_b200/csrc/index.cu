@@ -56,12 +56,27 @@ __global__ void __launch_bounds__(256) k_bbox(const float4* __restrict__ pts, in
     }
     bad += __shfl_xor_sync(0xffffffffu, bad, o);
   }
-  if ((threadIdx.x & 31) == 0) {
+  // one set of atomics per block, not per warp: they all hit the same seven words
+  __shared__ float s_lo[8][3], s_hi[8][3];
+  __shared__ uint32_t s_bad[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      if (lo[a] <= hi[a]) { atomicMin(out + a, f2ord(lo[a])); atomicMax(out + 3 + a, f2ord(hi[a])); }
-    }
-    if (bad) atomicAdd(out + 6, bad);
+    for (int a = 0; a < 3; ++a) { s_lo[warp][a] = lo[a]; s_hi[warp][a] = hi[a]; }
+    s_bad[warp] = bad;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const int a = threadIdx.x;
+    float l = MVR_INF, h = -MVR_INF;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { l = fminf(l, s_lo[w][a]); h = fmaxf(h, s_hi[w][a]); }
+    if (l <= h) { atomicMin(out + a, f2ord(l)); atomicMax(out + 3 + a, f2ord(h)); }
+  } else if (threadIdx.x == 3) {
+    uint32_t b = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) b += s_bad[w];
+    if (b) atomicAdd(out + 6, b);
   }
 }
 
@@ -72,7 +87,7 @@ cudaError_t launch_bbox_init(uint32_t* out7, cudaStream_t s) {
 
 cudaError_t launch_bbox(const float4* pts, int n, uint32_t* out7, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  int blocks = min((n + 255) / 256, 148 * 4);
+  int blocks = min((n + 1023) / 1024, 148 * 2);
   k_bbox<<<blocks, 256, 0, s>>>(pts, n, out7); count_launch();
   return cudaGetLastError();
 }
@@ -317,13 +332,6 @@ cudaError_t launch_cell_table(const uint32_t* sorted_keys, int n, int bits, uint
   long long threads = (long long)n + 1;
   int blocks = (int)((threads + 255) / 256);
   k_cell_table<<<blocks, 256, 0, s>>>(sorted_keys, n, C, start); count_launch();
-  return cudaGetLastError();
-}
-
-cudaError_t launch_cell_table_n(const uint32_t* sorted_keys, int n, uint32_t cells, uint32_t* start, cudaStream_t s) {
-  long long threads = (long long)n + 1;
-  int blocks = (int)((threads + 255) / 256);
-  k_cell_table<<<blocks, 256, 0, s>>>(sorted_keys, n, cells, start); count_launch();
   return cudaGetLastError();
 }
 

@@ -109,15 +109,23 @@ struct IcpState {
 };
 
 // ---- fused iteration (icp.cu) + per-align index (pair_index.cu) ---------------------------------
-enum { FUSED_THREADS = 256, FUSED_BLOCKS = 148 * 4 };
+#ifndef MVR_FUSED_THREADS
+#define MVR_FUSED_THREADS 256
+#endif
+// grid = min(ceil(items / FUSED_THREADS), FUSED_MAX_BLOCKS): a pure function of the cloud size
+enum { FUSED_THREADS = MVR_FUSED_THREADS, FUSED_WARPS = FUSED_THREADS / 32, FUSED_MAX_BLOCKS = 148 * 8 * (256 / FUSED_THREADS) };
 
-// Row-major key of every point (after the optional pinned transform by *guess), `moved` (nullable) = the
-// transformed points; keys of non-finite points = cells.
-cudaError_t launch_pair_keys(const float4* in, int n, const Mat4f* guess, PairGrid g, uint32_t cells, float4* moved, uint32_t* keys,
-                             uint32_t* vals, cudaStream_t s);
-// sorted[k] = {pts[perm[k]].xyz, bits(perm[k])}; copy (nullable) gets the same.
-cudaError_t launch_pair_gather(const float4* pts, const uint32_t* perm, int n, float4* sorted, float4* copy, cudaStream_t s);
-cudaError_t launch_cell_table_n(const uint32_t* sorted_keys, int n, uint32_t cells, uint32_t* start, cudaStream_t s);
+// Deterministic counting sort of a cloud by row-major cell (pair_index.cu): count (keys + arrival ranks; counters
+// has cells + 1 zeroed entries, the last one collects non-finite points), launch_scan_cells (bin.cu), scatter into
+// tmp in arrival order, rerank into ascending original index inside every cell.  guess (nullable) is applied to the
+// points first (pinned float transform).
+cudaError_t launch_pair_count(const float4* in, int n, const Mat4f* guess, PairGrid g, uint32_t cells, uint32_t* keys, uint32_t* rank,
+                              uint32_t* counters, cudaStream_t s);
+cudaError_t launch_pair_scatter(const float4* in, int n, const Mat4f* guess, const uint32_t* keys, const uint32_t* rank, const uint32_t* start,
+                                float4* tmp, cudaStream_t s);
+// sorted[k] = {moved point, bits(original index)}; copy (nullable) gets the same.
+cudaError_t launch_pair_rerank(const float4* tmp, int n, const uint32_t* keys, const uint32_t* start, float4* sorted, float4* copy,
+                               cudaStream_t s);
 
 struct FwdArgs {
   float4* cur;             // source, sorted by binning cell, current coordinates (updated in place), .w = original index
@@ -132,10 +140,10 @@ struct FwdArgs {
   double max2;             // gate, exact (PCL compares in double)
   float max_d2f;           // gate rounded up to float: bounds the search
   const float4* nrm;       // target normals by ORIGINAL index (point-to-plane only)
-  double* partials;        // FUSED_BLOCKS x REDUCE_MAX_VALS
+  double* partials;        // FUSED_MAX_BLOCKS x REDUCE_MAX_VALS
   IcpState* st;
   IterRec* log;
-  int first;               // first iteration of an align: the guess is already applied, no increment pending
+  int grid;                // blocks that work on this pair (a pure function of the cloud size): fused_grid(n_valid)
 };
 struct RevArgs {
   const float4* tgt;
@@ -146,15 +154,25 @@ struct RevArgs {
   PairGrid gs;
   int n_valid;
   const int32_t* corr_p;
+  int32_t* rnn;            // [target sorted position] sorted position of its mutual source partner, -1 none
   const float4* nrm;
   double* partials;
   IcpState* st;
   IterRec* log;
+  int grid;                // fused_grid(m_valid)
 };
 // est: which sums the iteration accumulates over its correspondences
 enum { EST_P2P = 0, EST_P2L = 1, EST_MOM = 2 /* point-to-point + second moments (LUM edge statistics) */ };
-cudaError_t launch_icp_forward(const FwdArgs& a, bool reciprocal, int est, cudaStream_t s);
-cudaError_t launch_icp_reverse(const RevArgs& a, int est, cudaStream_t s);
+// One launch advances EVERY pair of a group by one iteration half: blockIdx.y selects the pair, blockIdx.x < grid of
+// that pair does its work.  The arguments of all pairs travel by value in the kernel's parameter (constant) space, so
+// indexing them by pair costs no registers.  max_grid = the largest grid of the group.
+// first: first iteration of the aligns (the guess is already applied, no increment pending).
+enum { FUSED_MAX_PAIRS = 8 };
+struct FwdBatch { FwdArgs a[FUSED_MAX_PAIRS]; };
+struct RevBatch { RevArgs a[FUSED_MAX_PAIRS]; };
+int fused_grid(int items);
+cudaError_t launch_icp_forward(const FwdBatch& batch, int pairs, int max_grid, int first, bool reciprocal, int est, cudaStream_t s);
+cudaError_t launch_icp_reverse(const RevBatch& batch, int pairs, int max_grid, int est, cudaStream_t s);
 // corr_j[i] = original index of the matched target point, -1 = none, -2-j = passed the gate but failed
 // the reciprocal test (the layout launch_compact_corr consumes).
 cudaError_t launch_resolve_corr(const int32_t* corr_p, const int32_t* rnn, const float4* tgt_sorted, int n, int32_t* corr_j,

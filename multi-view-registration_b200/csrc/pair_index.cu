@@ -7,57 +7,82 @@
 // guessed source box.  The source then moves rigidly every iteration but keeps its cells: the search
 // (pair_search.cuh) carries the query into the binning frame instead of re-sorting 200k points 30 times.
 //
-//   k_pair_keys    : p <- guess * p (pinned float transform, ICP's transformCloud) when a
-//                    guess is given; key = row-major cell (z, y, x; x fastest), non-finite points get the
-//                    sentinel key `cells`; value = original index
-//   radix sort     : the stable LSD sort of index.cu on ceil(log2(cells + 1)) bits -> points of a cell
-//                    stay in ascending original index, so every sorted position, and with it the order
-//                    of every later reduction, is reproducible run to run
-//   k_pair_gather  : sorted[k] = {moved point, bits(original index)} (+ a second copy: the source keeps
-//                    its binning-time coordinates s0 next to the coordinates that move)
-//   k_cell_table   : start[c] = first sorted position of cell c (index.cu)
+// The build is a counting sort made deterministic (four launches, no multi-pass radix sort):
+//   k_pair_count   : p <- guess * p (pinned float transform, ICP's transformCloud) when a guess is
+//                    given; key = row-major cell (z, y, x; x fastest), non-finite points get the sentinel key
+//                    `cells`; rank = the point's arrival number in its cell (one atomicAdd on the cell counter)
+//   k_scan_cells   : exclusive scan of the counters -> start[c] = first sorted position of cell c (bin.cu)
+//   k_pair_scatter : tmp[start[key] + rank] = {moved point, bits(original index)} -- arrival order inside a cell
+//   k_pair_rerank  : the final position of a point = start[key] + number of points of its cell with a SMALLER
+//                    original index (its cell is ~10 contiguous records of tmp), so points of a cell end up in
+//                    ascending original index whatever order the atomics ran in: every sorted position, and with
+//                    it the order of every later reduction, is reproducible run to run.  The source also gets a
+//                    second copy s0 = its binning-time coordinates next to the coordinates that move.
 //
-// Algorithmic bytes per point: 16 read + 16 (32 with the s0 copy) written, + 4 B per cell.
+// Algorithmic bytes per point: 16 read + 16 (32 with the s0 copy) written, + 8 B per cell.
 #include "launch.h"
 #include "pair_search.cuh"
 
 namespace mvr {
 
-__global__ void __launch_bounds__(256) k_pair_keys(const float4* __restrict__ in, int n, Mat4f M, int apply, PairGrid g, uint32_t cells,
-                                                   float4* __restrict__ moved, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+__global__ void __launch_bounds__(256) k_pair_count(const float4* __restrict__ in, int n, Mat4f M, int apply, PairGrid g, uint32_t cells,
+                                                    uint32_t* __restrict__ keys, uint32_t* __restrict__ rank, uint32_t* __restrict__ counters) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 p = __ldg(in + i);
   const bool ok = finite3(p);
   if (apply && ok) p = xform_pinned(M, p);
-  if (moved) moved[i] = p;
-  keys[i] = ok ? pg_key(p, g) : cells;
-  vals[i] = (uint32_t)i;
+  const uint32_t key = ok ? pg_key(p, g) : cells;
+  keys[i] = key;
+  rank[i] = atomicAdd(counters + key, 1u);
 }
 
-__global__ void __launch_bounds__(256) k_pair_gather(const float4* __restrict__ pts, const uint32_t* __restrict__ perm, int n,
-                                                     float4* __restrict__ sorted, float4* __restrict__ copy) {
+__global__ void __launch_bounds__(256) k_pair_scatter(const float4* __restrict__ in, int n, Mat4f M, int apply, const uint32_t* __restrict__ keys,
+                                                      const uint32_t* __restrict__ rank, const uint32_t* __restrict__ start, float4* __restrict__ tmp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = __ldg(in + i);
+  if (apply && finite3(p)) p = xform_pinned(M, p);   // the same pinned arithmetic as k_pair_count: the same point
+  p.w = __uint_as_float((uint32_t)i);
+  tmp[__ldg(start + __ldg(keys + i)) + __ldg(rank + i)] = p;
+}
+
+__global__ void __launch_bounds__(256) k_pair_rerank(const float4* __restrict__ tmp, int n, const uint32_t* __restrict__ keys,
+                                                     const uint32_t* __restrict__ start, float4* __restrict__ sorted, float4* __restrict__ copy) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const uint32_t j = __ldg(perm + k);
-  float4 p = __ldg(pts + j);
-  p.w = __uint_as_float(j);
-  sorted[k] = p;
-  if (copy) copy[k] = p;
+  const float4 p = __ldg(tmp + k);
+  const uint32_t idx = __float_as_uint(p.w);
+  const uint32_t key = __ldg(keys + idx);
+  const uint32_t s = __ldg(start + key), e = __ldg(start + key + 1);
+  uint32_t r = 0;
+  for (uint32_t j = s; j < e; ++j) r += (__float_as_uint(__ldg(&tmp[j].w)) < idx) ? 1u : 0u;
+  sorted[s + r] = p;
+  if (copy) copy[s + r] = p;
 }
 
-cudaError_t launch_pair_keys(const float4* in, int n, const Mat4f* guess, PairGrid g, uint32_t cells, float4* moved, uint32_t* keys,
-                             uint32_t* vals, cudaStream_t s) {
+cudaError_t launch_pair_count(const float4* in, int n, const Mat4f* guess, PairGrid g, uint32_t cells, uint32_t* keys, uint32_t* rank,
+                              uint32_t* counters, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   Mat4f M{};
   if (guess) M = *guess;
-  k_pair_keys<<<(n + 255) / 256, 256, 0, s>>>(in, n, M, guess ? 1 : 0, g, cells, moved, keys, vals); count_launch();
+  k_pair_count<<<(n + 255) / 256, 256, 0, s>>>(in, n, M, guess ? 1 : 0, g, cells, keys, rank, counters); count_launch();
   return cudaGetLastError();
 }
 
-cudaError_t launch_pair_gather(const float4* pts, const uint32_t* perm, int n, float4* sorted, float4* copy, cudaStream_t s) {
+cudaError_t launch_pair_scatter(const float4* in, int n, const Mat4f* guess, const uint32_t* keys, const uint32_t* rank, const uint32_t* start,
+                                float4* tmp, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  k_pair_gather<<<(n + 255) / 256, 256, 0, s>>>(pts, perm, n, sorted, copy); count_launch();
+  Mat4f M{};
+  if (guess) M = *guess;
+  k_pair_scatter<<<(n + 255) / 256, 256, 0, s>>>(in, n, M, guess ? 1 : 0, keys, rank, start, tmp); count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pair_rerank(const float4* tmp, int n, const uint32_t* keys, const uint32_t* start, float4* sorted, float4* copy,
+                               cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  k_pair_rerank<<<(n + 255) / 256, 256, 0, s>>>(tmp, n, keys, start, sorted, copy); count_launch();
   return cudaGetLastError();
 }
 

@@ -61,20 +61,64 @@ __device__ __forceinline__ void pg_scan(const float4* __restrict__ pts, uint32_t
   }
 }
 
+// Segment list of one thread in shared memory: slot j of thread t lives at seg[j * PG_STRIDE + t] (bank = t).
+constexpr int PG_SEGS = 8;        // row segments collected before a flat scan
+constexpr int PG_STRIDE = FUSED_THREADS;
+
+// Flat scan of the thread's collected segments: ONE loop over all candidates of all rows, PG_UNROLL
+// independent loads per trip, so the trip count of a warp is the maximum over its lanes of the TOTAL
+// number of candidates (not the sum over rows of per-row maxima) and the loads of a trip overlap.
+// Past a segment's end the last point is simply evaluated again: a duplicate never wins a strict
+// lexicographic comparison.
+template <int UNROLL>
+__device__ __forceinline__ void pg_flat_scan(const float4* __restrict__ pts, const uint2* __restrict__ seg, int nseg, float qx, float qy,
+                                             float qz, NnBest& b) {
+  int j = 0;
+  uint32_t k = 0, e = 0;
+  for (;;) {
+    while (k >= e) {
+      if (j >= nseg) return;
+      const uint2 s = seg[j * PG_STRIDE];
+      ++j;
+      k = s.x; e = s.y;
+    }
+    float4 p[UNROLL];
+    uint32_t kk[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) { kk[u] = min(k + (uint32_t)u, e - 1u); p[u] = __ldg(pts + kk[u]); }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const float d = d2_pinned(qx, qy, qz, p[u].x, p[u].y, p[u].z);
+      const int id = __float_as_int(p[u].w);
+      if (lex_less(d, id, b.d2, b.idx)) { b.d2 = d; b.idx = id; b.pos = (int)kk[u]; }
+    }
+    k += UNROLL;
+  }
+}
+
 // Nearest point to q among `pts` (current coordinates, .w = original index) sorted by the row-major
 // cell of the positions they were BINNED at.  (ux, uy, uz): the query carried into the binning frame
 // (= q when the points have not moved).  dev / stretch: see the header (0 / 1 for a static cloud).
 // gate: nothing farther than this (float d2, rounded up) is of interest, +inf for none.  b may be
 // pre-seeded with a real candidate or with a bare distance bound (idx = INT_MAX).
+// seg: this thread's slot column of a PG_SEGS x PG_STRIDE shared-memory array.
+//
+// Two phases per batch of rows: (1) walk the rows of the ball's box, prune by their lower bounds, and
+// collect the surviving x runs as (start, end) segments; (2) scan all collected candidates in one flat
+// loop.  A loose bound (ball wider than a cell: first iterations, bare gates) is first tightened on the
+// query's own row.
+template <int UNROLL>
 __device__ __forceinline__ void pg_search(const PairGrid& g, const uint32_t* __restrict__ start, const float4* __restrict__ pts,
                                           int n_valid, float qx, float qy, float qz, float ux, float uy, float uz, float dev,
-                                          float stretch, float gate, NnBest& b) {
+                                          float stretch, float gate, NnBest& b, uint2* __restrict__ seg) {
   if (n_valid <= 0) return;
   const float tx = grid_t(ux, g.ox, g.inv_cell), ty = grid_t(uy, g.oy, g.inv_cell), tz = grid_t(uz, g.oz, g.inv_cell);
   const int cx = pg_cell(tx, g.nx), cy = pg_cell(ty, g.ny), cz = pg_cell(tz, g.nz);
   const float margin = MVR_CELL_MARGIN + 1.0e-6f * fmaxf(fabsf(tx), fmaxf(fabsf(ty), fabsf(tz))) + dev * stretch * g.inv_cell * 1.000001f;
   const float cell2 = g.cell_lo * g.cell_lo * MVR_REL_SHRINK / (stretch * stretch * 1.000001f);
   const float inv_cell2 = 1.000002f / cell2;
+  const float rscale = stretch * g.inv_cell * 1.000001f;
+  const float fx = (float)(g.nx - 1), fy = (float)(g.ny - 1), fz = (float)(g.nz - 1);
   const int rowlen = g.nx, slab = g.nx * g.ny;
 
   float lim = fminf(b.d2, gate);
@@ -95,35 +139,44 @@ __device__ __forceinline__ void pg_search(const PairGrid& g, const uint32_t* __r
     lim = b.d2;
   }
 
-  const float rc = sqrtf(lim) * stretch * g.inv_cell * 1.000001f + margin;
-  const int x0 = (int)fminf(fmaxf(floorf(tx - rc), 0.0f), (float)(g.nx - 1)), x1 = (int)fminf(fmaxf(floorf(tx + rc), 0.0f), (float)(g.nx - 1));
-  const int y0 = (int)fminf(fmaxf(floorf(ty - rc), 0.0f), (float)(g.ny - 1)), y1 = (int)fminf(fmaxf(floorf(ty + rc), 0.0f), (float)(g.ny - 1));
-  const int z0 = (int)fminf(fmaxf(floorf(tz - rc), 0.0f), (float)(g.nz - 1)), z1 = (int)fminf(fmaxf(floorf(tz + rc), 0.0f), (float)(g.nz - 1));
-
-  // own row first: it usually tightens the limit for all the others
-  if (cy >= y0 && cy <= y1 && cz >= z0 && cz <= z1) {
+  bool own_done = false;
+  float rc = sqrtf(lim) * rscale + margin;
+  if (rc > 1.25f) {
+    // loose bound: the own row usually tightens it for all the others
+    const int x0 = (int)fminf(fmaxf(floorf(tx - rc), 0.0f), fx), x1 = (int)fminf(fmaxf(floorf(tx + rc), 0.0f), fx);
     const uint32_t* row = start + (size_t)cz * slab + (size_t)cy * rowlen;
     pg_scan(pts, __ldg(row + x0), __ldg(row + x1 + 1), qx, qy, qz, b);
     lim = fminf(b.d2, gate);
+    rc = sqrtf(lim) * rscale + margin;
+    own_done = true;   // [x0, x1] of the own row covers whatever the tighter ball still needs there
   }
-  for (int z = z0; z <= z1; ++z) {
-    const float ez = fmaxf(cell_gap(tz, z, g.nz) - margin, 0.0f);
-    const float ez2 = ez * ez;
-    if (ez2 * cell2 > lim) continue;
-    for (int y = y0; y <= y1; ++y) {
-      if (y == cy && z == cz) continue;
+  const int x0 = (int)fminf(fmaxf(floorf(tx - rc), 0.0f), fx), x1 = (int)fminf(fmaxf(floorf(tx + rc), 0.0f), fx);
+  const int y0 = (int)fminf(fmaxf(floorf(ty - rc), 0.0f), fy), y1 = (int)fminf(fmaxf(floorf(ty + rc), 0.0f), fy);
+  const int z0 = (int)fminf(fmaxf(floorf(tz - rc), 0.0f), fz), z1 = (int)fminf(fmaxf(floorf(tz + rc), 0.0f), fz);
+
+  int y = y0, z = z0;
+  while (z <= z1) {
+    int nseg = 0;
+    // phase 1: collect up to PG_SEGS surviving rows
+    while (nseg < PG_SEGS && z <= z1) {
+      const float ez = fmaxf(cell_gap(tz, z, g.nz) - margin, 0.0f);
       const float ey = fmaxf(cell_gap(ty, y, g.ny) - margin, 0.0f);
-      const float eyz = ez2 + ey * ey;
-      if (eyz * cell2 > lim) continue;
-      // x extent of the ball inside this row
-      const float rem = fmaxf(lim * inv_cell2 - eyz, 0.0f);
-      const float rx = sqrtf(rem) * 1.000001f + margin + margin;
-      const int xa = max(x0, (int)fminf(fmaxf(floorf(tx - rx), 0.0f), (float)(g.nx - 1)));
-      const int xb = min(x1, (int)fminf(fmaxf(floorf(tx + rx), 0.0f), (float)(g.nx - 1)));
-      const uint32_t* row = start + (size_t)z * slab + (size_t)y * rowlen;
-      pg_scan(pts, __ldg(row + xa), __ldg(row + xb + 1), qx, qy, qz, b);
-      lim = fminf(b.d2, gate);
+      const float eyz = ez * ez + ey * ey;
+      if (!(eyz * cell2 > lim) && !(own_done && y == cy && z == cz)) {
+        // x extent of the ball inside this row
+        const float rem = fmaxf(lim * inv_cell2 - eyz, 0.0f);
+        const float rx = sqrtf(rem) * 1.000001f + margin + margin;
+        const int xa = max(x0, (int)fminf(fmaxf(floorf(tx - rx), 0.0f), fx));
+        const int xb = min(x1, (int)fminf(fmaxf(floorf(tx + rx), 0.0f), fx));
+        const uint32_t* row = start + (size_t)z * slab + (size_t)y * rowlen;
+        const uint32_t s = __ldg(row + xa), e = __ldg(row + xb + 1);
+        if (e > s) { seg[nseg * PG_STRIDE] = make_uint2(s, e); ++nseg; }
+      }
+      if (++y > y1) { y = y0; ++z; }
     }
+    // phase 2: every collected candidate in one flat loop
+    pg_flat_scan<UNROLL>(pts, seg, nseg, qx, qy, qz, b);
+    lim = fminf(b.d2, gate);
   }
 }
 

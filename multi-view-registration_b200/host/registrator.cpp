@@ -122,6 +122,27 @@ Registrator::Registrator(int device, int streams) : device_(device) {
 
 Registrator::~Registrator() {
   for (mvr_ctx* x : ctx_) mvr_ctx_destroy(x);
+  cudaSetDevice(device_);
+  for (DeviceBuffer& b : view_cache_) if (b.p) cudaFree(b.p);
+}
+
+bool Registrator::DeviceBuffer::ensure(size_t bytes) {
+  if (bytes <= cap) return true;
+  if (p) cudaFree(p);
+  p = nullptr; cap = 0;
+  const size_t want = bytes + bytes / 8 + 256;
+  if (cudaMalloc(&p, want) != cudaSuccess) { p = nullptr; return false; }
+  cap = want;
+  return true;
+}
+
+int Registrator::ensureContexts(int n) {
+  while ((int)ctx_.size() < n) {
+    mvr_ctx* c = nullptr;
+    if (mvr_ctx_create(device_, &c) != MVR_OK) return fail(MVR_ERR_CUDA, "mvr_ctx_create failed");
+    ctx_.push_back(c);
+  }
+  return MVR_OK;
 }
 
 double Registrator::objectRadius(int slot) const {
@@ -325,42 +346,84 @@ int Registrator::multiViewRegister(std::vector<View>& views, const mvr_turntable
   for (int v = 0; v < V; ++v) { views[(size_t)v].view = v; initRotation(views[(size_t)v], V); }
   int p0 = std::max(prm.pair_begin, 0), p1 = prm.pair_end <= 0 ? V : std::min(prm.pair_end, V);
   for (int p = 0; p < V; ++p) { reports[(size_t)p].source_view = (p + 1) % V; reports[(size_t)p].target_view = p; reports[(size_t)p].status = -1; reports[(size_t)p].fitness = -1; }
-  std::atomic<int> next(p0);
-  std::atomic<int> first_error(0);
+  // The pairs of this rank advance in lock-step: pair k lives in context k, one kernel launch per iteration half
+  // serves them all (mvr_icp_align_batch).  Every distinct host view is uploaded once.
+  const int P = p1 - p0;
+  if (P <= 0) return MVR_OK;
+  int rc = ensureContexts(P);
+  if (rc) return rc;
+  cudaSetDevice(device_);
   std::vector<double> radius((size_t)V, 1.0);
-  const int repeats = std::max(prm.repeat_times, 1);
-  auto worker = [&](int slot) {
-    cudaSetDevice(device_);
-    for (;;) {
-      const int p = next.fetch_add(1);
-      if (p >= p1) break;
-      const View& tgt = views[(size_t)p];
-      const View& src = views[(size_t)((p + 1) % V)];
-      // initial guess: where the turntable says the source sits in the target's frame
-      Matrix4f guess = toFloat(multiply(inverseRigid(tgt.pose), src.pose));
-      AlignResult a;
-      int iterations = 0;
-      uint64_t queries = 0;
-      double ms = 0;
-      for (int r = 0; r < repeats; ++r) {
-        a = pairwiseAlign(src, tgt, prm.icp, &guess, prm.want_fitness && r == repeats - 1, slot);
-        iterations += a.iterations; queries += a.nn_queries; ms += a.gpu_ms;
-        if (a.status != MVR_OK && a.status != MVR_ERR_TOO_FEW_CORRESPONDENCES) { int z = 0; first_error.compare_exchange_strong(z, a.status); break; }
-        guess = a.final_transformation;   // the next repeat continues from this result
-      }
-      fill_report(reports[(size_t)p], (p + 1) % V, p, a, iterations, queries, ms, a.final_transformation);
-      radius[(size_t)p] = a.target_radius;
+  cudaStream_t s0 = (cudaStream_t)mvr_ctx_get_stream(ctx_[0]);
+  std::vector<const float*> dview((size_t)V, nullptr);
+  if (view_cache_.size() < (size_t)V) view_cache_.resize((size_t)V);
+  for (int k = 0; k < P; ++k)
+    for (int e = 0; e < 2; ++e) {
+      const int v = (p0 + k + e) % V;
+      if (dview[(size_t)v] || views[(size_t)v].size == 0) continue;
+      const View& w = views[(size_t)v];
+      if (w.on_device) { dview[(size_t)v] = &w.points->x; continue; }
+      DeviceBuffer& b = view_cache_[(size_t)v];
+      if (!b.ensure(w.size * 16)) return fail(MVR_ERR_ALLOC, "view upload buffer");
+      if (cudaMemcpyAsync(b.p, w.points, w.size * 16, cudaMemcpyHostToDevice, s0) != cudaSuccess) return fail(MVR_ERR_CUDA, "view upload");
+      dview[(size_t)v] = (const float*)b.p;
     }
-  };
-  const int K = std::max(1, std::min((int)ctx_.size(), p1 - p0));
-  if (K == 1) {
-    worker(0);
-  } else {
-    std::vector<std::thread> th;
-    for (int k = 0; k < K; ++k) th.emplace_back(worker, k);
-    for (std::thread& t : th) t.join();
+  if (cudaStreamSynchronize(s0) != cudaSuccess) return fail(MVR_ERR_CUDA, "view upload");
+  std::vector<mvr_ctx*> cs((size_t)P);
+  std::vector<float> guesses((size_t)P * 16), finals((size_t)P * 16);
+  std::vector<int> st((size_t)P, 0), iterations((size_t)P, 0);
+  std::vector<uint64_t> queries((size_t)P, 0);
+  std::vector<double> ms((size_t)P, 0.0);
+  std::vector<mvr_icp_report> rep((size_t)P);
+  for (int k = 0; k < P; ++k) {
+    const int p = p0 + k;
+    const View& tgt = views[(size_t)p];
+    const View& src = views[(size_t)((p + 1) % V)];
+    mvr_ctx* c = ctx_[(size_t)k];
+    cs[(size_t)k] = c;
+    if ((rc = mvr_set_target_device(c, dview[(size_t)(p % V)], tgt.size))) return fail(rc, mvr_last_error(c));
+    radius[(size_t)p] = objectRadius(k);
+    // initial guess: where the turntable says the source sits in the target's frame
+    const Matrix4f g = toFloat(multiply(inverseRigid(tgt.pose), src.pose));
+    std::memcpy(&guesses[(size_t)k * 16], g.m, sizeof(g.m));
   }
-  if (first_error.load()) return fail(first_error.load(), "align failed");
+  // the source of pair p is the view that pair p + 1 has as its target: shared, not measured again
+  for (int k = 0; k < P; ++k) {
+    const int sv = (p0 + k + 1) % V;
+    const int j = ((sv - p0) % V + V) % V;   // the context whose target is view sv, if this rank has that pair
+    if (j < P) rc = mvr_cloud_share(ctx_[(size_t)k], MVR_CLOUD_SOURCE, ctx_[(size_t)j], MVR_CLOUD_TARGET);
+    else rc = mvr_set_source_device(ctx_[(size_t)k], dview[(size_t)sv], views[(size_t)sv].size);
+    if (rc) return fail(rc, mvr_last_error(ctx_[(size_t)k]));
+  }
+  const int repeats = std::max(prm.repeat_times, 1);
+  for (int r = 0; r < repeats; ++r) {
+    if ((rc = mvr_icp_align_batch(cs.data(), P, &prm.icp, guesses.data(), finals.data(), rep.data(), st.data()))) return fail(rc, mvr_last_error(cs[0]));
+    bool any = false;
+    for (int k = 0; k < P; ++k) {
+      if (st[(size_t)k] != MVR_OK && st[(size_t)k] != MVR_ERR_TOO_FEW_CORRESPONDENCES && st[(size_t)k] != MVR_ERR_NO_INPUT)
+        return fail(st[(size_t)k], mvr_last_error(cs[(size_t)k]));
+      if (st[(size_t)k] == MVR_ERR_NO_INPUT) {   // an empty view: the pair keeps its guess
+        std::memcpy(&finals[(size_t)k * 16], &guesses[(size_t)k * 16], 16 * sizeof(float));
+        rep[(size_t)k] = mvr_icp_report{};
+      }
+      iterations[(size_t)k] += rep[(size_t)k].iterations; queries[(size_t)k] += rep[(size_t)k].nn_queries; ms[(size_t)k] += rep[(size_t)k].gpu_ms;
+      any = true;
+    }
+    if (!any) break;
+    guesses = finals;   // the next repeat continues from this result
+  }
+  for (int k = 0; k < P; ++k) {
+    const int p = p0 + k;
+    AlignResult a;
+    a.status = st[(size_t)k];
+    std::memcpy(a.final_transformation.m, &finals[(size_t)k * 16], sizeof(a.final_transformation.m));
+    a.n_correspondences = rep[(size_t)k].n_correspondences; a.mse = rep[(size_t)k].mse; a.converged = rep[(size_t)k].converged != 0;
+    if (prm.want_fitness && (a.status == MVR_OK || a.status == MVR_ERR_TOO_FEW_CORRESPONDENCES)) {
+      double f = -1;
+      if (mvr_fitness_score(cs[(size_t)k], DBL_MAX, &f) == MVR_OK) a.fitness = f;
+    }
+    fill_report(reports[(size_t)p], (p + 1) % V, p, a, iterations[(size_t)k], queries[(size_t)k], ms[(size_t)k], a.final_transformation);
+  }
   if (p0 == 0 && p1 == V) {
     std::vector<Matrix4d> rel((size_t)V), abs_pose;
     std::vector<double> w((size_t)V);
@@ -370,7 +433,7 @@ int Registrator::multiViewRegister(std::vector<View>& views, const mvr_turntable
       rel[(size_t)p] = toDouble(f);
       w[(size_t)p] = reports[(size_t)p].status == MVR_OK ? (double)reports[(size_t)p].n_correspondences : 0.0;
     }
-    int rc = ringClose(rel, w, prm.loop_closure != 0, prm.lum_iterations > 0 ? prm.lum_iterations : 16, pivot_, radius[0], abs_pose);   // radius of view 0: the same whatever the stream count
+    rc = ringClose(rel, w, prm.loop_closure != 0, prm.lum_iterations > 0 ? prm.lum_iterations : 16, pivot_, radius[0], abs_pose);   // radius of view 0: the same whatever the stream count
     if (rc) return fail(rc, "loop closure failed");
     const Matrix4d base = views[0].pose;
     for (int v = 0; v < V; ++v) {

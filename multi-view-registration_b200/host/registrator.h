@@ -120,6 +120,9 @@ class Registrator {
  private:
   int accumulate(std::vector<View>& views, const std::vector<int>& order, const mvr_icp_params& icp, int repeat_times,
                  bool want_fitness, std::vector<mvr_pair_report>* reports);
+  int ensureContexts(int n);             // grow the context pool to n (batched aligns use one context per pair)
+  struct DeviceBuffer { void* p = nullptr; size_t cap = 0; bool ensure(size_t bytes); };
+  std::vector<DeviceBuffer> view_cache_;   // device copies of host views, one upload per view and registration
   double objectRadius(int slot) const;   // half the largest extent of the target cloud last given to context `slot`
   int fail(int code, const std::string& msg) { std::lock_guard<std::mutex> g(err_mu_); err_ = msg; return code; }
   std::mutex err_mu_;

@@ -269,6 +269,38 @@ def test_icp_fixed_iterations_matches_oracle_per_iteration(ctx, orc, mvr, synth,
     assert np.array_equal(r["cloud"], orc.transform(src, r["final"]))
 
 
+def test_icp_align_batch_equals_separate_aligns(mvr, synth):
+    """mvr_icp_align_batch: pairs of different sizes advancing in lock-step (one launch per iteration half for all of
+    them) return exactly what one mvr_icp_align per pair returns; criteria stop each pair on its own."""
+    sizes = [20_000, 7_000, 33_000, 0, 12_000]
+    ctxs, guesses = [], []
+    for k, n in enumerate(sizes):
+        c = mvr.Context(0)
+        tgt, _ = synth.turntable_view(k, 12, max(n, 1))
+        src, Ts = synth.turntable_view(k + 1, 12, max(n, 1))
+        Tt = synth.view_pose(k, 12)
+        c.set_target(tgt)
+        c.set_source(src[:n])
+        guesses.append((synth.perturbation() @ np.linalg.inv(Tt) @ Ts).astype(np.float32))
+        ctxs.append(c)
+    for prm in (mvr.default_params(max_iterations=9, max_dist=4.0, reciprocal=1, fixed_iterations=1),
+                mvr.default_params(max_iterations=40, max_dist=4.0, reciprocal=0, euclidean_fitness_epsilon=1e-3),
+                mvr.default_params(max_iterations=25, max_dist=3.0, reciprocal=1, transformation_epsilon=1e-7)):
+        got = mvr.icp_align_batch(ctxs, prm, guesses)
+        for k, c in enumerate(ctxs):
+            if sizes[k] == 0:
+                assert got[k]["status"] == mvr.ERR_NO_INPUT
+                continue
+            one = c.icp_align(prm, guess=guesses[k], n_source=sizes[k])
+            assert got[k]["status"] == one["status"] == 0
+            assert got[k]["iterations"] == one["iterations"] and got[k]["n_corr"] == one["n_corr"] and got[k]["reason"] == one["reason"]
+            assert np.array_equal(got[k]["final"], one["final"]) and got[k]["mse"] == one["mse"]
+    iters = [g["iterations"] for k, g in enumerate(got) if sizes[k]]
+    assert all(1 <= it <= 25 for it in iters)
+    for c in ctxs:
+        c.close()
+
+
 def test_icp_lockstep_correspondences_bit_exact(ctx, orc, mvr, synth):
     """Given the oracle's own per-iteration cloud, the GPU correspondences are bit-identical."""
     src, tgt, guess, _ = _pair(synth, 15_000)
