@@ -122,6 +122,11 @@ double mvr_debug_value(mvr_ctx* ctx, int k);
 /* Tuning knobs of the spatial index: cell edge (<= 0: automatic) and maximum bits per axis (1..10). */
 int mvr_ctx_set_index_options(mvr_ctx* ctx, float cell_edge, int max_bits);
 
+/* Tuning of mvr_nn_query / mvr_fitness_score: from `dense_ratio` queries per target point on (default 8; 0 = never)
+ * the warp-cooperative pass is used, with about `points_per_cell` target points per occupied grid cell (default 8).
+ * Results do not depend on either. */
+int mvr_ctx_set_nn_options(mvr_ctx* ctx, double points_per_cell, double dense_ratio);
+
 /* -- inputs: icp.setInputTarget / icp.setInputSource (mvr/src/registrator.cpp:566-567, 776-777,
  *    913-914) and CorrespondenceEstimation::setInputSource/Target (:497-498, 645-646).
  *    Host variants copy n*16 bytes to the device; *_device variants adopt a device pointer that the

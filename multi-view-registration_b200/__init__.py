@@ -159,6 +159,7 @@ def lib():
     L.mvr_debug_value.restype = C.c_double
     L.mvr_ctx_set_index_options.argtypes = [vp, C.c_float, C.c_int]
     L.mvr_ctx_set_batch_group.argtypes = [vp, C.c_int]
+    L.mvr_ctx_set_nn_options.argtypes = [vp, C.c_double, C.c_double]
     for name in ("mvr_set_target", "mvr_set_source", "mvr_set_target_device", "mvr_set_source_device", "mvr_set_target_normals"):
         getattr(L, name).argtypes = [vp, vp, C.c_size_t]
     L.mvr_index_build.argtypes = [vp, C.c_int, C.POINTER(Grid)]
@@ -298,6 +299,10 @@ class Context:
         self._ck(lib().mvr_ctx_set_index_options(self._h, C.c_float(cell_edge), int(max_bits)))
 
     # -- inputs --------------------------------------------------------------------------------
+    def set_nn_options(self, points_per_cell=8.0, dense_ratio=8.0):
+        """NN-query tuning: dense_ratio = queries per target point from which the warp-cooperative pass runs (0: never)."""
+        self._ck(lib().mvr_ctx_set_nn_options(self._h, float(points_per_cell), float(dense_ratio)))
+
     def set_batch_group(self, pairs):
         """Pairs per kernel launch of the batches this context leads (1..8)."""
         self._ck(lib().mvr_ctx_set_batch_group(self._h, int(pairs)))

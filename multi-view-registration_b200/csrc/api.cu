@@ -101,6 +101,9 @@ struct mvr_ctx {
   DevBuf normals; bool has_normals = false;
   DevBuf cur, corr_p, corr_j, corr_d2, rmin, rnn, partials, sums, out_cloud, qtmp, itmp, ftmp, scratch, misc, tiles, state, log;
   PairIndex pt, ps;              // target / source index of the running align
+  PairIndex nt, nq;              // target / query index of the dense NN pass (cell_nn.cu)
+  double nn_ppc = 8.0;           // its target points per occupied cell
+  double nn_dense_ratio = 8.0;   // queries per target point from which the dense pass is used (0: never)
   FwdArgs fa{}; RevArgs ra{};    // kernel arguments of the prepared align
   int group_pairs = 8;           // pairs per launch of a batch led by this context (mvr_ctx_set_batch_group)
   DevBuf pkeys, pvals, pmoved, pcount;   // build scratch of the per-align indices: keys, arrival ranks, arrival-order records, cell counters
@@ -375,9 +378,38 @@ int sort_queries(mvr_ctx* ctx, const float4* q, int n) {
   return list_bricks(ctx, c, ctx->tgt.grid.bits, 0, nullptr);
 }
 
+PairGrid make_pair_grid(const float lo[3], const float hi[3], double e, uint32_t* cells_out);
+bool same_pair_grid(const PairGrid& a, const PairGrid& b);
+int build_pair_index(mvr_ctx* ctx, PairIndex& ix, const float4* pts, int n, int n_bad, const Mat4f* guess, const PairGrid& g,
+                     uint32_t cells, bool keep_s0, bool ordered = true);
+
+// Many queries per target point: target and queries counting-sorted by the cells of one row-major grid, then the
+// warp-cooperative scan of cell_nn.cu.
+int nn_pass_dense(mvr_ctx* ctx, const float4* q, int n, int32_t* d_idx, float* d_d2) {
+  Cloud& t = ctx->tgt;
+  const int mv = t.n - t.n_bad;
+  const double e = ctx->cell_edge_opt > 0 ? ctx->cell_edge_opt : density_cell_edge(t.lo, t.hi, mv, ctx->nn_ppc);
+  uint32_t cells = 0;
+  const PairGrid g = make_pair_grid(t.lo, t.hi, e, &cells);
+  int rc;
+  if (!(ctx->nt.valid && ctx->nt.gen == t.gen && same_pair_grid(ctx->nt.g, g))) {
+    if ((rc = build_pair_index(ctx, ctx->nt, t.pts, t.n, t.n_bad, nullptr, g, cells, false))) return rc;
+    ctx->nt.gen = t.gen;
+  }
+  if ((rc = build_pair_index(ctx, ctx->nq, q, n, 0, nullptr, g, cells, false, false))) return rc;
+  ProfScope ps(ctx, MVR_K_NN, 24.0 * n + 16.0 * t.n, (double)n);
+  CK(launch_cell_nn(ctx->nq.sorted.as<float4>(), n, ctx->nq.start.as<uint32_t>() + cells, ctx->nt.sorted.as<float4>(),
+                    ctx->nt.start.as<uint32_t>(), g, mv, d_idx, d_d2, ctx->stream));
+  return MVR_OK;
+}
+
 // Exact un-gated NN of n device points in the target index; results at the queries' original index.
 int nn_pass(mvr_ctx* ctx, const float4* q, int n, int32_t* d_idx, float* d_d2) {
-  int rc = sort_queries(ctx, q, n);
+  if (ctx->nn_dense_ratio > 0 && (double)n >= ctx->nn_dense_ratio * (double)std::max(ctx->tgt.n - ctx->tgt.n_bad, 1))
+    return nn_pass_dense(ctx, q, n, d_idx, d_d2);
+  int rc = ensure_target_index(ctx, nullptr);
+  if (rc) return rc;
+  rc = sort_queries(ctx, q, n);
   if (rc) return rc;
   const Cloud& t = ctx->tgt;
   ProfScope ps(ctx, MVR_K_NN, 24.0 * n + 16.0 * t.n, (double)n);
@@ -472,12 +504,13 @@ bool same_pair_grid(const PairGrid& a, const PairGrid& b) { return std::memcmp(&
 
 // Index `n` points (n_bad of them non-finite) in grid g; guess (nullable) is applied first (pinned float
 // transform); keep_s0: also keep a copy of the sorted binning-time coordinates.
+// ordered = false leaves the points of a cell in arrival order (queries: their results go out by original index).
 int build_pair_index(mvr_ctx* ctx, PairIndex& ix, const float4* pts, int n, int n_bad, const Mat4f* guess, const PairGrid& g,
-                     uint32_t cells, bool keep_s0) {
+                     uint32_t cells, bool keep_s0, bool ordered) {
   const size_t nn = (size_t)std::max(n, 1);
   CK(ctx->pkeys.ensure(nn * sizeof(uint32_t)));
   CK(ctx->pvals.ensure(nn * sizeof(uint32_t)));
-  CK(ctx->pmoved.ensure(nn * sizeof(float4)));
+  if (ordered) CK(ctx->pmoved.ensure(nn * sizeof(float4)));
   CK(ix.sorted.ensure(nn * sizeof(float4)));
   CK(ix.start.ensure(((size_t)cells + 2) * sizeof(uint32_t)));
   if (keep_s0) CK(ix.s0.ensure(nn * sizeof(float4)));
@@ -497,9 +530,10 @@ int build_pair_index(mvr_ctx* ctx, PairIndex& ix, const float4* pts, int n, int 
                        ctx->scan_epoch, nullptr, ctx->stream));
   ctx->scan_epoch = (ctx->scan_epoch % 0x3fffffffu) + 1;
   CK(launch_pair_scatter(pts, n, guess, ctx->pkeys.as<uint32_t>(), ctx->pvals.as<uint32_t>(), ix.start.as<uint32_t>(),
-                         ctx->pmoved.as<float4>(), ctx->stream));
-  CK(launch_pair_rerank(ctx->pmoved.as<float4>(), n, ctx->pkeys.as<uint32_t>(), ix.start.as<uint32_t>(), ix.sorted.as<float4>(),
-                        keep_s0 ? ix.s0.as<float4>() : nullptr, ctx->stream));
+                         ordered ? ctx->pmoved.as<float4>() : ix.sorted.as<float4>(), ctx->stream));
+  if (ordered)
+    CK(launch_pair_rerank(ctx->pmoved.as<float4>(), n, ctx->pkeys.as<uint32_t>(), ix.start.as<uint32_t>(), ix.sorted.as<float4>(),
+                          keep_s0 ? ix.s0.as<float4>() : nullptr, ctx->stream));
   ix.g = g; ix.cells = cells; ix.n_valid = n - n_bad; ix.valid = true;
   return MVR_OK;
 }
@@ -615,7 +649,7 @@ int mvr_ctx_destroy(mvr_ctx* ctx) {
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   ctx->tgt.release(); ctx->src.release(); ctx->qry.release(); ctx->normals.release();
-  ctx->pt.release(); ctx->ps.release();
+  ctx->pt.release(); ctx->ps.release(); ctx->nt.release(); ctx->nq.release();
   ctx->pkeys.release(); ctx->pvals.release(); ctx->pmoved.release(); ctx->pcount.release();
   DevBuf* bufs[] = {&ctx->cur, &ctx->corr_p, &ctx->rmin, &ctx->rnn, &ctx->corr_j, &ctx->corr_d2, &ctx->partials, &ctx->sums, &ctx->out_cloud, &ctx->qtmp,
                     &ctx->itmp, &ctx->ftmp, &ctx->scratch, &ctx->misc, &ctx->tiles, &ctx->state, &ctx->log};
@@ -672,6 +706,14 @@ int mvr_ctx_set_index_options(mvr_ctx* ctx, float cell_edge, int max_bits) {
   ctx->max_bits_opt = max_bits;
   ctx->tgt.index_valid = false;
   ctx->src.index_valid = false;
+  return MVR_OK;
+}
+
+int mvr_ctx_set_nn_options(mvr_ctx* ctx, double points_per_cell, double dense_ratio) {
+  if (!ctx || !(points_per_cell > 0) || !(dense_ratio >= 0)) return MVR_ERR_BAD_ARG;
+  ctx->nn_ppc = points_per_cell;
+  ctx->nn_dense_ratio = dense_ratio;
+  ctx->nt.valid = false;
   return MVR_OK;
 }
 
@@ -774,8 +816,6 @@ int mvr_nn_query_device(mvr_ctx* ctx, const float* d_q, size_t n, int32_t* d_idx
   if (n > (size_t)INT_MAX / 2) return fail(ctx, MVR_ERR_BAD_ARG, "too many queries");
   cudaSetDevice(ctx->device);
   if (ctx->tgt.gen == 0) return fail(ctx, MVR_ERR_NO_INPUT, "target not set");
-  int rc = ensure_target_index(ctx, nullptr);
-  if (rc) return rc;
   if (n == 0) return MVR_OK;
   return nn_pass(ctx, (const float4*)d_q, (int)n, d_idx, d_d2);
 }
@@ -1143,8 +1183,7 @@ int mvr_fitness_score(mvr_ctx* ctx, double max_range, double* score) {
   const int n = ctx->src.n;
   *score = DBL_MAX;
   if (n == 0 || ctx->tgt.n == 0) return MVR_OK;
-  int rc = ensure_target_index(ctx, nullptr);
-  if (rc) return rc;
+  int rc = MVR_OK;
   const float4* cloud = ctx->have_out ? ctx->out_cloud.as<float4>() : ctx->src.pts;
   CK(ctx->itmp.ensure((size_t)n * sizeof(int32_t)));
   CK(ctx->ftmp.ensure((size_t)n * sizeof(float)));

@@ -1,0 +1,163 @@
+// cell_nn.cu -- exact 1-NN for MANY queries per target point: warp-cooperative scan of staged cells.
+//
+// What pcl::KdTreeFLANN::nearestKSearch(k = 1) answers for the reference (getFitnessScore, the correspondence
+// estimators; mvr/src/registrator.cpp:502, 572, 649, 923), for the regime of BASELINE.json's throughput sweep:
+// up to 16 queries per target point.  There the per-thread ball walk of pair_search.cuh wastes most of a warp
+// (every lane follows its own rows and cell lengths); here the lanes of a warp share their candidates instead.
+//
+//   * target and queries are counting-sorted by the cells of ONE row-major grid (pair_index.cu), cell edge chosen
+//     for a handful of target points per occupied cell;
+//   * a warp takes 32 consecutive sorted queries -- with many queries per cell they mostly sit in one cell -- and,
+//     for each distinct cell among them, stages the target points of the cell's 3 x 3 x 3 neighbourhood (nine
+//     contiguous x runs) in shared memory, 32 at a time with one coalesced load, after which every lane of that
+//     cell compares ALL staged points against its query: uniform trip counts, broadcast shared-memory reads, no
+//     divergence inside a cell;
+//   * the neighbourhood holds the true neighbour whenever the best distance found is smaller than the distance
+//     from the query to the neighbourhood's boundary (checked per query with the conservative cell geometry of
+//     nn_search.cuh); the few queries that fail the test finish with the seeded general search of pair_search.cuh.
+//
+// Ties resolve to the lowest original index: the comparison key is (d2 bits, index) as one 64-bit integer.
+// Algorithmic bytes: 16 B per query read + 8 B result, 16 B per target point, 8 B per cell-table entry.
+#include "launch.h"
+#include "pair_search.cuh"
+
+namespace mvr {
+
+constexpr int CN_THREADS = 256;
+constexpr int CN_WARPS = CN_THREADS / 32;
+
+struct CellNnArgs {
+  const float4* q;          // queries sorted by cell, .w = bits(original index); finite ones first
+  int nq;
+  const uint32_t* q_valid;  // device: number of finite queries (= the query cell table's entry of the sentinel cell)
+  const float4* tgt;        // target sorted by cell, .w = bits(original index)
+  const uint32_t* tstart;
+  PairGrid g;
+  int m_valid;
+  int32_t* out_idx;         // by ORIGINAL query index
+  float* out_d2;
+};
+
+__device__ __forceinline__ void cn_eval(const float4 p, int pos, float qx, float qy, float qz, unsigned long long& bkey, int& bpos) {
+  const float d = d2_pinned(qx, qy, qz, p.x, p.y, p.z);
+  // d >= 0 or NaN: its bits order like the value, NaN sorts above +inf and never wins
+  const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)__float_as_uint(p.w);
+  if (key < bkey) { bkey = key; bpos = pos; }
+}
+
+// Distance (cells) from scaled coordinate t in cell c to the nearest face of the block [c - h, c + h] that still has
+// grid behind it (+inf if the block reaches both ends of the axis).
+__device__ __forceinline__ float cn_face(float t, int c, int n, int h) {
+  float u = MVR_INF;
+  if (c - h > 0) u = fminf(u, t - (float)(c - h));
+  if (c + h < n - 1) u = fminf(u, (float)(c + h + 1) - t);
+  return u;
+}
+
+__global__ void __launch_bounds__(CN_THREADS, 4) k_cell_nn(CellNnArgs a) {
+  __shared__ float4 s_pts[CN_WARPS][PG_SEGS * 32 / 2];   // 32 staged points per warp; the fallback's segment list (PG_SEGS x 32 uint2) reuses it
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const PairGrid g = a.g;
+  const int rowlen = g.nx, slab = g.nx * g.ny;
+  const int nwarps = gridDim.x * CN_WARPS;
+  const int chunks = (a.nq + 31) / 32;
+  const int nq_valid = (int)__ldg(a.q_valid);
+  const float cell2 = g.cell_lo * g.cell_lo * MVR_REL_SHRINK;
+  for (int chunk = blockIdx.x * CN_WARPS + warp; chunk < chunks; chunk += nwarps) {
+    const int i = chunk * 32 + lane;
+    const bool valid = i < nq_valid && a.m_valid > 0;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < a.nq) q = __ldg(a.q + i);
+    float tx = 0.f, ty = 0.f, tz = 0.f;
+    int cx = 0, cy = 0, cz = 0;
+    uint32_t ckey = 0xffffffffu;
+    if (valid) {
+      tx = grid_t(q.x, g.ox, g.inv_cell); ty = grid_t(q.y, g.oy, g.inv_cell); tz = grid_t(q.z, g.oz, g.inv_cell);
+      cx = pg_cell(tx, g.nx); cy = pg_cell(ty, g.ny); cz = pg_cell(tz, g.nz);
+      ckey = (uint32_t)((cz * g.ny + cy) * g.nx + cx);
+    }
+    unsigned long long bkey = 0x7f8000007fffffffull;   // (+inf, INT_MAX)
+    int bpos = -1;
+
+    // ---- level 1: the 3 x 3 x 3 neighbourhood of every distinct cell of the chunk, shared by the lanes of that cell
+    unsigned int todo = __ballot_sync(0xffffffffu, valid);
+    while (todo) {
+      const int leader = __ffs(todo) - 1;
+      const uint32_t lkey = __shfl_sync(0xffffffffu, ckey, leader);
+      const int lx = __shfl_sync(0xffffffffu, cx, leader), ly = __shfl_sync(0xffffffffu, cy, leader), lz = __shfl_sync(0xffffffffu, cz, leader);
+      const bool mine = valid && ckey == lkey;
+      todo &= ~__ballot_sync(0xffffffffu, mine);
+      // the nine x runs of the neighbourhood: lane r < 9 fetches row (ly + r % 3 - 1, lz + r / 3 - 1)
+      uint32_t rs = 0, re = 0;
+      if (lane < 9) {
+        const int y = ly + lane % 3 - 1, z = lz + lane / 3 - 1;
+        if (y >= 0 && y < g.ny && z >= 0 && z < g.nz) {
+          const uint32_t* row = a.tstart + (size_t)z * slab + (size_t)y * rowlen;
+          rs = __ldg(row + max(lx - 1, 0));
+          re = __ldg(row + min(lx + 1, g.nx - 1) + 1);
+        }
+      }
+      // run by run, 32 points at a time: one coalesced load into the warp's staging area, then every lane of the cell
+      // compares all of them (measured on B200: staging all nine runs at once with cp.async was slower)
+#pragma unroll 1
+      for (int r = 0; r < 9; ++r) {
+        const uint32_t s = __shfl_sync(0xffffffffu, rs, r), e = __shfl_sync(0xffffffffu, re, r);
+        for (uint32_t t0 = s; t0 < e; t0 += 32u) {
+          const int cnt = (int)min(32u, e - t0);
+          if (lane < cnt) s_pts[warp][lane] = __ldg(a.tgt + t0 + lane);
+          __syncwarp();
+          if (mine) {
+            int c = 0;
+            for (; c + 4 <= cnt; c += 4) {
+              const float4 p0 = s_pts[warp][c], p1 = s_pts[warp][c + 1], p2 = s_pts[warp][c + 2], p3 = s_pts[warp][c + 3];
+              cn_eval(p0, (int)t0 + c, q.x, q.y, q.z, bkey, bpos);
+              cn_eval(p1, (int)t0 + c + 1, q.x, q.y, q.z, bkey, bpos);
+              cn_eval(p2, (int)t0 + c + 2, q.x, q.y, q.z, bkey, bpos);
+              cn_eval(p3, (int)t0 + c + 3, q.x, q.y, q.z, bkey, bpos);
+            }
+            for (; c < cnt; ++c) cn_eval(s_pts[warp][c], (int)t0 + c, q.x, q.y, q.z, bkey, bpos);
+          }
+          __syncwarp();
+        }
+      }
+    }
+
+    // Is a neighbourhood of half-width h enough?  Everything outside it is farther than cn_face cells away.
+    const float margin = MVR_CELL_MARGIN + 1.0e-6f * fmaxf(fabsf(tx), fmaxf(fabsf(ty), fabsf(tz)));
+    auto enough = [&](int h) {
+      const float u = fminf(cn_face(tx, cx, g.nx, h), fminf(cn_face(ty, cy, g.ny, h), cn_face(tz, cz, g.nz, h)));
+      const float bu = fmaxf(u - margin, 0.0f);
+      return (u == MVR_INF) || (__uint_as_float((uint32_t)(bkey >> 32)) < bu * bu * cell2);
+    };
+    const bool open = valid && !enough(1);
+
+    __syncwarp();
+    if (valid) {
+      NnBest b{__uint_as_float((uint32_t)(bkey >> 32)), (int)(uint32_t)bkey, bpos};
+      // ---- the few queries the neighbourhood cannot settle (far from the cloud): the seeded general search
+      //      (its segment list lives in the warp's staging area, which the warp is done with)
+      if (open) pg_search<4, 32>(g, a.tstart, a.tgt, a.m_valid, q.x, q.y, q.z, q.x, q.y, q.z, 0.0f, 1.0f, MVR_INF, b,
+                                 reinterpret_cast<uint2*>(&s_pts[warp][0]) + lane);
+      const int oi = __float_as_int(q.w);
+      a.out_idx[oi] = b.pos >= 0 ? b.idx : -1;
+      a.out_d2[oi] = b.pos >= 0 ? b.d2 : MVR_INF;
+    } else if (i < a.nq) {
+      const int oi = __float_as_int(q.w);
+      a.out_idx[oi] = -1;
+      a.out_d2[oi] = MVR_INF;
+    }
+    __syncwarp();   // the staging area is reused by the next chunk
+  }
+}
+
+cudaError_t launch_cell_nn(const float4* q_sorted, int nq, const uint32_t* d_nq_valid, const float4* tgt_sorted, const uint32_t* tstart, PairGrid g,
+                           int m_valid, int32_t* out_idx, float* out_d2, cudaStream_t s) {
+  if (nq <= 0) return cudaSuccess;
+  CellNnArgs a{q_sorted, nq, d_nq_valid, tgt_sorted, tstart, g, m_valid, out_idx, out_d2};
+  const int chunks = (nq + 31) / 32;
+  const int blocks = std::min((chunks + CN_WARPS - 1) / CN_WARPS, 148 * 4 * 8);
+  k_cell_nn<<<blocks, CN_THREADS, 0, s>>>(a); count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace mvr

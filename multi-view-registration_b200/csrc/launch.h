@@ -189,6 +189,12 @@ size_t compact_scratch_elems(int n);
 cudaError_t launch_compact_corr(const int32_t* corr_j, const float* corr_d2, int n, uint32_t* scratch, int32_t* out_q,
                                 int32_t* out_m, float* out_d2, uint32_t* count_out, cudaStream_t s);
 
+// ---- cell_nn.cu ----------------------------------------------------------------------------
+// Exact un-gated 1-NN of queries sorted by the cells of the target's row-major grid g (warp-cooperative; for many
+// queries per target point).  d_nq_valid: device count of finite queries (they come first).  Results by original index.
+cudaError_t launch_cell_nn(const float4* q_sorted, int nq, const uint32_t* d_nq_valid, const float4* tgt_sorted, const uint32_t* tstart,
+                           PairGrid g, int m_valid, int32_t* out_idx, float* out_d2, cudaStream_t s);
+
 // ---- normals.cu ----------------------------------------------------------------------------
 cudaError_t launch_normals(IndexDev ix, const float4* pts_orig, int n, int k, float3 viewpoint, float4* out_nxyzc,
                            int32_t* out_nbr, cudaStream_t s);

@@ -1,0 +1,92 @@
+"""Timings of BASELINE.json's configs 1, 4 and 5 (the bench line is config 2/3): python scripts/gpu_configs.py out.json
+Device times are CUDA-event times reported by the library (mvr_icp_report.gpu_ms / per-kernel stats); parity of the
+same code paths is what tests/ checks, here only sizes change."""
+import sys, os, json, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import mvr_b200, mvr_b200.synth as synth
+
+out = {}
+peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+PEAK = float(peaks.get("hbm_gbs", 6650.0))
+ctx = mvr_b200.Context(0)
+ctx.set_profiling(True)
+
+# ---- config 1: 2-view pairwise point-to-point ICP, 50k pts/view, 30 fixed iterations -----------------------------
+n = 50_000
+tgt, _ = synth.turntable_view(0, 24, n)
+src, Ts = synth.turntable_view(1, 24, n)
+guess = (synth.perturbation() @ Ts).astype(np.float32)
+ctx.set_target(tgt); ctx.set_source(src)
+c1 = {}
+for recip in (1, 0):
+    p = mvr_b200.default_params(max_iterations=30, max_dist=4.0, reciprocal=recip, fixed_iterations=1)
+    best = None
+    for rep in range(5):
+        t0 = time.perf_counter(); r = ctx.icp_align(p, guess=guess, n_source=n); wall = time.perf_counter() - t0
+        if best is None or r["gpu_ms"] < best["gpu_ms"]:
+            best = dict(gpu_ms=r["gpu_ms"], wall_ms=1e3 * wall, n_corr=r["n_corr"], mse=r["mse"], nn_queries=r["nn_queries"])
+    best["queries_per_s"] = best["nn_queries"] / (best["gpu_ms"] * 1e-3)
+    c1["reciprocal" if recip else "one_way"] = best
+out["config1_pair_50k_30it"] = c1
+print("config1", json.dumps(c1), flush=True)
+
+# ---- config 4: point-to-plane ICP at 2M pts/view with kNN (k = 16) PCA normals ------------------------------------
+n = 2_000_000
+tgt, _ = synth.turntable_view(0, 24, n)
+src, Ts = synth.turntable_view(1, 24, n)
+guess = (synth.perturbation() @ Ts).astype(np.float32)
+ctx.set_target(tgt); ctx.set_source(src)
+ctx.kernel_stats(reset=True)
+t0 = time.perf_counter(); nrm = ctx.estimate_normals(mvr_b200.TARGET, n, 16, viewpoint=(0.0, 0.0, 0.0)); wall_n = time.perf_counter() - t0
+st = ctx.kernel_stats(reset=True)
+c4 = {"normals_k16": {"kernel_ms": st["normals"]["ms"], "wall_ms_incl_index_and_d2h": 1e3 * wall_n, "points_per_s": n / (st["normals"]["ms"] * 1e-3),
+                      "alg_GBps": st["normals"]["bytes"] / (st["normals"]["ms"] * 1e-3) / 1e9}}
+for name, est, recip in (("p2l_one_way", mvr_b200.POINT_TO_PLANE, 0), ("p2l_reciprocal", mvr_b200.POINT_TO_PLANE, 1), ("p2p_reciprocal", mvr_b200.POINT_TO_POINT, 1)):
+    p = mvr_b200.default_params(max_iterations=30, max_dist=4.0, reciprocal=recip, fixed_iterations=1, estimator=est)
+    best = None
+    for rep in range(3):
+        ctx.kernel_stats(reset=True)
+        r = ctx.icp_align(p, guess=guess, n_source=n)
+        st = ctx.kernel_stats(reset=True)
+        if best is None or r["gpu_ms"] < best["gpu_ms"]:
+            best = dict(gpu_ms=r["gpu_ms"], iter_us=1e3 * st["corr"]["ms"] / 30, index_build_ms=st["sort"]["ms"], n_corr=r["n_corr"], mse=r["mse"], nn_queries=r["nn_queries"],
+                        alg_GBps=st["corr"]["bytes"] / (st["corr"]["ms"] * 1e-3) / 1e9)
+    best["queries_per_s"] = best["nn_queries"] / (best["gpu_ms"] * 1e-3)
+    best["roofline_frac"] = best["alg_GBps"] / PEAK
+    c4[name] = best
+out["config4_2M_pts"] = c4
+print("config4", json.dumps(c4), flush=True)
+
+# ---- config 5: NN-query throughput sweep against a 1M-point target -------------------------------------------------
+m = 1_000_000
+sweep = []
+tgt = synth.full_object(m)
+ctx.set_target(tgt)
+for nq in (10_000, 31_600, 100_000, 316_000, 1_000_000, 3_160_000, 10_000_000, 16_000_000):
+    for order in ("random", "morton"):
+        _, q = synth.nn_sweep_case(m, nq, order=order)
+        tq = torch.from_numpy(q).cuda(); ti = torch.empty(nq, dtype=torch.int32, device="cuda"); td = torch.empty(nq, dtype=torch.float32, device="cuda")
+        best = None
+        for rep in range(4):
+            ctx.set_target(tgt)   # a fresh index every time: its build is reported separately
+            ctx.kernel_stats(reset=True)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            ctx.nn_query_device(tq.data_ptr(), nq, ti.data_ptr(), td.data_ptr()); ctx.synchronize()
+            wall = time.perf_counter() - t0
+            st = ctx.kernel_stats(reset=True)
+            rec = dict(queries=nq, order=order, nn_kernel_ms=st["nn"]["ms"], query_sort_ms=st["sort"]["ms"] + st["table"]["ms"] + st["transform"]["ms"],
+                       call_wall_ms=1e3 * wall)
+            if best is None or rec["nn_kernel_ms"] < best["nn_kernel_ms"]:
+                best = rec
+        best["Gq_per_s_kernel"] = nq / (best["nn_kernel_ms"] * 1e-3) / 1e9
+        best["Gq_per_s_call"] = nq / (best["call_wall_ms"] * 1e-3) / 1e9
+        best["alg_GBps"] = (24.0 * nq + 16.0 * m) / (best["nn_kernel_ms"] * 1e-3) / 1e9
+        best["roofline_frac"] = best["alg_GBps"] / PEAK
+        sweep.append(best)
+        print("config5", json.dumps(best), flush=True)
+        del tq, ti, td
+out["config5_nn_sweep_1M_target"] = sweep
+out["peak_hbm_GBps"] = PEAK
+json.dump(out, open(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/configs.json", "w"), indent=1)

@@ -80,6 +80,30 @@ def test_nn_bit_exact(ctx, orc, synth, m, n):
     assert np.array_equal(d2.view(np.uint32), od.view(np.uint32))
 
 
+@pytest.mark.parametrize("ppc", [1.0, 6.0, 40.0])
+@pytest.mark.parametrize("m,n", [(1, 50), (300, 5000), (20_000, 200_000)])
+def test_nn_dense_pass_bit_exact(ctx, orc, synth, m, n, ppc):
+    """The warp-cooperative pass (many queries per target point) against the kd-tree oracle, for coarse and fine cells,
+    queries near the surface, far from it and outside the grid, with non-finite points on both sides."""
+    tgt, q = synth.nn_sweep_case(m, n)
+    rng = np.random.default_rng(m + n)
+    far = rng.choice(n, size=max(1, n // 50), replace=False)
+    q[far, :3] += rng.normal(size=(len(far), 3)).astype(np.float32) * 60.0      # well off the surface / outside the grid
+    q[rng.choice(n, size=3, replace=False), 1] = np.nan
+    if m > 10:
+        tgt[[1, 7], 0] = np.inf
+    ctx.set_nn_options(ppc, 1e-9)      # always dense
+    ctx.set_target(tgt)
+    idx, d2 = ctx.nn_query(q)
+    ctx.set_nn_options(6.0, 0.0)       # never dense: the brick pass
+    ctx.set_target(tgt)
+    idx2, d22 = ctx.nn_query(q)
+    ctx.set_nn_options(8.0, 8.0)
+    oi, od = orc.nn_kdtree(tgt, q)
+    assert np.array_equal(idx, oi) and np.array_equal(d2.view(np.uint32), od.view(np.uint32))
+    assert np.array_equal(idx2, oi) and np.array_equal(d22.view(np.uint32), od.view(np.uint32))
+
+
 def test_nn_ties_resolve_to_lowest_index(ctx, orc):
     rng = np.random.default_rng(5)
     base = random_cloud(rng, 500, scale=3.0)
