@@ -13,6 +13,17 @@
 #include "small_solve.h"
 
 // candidates evaluated per trip of the flat scan = independent 16-byte loads in flight per thread (measured: 8 > 4 > 2)
+// resident 256-thread blocks per SM the register allocation aims at (forward reciprocal half / reverse half);
+// measured on B200, same box, 24 x 200k pairs: (4, 3) 37.5 ms, (5, 3) 36.5, (4, 4) 34.9, (5, 4) 33.9, (5, 5) 34.3, (6, 6) 36.4
+#ifndef MVR_FWD_MINBLOCKS
+#define MVR_FWD_MINBLOCKS 5
+#endif
+#ifndef MVR_FWD1_MINBLOCKS
+#define MVR_FWD1_MINBLOCKS 3   // one-way forward kernel (search + estimator sums)
+#endif
+#ifndef MVR_REV_MINBLOCKS
+#define MVR_REV_MINBLOCKS 4
+#endif
 #ifndef MVR_PG_UNROLL
 #define MVR_PG_UNROLL 8
 #endif
@@ -306,7 +317,7 @@ __device__ __forceinline__ void acc_pair(double (&v)[NV], float4 s, float4 t, co
 // re-reads the matches the block found and accumulates the estimator sums (registers: 18-30 doubles).  The
 // two never overlap, so the kernel's register budget is the larger of the two, not their sum.
 template <bool RECIP, int EST>
-__global__ void __launch_bounds__(FUSED_THREADS, (RECIP ? 4 : 3) * (256 / FUSED_THREADS)) k_icp_forward(const __grid_constant__ FwdBatch batch, int first) {
+__global__ void __launch_bounds__(FUSED_THREADS, (RECIP ? MVR_FWD_MINBLOCKS : MVR_FWD1_MINBLOCKS) * (256 / FUSED_THREADS)) k_icp_forward(const __grid_constant__ FwdBatch batch, int first) {
   // this pair's arguments: parameter space -> shared memory (a dynamically indexed parameter would be copied to
   // local memory and pin registers)
   __shared__ FwdArgs s_args;
@@ -387,7 +398,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (RECIP ? 4 : 3) * (256 / FUSED_
 // (in order) into a queue so that every lane of every warp searches.  Results go to rnn[j] = sorted position
 // of the mutual partner, -1 otherwise; phase B sums over them.
 template <int EST>
-__global__ void __launch_bounds__(FUSED_THREADS, 3 * (256 / FUSED_THREADS)) k_icp_reverse(const __grid_constant__ RevBatch batch) {
+__global__ void __launch_bounds__(FUSED_THREADS, MVR_REV_MINBLOCKS * (256 / FUSED_THREADS)) k_icp_reverse(const __grid_constant__ RevBatch batch) {
   __shared__ RevArgs s_args;
   static_assert(sizeof(RevArgs) % 4 == 0 && sizeof(RevArgs) / 4 <= FUSED_THREADS, "argument block");
   if (threadIdx.x < sizeof(RevArgs) / 4) ((uint32_t*)&s_args)[threadIdx.x] = ((const uint32_t*)&batch.a[blockIdx.y])[threadIdx.x];
@@ -477,8 +488,21 @@ int fused_grid(int items) {
   return blocks < 1 ? 1 : (blocks > FUSED_MAX_BLOCKS ? FUSED_MAX_BLOCKS : blocks);
 }
 
+#ifdef MVR_SMEM_CARVEOUT
+static void set_carveout_once() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  cudaFuncSetAttribute(k_icp_forward<true, EST_P2P>, cudaFuncAttributePreferredSharedMemoryCarveout, MVR_SMEM_CARVEOUT);
+  cudaFuncSetAttribute(k_icp_reverse<EST_P2P>, cudaFuncAttributePreferredSharedMemoryCarveout, MVR_SMEM_CARVEOUT);
+}
+#else
+static void set_carveout_once() {}
+#endif
+
 cudaError_t launch_icp_forward(const FwdBatch& d_batch, int pairs, int max_grid, int first, bool reciprocal, int est, cudaStream_t s) {
   if (pairs <= 0 || pairs > FUSED_MAX_PAIRS) return pairs <= 0 ? cudaSuccess : cudaErrorInvalidValue;
+  set_carveout_once();
   const dim3 grid((unsigned)max_grid, (unsigned)pairs);
   if (reciprocal) {
     // the reciprocal forward half accumulates nothing: one instantiation serves every estimator

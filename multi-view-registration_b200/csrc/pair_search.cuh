@@ -62,7 +62,10 @@ __device__ __forceinline__ void pg_scan(const float4* __restrict__ pts, uint32_t
 }
 
 // Segment list of one thread in shared memory: slot j of thread t lives at seg[j * PG_STRIDE + t] (bank = t).
-constexpr int PG_SEGS = 8;        // row segments collected before a flat scan
+#ifndef MVR_PG_SEGS
+#define MVR_PG_SEGS 8
+#endif
+constexpr int PG_SEGS = MVR_PG_SEGS;   // row segments collected before a flat scan
 constexpr int PG_STRIDE = FUSED_THREADS;
 
 // Flat scan of the thread's collected segments: ONE loop over all candidates of all rows, UNROLL independent loads per
