@@ -306,6 +306,24 @@ int mvr_get_bbox(mvr_ctx* ctx, int which, float lo[3], float hi[3]);
  * view poses (poses: count x float[16] column-major).  pivot/axis are in-out. */
 int mvr_refine_axis(const float* poses, int count, double pivot[3], double axis[3]);
 
+/* -- either side of the path -----------------------------------------------------
+ * Persistence in the reference's text formats: transformation.txt of a view (PointCloud::loadTransformation /
+ * saveTransformation, mvr/src/point_cloud.cpp:305-347; pose = double[16] column-major, p' = M p), axis.txt of an object
+ * (Registrator::load / save, mvr/src/registrator.cpp:258-328), points.asc of the merged model (:385-395). */
+int mvr_transformation_load(const char* path, double* pose);
+int mvr_transformation_save(const char* path, const double* pose);
+int mvr_axis_load(const char* path, double pivot[3], double axis[3]);
+int mvr_axis_save(const char* path, const double pivot[3], const double axis[3]);
+int mvr_points_save_asc(const char* path, const void* rich_points, size_t n);
+/* Registrator::saveRegisteredPoints (mvr/src/registrator.cpp:344-383): the registered views, each posed on the GPU,
+ * concatenated in view order.  views[v]: counts[v] host records of 48 bytes (pcl::PointXYZRGBNormal: xyz at byte 0,
+ * normal at 16, packed colour at 32, curvature at 36); poses: n_views x double[16] column-major; registered
+ * (nullable: all): PointCloud::isRegistered() per view.  full_matrix_normals = 1 reproduces the reference, which
+ * runs the normals through the whole matrix, translation included (:367-371); 0 rotates them only.
+ * out = NULL only reports the record count. */
+int mvr_merge_registered(mvr_ctx* ctx, const void* const* views, const size_t* counts, const double* poses, const int* registered,
+                         int n_views, int full_matrix_normals, void* out, size_t* out_count);
+
 #ifdef __cplusplus
 }
 #endif

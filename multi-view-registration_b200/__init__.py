@@ -192,6 +192,12 @@ def lib():
     L.mvr_ring_close.argtypes = [fp, dp, C.c_int, C.c_int, C.c_int, dp, C.c_double, fp]
     L.mvr_get_bbox.argtypes = [vp, C.c_int, fp, fp]
     L.mvr_refine_axis.argtypes = [fp, C.c_int, dp, dp]
+    L.mvr_transformation_load.argtypes = [C.c_char_p, dp]
+    L.mvr_transformation_save.argtypes = [C.c_char_p, dp]
+    L.mvr_axis_load.argtypes = [C.c_char_p, dp, dp]
+    L.mvr_axis_save.argtypes = [C.c_char_p, dp, dp]
+    L.mvr_points_save_asc.argtypes = [C.c_char_p, vp, C.c_size_t]
+    L.mvr_merge_registered.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), dp, ip, C.c_int, C.c_int, vp, C.POINTER(C.c_size_t)]
     L.mvr_pair_moments_compute.argtypes = [vp, C.c_double, C.c_int, fp, C.POINTER(PairMoments)]
     L.mvr_lum_relax.argtypes = [C.POINTER(PairMoments), ip, ip, C.c_int, C.c_int, C.c_int, dp]
     L.mvr_pair_moments_transform.argtypes = [C.POINTER(PairMoments), dp, dp, C.POINTER(PairMoments)]
@@ -396,6 +402,22 @@ class Context:
         self._ck(lib().mvr_pair_moments_compute(self._h, float(max_dist), int(bool(reciprocal)), _fp(g) if g is not None else None, C.byref(m)))
         return m
 
+    def merge_registered(self, views, poses, registered=None, full_matrix_normals=True):
+        """Registrator::saveRegisteredPoints: views = list of RICH_POINT arrays, poses = list of 4x4; returns the merged array."""
+        arrs = [np.ascontiguousarray(v, dtype=RICH_POINT) for v in views]
+        V = len(arrs)
+        ptrs = (C.c_void_p * max(V, 1))(*[a.ctypes.data for a in arrs])
+        counts = (C.c_size_t * max(V, 1))(*[len(a) for a in arrs])
+        P = np.ascontiguousarray(np.stack([np.asarray(T, dtype=np.float64).T.reshape(16) for T in poses])) if V else np.zeros((1, 16))
+        reg = None if registered is None else np.ascontiguousarray(registered, dtype=np.int32)
+        total = C.c_size_t(0)
+        self._ck(lib().mvr_merge_registered(self._h, ptrs, counts, _dp(P), _ip(reg) if reg is not None else None, V, int(bool(full_matrix_normals)), None, C.byref(total)))
+        out = np.empty(total.value, dtype=RICH_POINT)
+        if total.value:
+            self._ck(lib().mvr_merge_registered(self._h, ptrs, counts, _dp(P), _ip(reg) if reg is not None else None, V, int(bool(full_matrix_normals)),
+                                                out.ctypes.data, C.byref(total)))
+        return out
+
     def fitness_score(self, max_range=None):
         import sys
         s = C.c_double(0)
@@ -462,6 +484,50 @@ def ring_close(rel_poses, weights=None, relax=True, iterations=16, centre=None, 
     if rc != OK:
         raise MvrError(rc, lib().mvr_status_string(rc).decode())
     return [pose_to_numpy(out[k]) for k in range(V)]
+
+
+# ---- persistence in the reference's text formats (transformation.txt, axis.txt, points.asc) ----------------------------
+RICH_POINT = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("pad0", "<f4"),
+                       ("normal_x", "<f4"), ("normal_y", "<f4"), ("normal_z", "<f4"), ("pad1", "<f4"),
+                       ("b", "u1"), ("g", "u1"), ("r", "u1"), ("a", "u1"), ("curvature", "<f4"), ("pad2", "<f4", (2,))])   # pcl::PointXYZRGBNormal
+assert RICH_POINT.itemsize == 48
+
+
+def transformation_load(path):
+    m = np.empty(16, dtype=np.float64)
+    rc = lib().mvr_transformation_load(os.fsencode(path), _dp(m))
+    if rc != OK:
+        raise MvrError(rc, "cannot read " + str(path))
+    return m.reshape(4, 4).T.copy()
+
+
+def transformation_save(path, pose):
+    m = np.ascontiguousarray(np.asarray(pose, dtype=np.float64).T).reshape(16)
+    rc = lib().mvr_transformation_save(os.fsencode(path), _dp(m))
+    if rc != OK:
+        raise MvrError(rc, "cannot write " + str(path))
+
+
+def axis_load(path):
+    pv, ax = np.empty(3), np.empty(3)
+    rc = lib().mvr_axis_load(os.fsencode(path), _dp(pv), _dp(ax))
+    if rc != OK:
+        raise MvrError(rc, "cannot read " + str(path))
+    return pv, ax
+
+
+def axis_save(path, pivot, axis):
+    pv, ax = np.ascontiguousarray(pivot, dtype=np.float64), np.ascontiguousarray(axis, dtype=np.float64)
+    rc = lib().mvr_axis_save(os.fsencode(path), _dp(pv), _dp(ax))
+    if rc != OK:
+        raise MvrError(rc, "cannot write " + str(path))
+
+
+def points_save_asc(path, rich_points):
+    a = np.ascontiguousarray(rich_points, dtype=RICH_POINT)
+    rc = lib().mvr_points_save_asc(os.fsencode(path), a.ctypes.data, len(a))
+    if rc != OK:
+        raise MvrError(rc, "cannot write " + str(path))
 
 
 def icp_align_batch(contexts, params, guesses=None):

@@ -1224,6 +1224,35 @@ int mvr_apply_pose_device(mvr_ctx* ctx, const void* d_points, size_t n, size_t s
   return MVR_OK;
 }
 
+int mvr_merge_registered(mvr_ctx* ctx, const void* const* views, const size_t* counts, const double* poses, const int* registered,
+                         int n_views, int full_matrix_normals, void* out, size_t* out_count) {
+  if (!ctx || n_views < 0 || !out_count || (n_views && (!views || !counts || !poses))) return MVR_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  size_t total = 0;
+  for (int v = 0; v < n_views; ++v) {
+    if (registered && !registered[v]) continue;
+    if (counts[v] && !views[v]) return fail(ctx, MVR_ERR_BAD_ARG, "null view");
+    if (counts[v] > (size_t)INT_MAX / 4) return fail(ctx, MVR_ERR_BAD_ARG, "view too large");
+    total += counts[v];
+  }
+  *out_count = total;
+  if (!out || total == 0) return MVR_OK;   // out == NULL: size query
+  CK(ctx->scratch.ensure(total * 48));
+  size_t biggest = 0;
+  for (int v = 0; v < n_views; ++v) if (!registered || registered[v]) biggest = std::max(biggest, counts[v]);
+  CK(ctx->qtmp.ensure(std::max<size_t>(biggest, 1) * 48));
+  size_t at = 0;
+  for (int v = 0; v < n_views; ++v) {
+    if ((registered && !registered[v]) || counts[v] == 0) continue;
+    CK(cudaMemcpyAsync(ctx->qtmp.p, views[v], counts[v] * 48, cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_merge_rich(ctx->qtmp.p, (int)counts[v], poses + 16 * v, full_matrix_normals, (char*)ctx->scratch.p + at * 48, ctx->stream));
+    at += counts[v];
+  }
+  CK(cudaMemcpyAsync(out, ctx->scratch.p, total * 48, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MVR_OK;
+}
+
 int mvr_copy_aligned_device(mvr_ctx* ctx, float* d_out) {
   if (!ctx || !d_out) return MVR_ERR_BAD_ARG;
   cudaSetDevice(ctx->device);

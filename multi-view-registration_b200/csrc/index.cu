@@ -135,6 +135,36 @@ __global__ void __launch_bounds__(256) k_apply_pose(const char* __restrict__ in,
   out[i] = r;
 }
 
+// Registrator::saveRegisteredPoints (mvr/src/registrator.cpp:344-400) for one view: every 48-byte
+// pcl::PointXYZRGBNormal record {xyz pad | normal pad | rgb curvature pad pad} gets p' = pose * p and, exactly like the
+// reference (matrix.preMult(normal), :367-371), n' = pose * n with the TRANSLATION applied too (full_matrix_normals = 1);
+// full_matrix_normals = 0 rotates the normal only.  Double arithmetic narrowed to float; colour and curvature copied.
+__global__ void __launch_bounds__(256) k_merge_rich(const float4* __restrict__ in, int n, Mat4d M, int full_matrix_normals, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 a = __ldg(in + 3 * (size_t)i), b = __ldg(in + 3 * (size_t)i + 1), c = __ldg(in + 3 * (size_t)i + 2);
+  float4 r;
+  r.x = (float)(M.m[0] * a.x + M.m[4] * a.y + M.m[8] * a.z + M.m[12]);
+  r.y = (float)(M.m[1] * a.x + M.m[5] * a.y + M.m[9] * a.z + M.m[13]);
+  r.z = (float)(M.m[2] * a.x + M.m[6] * a.y + M.m[10] * a.z + M.m[14]);
+  r.w = a.w;
+  const double t = full_matrix_normals ? 1.0 : 0.0;
+  float4 q;
+  q.x = (float)(M.m[0] * b.x + M.m[4] * b.y + M.m[8] * b.z + t * M.m[12]);
+  q.y = (float)(M.m[1] * b.x + M.m[5] * b.y + M.m[9] * b.z + t * M.m[13]);
+  q.z = (float)(M.m[2] * b.x + M.m[6] * b.y + M.m[10] * b.z + t * M.m[14]);
+  q.w = b.w;
+  out[3 * (size_t)i] = r; out[3 * (size_t)i + 1] = q; out[3 * (size_t)i + 2] = c;
+}
+
+cudaError_t launch_merge_rich(const void* in48, int n, const double* M16, int full_matrix_normals, void* out48, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  Mat4d M;
+  for (int k = 0; k < 16; ++k) M.m[k] = M16[k];
+  k_merge_rich<<<(n + 255) / 256, 256, 0, s>>>((const float4*)in48, n, M, full_matrix_normals, (float4*)out48); count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_apply_pose(const void* in, size_t stride, int n, const double* M16, float4* out, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   Mat4d M;

@@ -189,6 +189,9 @@ size_t compact_scratch_elems(int n);
 cudaError_t launch_compact_corr(const int32_t* corr_j, const float* corr_d2, int n, uint32_t* scratch, int32_t* out_q,
                                 int32_t* out_m, float* out_d2, uint32_t* count_out, cudaStream_t s);
 
+// 48-byte PointXYZRGBNormal records: position and normal through pose (index.cu k_merge_rich).
+cudaError_t launch_merge_rich(const void* in48, int n, const double* M16, int full_matrix_normals, void* out48, cudaStream_t s);
+
 // ---- cell_nn.cu ----------------------------------------------------------------------------
 // Exact un-gated 1-NN of queries sorted by the cells of the target's row-major grid g (warp-cooperative; for many
 // queries per target point).  d_nq_valid: device count of finite queries (they come first).  Results by original index.

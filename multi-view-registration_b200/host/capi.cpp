@@ -192,6 +192,37 @@ void mvr_pair_moments_transform(const mvr_pair_moments* in, const double* pose, 
   *out = tmp;
 }
 
+// ---- persistence in the reference's text formats ---------------------------------------------------------------
+int mvr_transformation_load(const char* path, double* pose) {
+  if (!path || !pose) return MVR_ERR_BAD_ARG;
+  Matrix4d m;
+  if (!loadTransformation(path, m)) return MVR_ERR_NO_INPUT;
+  std::memcpy(pose, m.m, sizeof(m.m));
+  return MVR_OK;
+}
+
+int mvr_transformation_save(const char* path, const double* pose) {
+  if (!path || !pose) return MVR_ERR_BAD_ARG;
+  Matrix4d m;
+  std::memcpy(m.m, pose, sizeof(m.m));
+  return saveTransformation(path, m) ? MVR_OK : MVR_ERR_BAD_ARG;
+}
+
+int mvr_axis_load(const char* path, double pivot[3], double axis[3]) {
+  if (!path || !pivot || !axis) return MVR_ERR_BAD_ARG;
+  return loadAxis(path, pivot, axis) ? MVR_OK : MVR_ERR_NO_INPUT;
+}
+
+int mvr_axis_save(const char* path, const double pivot[3], const double axis[3]) {
+  if (!path || !pivot || !axis) return MVR_ERR_BAD_ARG;
+  return saveAxis(path, pivot, axis) ? MVR_OK : MVR_ERR_BAD_ARG;
+}
+
+int mvr_points_save_asc(const char* path, const void* rich_points, size_t n) {
+  if (!path || (n && !rich_points)) return MVR_ERR_BAD_ARG;
+  return savePointsAsc(path, rich_points, n) ? MVR_OK : MVR_ERR_BAD_ARG;
+}
+
 int mvr_refine_axis(const float* poses, int count, double pivot[3], double axis[3]) {
   if (count < 0 || (count && !poses) || !pivot || !axis) return MVR_ERR_BAD_ARG;
   std::vector<Matrix4d> P((size_t)count);

@@ -167,26 +167,69 @@ void Registrator::initRotation(View& v, int n_views) const {
   v.pose_is_identity = false;
 }
 
-bool Registrator::load(const char* axis_txt) {
-  // axis.txt: pivot x y z, then normal x y z (mvr/src/registrator.cpp:258-292)
-  FILE* f = std::fopen(axis_txt, "r");
+// ---- persistence (formats: see registrator.h) ---------------------------------------------------------------------
+bool loadTransformation(const char* path, Matrix4d& pose) {
+  FILE* f = std::fopen(path, "r");
+  if (!f) return false;
+  Matrix4d m = identity4d();
+  int got = 0;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {   // file row i, column j = element (i, j) of the column-vector matrix
+      double e;
+      if (std::fscanf(f, "%lf", &e) == 1) { m.m[j * 4 + i] = e; ++got; }
+    }
+  std::fclose(f);
+  if (got != 16) return false;
+  pose = m;
+  return true;
+}
+
+bool saveTransformation(const char* path, const Matrix4d& pose) {
+  FILE* f = std::fopen(path, "w");
+  if (!f) return false;
+  for (int i = 0; i < 4; ++i) {
+    for (int j = 0; j < 4; ++j) std::fprintf(f, "%lf ", pose.m[j * 4 + i]);
+    std::fprintf(f, "\n");
+  }
+  return std::fclose(f) == 0;
+}
+
+bool loadAxis(const char* path, double pivot[3], double axis[3]) {
+  FILE* f = std::fopen(path, "r");
   if (!f) return false;
   double v[6];
   int got = 0;
   for (int k = 0; k < 6; ++k) got += std::fscanf(f, "%lf", &v[k]) == 1;
   std::fclose(f);
   if (got != 6) return false;
-  for (int k = 0; k < 3; ++k) { pivot_[k] = v[k]; axis_[k] = v[3 + k]; }
+  for (int k = 0; k < 3; ++k) { pivot[k] = v[k]; axis[k] = v[3 + k]; }
   return true;
 }
 
-bool Registrator::save(const char* axis_txt) const {
-  FILE* f = std::fopen(axis_txt, "w");
+bool saveAxis(const char* path, const double pivot[3], const double axis[3]) {
+  FILE* f = std::fopen(path, "w");
   if (!f) return false;
-  std::fprintf(f, "%lf %lf %lf\n%lf %lf %lf\n", pivot_[0], pivot_[1], pivot_[2], axis_[0], axis_[1], axis_[2]);
-  std::fclose(f);
-  return true;
+  // the reference holds both as osg::Vec3 (float) and prints them with %f
+  std::fprintf(f, "%f %f %f\n", (double)(float)pivot[0], (double)(float)pivot[1], (double)(float)pivot[2]);
+  std::fprintf(f, "%f %f %f\n", (double)(float)axis[0], (double)(float)axis[1], (double)(float)axis[2]);
+  return std::fclose(f) == 0;
 }
+
+bool savePointsAsc(const char* path, const void* rich_points48, size_t n) {
+  FILE* f = std::fopen(path, "w");
+  if (!f) return false;
+  const unsigned char* p = static_cast<const unsigned char*>(rich_points48);
+  for (size_t i = 0; i < n; ++i, p += 48) {
+    float xyz[3];
+    std::memcpy(xyz, p, sizeof(xyz));
+    // pcl::PointXYZRGBNormal packs the colour as b, g, r, a at byte 32
+    std::fprintf(f, "%f %f %f %d %d %d\n", xyz[0], xyz[1], xyz[2], (int)p[34], (int)p[33], (int)p[32]);
+  }
+  return std::fclose(f) == 0;
+}
+
+bool Registrator::load(const char* axis_txt) { return loadAxis(axis_txt, pivot_, axis_); }
+bool Registrator::save(const char* axis_txt) const { return saveAxis(axis_txt, pivot_, axis_); }
 
 int Registrator::getTransformedPoints(const View& v, PointCloudXYZ& out) {
   if (!ok()) return fail(MVR_ERR_CUDA, "no GPU context");

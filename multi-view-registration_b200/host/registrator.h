@@ -136,6 +136,17 @@ class Registrator {
 // Ring loop closure (host): see lum.cpp.
 int ringClose(const std::vector<Matrix4d>& rel, const std::vector<double>& weight, bool relax, int iterations,
               const double* centre, double rot_scale, std::vector<Matrix4d>& abs_out);
+// Persistence in the reference's text formats (host).
+//   transformation.txt (PointCloud::load/saveTransformation, mvr/src/point_cloud.cpp:305-347): the pose of a view, four
+//     lines of four "%lf " numbers; the reference writes matrix(j, i) of its row-vector osg::Matrix, i.e. the
+//     column-vector matrix row by row.
+//   axis.txt (Registrator::load/save, mvr/src/registrator.cpp:258-328): "px py pz\nnx ny nz\n", "%f".
+//   points.asc (Registrator::saveRegisteredPoints, :385-395): "x y z r g b\n" per point, "%f %f %f %d %d %d".
+bool loadTransformation(const char* path, Matrix4d& pose);
+bool saveTransformation(const char* path, const Matrix4d& pose);
+bool loadAxis(const char* path, double pivot[3], double axis[3]);
+bool saveAxis(const char* path, const double pivot[3], const double axis[3]);
+bool savePointsAsc(const char* path, const void* rich_points48, size_t n);
 // LUM relaxation on correspondence moments (host): see lum.cpp.  edges[e] joins views src[e] -> tgt[e], sums in
 // the common world frame; X = rigid corrections, X[0] = identity.
 void momentsTransform(const mvr_pair_moments& in, const Matrix4d& pose, const double* new_origin, mvr_pair_moments& out);

@@ -308,3 +308,41 @@ def test_lum_outer_loops_descend_steadily_on_oracle_correspondences(mvr, orc, sy
         P = [X[v] @ P[v] for v in range(V)]
     assert e0 > 0.02 and rot_err(P) < 0.75 * e0
     assert all(b < a * 1.01 for a, b in zip(msd, msd[1:])) and msd[-1] < 0.7 * msd[0]
+
+
+# ---- persistence in the reference's text formats (mvr/src/point_cloud.cpp:305-347, mvr/src/registrator.cpp:258-328, 385-395) ----
+def test_transformation_txt_format_and_round_trip(mvr, tmp_path):
+    T = np.array([[0.5, -0.8660254, 0.0, 12.25], [0.8660254, 0.5, 0.0, -3.5], [0.0, 0.0, 1.0, 900.125], [0.0, 0.0, 0.0, 1.0]])
+    f = tmp_path / "transformation.txt"
+    mvr.transformation_save(f, T)
+    # the reference prints matrix(j, i) of its row-vector matrix with "%lf ": the column-vector matrix row by row
+    want = "".join("".join("%f " % T[i, j] for j in range(4)) + "\n" for i in range(4))
+    assert f.read_text() == want
+    np.testing.assert_allclose(mvr.transformation_load(f), T, atol=5e-7)
+    # a file the reference wrote (hand-made here): element (i, j) is the j-th number of line i
+    g = tmp_path / "ref.txt"
+    g.write_text("1 0 0 5\n0 0 -1 6\n0 1 0 7\n0 0 0 1\n")
+    np.testing.assert_array_equal(mvr.transformation_load(g), [[1, 0, 0, 5], [0, 0, -1, 6], [0, 1, 0, 7], [0, 0, 0, 1]])
+    with pytest.raises(mvr.MvrError):
+        mvr.transformation_load(tmp_path / "missing.txt")
+    (tmp_path / "short.txt").write_text("1 2 3\n")
+    with pytest.raises(mvr.MvrError):
+        mvr.transformation_load(tmp_path / "short.txt")
+
+
+def test_axis_txt_format_and_round_trip(mvr, tmp_path):
+    f = tmp_path / "axis.txt"
+    mvr.axis_save(f, [-13.382786, 50.223461, 917.4776], [-0.054323, -0.814921, -0.57702])
+    assert f.read_text() == "-13.382786 50.223461 917.477600\n-0.054323 -0.814921 -0.577020\n"
+    pv, ax = mvr.axis_load(f)
+    np.testing.assert_allclose(pv, [-13.382786, 50.223461, 917.4776], atol=1e-6)
+    np.testing.assert_allclose(ax, [-0.054323, -0.814921, -0.57702], atol=1e-6)
+
+
+def test_points_asc_format(mvr, tmp_path):
+    pts = np.zeros(2, dtype=mvr.RICH_POINT)
+    pts["x"], pts["y"], pts["z"] = [1.5, -2.25], [0.0, 3.0], [900.0, 901.5]
+    pts["r"], pts["g"], pts["b"] = [255, 1], [128, 2], [0, 3]
+    f = tmp_path / "points.asc"
+    mvr.points_save_asc(f, pts)
+    assert f.read_text() == "1.500000 0.000000 900.000000 255 128 0\n-2.250000 3.000000 901.500000 1 2 3\n"

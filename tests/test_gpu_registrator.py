@@ -206,3 +206,43 @@ def test_registration_lum_matches_the_oracle_loop(mvr, orc, synth, seq):
         # a handful of borderline pairs may differ (the guesses agree to float rounding only): poses to ~1e-5
         assert rot_angle(got[v], P[v]) < 5e-5
         assert np.linalg.norm(got[v][:3, 3].astype(np.float64) - P[v][:3, 3]) < 5e-2
+
+
+def test_merge_registered_matches_reference_arithmetic(mvr, synth):
+    """Registrator::saveRegisteredPoints (mvr/src/registrator.cpp:344-383): registered views posed (double math narrowed
+    to float) and concatenated; normals go through the whole matrix like the reference's preMult, or are only rotated."""
+    rng = np.random.default_rng(12)
+    views, poses, reg = [], [], [1, 0, 1, 1]
+    for v in range(4):
+        n = [1000, 500, 0, 777][v]
+        a = np.zeros(n, dtype=mvr.RICH_POINT)
+        for k in ("x", "y", "z", "normal_x", "normal_y", "normal_z", "curvature"):
+            a[k] = rng.normal(size=n).astype(np.float32) * (100.0 if k in "xyz" else 1.0)
+        a["r"], a["g"], a["b"] = rng.integers(0, 256, n), rng.integers(0, 256, n), rng.integers(0, 256, n)
+        views.append(a)
+        poses.append(synth.view_pose(v, 12) @ synth.perturbation())
+    ctx = mvr.Context(0)
+    for full in (True, False):
+        got = ctx.merge_registered(views, poses, registered=reg, full_matrix_normals=full)
+        want = []
+        for v in range(4):
+            if not reg[v]:
+                continue
+            a = views[v].copy()
+            P = np.stack([a["x"], a["y"], a["z"]], axis=1).astype(np.float64)
+            N = np.stack([a["normal_x"], a["normal_y"], a["normal_z"]], axis=1).astype(np.float64)
+            R, t = poses[v][:3, :3], poses[v][:3, 3]
+            # the same left-to-right sum the kernel evaluates: ((m0 x + m4 y) + m8 z) + m12
+            Pp = ((R[:, 0] * P[:, :1] + R[:, 1] * P[:, 1:2]) + R[:, 2] * P[:, 2:3]) + t
+            Np = ((R[:, 0] * N[:, :1] + R[:, 1] * N[:, 1:2]) + R[:, 2] * N[:, 2:3]) + (t if full else 0.0 * t)
+            a["x"], a["y"], a["z"] = Pp[:, 0].astype(np.float32), Pp[:, 1].astype(np.float32), Pp[:, 2].astype(np.float32)
+            a["normal_x"], a["normal_y"], a["normal_z"] = Np[:, 0].astype(np.float32), Np[:, 1].astype(np.float32), Np[:, 2].astype(np.float32)
+            want.append(a)
+        want = np.concatenate(want)
+        assert len(got) == len(want) == 1777
+        for k in ("r", "g", "b", "curvature"):
+            assert np.array_equal(got[k], want[k])
+        for k in ("x", "y", "z", "normal_x", "normal_y", "normal_z"):
+            np.testing.assert_allclose(got[k], want[k], rtol=0, atol=np.abs(want[k]).max() * 2.0 ** -23)   # within 1 float ulp (device FMA contraction is off)
+    assert len(ctx.merge_registered(views, poses, registered=[0, 0, 0, 0])) == 0
+    ctx.close()
