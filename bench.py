@@ -340,9 +340,21 @@ def run_native(a):
         bytes_per_launch = c["bytes"] / max(c["launches"], 1)
         ach = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
         total_kernel_ms = sum(v["ms"] for v in st.values())
+        # DRAM traffic of the same launch pair from the committed ncu --set full capture (cold cache), if it was taken
+        # with the same number of pairs per launch
+        traffic, traffic_src = None, None
+        try:
+            import glob, re
+            caps = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_icp_fused_ncu_full.txt")))
+            if caps:
+                m = re.search(r"one iteration of (\d+) pairs\): ([0-9.]+) MB", open(caps[-1]).read())
+                if m and int(m.group(1)) == min(8, p1 - p0):
+                    traffic, traffic_src = float(m.group(2)) * 1e6, os.path.relpath(caps[-1], ROOT) + " (ncu --set full, caches flushed per replay)"
+        except OSError:
+            pass
         roof = {"bound": "hbm", "kernel": "k_icp_forward + k_icp_reverse (one ICP iteration of every pair of the rank: forward search, reciprocal "
                                           "search, estimator sums, solve; two launches serve the whole batch)",
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "bytes_per_launch": bytes_per_launch, "avg_launch_us": avg_ms * 1e3, "launches": c["launches"],
                 "share_of_kernel_time": c["ms"] / total_kernel_ms if total_kernel_ms > 0 else None,
