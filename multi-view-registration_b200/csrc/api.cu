@@ -6,6 +6,8 @@
 // Cholesky solve and the convergence test run here on 18-29 doubles per iteration.
 // There is no CPU fallback for any device stage.
 #include <cfloat>
+#include <chrono>
+#include <cstdlib>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -992,10 +994,7 @@ static int align_run(mvr_ctx* const* ctxs, int count, const mvr_icp_params* prm,
   mvr_ctx* ctx = ctxs[0];   // the lead: its stream carries the batch, CK() reports into it
   cudaSetDevice(ctx->device);
   const bool reciprocal = prm->use_reciprocal_correspondences != 0;
-  for (int k = 1; k < count; ++k) {   // the lead stream continues after every context's preparation
-    CK(cudaEventRecord(ctxs[k]->ev_b, ctxs[k]->stream));
-    CK(cudaStreamWaitEvent(ctx->stream, ctxs[k]->ev_b, 0));
-  }
+  for (int k = 1; k < count; ++k) CK(cudaEventRecord(ctxs[k]->ev_b, ctxs[k]->stream));   // "context k is prepared"
   CK(cudaEventRecord(ctx->ev_a, ctx->stream));
   const int gsz = std::max(1, std::min(ctx->group_pairs, (int)FUSED_MAX_PAIRS));
   for (int g0 = 0; g0 < count; g0 += gsz) {
@@ -1007,6 +1006,9 @@ static int align_run(mvr_ctx* const* ctxs, int count, const mvr_icp_params* prm,
     long long n_tot = 0, m_tot = 0;
     for (int k = 0; k < gn; ++k) {
       mvr_ctx* c = ctxs[g0 + k];
+      // the lead stream waits for the preparation of THIS group only: later groups' index builds (on their own
+      // streams) overlap with this group's iterations
+      if (c != ctx) CK(cudaStreamWaitEvent(ctx->stream, c->ev_b, 0));
       fb.a[k] = c->fa; rb.a[k] = c->ra;
       gf = std::max(gf, c->fa.grid); gr = std::max(gr, c->ra.grid);
       if (!c->h_state->done) done = false;
@@ -1118,12 +1120,17 @@ int mvr_icp_align_batch(mvr_ctx* const* ctxs, int count, const mvr_icp_params* p
   const int est = prm->estimator == MVR_POINT_TO_PLANE ? EST_P2L : EST_P2P;
   std::vector<mvr_ctx*> ok;
   std::vector<int> slot;
+  const bool timing = std::getenv("MVR_DEBUG_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
   for (int k = 0; k < count; ++k) {
     statuses[k] = align_prepare(ctxs[k], prm, guesses ? guesses + 16 * k : nullptr, est);
     if (statuses[k] == MVR_OK) { ok.push_back(ctxs[k]); slot.push_back(k); }
   }
   if (ok.empty()) return MVR_OK;
+  const double t1 = now();
   int rc = align_run(ok.data(), (int)ok.size(), prm, est);
+  if (timing) std::fprintf(stderr, "[timing]   prepare (host enqueue) %.3f ms, run %.3f ms\n", t1 - t0, now() - t1);
   if (rc) { if (ok[0] != ctxs[0]) ctxs[0]->err = ok[0]->err; return rc; }
   for (size_t j = 0; j < ok.size(); ++j) statuses[slot[j]] = align_finish_enqueue(ok[j], ok[0], nullptr);
   if (cudaStreamSynchronize(ok[0]->stream) != cudaSuccess) return fail(ctxs[0], MVR_ERR_CUDA, "batch tail failed");

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <cfloat>
 #include <climits>
 #include <cmath>
@@ -393,6 +394,9 @@ int Registrator::multiViewRegister(std::vector<View>& views, const mvr_turntable
   // serves them all (mvr_icp_align_batch).  Every distinct host view is uploaded once.
   const int P = p1 - p0;
   if (P <= 0) return MVR_OK;
+  const bool timing = std::getenv("MVR_DEBUG_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = now();
   int rc = ensureContexts(P);
   if (rc) return rc;
   cudaSetDevice(device_);
@@ -430,6 +434,7 @@ int Registrator::multiViewRegister(std::vector<View>& views, const mvr_turntable
     const Matrix4f g = toFloat(multiply(inverseRigid(tgt.pose), src.pose));
     std::memcpy(&guesses[(size_t)k * 16], g.m, sizeof(g.m));
   }
+  const double t_set = now();
   // the source of pair p is the view that pair p + 1 has as its target: shared, not measured again
   for (int k = 0; k < P; ++k) {
     const int sv = (p0 + k + 1) % V;
@@ -438,6 +443,7 @@ int Registrator::multiViewRegister(std::vector<View>& views, const mvr_turntable
     else rc = mvr_set_source_device(ctx_[(size_t)k], dview[(size_t)sv], views[(size_t)sv].size);
     if (rc) return fail(rc, mvr_last_error(ctx_[(size_t)k]));
   }
+  const double t_share = now();
   const int repeats = std::max(prm.repeat_times, 1);
   for (int r = 0; r < repeats; ++r) {
     if ((rc = mvr_icp_align_batch(cs.data(), P, &prm.icp, guesses.data(), finals.data(), rep.data(), st.data()))) return fail(rc, mvr_last_error(cs[0]));
@@ -467,6 +473,8 @@ int Registrator::multiViewRegister(std::vector<View>& views, const mvr_turntable
     }
     fill_report(reports[(size_t)p], (p + 1) % V, p, a, iterations[(size_t)k], queries[(size_t)k], ms[(size_t)k], a.final_transformation);
   }
+  const double t_align = now();
+  if (timing) std::fprintf(stderr, "[timing] upload+set_target %.3f ms, share %.3f ms, align_batch %.3f ms\n", t_set - t_begin, t_share - t_set, t_align - t_share);
   if (p0 == 0 && p1 == V) {
     std::vector<Matrix4d> rel((size_t)V), abs_pose;
     std::vector<double> w((size_t)V);
