@@ -983,7 +983,7 @@ static int align_prepare(mvr_ctx* ctx, const mvr_icp_params* prm, const float* g
   ra = RevArgs{};
   ra.tgt = fa.tgt; ra.m_valid = pt.n_valid; ra.rmin = fa.rmin; ra.cur = fa.cur; ra.sstart = psx.start.as<uint32_t>(); ra.gs = psx.g;
   ra.n_valid = psx.n_valid; ra.corr_p = fa.corr_p; ra.rnn = reciprocal ? ctx->rnn.as<int32_t>() : nullptr; ra.nrm = fa.nrm;
-  ra.partials = fa.partials; ra.st = d_st; ra.log = d_log; ra.grid = fused_grid(pt.n_valid);
+  ra.partials = fa.partials; ra.st = d_st; ra.log = d_log; ra.grid = fused_grid_rev(pt.n_valid);
   return MVR_OK;
 }
 

@@ -483,6 +483,22 @@ __global__ void __launch_bounds__(FUSED_THREADS, MVR_REV_MINBLOCKS * (256 / FUSE
   reduce_and_finish<NV>(v, a.partials, st, a.log, a.grid);
 }
 
+// The reverse half searches only the chosen target points (about half of them): a block takes several chunks of 256
+// target points so that its compacted queue fills whole batches of 256.  Measured on B200 (same box; 24 x 200k pairs in
+// groups of 8 / one 200k pair alone): 1 chunk 33.9 ms / 2.32 ms, 2 chunks 30.0 / 2.18, 4 chunks 29.1 / 2.50, 8 chunks
+// 30.7 / 3.10 -- two chunks, four once a cloud fills the GPU on its own.  A pure function of the cloud size, so that the
+// block partition, and with it the order of the sums, does not depend on what else runs in the batch.
+int fused_grid_rev(int items) {
+  const int chunks = (items + FUSED_THREADS - 1) / FUSED_THREADS;
+#ifdef MVR_REV_CHUNKS
+  const int per = MVR_REV_CHUNKS;
+#else
+  const int per = items >= 400000 ? 4 : 2;
+#endif
+  const int blocks = (chunks + per - 1) / per;
+  return blocks < 1 ? 1 : (blocks > FUSED_MAX_BLOCKS ? FUSED_MAX_BLOCKS : blocks);
+}
+
 int fused_grid(int items) {
   const int blocks = (items + FUSED_THREADS - 1) / FUSED_THREADS;
   return blocks < 1 ? 1 : (blocks > FUSED_MAX_BLOCKS ? FUSED_MAX_BLOCKS : blocks);

@@ -159,7 +159,7 @@ struct RevArgs {
   double* partials;
   IcpState* st;
   IterRec* log;
-  int grid;                // fused_grid(m_valid)
+  int grid;                // fused_grid_rev(m_valid)
 };
 // est: which sums the iteration accumulates over its correspondences
 enum { EST_P2P = 0, EST_P2L = 1, EST_MOM = 2 /* point-to-point + second moments (LUM edge statistics) */ };
@@ -171,6 +171,7 @@ enum { FUSED_MAX_PAIRS = 8 };
 struct FwdBatch { FwdArgs a[FUSED_MAX_PAIRS]; };
 struct RevBatch { RevArgs a[FUSED_MAX_PAIRS]; };
 int fused_grid(int items);
+int fused_grid_rev(int items);   // blocks of the reverse half
 cudaError_t launch_icp_forward(const FwdBatch& batch, int pairs, int max_grid, int first, bool reciprocal, int est, cudaStream_t s);
 cudaError_t launch_icp_reverse(const RevBatch& batch, int pairs, int max_grid, int est, cudaStream_t s);
 // corr_j[i] = original index of the matched target point, -1 = none, -2-j = passed the gate but failed
