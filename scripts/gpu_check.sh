@@ -11,7 +11,7 @@ python bench.py --steps 5 --warmup 3 > gpurun_out/bench_${TAG}.json 2> gpurun_ou
 if [ "${NCU:-1}" = "1" ]; then
   SMALL="python bench.py --steps 1 --warmup 3 --no-e2e --cpu-sample-pairs 0"   # the bench workload itself, one timed step
   $SMALL > gpurun_out/plain_${TAG}.log 2>&1 &&
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_${TAG}.csv $SMALL > gpurun_out/ncu_launches_${TAG}.log 2>&1
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 2600 --csv --log-file gpurun_out/launches_${TAG}.csv $SMALL > gpurun_out/ncu_launches_${TAG}.log 2>&1
   echo "ncu launches rc=$?"
   $SMALL > gpurun_out/plain2_${TAG}.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:${KREGEX} -s 400 -c 2 -f -o gpurun_out/prof_${TAG} $SMALL > gpurun_out/ncu_full_${TAG}.log 2>&1

@@ -28,7 +28,7 @@ for r in rows[hi + 1:]:
     a[1] += v
 tot = sum(a[1] for a in agg.values())
 with open(os.path.join(P, "%s_ncu_launches_summary.txt" % rnd), "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 python bench.py --steps 1 --warmup 3 --no-e2e --cpu-sample-pairs 0\n")
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 2600 python bench.py --steps 1 --warmup 3 --no-e2e --cpu-sample-pairs 0\n")
     f.write("# per-launch times are cold-cache and serialised: the SHARE of a kernel is what compares with bench.py's live measurement\n")
     f.write("# (bench.py roofline.share_of_kernel_time = %.3f for k_icp_forward + k_icp_reverse)\n" % (bench["roofline"]["share_of_kernel_time"] or 0))
     for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
