@@ -939,9 +939,8 @@ static int align_prepare(mvr_ctx* ctx, const mvr_icp_params* prm, const float* g
   if (reciprocal) {
     CK(ctx->rmin.ensure((size_t)std::max(m, 1) * sizeof(uint32_t)));
     CK(launch_fill_u32(ctx->rmin.as<uint32_t>(), (size_t)std::max(m, 1), 0x7f800000u, ctx->stream));   // +inf: "chosen by nobody"
-    CK(ctx->rnn.ensure((size_t)std::max(m, 1) * sizeof(int32_t)));
   }
-  CK(ctx->partials.ensure((size_t)FUSED_MAX_BLOCKS * REDUCE_MAX_VALS * sizeof(double)));
+  CK(ctx->partials.ensure((size_t)std::max((int)FUSED_MAX_BLOCKS, fused_grid_rev(m)) * REDUCE_MAX_VALS * sizeof(double)));
   CK(ctx->out_cloud.ensure((size_t)n * sizeof(float4)));
   CK(ctx->state.ensure(sizeof(IcpState)));
   CK(ctx->log.ensure((size_t)ICP_MAX_LOG * sizeof(IterRec)));
@@ -982,8 +981,8 @@ static int align_prepare(mvr_ctx* ctx, const mvr_icp_params* prm, const float* g
   RevArgs& ra = ctx->ra;
   ra = RevArgs{};
   ra.tgt = fa.tgt; ra.m_valid = pt.n_valid; ra.rmin = fa.rmin; ra.cur = fa.cur; ra.sstart = psx.start.as<uint32_t>(); ra.gs = psx.g;
-  ra.n_valid = psx.n_valid; ra.corr_p = fa.corr_p; ra.rnn = reciprocal ? ctx->rnn.as<int32_t>() : nullptr; ra.nrm = fa.nrm;
-  ra.partials = fa.partials; ra.st = d_st; ra.log = d_log; ra.grid = fused_grid_rev(pt.n_valid);
+  ra.n_valid = psx.n_valid; ra.corr_p = fa.corr_p; ra.nrm = fa.nrm;
+  ra.partials = fa.partials; ra.st = d_st; ra.log = d_log; ra.grid = fused_grid_rev(pt.n_valid); ra.per = fused_rev_chunks(pt.n_valid);
   return MVR_OK;
 }
 

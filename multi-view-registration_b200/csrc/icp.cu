@@ -394,9 +394,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, (RECIP ? MVR_FWD_MINBLOCKS : MV
   }
 }
 
-// Reciprocal half.  Only the target points some source point chose are searched; a block compacts them
-// (in order) into a queue so that every lane of every warp searches.  Results go to rnn[j] = sorted position
-// of the mutual partner, -1 otherwise; phase B sums over them.
+// Reciprocal half.  Only the target points some source point chose are searched: a block compacts the chosen ones
+// of its `per` chunks of 256 target points (in order, deterministic) into a list in shared memory, every thread then
+// searches its entries of the list, and sums over its own mutual pairs afterwards (phase B needs no barrier: a thread
+// revisits exactly the entries it searched, so a warp that is done does not wait for the slowest one of the block).
+constexpr int REV_MAX_CHUNKS = 4;
 template <int EST>
 __global__ void __launch_bounds__(FUSED_THREADS, MVR_REV_MINBLOCKS * (256 / FUSED_THREADS)) k_icp_reverse(const __grid_constant__ RevBatch batch) {
   __shared__ RevArgs s_args;
@@ -408,18 +410,37 @@ __global__ void __launch_bounds__(FUSED_THREADS, MVR_REV_MINBLOCKS * (256 / FUSE
   IcpState* __restrict__ st = a.st;
   if (st->done) return;
   __shared__ uint2 s_seg[PG_SEGS * PG_STRIDE];
-  __shared__ int s_q[2 * FUSED_THREADS];
-  __shared__ int s_wcnt[FUSED_THREADS / 32];
-  __shared__ int s_qn;
+  __shared__ int s_q[REV_MAX_CHUNKS * FUSED_THREADS];   // the block's chosen target points (sorted positions), in order
+  __shared__ int s_p[REV_MAX_CHUNKS * FUSED_THREADS];   // their mutual partner (sorted source position), -1 none
+  __shared__ int s_wcnt[FUSED_WARPS];
   uint2* seg = s_seg + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // ---- the block's list
+  const int chunks = (a.m_valid + FUSED_THREADS - 1) / FUSED_THREADS;
+  int qn = 0;   // the same in every thread
+  for (int cc = 0; cc < a.per; ++cc) {
+    const int c = blockIdx.x * a.per + cc;
+    if (c >= chunks) break;
+    const int j = c * FUSED_THREADS + threadIdx.x;
+    const bool chosen = j < a.m_valid && a.rmin[j] != 0x7f800000u;
+    const unsigned int bal = __ballot_sync(0xffffffffu, chosen);
+    if (lane == 0) s_wcnt[warp] = __popc(bal);
+    __syncthreads();
+    int ofs = qn, tot = 0;
+#pragma unroll
+    for (int w = 0; w < FUSED_WARPS; ++w) { const int n = s_wcnt[w]; if (w < warp) ofs += n; tot += n; }
+    if (chosen) s_q[ofs + __popc(bal & ((1u << lane) - 1u))] = j;
+    qn += tot;
+    __syncthreads();
+  }
+
+  // ---- phase A: the searches
   const float stretch = st->stretch;
   const float dev0 = __uint_as_float(st->dev_bits) * 1.000001f;
   unsigned int missed = 0;
-  if (threadIdx.x == 0) s_qn = 0;
-  __syncthreads();
-
-  auto search_one = [&](int j) {
+  for (int k = threadIdx.x; k < qn; k += FUSED_THREADS) {
+    const int j = s_q[k];
     const uint32_t r = a.rmin[j];
     a.rmin[j] = 0x7f800000u;          // re-armed for the next iteration
     const float4 t = __ldg(a.tgt + j);
@@ -432,71 +453,43 @@ __global__ void __launch_bounds__(FUSED_THREADS, MVR_REV_MINBLOCKS * (256 / FUSE
     NnBest b{__uint_as_float(r), 0x7fffffff, -1};
     pg_search<MVR_PG_UNROLL>(a.gs, a.sstart, a.cur, a.n_valid, t.x, t.y, t.z, ux, uy, uz, dev, stretch, MVR_INF, b, seg);
     if (b.pos < 0) ++missed;
-    a.rnn[j] = (b.pos >= 0 && __ldg(a.corr_p + b.pos) == j) ? b.pos : -1;   // mutual, or the nearest source point chose another target
-  };
-
-  const int chunks = (a.m_valid + FUSED_THREADS - 1) / FUSED_THREADS;
-  for (int c = blockIdx.x; c < chunks; c += a.grid) {
-    const int j = c * FUSED_THREADS + threadIdx.x;
-    const bool chosen = j < a.m_valid && a.rmin[j] != 0x7f800000u;
-    if (j < a.m_valid && !chosen) a.rnn[j] = -1;
-    const unsigned int bal = __ballot_sync(0xffffffffu, chosen);
-    if (lane == 0) s_wcnt[warp] = __popc(bal);
-    __syncthreads();
-    int ofs = s_qn, tot = 0;
-#pragma unroll
-    for (int w = 0; w < FUSED_THREADS / 32; ++w) { const int n = s_wcnt[w]; if (w < warp) ofs += n; tot += n; }
-    if (chosen) s_q[ofs + __popc(bal & ((1u << lane) - 1u))] = j;
-    __syncthreads();
-    int qn = s_qn + tot;   // the same in every thread
-    if (qn >= FUSED_THREADS) {
-      search_one(s_q[threadIdx.x]);
-      __syncthreads();
-      const int rest = qn - FUSED_THREADS;
-      const int mv = threadIdx.x < rest ? s_q[FUSED_THREADS + threadIdx.x] : 0;
-      __syncthreads();
-      if (threadIdx.x < rest) s_q[threadIdx.x] = mv;
-      qn = rest;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) s_qn = qn;
-    __syncthreads();
+    s_p[k] = (b.pos >= 0 && __ldg(a.corr_p + b.pos) == j) ? b.pos : -1;   // mutual, or the nearest source point chose another target
   }
-  if (threadIdx.x < s_qn) search_one(s_q[threadIdx.x]);
   if (missed) atomicAdd((unsigned long long*)&st->dbg[2], (unsigned long long)missed);   // must stay 0: a chooser was not found again
-  __syncthreads();   // rnn of this block's chunks is complete (written by whichever thread drew the item)
 
+  // ---- phase B: the sums over this thread's own mutual pairs
   const double ox = st->ox, oy = st->oy, oz = st->oz;
   constexpr int NV = EstVals<EST>::value;
   double v[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) v[k] = 0.0;
-  for (int c = blockIdx.x; c < chunks; c += a.grid) {
-    const int j = c * FUSED_THREADS + threadIdx.x;
-    if (j >= a.m_valid) continue;
-    const int r = a.rnn[j];
+  for (int k = threadIdx.x; k < qn; k += FUSED_THREADS) {
+    const int r = s_p[k];
     if (r < 0) continue;
-    const float4 t = __ldg(a.tgt + j);
+    const float4 t = __ldg(a.tgt + s_q[k]);
     const float4 s = a.cur[r];
     acc_pair<EST>(v, s, t, a.nrm, d2_pinned(t.x, t.y, t.z, s.x, s.y, s.z), ox, oy, oz);
   }
   reduce_and_finish<NV>(v, a.partials, st, a.log, a.grid);
 }
 
-// The reverse half searches only the chosen target points (about half of them): a block takes several chunks of 256
-// target points so that its compacted queue fills whole batches of 256.  Measured on B200 (same box; 24 x 200k pairs in
-// groups of 8 / one 200k pair alone): 1 chunk 33.9 ms / 2.32 ms, 2 chunks 30.0 / 2.18, 4 chunks 29.1 / 2.50, 8 chunks
+// Chunks of 256 target points per block of the reverse half: enough for its compacted list to fill whole rounds of
+// 256 searches (about half of the target points are chosen).  Measured on B200 (same box; 24 x 200k pairs in groups of
+// 8 / one 200k pair alone): 1 chunk 33.9 ms / 2.32 ms, 2 chunks 30.0 / 2.18, 4 chunks 29.1 / 2.50, 8 chunks
 // 30.7 / 3.10 -- two chunks, four once a cloud fills the GPU on its own.  A pure function of the cloud size, so that the
 // block partition, and with it the order of the sums, does not depend on what else runs in the batch.
+int fused_rev_chunks(int items) {
+#ifdef MVR_REV_CHUNKS
+  return MVR_REV_CHUNKS;
+#else
+  return items >= 400000 ? 4 : 2;
+#endif
+}
 int fused_grid_rev(int items) {
   const int chunks = (items + FUSED_THREADS - 1) / FUSED_THREADS;
-#ifdef MVR_REV_CHUNKS
-  const int per = MVR_REV_CHUNKS;
-#else
-  const int per = items >= 400000 ? 4 : 2;
-#endif
-  const int blocks = (chunks + per - 1) / per;
-  return blocks < 1 ? 1 : (blocks > FUSED_MAX_BLOCKS ? FUSED_MAX_BLOCKS : blocks);
+  const int per = fused_rev_chunks(items);
+  const int blocks = (chunks + per - 1) / per;   // not capped: every block takes exactly `per` chunks
+  return blocks < 1 ? 1 : blocks;
 }
 
 int fused_grid(int items) {

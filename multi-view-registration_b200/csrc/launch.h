@@ -140,7 +140,7 @@ struct FwdArgs {
   double max2;             // gate, exact (PCL compares in double)
   float max_d2f;           // gate rounded up to float: bounds the search
   const float4* nrm;       // target normals by ORIGINAL index (point-to-plane only)
-  double* partials;        // FUSED_MAX_BLOCKS x REDUCE_MAX_VALS
+  double* partials;        // max(grid of the forward half, grid of the reverse half) x REDUCE_MAX_VALS
   IcpState* st;
   IterRec* log;
   int grid;                // blocks that work on this pair (a pure function of the cloud size): fused_grid(n_valid)
@@ -154,12 +154,12 @@ struct RevArgs {
   PairGrid gs;
   int n_valid;
   const int32_t* corr_p;
-  int32_t* rnn;            // [target sorted position] sorted position of its mutual source partner, -1 none
   const float4* nrm;
   double* partials;
   IcpState* st;
   IterRec* log;
   int grid;                // fused_grid_rev(m_valid)
+  int per;                 // fused_rev_chunks(m_valid): chunks of 256 target points per block (<= 4)
 };
 // est: which sums the iteration accumulates over its correspondences
 enum { EST_P2P = 0, EST_P2L = 1, EST_MOM = 2 /* point-to-point + second moments (LUM edge statistics) */ };
@@ -171,7 +171,8 @@ enum { FUSED_MAX_PAIRS = 8 };
 struct FwdBatch { FwdArgs a[FUSED_MAX_PAIRS]; };
 struct RevBatch { RevArgs a[FUSED_MAX_PAIRS]; };
 int fused_grid(int items);
-int fused_grid_rev(int items);   // blocks of the reverse half
+int fused_grid_rev(int items);   // blocks of the reverse half (not capped)
+int fused_rev_chunks(int items);
 cudaError_t launch_icp_forward(const FwdBatch& batch, int pairs, int max_grid, int first, bool reciprocal, int est, cudaStream_t s);
 cudaError_t launch_icp_reverse(const RevBatch& batch, int pairs, int max_grid, int est, cudaStream_t s);
 // corr_j[i] = original index of the matched target point, -1 = none, -2-j = passed the gate but failed
