@@ -260,7 +260,7 @@ int ringClose(const std::vector<Matrix4d>& rel_in, const std::vector<double>& we
       for (int k = 0; k < 6; ++k) { d.v[k] = g[(size_t)6 * (v - 1) + k]; step = std::fmax(step, std::fabs(d.v[k])); }
       X[(size_t)v] = multiply(X[(size_t)v], se3_exp(d));
     }
-    if (step < 1e-14 || cost < 1e-30) break;
+    if (step < 1e-12 || cost < 1e-30) break;   // converged (rotations in rad, translations in mm): further sweeps change nothing
   }
   for (int v = 0; v < V; ++v) X[(size_t)v] = multiply(multiply(S, X[(size_t)v]), Si);
   return MVR_OK;

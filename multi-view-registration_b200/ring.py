@@ -50,15 +50,22 @@ def gather_records(mine, rank, world, n_pairs, dist=None, device=None):
         return np.asarray(mine, dtype=np.float32).reshape(n_pairs, REC)
     import torch
     block = max(pair_range(r, world, n_pairs)[1] - pair_range(r, world, n_pairs)[0] for r in range(world))
-    pad = torch.zeros(block * REC, dtype=torch.float32, device=device)
+    pad = torch.zeros(block * REC, dtype=torch.float32)
     flat = torch.from_numpy(np.ascontiguousarray(mine, dtype=np.float32).reshape(-1))
-    pad[:flat.numel()] = flat.to(pad.device)
-    parts = [torch.zeros_like(pad) for _ in range(world)]
-    dist.all_gather(parts, pad)
+    pad[:flat.numel()] = flat
+    pad = pad.to(device) if device is not None else pad
+    out = torch.empty(world * block * REC, dtype=torch.float32, device=pad.device)
+    if hasattr(dist, "all_gather_into_tensor") and pad.is_cuda:
+        dist.all_gather_into_tensor(out, pad)          # one exchange, one device-to-host read
+    else:                                              # gloo (CPU tests)
+        parts = [torch.zeros_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad)
+        out = torch.cat(parts)
+    host = out.cpu().numpy().reshape(world, block, REC)
     rows = []
     for r in range(world):
         a, b = pair_range(r, world, n_pairs)
-        rows.append(parts[r].cpu().numpy().reshape(block, REC)[:b - a])
+        rows.append(host[r, :b - a])
     return np.concatenate(rows, axis=0)
 
 
