@@ -198,6 +198,12 @@ typedef struct {
 } mvr_pair_moments;
 int mvr_pair_moments_compute(mvr_ctx* ctx, double max_dist, int reciprocal, const float* guess, mvr_pair_moments* out);
 
+/* The edges of a whole pose graph at once: context k holds edge k's source and target; one launch per search half
+ * serves a group of edges (like mvr_icp_align_batch).  statuses[k] = 0 also for an edge without correspondences
+ * (out[k].n = 0). */
+int mvr_pair_moments_compute_batch(mvr_ctx* const* ctxs, int count, double max_dist, int reciprocal, const float* guesses,
+                                   mvr_pair_moments* out, int* statuses);
+
 /* -- extensions named by the north star (no reference call site) -------------------------------- */
 /* pcl::NormalEstimation semantics: kNN(k) PCA normals of a cloud, flipped towards viewpoint.
  * out: n x {nx, ny, nz, curvature}.  neighbours (nullable): n x k int32, ascending (d2, index). */

@@ -1164,6 +1164,54 @@ int mvr_pair_moments_compute(mvr_ctx* ctx, double max_dist, int reciprocal, cons
   return MVR_OK;
 }
 
+static void moments_from_state(const IcpState& h, bool have, mvr_pair_moments* out) {
+  std::memset(out, 0, sizeof(*out));
+  out->origin[0] = h.ox; out->origin[1] = h.oy; out->origin[2] = h.oz;
+  if (!have) return;
+  out->n = h.sums[0];
+  for (int k = 0; k < 3; ++k) { out->sa[k] = h.sums[1 + k]; out->sb[k] = h.sums[4 + k]; }
+  for (int k = 0; k < 9; ++k) out->sba[k] = h.sums[7 + k];
+  out->d2 = h.sums[16];
+  for (int k = 0; k < 6; ++k) { out->saa[k] = h.sums[17 + k]; out->sbb[k] = h.sums[23 + k]; }
+}
+
+int mvr_pair_moments_compute_batch(mvr_ctx* const* ctxs, int count, double max_dist, int reciprocal, const float* guesses,
+                                   mvr_pair_moments* out, int* statuses) {
+  if (count < 0 || (count && (!ctxs || !out || !statuses))) return MVR_ERR_BAD_ARG;
+  if (count == 0) return MVR_OK;
+  for (int k = 0; k < count; ++k) {
+    if (!ctxs[k]) return MVR_ERR_BAD_ARG;
+    for (int j = 0; j < k; ++j) if (ctxs[j] == ctxs[k]) return fail(ctxs[0], MVR_ERR_BAD_ARG, "a context appears twice in the batch");
+    if (ctxs[k]->device != ctxs[0]->device) return fail(ctxs[0], MVR_ERR_BAD_ARG, "the contexts of a batch must share a device");
+  }
+  mvr_icp_params one;
+  mvr_icp_params_default(&one);
+  one.max_iterations = 1; one.fixed_iterations = 1;
+  one.use_reciprocal_correspondences = reciprocal ? 1 : 0;
+  one.max_correspondence_distance = max_dist;
+  one.min_correspondences = 1;
+  std::vector<mvr_ctx*> ok;
+  std::vector<int> slot;
+  for (int k = 0; k < count; ++k) {
+    std::memset(out + k, 0, sizeof(mvr_pair_moments));
+    statuses[k] = align_prepare(ctxs[k], &one, guesses ? guesses + 16 * k : nullptr, EST_MOM);
+    if (statuses[k] == MVR_OK) { ok.push_back(ctxs[k]); slot.push_back(k); }
+  }
+  if (ok.empty()) return MVR_OK;
+  int rc = align_run(ok.data(), (int)ok.size(), &one, EST_MOM);
+  if (rc) { if (ok[0] != ctxs[0]) ctxs[0]->err = ok[0]->err; return rc; }
+  for (size_t j = 0; j < ok.size(); ++j) {
+    const IcpState& h = *ok[j]->h_state;
+    const int k = slot[j];
+    if (h.dbg[2] != 0) { statuses[k] = fail(ok[j], MVR_ERR_CUDA, "internal error: a reciprocal search lost its chooser (search bound violated)"); continue; }
+    const bool have = h.status == MVR_OK;
+    statuses[k] = (have || h.status == MVR_ERR_TOO_FEW_CORRESPONDENCES) ? MVR_OK : h.status;
+    moments_from_state(h, have, out + k);
+    ok[j]->have_out = false;
+  }
+  return MVR_OK;
+}
+
 double mvr_debug_value(mvr_ctx* ctx, int k) {
   if (!ctx || !ctx->h_state || k < 0 || k >= 4) return 0.0;
   return (double)ctx->h_state->dbg[k];

@@ -401,21 +401,10 @@ int Registrator::multiViewRegister(std::vector<View>& views, const mvr_turntable
   if (rc) return rc;
   cudaSetDevice(device_);
   std::vector<double> radius((size_t)V, 1.0);
-  cudaStream_t s0 = (cudaStream_t)mvr_ctx_get_stream(ctx_[0]);
-  std::vector<const float*> dview((size_t)V, nullptr);
-  if (view_cache_.size() < (size_t)V) view_cache_.resize((size_t)V);
-  for (int k = 0; k < P; ++k)
-    for (int e = 0; e < 2; ++e) {
-      const int v = (p0 + k + e) % V;
-      if (dview[(size_t)v] || views[(size_t)v].size == 0) continue;
-      const View& w = views[(size_t)v];
-      if (w.on_device) { dview[(size_t)v] = &w.points->x; continue; }
-      DeviceBuffer& b = view_cache_[(size_t)v];
-      if (!b.ensure(w.size * 16)) return fail(MVR_ERR_ALLOC, "view upload buffer");
-      if (cudaMemcpyAsync(b.p, w.points, w.size * 16, cudaMemcpyHostToDevice, s0) != cudaSuccess) return fail(MVR_ERR_CUDA, "view upload");
-      dview[(size_t)v] = (const float*)b.p;
-    }
-  if (cudaStreamSynchronize(s0) != cudaSuccess) return fail(MVR_ERR_CUDA, "view upload");
+  std::vector<int> need;
+  for (int k = 0; k < P; ++k) { need.push_back((p0 + k) % V); need.push_back((p0 + k + 1) % V); }
+  std::vector<const float*> dview;
+  if ((rc = uploadViews(views, need, dview))) return rc;
   std::vector<mvr_ctx*> cs((size_t)P);
   std::vector<float> guesses((size_t)P * 16), finals((size_t)P * 16);
   std::vector<int> st((size_t)P, 0), iterations((size_t)P, 0);
@@ -507,11 +496,31 @@ int Registrator::edgeMoments(const View& source, const View& target, double max_
   return rc;
 }
 
+int Registrator::uploadViews(const std::vector<View>& views, const std::vector<int>& which, std::vector<const float*>& dview) {
+  const int V = (int)views.size();
+  dview.assign((size_t)V, nullptr);
+  if (view_cache_.size() < (size_t)V) view_cache_.resize((size_t)V);
+  cudaSetDevice(device_);
+  cudaStream_t s0 = (cudaStream_t)mvr_ctx_get_stream(ctx_[0]);
+  for (int v : which) {
+    if (dview[(size_t)v] || views[(size_t)v].size == 0) continue;
+    const View& w = views[(size_t)v];
+    if (w.on_device) { dview[(size_t)v] = &w.points->x; continue; }
+    DeviceBuffer& b = view_cache_[(size_t)v];
+    if (!b.ensure(w.size * 16)) return fail(MVR_ERR_ALLOC, "view upload buffer");
+    if (cudaMemcpyAsync(b.p, w.points, w.size * 16, cudaMemcpyHostToDevice, s0) != cudaSuccess) return fail(MVR_ERR_CUDA, "view upload");
+    dview[(size_t)v] = (const float*)b.p;
+  }
+  if (cudaStreamSynchronize(s0) != cudaSuccess) return fail(MVR_ERR_CUDA, "view upload");
+  return MVR_OK;
+}
+
 int Registrator::registrationLUM(std::vector<View>& views, int max_iterations, double max_distance) {
   // mvr/src/registrator.cpp:611-678: every view gets its turntable pose, then max(1, max_iterations / 16) outer
   // loops of { reciprocal correspondences on the ring edges i -> (i + 1) % V (:640-651), lum.compute() with 16
-  // sweeps (:630, 653), pose <- lum_T * pose (:655-661) }.  The correspondences of an edge are reduced on the GPU
-  // to their moments (mvr_pair_moments_compute); the relaxation itself is host work on 30 doubles per edge (lum.cpp).
+  // sweeps (:630, 653), pose <- lum_T * pose (:655-661) }.  The correspondences of all edges are reduced on the GPU
+  // to their moments in one batch (edge k lives in context k, every view is uploaded once and shared between the two
+  // edges it belongs to); the relaxation itself is host work on 30 doubles per edge (lum.cpp).
   if (!ok()) return fail(MVR_ERR_CUDA, "no GPU context");
   const int V = (int)views.size();
   if (V < 2) return MVR_OK;
@@ -521,35 +530,41 @@ int Registrator::registrationLUM(std::vector<View>& views, int max_iterations, d
   const int E = (V == 2) ? 1 : V;   // two views: one edge, not the same pair twice
   std::vector<int> es((size_t)E), et((size_t)E);
   for (int i = 0; i < E; ++i) { es[(size_t)i] = i; et[(size_t)i] = (i + 1) % V; }
+  int rc = ensureContexts(E);
+  if (rc) return rc;
+  std::vector<int> all;
+  for (int v = 0; v < V; ++v) all.push_back(v);
+  std::vector<const float*> dview;
+  if ((rc = uploadViews(views, all, dview))) return rc;
+  // edge i: target = view i + 1 (measured once), source = view i = the target of edge i - 1 (shared)
+  std::vector<mvr_ctx*> cs((size_t)E);
+  for (int i = 0; i < E; ++i) {
+    cs[(size_t)i] = ctx_[(size_t)i];
+    if ((rc = mvr_set_target_device(cs[(size_t)i], dview[(size_t)et[(size_t)i]], views[(size_t)et[(size_t)i]].size))) return fail(rc, mvr_last_error(cs[(size_t)i]));
+  }
+  for (int i = 0; i < E; ++i) {
+    const int j = (i - 1 + E) % E;   // the edge whose target is view i
+    if (E > 1 && et[(size_t)j] == es[(size_t)i]) rc = mvr_cloud_share(cs[(size_t)i], MVR_CLOUD_SOURCE, cs[(size_t)j], MVR_CLOUD_TARGET);
+    else rc = mvr_set_source_device(cs[(size_t)i], dview[(size_t)es[(size_t)i]], views[(size_t)es[(size_t)i]].size);
+    if (rc) return fail(rc, mvr_last_error(cs[(size_t)i]));
+  }
+  std::vector<float> guesses((size_t)E * 16);
+  std::vector<mvr_pair_moments> mom((size_t)E), edges((size_t)E);
+  std::vector<int> st((size_t)E, 0);
   for (int loop = 0; loop < outer; ++loop) {
-    std::vector<mvr_pair_moments> edges((size_t)E);
-    std::atomic<int> next(0);
-    std::atomic<int> bad(0);
-    auto worker = [&](int slot) {
-      cudaSetDevice(device_);
-      for (;;) {
-        const int i = next.fetch_add(1);
-        if (i >= E) break;
-        const View& s = views[(size_t)es[(size_t)i]];
-        const View& t = views[(size_t)et[(size_t)i]];
-        // the source posed into t's sensor frame; the moments come back in that frame and move to the world with pose_t
-        const Matrix4f guess = toFloat(multiply(inverseRigid(t.pose), s.pose));
-        mvr_pair_moments m;
-        const int rc = edgeMoments(s, t, max_distance, guess, slot, m);
-        if (rc) { bad.store(rc); continue; }
-        momentsTransform(m, t.pose, nullptr, edges[(size_t)i]);
-      }
-    };
-    const int K = std::max(1, std::min((int)ctx_.size(), E));
-    if (K == 1) worker(0);
-    else {
-      std::vector<std::thread> th;
-      for (int k = 0; k < K; ++k) th.emplace_back(worker, k);
-      for (std::thread& t : th) t.join();
+    for (int i = 0; i < E; ++i) {
+      // the source posed into the target's sensor frame; the moments come back in that frame and move to the world with pose_t
+      const Matrix4f g = toFloat(multiply(inverseRigid(views[(size_t)et[(size_t)i]].pose), views[(size_t)es[(size_t)i]].pose));
+      std::memcpy(&guesses[(size_t)i * 16], g.m, sizeof(g.m));
     }
-    if (bad.load()) return bad.load();
+    if ((rc = mvr_pair_moments_compute_batch(cs.data(), E, max_distance, 1, guesses.data(), mom.data(), st.data()))) return fail(rc, mvr_last_error(cs[0]));
+    for (int i = 0; i < E; ++i) {
+      if (st[(size_t)i] == MVR_ERR_NO_INPUT) { edges[(size_t)i] = mvr_pair_moments{}; continue; }   // an empty view: no information
+      if (st[(size_t)i]) return fail(st[(size_t)i], mvr_last_error(cs[(size_t)i]));
+      momentsTransform(mom[(size_t)i], views[(size_t)et[(size_t)i]].pose, nullptr, edges[(size_t)i]);
+    }
     std::vector<Matrix4d> X;
-    const int rc = lumRelax(edges, es.data(), et.data(), V, lum_max_iterations, X);
+    rc = lumRelax(edges, es.data(), et.data(), V, lum_max_iterations, X);
     if (std::getenv("MVR_DEBUG_LUM")) {
       double c = 0, n = 0;
       for (const mvr_pair_moments& e : edges) { c += e.d2; n += e.n; }

@@ -121,6 +121,8 @@ class Registrator {
   int accumulate(std::vector<View>& views, const std::vector<int>& order, const mvr_icp_params& icp, int repeat_times,
                  bool want_fitness, std::vector<mvr_pair_report>* reports);
   int ensureContexts(int n);             // grow the context pool to n (batched aligns use one context per pair)
+  // device pointers of the listed views: device views as given, host views uploaded once into view_cache_
+  int uploadViews(const std::vector<View>& views, const std::vector<int>& which, std::vector<const float*>& dview);
   struct DeviceBuffer { void* p = nullptr; size_t cap = 0; bool ensure(size_t bytes); };
   std::vector<DeviceBuffer> view_cache_;   // device copies of host views, one upload per view and registration
   double objectRadius(int slot) const;   // half the largest extent of the target cloud last given to context `slot`
