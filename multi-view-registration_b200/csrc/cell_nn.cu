@@ -54,7 +54,10 @@ __device__ __forceinline__ float cn_face(float t, int c, int n, int h) {
   return u;
 }
 
-__global__ void __launch_bounds__(CN_THREADS, 4) k_cell_nn(CellNnArgs a) {
+#ifndef MVR_CN_MINBLOCKS
+#define MVR_CN_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(CN_THREADS, MVR_CN_MINBLOCKS) k_cell_nn(CellNnArgs a) {
   __shared__ float4 s_pts[CN_WARPS][PG_SEGS * 32 / 2];   // 32 staged points per warp; the fallback's segment list (PG_SEGS x 32 uint2) reuses it
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const PairGrid g = a.g;

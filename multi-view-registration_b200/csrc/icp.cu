@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (RECIP ? MVR_FWD_MINBLOCKS : MV
       const double ex = st->cum[0] * s.x + st->cum[4] * s.y + st->cum[8] * s.z + st->cum[12] - (double)p.x;
       const double ey = st->cum[1] * s.x + st->cum[5] * s.y + st->cum[9] * s.z + st->cum[13] - (double)p.y;
       const double ez = st->cum[2] * s.x + st->cum[6] * s.y + st->cum[10] * s.z + st->cum[14] - (double)p.z;
-      devmax = fmaxf(devmax, (float)sqrt(ex * ex + ey * ey + ez * ez) * 1.000001f);
+      devmax = fmaxf(devmax, __double2float_ru(ex * ex + ey * ey + ez * ez));   // squared; one float sqrt per thread below
     }
     NnBest b{MVR_INF, 0x7fffffff, -1};
     const int j0 = a.corr_p[i];
@@ -370,6 +370,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (RECIP ? MVR_FWD_MINBLOCKS : MV
   }
   if (RECIP) {
     // warp-level: no block barrier, a warp that is done is done
+    devmax = sqrtf(devmax) * 1.000001f;   // a double sqrt per point costs ~70 instructions; the maximum of the squares needs one
     const unsigned int wd = __reduce_max_sync(0xffffffffu, __float_as_uint(devmax));   // non-negative floats order like their bits
     const unsigned int wg = __reduce_add_sync(0xffffffffu, ngate);
     if ((threadIdx.x & 31) == 0) {
