@@ -290,6 +290,11 @@ int mvr_pairwise_align(mvr_registrator* r, const mvr_view* source, const mvr_vie
  * gather).  reports: one per pair (ring: V entries indexed by pair; accumulate: V-1 entries, views 1..V-1). */
 int mvr_register_turntable(mvr_registrator* r, const mvr_view* views, int n_views, const mvr_turntable_params* prm,
                            float* poses, mvr_pair_report* reports);
+/* Registrator::computeError (mvr/src/registrator.cpp:466-515): reciprocal correspondences (gate max_distance) between
+ * neighbouring registered views (i, i + 1) and (V - 1, 0), each view posed by its init_pose first (getTransformedPoints).
+ * Pair k: counts[k] correspondences with mean squared distance mean_d2[k]; arrays hold n_views entries. */
+int mvr_compute_error(mvr_registrator* r, const mvr_view* views, int n_views, double max_distance, size_t* counts, double* mean_d2,
+                      int* n_pairs);
 /* Host-side loop closure over gathered ring pairs: rel[p] = pose of view (p+1)%V in view p's frame, w[p] its
  * weight (e.g. n_correspondences; <= 0 drops the edge).  centre (nullable) = where the object sits in every
  * view's frame (the turntable pivot), rot_scale = its radius: residuals are point displacements of such an

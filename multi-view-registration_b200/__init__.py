@@ -189,6 +189,7 @@ def lib():
     L.mvr_registrator_streams.argtypes = [vp]
     L.mvr_pairwise_align.argtypes = [vp, C.POINTER(ViewDesc), C.POINTER(ViewDesc), C.POINTER(IcpParams), fp, fp, C.POINTER(IcpReport)]
     L.mvr_register_turntable.argtypes = [vp, C.POINTER(ViewDesc), C.c_int, C.POINTER(TurntableParams), fp, C.POINTER(PairReport)]
+    L.mvr_compute_error.argtypes = [vp, C.POINTER(ViewDesc), C.c_int, C.c_double, C.POINTER(C.c_size_t), dp, C.POINTER(C.c_int)]
     L.mvr_ring_close.argtypes = [fp, dp, C.c_int, C.c_int, C.c_int, dp, C.c_double, fp]
     L.mvr_get_bbox.argtypes = [vp, C.c_int, fp, fp]
     L.mvr_refine_axis.argtypes = [fp, C.c_int, dp, dp]
@@ -639,6 +640,18 @@ class Registrator:
             raise MvrError(rc, (lib().mvr_registrator_last_error(self._h) or b"").decode())
         return dict(status=rc, final=pose_to_numpy(fin), iterations=rep.iterations, n_corr=rep.n_correspondences, mse=rep.mse,
                     gpu_ms=rep.gpu_ms, nn_queries=int(rep.nn_queries))
+
+    def compute_error(self, views, poses, max_distance):
+        """Registrator::computeError: [(count, mean squared distance)] of the reciprocal correspondences of neighbouring views."""
+        V = len(views)
+        arr, keep = self._views(views, poses)
+        counts = (C.c_size_t * max(V, 1))()
+        msd = np.zeros(max(V, 1), dtype=np.float64)
+        n = C.c_int(0)
+        rc = lib().mvr_compute_error(self._h, arr, V, float(max_distance), counts, _dp(msd), C.byref(n))
+        if rc != OK:
+            raise MvrError(rc, (lib().mvr_registrator_last_error(self._h) or b"").decode())
+        return [(int(counts[k]), float(msd[k])) for k in range(n.value)]
 
     def register_turntable(self, views, params, init_poses=None):
         """Returns (poses: list of V 4x4 float32, reports: list of dict)."""

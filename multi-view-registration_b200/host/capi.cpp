@@ -152,6 +152,22 @@ int mvr_register_turntable(mvr_registrator* r, const mvr_view* views, int n_view
   return rc;
 }
 
+int mvr_compute_error(mvr_registrator* r, const mvr_view* views, int n_views, double max_distance, size_t* counts, double* mean_d2,
+                      int* n_pairs) {
+  if (!r || n_views < 0 || (n_views && !views) || !n_pairs) return MVR_ERR_BAD_ARG;
+  std::vector<View> v;
+  fill_views(views, n_views, v);
+  for (int k = 0; k < n_views; ++k) v[(size_t)k].registered = true;   // the caller passes the registered views only
+  std::vector<std::pair<size_t, double> > out;
+  const int rc = r->reg->computeError(v, max_distance, out);
+  *n_pairs = (int)out.size();
+  for (size_t k = 0; k < out.size(); ++k) {
+    if (counts) counts[k] = out[k].first;
+    if (mean_d2) mean_d2[k] = out[k].second;
+  }
+  return rc;
+}
+
 int mvr_ring_close(const float* rel_poses, const double* weights, int n_views, int relax, int iterations, const double* centre,
                    double rot_scale, float* poses) {
   if (!rel_poses || !poses || n_views < 1) return MVR_ERR_BAD_ARG;

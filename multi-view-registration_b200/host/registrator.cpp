@@ -84,17 +84,6 @@ struct DeviceCloud {
     p = q; cap = want;
     return true;
   }
-  bool grow_keep(size_t n, size_t used, cudaStream_t s) {   // like ensure(), keeping the first `used` points
-    if (n <= cap) return true;
-    float* q = nullptr;
-    size_t want = n + n / 2 + 64;
-    if (cudaMalloc((void**)&q, want * 16) != cudaSuccess) return false;
-    if (p && used) cudaMemcpyAsync(q, p, used * 16, cudaMemcpyDeviceToDevice, s);
-    cudaStreamSynchronize(s);
-    if (p) cudaFree(p);
-    p = q; cap = want;
-    return true;
-  }
   ~DeviceCloud() { if (p) cudaFree(p); }
 };
 
@@ -590,7 +579,6 @@ int Registrator::computeError(std::vector<View>& views, double max_distance, std
   out.clear();
   const int V = (int)views.size();
   mvr_ctx* c = ctx_[0];
-  DeviceCloud a, b, raw;
   for (int i = 0; i < V; ++i) {
     const int j = (i + 1) % V;
     if (V == 2 && i == 1) break;

@@ -246,3 +246,20 @@ def test_merge_registered_matches_reference_arithmetic(mvr, synth):
             np.testing.assert_allclose(got[k], want[k], rtol=0, atol=np.abs(want[k]).max() * 2.0 ** -23)   # within 1 float ulp (device FMA contraction is off)
     assert len(ctx.merge_registered(views, poses, registered=[0, 0, 0, 0])) == 0
     ctx.close()
+
+
+def test_compute_error_matches_oracle(mvr, orc, synth, seq):
+    """Registrator::computeError (mvr/src/registrator.cpp:466-515): per neighbouring pair the reciprocal correspondences of
+    the POSED clouds; counts equal the oracle's, mean squared distances to float accumulation accuracy."""
+    V, n, views, poses, init = seq
+    reg = mvr.Registrator(0, 1)
+    got = reg.compute_error(views, init, 4.0)
+    assert len(got) == V
+    for i, (cnt, msd) in enumerate(got):
+        j = (i + 1) % V
+        a = orc.apply_pose_double(views[i], init[i])
+        b = orc.apply_pose_double(views[j], init[j])
+        q, m, d2 = orc.correspondences(a, b, 4.0, True)
+        assert cnt == len(q)
+        assert abs(msd - float(d2.astype(np.float64).mean())) <= 1e-9 * msd
+    reg.close()
