@@ -73,14 +73,15 @@ constexpr int PG_STRIDE = FUSED_THREADS;
 // rows of per-row maxima) and the loads of a trip overlap.  Past a segment's end the last point is simply evaluated
 // again: a duplicate never wins a strict lexicographic comparison.  (Measured on B200, same box: 8 loads per trip
 // beat 4 by 2.5 % and 2 by 20 %; reading whole groups past the segment end into the next cells' points -- also exact --
-// was 3 % slower, as was dropping the per-row x narrowing for narrow boxes.)
+// was 3 % slower, as was dropping the per-row x narrowing for narrow boxes; guarding every candidate of a trip by its
+// own range test instead of re-reading the last point turned into divergent branches and was 70 % slower.)
 template <int UNROLL, int STRIDE = PG_STRIDE>
 __device__ __forceinline__ void pg_flat_scan(const float4* __restrict__ pts, const uint2* __restrict__ seg, int nseg, float qx, float qy,
                                              float qz, NnBest& b) {
   int j = 0;
   uint32_t k = 0, e = 0;
   for (;;) {
-    while (k >= e) {
+    if (k >= e) {   // collected segments are never empty: one step always lands on a candidate
       if (j >= nseg) return;
       const uint2 s = seg[j * STRIDE];
       ++j;
