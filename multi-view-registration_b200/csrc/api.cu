@@ -1243,7 +1243,19 @@ int mvr_fitness_score(mvr_ctx* ctx, double max_range, double* score) {
   CK(ctx->ftmp.ensure((size_t)n * sizeof(float)));
   CK(ctx->partials.ensure((size_t)REDUCE_BLOCKS * REDUCE_MAX_VALS * sizeof(double)));
   CK(ctx->sums.ensure(REDUCE_MAX_VALS * sizeof(double)));
-  if ((rc = nn_pass(ctx, cloud, n, ctx->itmp.as<int32_t>(), ctx->ftmp.as<float>()))) return rc;
+  {
+    // the target index of the last align if it is still valid, else one over the target's own box
+    PairIndex& pt = ctx->pt;
+    if (!(pt.valid && pt.gen == ctx->tgt.gen)) {
+      uint32_t cells = 0;
+      const PairGrid gt = make_pair_grid(ctx->tgt.lo, ctx->tgt.hi, pair_cell_edge(ctx, ctx->tgt, INFINITY), &cells);
+      if ((rc = build_pair_index(ctx, pt, ctx->tgt.pts, ctx->tgt.n, ctx->tgt.n_bad, nullptr, gt, cells, false))) return rc;
+      pt.gen = ctx->tgt.gen;
+    }
+    ProfScope ps(ctx, MVR_K_NN, 24.0 * n + 16.0 * ctx->tgt.n, (double)n);
+    CK(launch_pair_nn(cloud, n, pt.sorted.as<float4>(), pt.start.as<uint32_t>(), pt.g, pt.n_valid, ctx->itmp.as<int32_t>(), ctx->ftmp.as<float>(),
+                      ctx->stream));
+  }
   CK(launch_reduce_fitness(ctx->itmp.as<int32_t>(), ctx->ftmp.as<float>(), n, max_range, ctx->partials.as<double>(),
                            ctx->sums.as<double>(), ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_sums, ctx->sums.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -175,6 +175,9 @@ int fused_grid_rev(int items);   // blocks of the reverse half (not capped)
 int fused_rev_chunks(int items);
 cudaError_t launch_icp_forward(const FwdBatch& batch, int pairs, int max_grid, int first, bool reciprocal, int est, cudaStream_t s);
 cudaError_t launch_icp_reverse(const RevBatch& batch, int pairs, int max_grid, int est, cudaStream_t s);
+// Un-gated exact 1-NN of n unsorted queries in a per-align (row-major) target index; results in query order.
+cudaError_t launch_pair_nn(const float4* q, int n, const float4* tgt_sorted, const uint32_t* tstart, PairGrid g, int m_valid,
+                           int32_t* out_idx, float* out_d2, cudaStream_t s);
 // corr_j[i] = original index of the matched target point, -1 = none, -2-j = passed the gate but failed
 // the reciprocal test (the layout launch_compact_corr consumes).
 cudaError_t launch_resolve_corr(const int32_t* corr_p, const int32_t* rnn, const float4* tgt_sorted, int n, int32_t* corr_j,
