@@ -367,23 +367,12 @@ int ensure_target_index(mvr_ctx* ctx, const mvr_grid* want) {
   return list_bricks(ctx, t, g.bits, 6, nullptr);
 }
 
-// Present `n` query points (device) brick by brick of the target grid: fills ctx->qry (brick table).
-int sort_queries(mvr_ctx* ctx, const float4* q, int n) {
-  Cloud& c = ctx->qry;
-  c.pts = q; c.n = n; c.n_bad = 0; c.gen++;
-  // a grid of 4x larger cells with the same origin bins exactly like (fine cell >> 2): scaling by a
-  // power of two commutes with the float rounding of grid_t()
-  mvr_grid g = ctx->tgt.grid;
-  g.bits -= 2; g.inv_cell *= 0.25f; g.cell *= 4.0f;
-  int rc = bin_index(ctx, c, const_cast<float4*>(q), g, nullptr, nullptr);
-  if (rc) return rc;
-  return list_bricks(ctx, c, ctx->tgt.grid.bits, 0, nullptr);
-}
-
 PairGrid make_pair_grid(const float lo[3], const float hi[3], double e, uint32_t* cells_out);
 bool same_pair_grid(const PairGrid& a, const PairGrid& b);
 int build_pair_index(mvr_ctx* ctx, PairIndex& ix, const float4* pts, int n, int n_bad, const Mat4f* guess, const PairGrid& g,
                      uint32_t cells, bool keep_s0, bool ordered = true);
+
+double pair_cell_edge(mvr_ctx* ctx, const Cloud& c, double max_dist);
 
 // Many queries per target point: target and queries counting-sorted by the cells of one row-major grid, then the
 // warp-cooperative scan of cell_nn.cu.
@@ -409,13 +398,23 @@ int nn_pass_dense(mvr_ctx* ctx, const float4* q, int n, int32_t* d_idx, float* d
 int nn_pass(mvr_ctx* ctx, const float4* q, int n, int32_t* d_idx, float* d_d2) {
   if (ctx->nn_dense_ratio > 0 && (double)n >= ctx->nn_dense_ratio * (double)std::max(ctx->tgt.n - ctx->tgt.n_bad, 1))
     return nn_pass_dense(ctx, q, n, d_idx, d_d2);
-  int rc = ensure_target_index(ctx, nullptr);
-  if (rc) return rc;
-  rc = sort_queries(ctx, q, n);
-  if (rc) return rc;
-  const Cloud& t = ctx->tgt;
+  // The row walk of pair_search.cuh on the target's per-align index: small batches as they come, large ones sorted by
+  // cell first (locality).  It also gets through the empty space around far queries quickly, which a cell-by-cell ring
+  // expansion does not.
+  Cloud& t = ctx->tgt;
+  PairIndex& pt = ctx->pt;
+  int rc;
+  if (!(pt.valid && pt.gen == t.gen)) {
+    uint32_t cells = 0;
+    const PairGrid gt = make_pair_grid(t.lo, t.hi, pair_cell_edge(ctx, t, INFINITY), &cells);
+    if ((rc = build_pair_index(ctx, pt, t.pts, t.n, t.n_bad, nullptr, gt, cells, false))) return rc;
+    pt.gen = t.gen;
+  }
+  const bool sorted = n > 262144;
+  if (sorted && (rc = build_pair_index(ctx, ctx->nq, q, n, 0, nullptr, pt.g, pt.cells, false, false))) return rc;
   ProfScope ps(ctx, MVR_K_NN, 24.0 * n + 16.0 * t.n, (double)n);
-  CK(launch_brick_nn(ctx->qry.qdev(0), n, t.dev(), ctx->qry.bricks.as<uint32_t>(), ctx->qry.brick_count(), d_idx, d_d2, ctx->stream));
+  CK(launch_pair_nn(sorted ? ctx->nq.sorted.as<float4>() : q, n, sorted, pt.sorted.as<float4>(), pt.start.as<uint32_t>(), pt.g, pt.n_valid, d_idx,
+                    d_d2, ctx->stream));
   return MVR_OK;
 }
 
@@ -1243,19 +1242,7 @@ int mvr_fitness_score(mvr_ctx* ctx, double max_range, double* score) {
   CK(ctx->ftmp.ensure((size_t)n * sizeof(float)));
   CK(ctx->partials.ensure((size_t)REDUCE_BLOCKS * REDUCE_MAX_VALS * sizeof(double)));
   CK(ctx->sums.ensure(REDUCE_MAX_VALS * sizeof(double)));
-  {
-    // the target index of the last align if it is still valid, else one over the target's own box
-    PairIndex& pt = ctx->pt;
-    if (!(pt.valid && pt.gen == ctx->tgt.gen)) {
-      uint32_t cells = 0;
-      const PairGrid gt = make_pair_grid(ctx->tgt.lo, ctx->tgt.hi, pair_cell_edge(ctx, ctx->tgt, INFINITY), &cells);
-      if ((rc = build_pair_index(ctx, pt, ctx->tgt.pts, ctx->tgt.n, ctx->tgt.n_bad, nullptr, gt, cells, false))) return rc;
-      pt.gen = ctx->tgt.gen;
-    }
-    ProfScope ps(ctx, MVR_K_NN, 24.0 * n + 16.0 * ctx->tgt.n, (double)n);
-    CK(launch_pair_nn(cloud, n, pt.sorted.as<float4>(), pt.start.as<uint32_t>(), pt.g, pt.n_valid, ctx->itmp.as<int32_t>(), ctx->ftmp.as<float>(),
-                      ctx->stream));
-  }
+  if ((rc = nn_pass(ctx, cloud, n, ctx->itmp.as<int32_t>(), ctx->ftmp.as<float>()))) return rc;
   CK(launch_reduce_fitness(ctx->itmp.as<int32_t>(), ctx->ftmp.as<float>(), n, max_range, ctx->partials.as<double>(),
                            ctx->sums.as<double>(), ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_sums, ctx->sums.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

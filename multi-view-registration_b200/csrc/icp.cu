@@ -540,6 +540,8 @@ cudaError_t launch_icp_reverse(const RevBatch& d_batch, int pairs, int max_grid,
 // (mvr/src/registrator.cpp:572, 923, 1015).  The aligned source of a turntable pair has a part the target does not cover;
 // those queries are tens of cells away from the nearest target point, and the row walk of pair_search.cuh (two table
 // loads decide a whole row of cells) gets through that empty space ~30x faster than a cell-by-cell ring expansion.
+// BY_W: the queries were sorted by cell (locality for large batches) and carry their original index in .w.
+template <bool BY_W>
 __global__ void __launch_bounds__(FUSED_THREADS, 4) k_pair_nn(const float4* __restrict__ q, int n, const float4* __restrict__ tgt,
                                                               const uint32_t* __restrict__ tstart, PairGrid g, int m_valid,
                                                               int32_t* __restrict__ out_idx, float* __restrict__ out_d2) {
@@ -549,14 +551,18 @@ __global__ void __launch_bounds__(FUSED_THREADS, 4) k_pair_nn(const float4* __re
   const float4 p = __ldg(q + i);
   NnBest b{MVR_INF, 0x7fffffff, -1};
   if (finite3(p)) pg_search<MVR_PG_UNROLL>(g, tstart, tgt, m_valid, p.x, p.y, p.z, p.x, p.y, p.z, 0.0f, 1.0f, MVR_INF, b, s_seg + threadIdx.x);
-  out_idx[i] = b.pos >= 0 ? b.idx : -1;
-  out_d2[i] = b.pos >= 0 ? b.d2 : MVR_INF;
+  const int o = BY_W ? __float_as_int(p.w) : i;
+  out_idx[o] = b.pos >= 0 ? b.idx : -1;
+  out_d2[o] = b.pos >= 0 ? b.d2 : MVR_INF;
 }
 
-cudaError_t launch_pair_nn(const float4* q, int n, const float4* tgt_sorted, const uint32_t* tstart, PairGrid g, int m_valid,
+cudaError_t launch_pair_nn(const float4* q, int n, bool by_w, const float4* tgt_sorted, const uint32_t* tstart, PairGrid g, int m_valid,
                            int32_t* out_idx, float* out_d2, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  k_pair_nn<<<(n + FUSED_THREADS - 1) / FUSED_THREADS, FUSED_THREADS, 0, s>>>(q, n, tgt_sorted, tstart, g, m_valid, out_idx, out_d2); count_launch();
+  const int blocks = (n + FUSED_THREADS - 1) / FUSED_THREADS;
+  if (by_w) k_pair_nn<true><<<blocks, FUSED_THREADS, 0, s>>>(q, n, tgt_sorted, tstart, g, m_valid, out_idx, out_d2);
+  else k_pair_nn<false><<<blocks, FUSED_THREADS, 0, s>>>(q, n, tgt_sorted, tstart, g, m_valid, out_idx, out_d2);
+  count_launch();
   return cudaGetLastError();
 }
 

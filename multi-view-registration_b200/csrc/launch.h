@@ -175,8 +175,9 @@ int fused_grid_rev(int items);   // blocks of the reverse half (not capped)
 int fused_rev_chunks(int items);
 cudaError_t launch_icp_forward(const FwdBatch& batch, int pairs, int max_grid, int first, bool reciprocal, int est, cudaStream_t s);
 cudaError_t launch_icp_reverse(const RevBatch& batch, int pairs, int max_grid, int est, cudaStream_t s);
-// Un-gated exact 1-NN of n unsorted queries in a per-align (row-major) target index; results in query order.
-cudaError_t launch_pair_nn(const float4* q, int n, const float4* tgt_sorted, const uint32_t* tstart, PairGrid g, int m_valid,
+// Un-gated exact 1-NN of n queries in a per-align (row-major) target index.  by_w = false: results in query order;
+// by_w = true: the queries were sorted by cell and carry their original index in .w, results by original index.
+cudaError_t launch_pair_nn(const float4* q, int n, bool by_w, const float4* tgt_sorted, const uint32_t* tstart, PairGrid g, int m_valid,
                            int32_t* out_idx, float* out_d2, cudaStream_t s);
 // corr_j[i] = original index of the matched target point, -1 = none, -2-j = passed the gate but failed
 // the reciprocal test (the layout launch_compact_corr consumes).

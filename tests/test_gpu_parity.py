@@ -95,7 +95,7 @@ def test_nn_dense_pass_bit_exact(ctx, orc, synth, m, n, ppc):
     ctx.set_nn_options(ppc, 1e-9)      # always dense
     ctx.set_target(tgt)
     idx, d2 = ctx.nn_query(q)
-    ctx.set_nn_options(6.0, 0.0)       # never dense: the brick pass
+    ctx.set_nn_options(6.0, 0.0)       # never dense: the per-thread row walk
     ctx.set_target(tgt)
     idx2, d22 = ctx.nn_query(q)
     ctx.set_nn_options(8.0, 8.0)
