@@ -311,7 +311,7 @@ class Context:
         self._ck(lib().mvr_ctx_set_nn_options(self._h, float(points_per_cell), float(dense_ratio)))
 
     def set_batch_group(self, pairs):
-        """Pairs per kernel launch of the batches this context leads (1..8)."""
+        """Pairs per kernel launch of the batches this context leads (1..24)."""
         self._ck(lib().mvr_ctx_set_batch_group(self._h, int(pairs)))
 
     def set_target(self, pts):

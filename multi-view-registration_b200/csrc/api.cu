@@ -107,7 +107,7 @@ struct mvr_ctx {
   double nn_ppc = 8.0;           // its target points per occupied cell
   double nn_dense_ratio = 8.0;   // queries per target point from which the dense pass is used (0: never)
   FwdArgs fa{}; RevArgs ra{};    // kernel arguments of the prepared align
-  int group_pairs = 8;           // pairs per launch of a batch led by this context (mvr_ctx_set_batch_group)
+  int group_pairs = 24;          // pairs per launch of a batch led by this context (mvr_ctx_set_batch_group)
   DevBuf pkeys, pvals, pmoved, pcount;   // build scratch of the per-align indices: keys, arrival ranks, arrival-order records, cell counters
   uint32_t scan_epoch = 1;
   IcpState* h_state = nullptr;   // pinned staging copy of the device IcpState
@@ -986,8 +986,9 @@ static int align_prepare(mvr_ctx* ctx, const mvr_icp_params* prm, const float* g
 }
 
 // The iterations of `count` prepared contexts (same device, same params) on the first one's stream.  The pairs
-// advance in lock-step in groups of ctx->group_pairs (<= FUSED_MAX_PAIRS): a group runs to completion before the next
-// one starts, so that its working set (~20 MB per 200k-point pair) stays in the 126 MB L2 across its iterations.
+// advance in lock-step in groups of ctx->group_pairs (<= FUSED_MAX_PAIRS = 24, the kernel parameter space): a group runs
+// to completion before the next one starts.  Measured on B200 (24 x 200k pairs): groups of 6 / 8 / 12 / 24 pairs take
+// 28.3 / 27.7 / 26.8 / 25.3 ms -- fewer launch tails outweigh the L2 misses of a working set of 24 x 20 MB.
 static int align_run(mvr_ctx* const* ctxs, int count, const mvr_icp_params* prm, int est) {
   mvr_ctx* ctx = ctxs[0];   // the lead: its stream carries the batch, CK() reports into it
   cudaSetDevice(ctx->device);

@@ -167,7 +167,7 @@ enum { EST_P2P = 0, EST_P2L = 1, EST_MOM = 2 /* point-to-point + second moments 
 // that pair does its work.  The arguments of all pairs travel by value in the kernel's parameter (constant) space, so
 // indexing them by pair costs no registers.  max_grid = the largest grid of the group.
 // first: first iteration of the aligns (the guess is already applied, no increment pending).
-enum { FUSED_MAX_PAIRS = 8 };
+enum { FUSED_MAX_PAIRS = 24 };
 struct FwdBatch { FwdArgs a[FUSED_MAX_PAIRS]; };
 struct RevBatch { RevArgs a[FUSED_MAX_PAIRS]; };
 int fused_grid(int items);

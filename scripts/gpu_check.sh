@@ -14,6 +14,6 @@ if [ "${NCU:-1}" = "1" ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none -c 2600 --csv --log-file gpurun_out/launches_${TAG}.csv $SMALL > gpurun_out/ncu_launches_${TAG}.log 2>&1
   echo "ncu launches rc=$?"
   $SMALL > gpurun_out/plain2_${TAG}.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:${KREGEX} -s 400 -c 2 -f -o gpurun_out/prof_${TAG} $SMALL > gpurun_out/ncu_full_${TAG}.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:${KREGEX} -s 200 -c 2 -f -o gpurun_out/prof_${TAG} $SMALL > gpurun_out/ncu_full_${TAG}.log 2>&1
   echo "ncu full rc=$?"
 fi

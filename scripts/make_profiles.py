@@ -54,8 +54,8 @@ rr = list(csv.reader(out.splitlines()))
 hh, uu = rr[0], rr[1]
 traffic = 0.0
 with open(os.path.join(P, "%s_icp_fused_ncu_full.txt" % rnd), "w") as f:
-    f.write("# ncu --set full --clock-control none --import-source on -k regex:k_icp -s 400 -c 2 python bench.py --steps 1 --warmup 3 --no-e2e --cpu-sample-pairs 0\n")
-    f.write("# one forward + one reverse launch of a group of 8 pairs (24 views x 200k points), mid-align; caches flushed by ncu before each replay\n")
+    f.write("# ncu --set full --clock-control none --import-source on -k regex:k_icp -s 200 -c 2 python bench.py --steps 1 --warmup 3 --no-e2e --cpu-sample-pairs 0\n")
+    f.write("# one forward + one reverse launch of all 24 pairs (24 views x 200k points), mid-align; caches flushed by ncu before each replay\n")
     for r in rr[2:]:
         f.write("== %s\n" % r[hh.index("Kernel Name")])
         for k in KEYS:
@@ -64,5 +64,5 @@ with open(os.path.join(P, "%s_icp_fused_ncu_full.txt" % rnd), "w") as f:
         for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             v, u = float(r[hh.index(k)].replace(",", "")), uu[hh.index(k)]
             traffic += v * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
-    f.write("== DRAM traffic of the launch pair (one iteration of 8 pairs): %.1f MB; algorithmic bytes: %.1f MB\n" % (traffic / 1e6, bench["roofline"]["bytes_per_launch"] / 1e6))
+    f.write("== DRAM traffic of the launch pair (one iteration of %d pairs): %.1f MB; algorithmic bytes: %.1f MB\n" % (bench["roofline"]["pairs_per_launch"], traffic / 1e6, bench["roofline"]["bytes_per_launch"] / 1e6))
 print("profiles written; dram traffic per launch pair %.0f bytes" % traffic)
