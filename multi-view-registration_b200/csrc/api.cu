@@ -61,22 +61,17 @@ struct Cloud {
   uint64_t index_gen = 0;
   mvr_grid grid{};
   GridDev gd{};
-  DevBuf keys, vals, keys_alt, vals_alt, hist, counters, sorted, table, bricks, brick_cnt;
+  DevBuf keys, vals, keys_alt, vals_alt, hist, counters, sorted, table;
   uint32_t* sorted_keys = nullptr;
   uint32_t* perm = nullptr;
-  // occupied-brick list of the current index (search.cu): bricks[0 .. *brick_count())
-  int cnt_par = 0;               // which of the two counters the NEXT list launch fills
-  bool has_bricks = false;
-  const uint32_t* brick_count() const { return brick_cnt.as<uint32_t>() + (cnt_par ^ 1); }
   IndexDev dev() const {
     IndexDev ix;
     ix.pts = sorted.as<float4>(); ix.start = table.as<uint32_t>(); ix.g = gd; ix.n_valid = n - n_bad;
     return ix;
   }
-  QueryDev qdev(int shift) const { return QueryDev{sorted.as<float4>(), table.as<uint32_t>(), shift}; }
   void release() {
     own.release(); keys.release(); vals.release(); keys_alt.release(); vals_alt.release(); hist.release();
-    counters.release(); sorted.release(); table.release(); bricks.release(); brick_cnt.release();
+    counters.release(); sorted.release(); table.release();
   }
 };
 
@@ -99,7 +94,7 @@ struct mvr_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
-  Cloud tgt, src, qry;          // qry: scratch cloud used to present queries in cell order
+  Cloud tgt, src;
   DevBuf normals; bool has_normals = false;
   DevBuf cur, corr_p, corr_j, corr_d2, rmin, rnn, partials, sums, out_cloud, qtmp, itmp, ftmp, scratch, misc, tiles, state, log;
   PairIndex pt, ps;              // target / source index of the running align
@@ -107,6 +102,7 @@ struct mvr_ctx {
   double nn_ppc = 8.0;           // its target points per occupied cell
   double nn_dense_ratio = 8.0;   // queries per target point from which the dense pass is used (0: never)
   FwdArgs fa{}; RevArgs ra{};    // kernel arguments of the prepared align
+  bool want_rnn = false;         // the next prepared align also records the mutual partners (mvr_correspondences)
   int group_pairs = 24;          // pairs per launch of a batch led by this context (mvr_ctx_set_batch_group)
   DevBuf pkeys, pvals, pmoved, pcount;   // build scratch of the per-align indices: keys, arrival ranks, arrival-order records, cell counters
   uint32_t scan_epoch = 1;
@@ -193,8 +189,8 @@ mvr_grid make_grid(const float lo[3], const float hi[3], double cell, int max_bi
   if (!(ext > 0) || !std::isfinite(ext)) ext = 1.0;
   if (!(cell > 0) || !std::isfinite(cell)) cell = ext;
   if (max_bits > 10) max_bits = 10;
-  if (max_bits < 3) max_bits = 3;   // the brick search works on 4 x 4 x 4-cell bricks with a 2-cell halo
-  int bits = 3;
+  if (max_bits < 1) max_bits = 1;
+  int bits = std::min(3, max_bits);
   while (bits < max_bits && cell * (double)(1 << bits) < ext * 1.0001) ++bits;
   if (cell * (double)(1 << bits) < ext * 1.0001) cell = ext * 1.0001 / (double)(1 << bits);
   for (int a = 0; a < 3; ++a) g.origin[a] = lo[a];
@@ -282,7 +278,6 @@ int build_index(mvr_ctx* ctx, Cloud& c, const float4* pts, const mvr_grid& g) {
   }
   c.index_valid = true;
   c.exportable = true;
-  c.has_bricks = false;
   c.index_gen = c.gen;
   return MVR_OK;
 }
@@ -325,46 +320,13 @@ int bin_index(mvr_ctx* ctx, Cloud& c, float4* pts, const mvr_grid& g, const floa
   }
   c.index_valid = true;
   c.exportable = false;
-  c.has_bricks = false;
   c.index_gen = c.gen;
-  return MVR_OK;
-}
-
-// List the occupied bricks of c's current index (table granularity `shift`: 6 = cell table, 0 = brick
-// table; fine_bits = bits of the grid the bricks belong to).
-int list_bricks(mvr_ctx* ctx, Cloud& c, int fine_bits, int shift, const int* d_done) {
-  const size_t nb = (size_t)1 << (3 * (fine_bits - 2));
-  CK(c.bricks.ensure((std::min(nb, (size_t)std::max(c.n, 1)) + 1) * sizeof(uint32_t)));
-  if (!c.brick_cnt.p) {
-    CK(c.brick_cnt.ensure(2 * sizeof(uint32_t)));
-    CK(cudaMemsetAsync(c.brick_cnt.p, 0, c.brick_cnt.cap, ctx->stream));
-    c.cnt_par = 0;
-  }
-  uint32_t* cnt = c.brick_cnt.as<uint32_t>();
-  CK(launch_list_bricks(c.table.as<uint32_t>(), fine_bits, shift, c.bricks.as<uint32_t>(), cnt + c.cnt_par, cnt + (c.cnt_par ^ 1), d_done,
-                        ctx->stream));
-  c.cnt_par ^= 1;
-  c.has_bricks = true;
   return MVR_OK;
 }
 
 mvr_grid auto_grid(mvr_ctx* ctx, const Cloud& c) {
   double e = ctx->cell_edge_opt > 0 ? ctx->cell_edge_opt : density_cell_edge(c.lo, c.hi, c.n - c.n_bad, 6.0);
   return make_grid(c.lo, c.hi, e, ctx->max_bits_opt);
-}
-
-// Target index usable by the brick search: counting-sorted in grid `want` (or an automatic one), with
-// its occupied-brick list.
-int ensure_target_index(mvr_ctx* ctx, const mvr_grid* want) {
-  Cloud& t = ctx->tgt;
-  if (t.index_valid && t.index_gen == t.gen && t.grid.bits >= 3 && (!want || same_grid(*want, t.grid))) {
-    // also true for an index the caller built with mvr_index_build: same layout, only the brick list is missing
-    return t.has_bricks ? MVR_OK : list_bricks(ctx, t, t.grid.bits, 6, nullptr);
-  }
-  mvr_grid g = want ? *want : auto_grid(ctx, t);
-  int rc = bin_index(ctx, t, const_cast<float4*>(t.pts), g, nullptr, nullptr);
-  if (rc) return rc;
-  return list_bricks(ctx, t, g.bits, 6, nullptr);
 }
 
 PairGrid make_pair_grid(const float lo[3], const float hi[3], double e, uint32_t* cells_out);
@@ -426,40 +388,6 @@ float gate_float(double max_dist) {
   float f = (float)m2;
   if ((double)f < m2) f = std::nextafterf(f, INFINITY);
   return std::nextafterf(f, INFINITY);
-}
-
-// The ONE grid both clouds of an align / correspondence pass are binned in.  It covers the target box
-// and the (guess-transformed) source box, so clamping at the grid boundary stays rare.  Cell edge:
-// gate / 2 when the point density allows (then the brick search's two-cell halo covers the gate and a
-// gated search never leaves shared memory), otherwise bounded to 2 .. 12 points per occupied cell.
-mvr_grid pair_grid(mvr_ctx* ctx, const float* G, double max_dist) {
-  const Cloud &t = ctx->tgt, &s = ctx->src;
-  float lo[3], hi[3];
-  for (int a = 0; a < 3; ++a) { lo[a] = t.lo[a]; hi[a] = t.hi[a]; }
-  if (t.n - t.n_bad <= 0) for (int a = 0; a < 3; ++a) { lo[a] = INFINITY; hi[a] = -INFINITY; }
-  if (s.n - s.n_bad > 0) {
-    for (int corner = 0; corner < 8; ++corner) {
-      double p[3] = {(corner & 1) ? s.hi[0] : s.lo[0], (corner & 2) ? s.hi[1] : s.lo[1], (corner & 4) ? s.hi[2] : s.lo[2]};
-      for (int a = 0; a < 3; ++a) {
-        double v = G[a] * p[0] + G[4 + a] * p[1] + G[8 + a] * p[2] + G[12 + a];
-        if (std::isfinite(v)) { lo[a] = std::min(lo[a], (float)v); hi[a] = std::max(hi[a], (float)v); }
-      }
-    }
-  }
-  for (int a = 0; a < 3; ++a) if (!(lo[a] <= hi[a])) { lo[a] = 0.f; hi[a] = 0.f; }
-  double e;
-  if (ctx->cell_edge_opt > 0) {
-    e = ctx->cell_edge_opt;
-  } else {
-    const Cloud& d = (t.n - t.n_bad > 0) ? t : s;
-    const double e_lo = density_cell_edge(d.lo, d.hi, d.n - d.n_bad, 2.0), e_hi = density_cell_edge(d.lo, d.hi, d.n - d.n_bad, 12.0);
-    const double m2 = max_dist * max_dist;
-    e = (m2 < 1e30) ? std::min(std::max(0.5 * max_dist * 1.002, e_lo), e_hi) : density_cell_edge(d.lo, d.hi, d.n - d.n_bad, 6.0);
-  }
-  float l[3], h[3];
-  for (int a = 0; a < 3; ++a) { l[a] = lo[a] - (float)e; h[a] = hi[a] + (float)e; }
-  const int cap = (ctx->cell_edge_opt > 0) ? 10 : ((std::max(t.n, s.n) > 1500000) ? 8 : 7);   // per-iteration table scan: 2 M (16 M) entries
-  return make_grid(l, h, e, std::min(ctx->max_bits_opt, cap));
 }
 
 // ---- per-align row-major index (pair_index.cu) ---------------------------------------------------
@@ -552,44 +480,6 @@ int ensure_pinned(mvr_ctx* ctx) {
 // each source point once more as a candidate (16 B).  Cell-table entries are NOT counted (conservative).
 double corr_bytes(int n, int m, bool reciprocal) { return 24.0 * n + 16.0 * m + (reciprocal ? 16.0 * n : 0.0); }
 
-// Per-align search state: target indexed in grid g, reciprocal scratch armed.
-int prepare_pair(mvr_ctx* ctx, const mvr_grid& g, bool reciprocal) {
-  int rc = ensure_target_index(ctx, &g);
-  if (rc) return rc;
-  const size_t n = (size_t)std::max(ctx->src.n, 1), m = (size_t)std::max(ctx->tgt.n, 1);
-  CK(ctx->corr_p.ensure(n * sizeof(int32_t)));
-  CK(ctx->corr_d2.ensure(n * sizeof(float)));
-  if (reciprocal) {
-    CK(ctx->rmin.ensure(m * sizeof(uint32_t)));
-    CK(ctx->rnn.ensure(m * sizeof(int32_t)));
-    CK(launch_fill_u32(ctx->rmin.as<uint32_t>(), m, 0x7f800000u, ctx->stream));   // +inf: "chosen by nobody"
-  }
-  return MVR_OK;
-}
-
-// One ICP iteration's search half on the current source coordinates `cur`: apply the pending delta
-// in place, re-index the source in the pair grid (PCL rebuilds the source kd-tree every iteration when
-// reciprocal; the cell order also gives every brick its queries as one run), forward search
-// source -> target with the gate, then, if reciprocal, the nearest source point of every chosen target.
-int correspond_pass(mvr_ctx* ctx, float4* cur, const mvr_grid& g, bool reciprocal, double max_dist, const float* d_delta,
-                    const int* d_done) {
-  Cloud &s = ctx->src, &t = ctx->tgt;
-  const int n = s.n;
-  const double max2 = max_dist * max_dist;
-  const float max_d2f = gate_float(max_dist);
-  int rc = bin_index(ctx, s, cur, g, d_delta, d_done);
-  if (rc) return rc;
-  s.index_valid = false;   // the index describes `cur`, not the caller's source cloud
-  if ((rc = list_bricks(ctx, s, g.bits, 6, d_done))) return rc;
-  ProfScope ps(ctx, MVR_K_CORR, corr_bytes(n, t.n, reciprocal), (double)n);
-  CK(launch_brick_forward(s.qdev(6), n, t.dev(), s.bricks.as<uint32_t>(), s.brick_count(), max2, max_d2f, ctx->corr_p.as<int32_t>(),
-                          ctx->corr_d2.as<float>(), reciprocal ? ctx->rmin.as<uint32_t>() : nullptr, d_done, ctx->stream));
-  if (reciprocal)
-    CK(launch_brick_reverse(t.qdev(6), t.n, s.dev(), t.bricks.as<uint32_t>(), t.brick_count(), ctx->rmin.as<uint32_t>(),
-                            ctx->rnn.as<int32_t>(), d_done, ctx->stream));
-  return MVR_OK;
-}
-
 }  // namespace
 
 // =================================================================================================
@@ -649,7 +539,7 @@ int mvr_ctx_destroy(mvr_ctx* ctx) {
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
-  ctx->tgt.release(); ctx->src.release(); ctx->qry.release(); ctx->normals.release();
+  ctx->tgt.release(); ctx->src.release(); ctx->normals.release();
   ctx->pt.release(); ctx->ps.release(); ctx->nt.release(); ctx->nq.release();
   ctx->pkeys.release(); ctx->pvals.release(); ctx->pmoved.release(); ctx->pcount.release();
   DevBuf* bufs[] = {&ctx->cur, &ctx->corr_p, &ctx->rmin, &ctx->rnn, &ctx->corr_j, &ctx->corr_d2, &ctx->partials, &ctx->sums, &ctx->out_cloud, &ctx->qtmp,
@@ -838,6 +728,9 @@ int mvr_nn_query(mvr_ctx* ctx, const float* q, size_t n, int32_t* idx, float* d2
   return MVR_OK;
 }
 
+static int align_prepare(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, int est);
+static int align_run(mvr_ctx* const* ctxs, int count, const mvr_icp_params* prm, int est);
+
 int mvr_correspondences(mvr_ctx* ctx, double max_dist, int reciprocal, int32_t* iq, int32_t* im, float* dist, size_t* count) {
   if (!ctx || !count) return MVR_ERR_BAD_ARG;
   cudaSetDevice(ctx->device);
@@ -845,24 +738,32 @@ int mvr_correspondences(mvr_ctx* ctx, double max_dist, int reciprocal, int32_t* 
   if (ctx->tgt.gen == 0 || ctx->src.gen == 0) return fail(ctx, MVR_ERR_NO_INPUT, "source/target not set");
   if (!(max_dist >= 0)) return fail(ctx, MVR_ERR_BAD_ARG, "max_dist must be >= 0");
   const int n = ctx->src.n;
-  if (n == 0) return MVR_OK;
+  if (n == 0 || ctx->tgt.n == 0) return MVR_OK;
   if (!iq || !im || !dist) return MVR_ERR_BAD_ARG;
-  float I[16];
-  mat_identity(I);
-  const mvr_grid g = pair_grid(ctx, I, max_dist);
-  int rc = prepare_pair(ctx, g, reciprocal != 0);
+  // one correspondence pass of the fused iteration (no guess: the source as it is), then its pairs by source index
+  mvr_icp_params one;
+  mvr_icp_params_default(&one);
+  one.max_iterations = 1; one.fixed_iterations = 1;
+  one.use_reciprocal_correspondences = reciprocal ? 1 : 0;
+  one.max_correspondence_distance = max_dist;
+  one.min_correspondences = 1;
+  ctx->want_rnn = true;
+  int rc = align_prepare(ctx, &one, nullptr, EST_P2P);
+  ctx->want_rnn = false;
   if (rc) return rc;
-  rc = correspond_pass(ctx, const_cast<float4*>(ctx->src.pts), g, reciprocal != 0, max_dist, nullptr, nullptr);
-  if (rc) return rc;
+  if ((rc = align_run(&ctx, 1, &one, EST_P2P))) return rc;
+  if (ctx->h_state->dbg[2] != 0) return fail(ctx, MVR_ERR_CUDA, "internal error: a reciprocal search lost its chooser (search bound violated)");
   CK(ctx->corr_j.ensure((size_t)n * sizeof(int32_t)));
+  CK(ctx->corr_d2.ensure((size_t)n * sizeof(float)));
   CK(ctx->scratch.ensure(compact_scratch_elems(n) * sizeof(uint32_t) + 64));
   CK(ctx->itmp.ensure((size_t)2 * n * sizeof(int32_t)));
   CK(ctx->ftmp.ensure((size_t)n * sizeof(float)));
   CK(ctx->misc.ensure(64));
   int32_t* dq = ctx->itmp.as<int32_t>();
   int32_t* dm = dq + n;
-  CK(launch_resolve_corr(ctx->corr_p.as<int32_t>(), reciprocal ? ctx->rnn.as<int32_t>() : nullptr, ctx->tgt.sorted.as<float4>(), n,
-                         ctx->corr_j.as<int32_t>(), ctx->stream));
+  CK(cudaMemsetAsync(ctx->corr_j.p, 0xff, (size_t)n * sizeof(int32_t), ctx->stream));   // -1: no correspondence
+  CK(launch_resolve_pairs(ctx->fa.cur, ctx->fa.n_valid, ctx->fa.corr_p, ctx->ra.rnn, ctx->fa.tgt, ctx->corr_j.as<int32_t>(),
+                          ctx->corr_d2.as<float>(), ctx->stream));
   CK(launch_compact_corr(ctx->corr_j.as<int32_t>(), ctx->corr_d2.as<float>(), n, ctx->scratch.as<uint32_t>(), dq, dm,
                          ctx->ftmp.as<float>(), ctx->misc.as<uint32_t>(), ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_small, ctx->misc.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -981,6 +882,8 @@ static int align_prepare(mvr_ctx* ctx, const mvr_icp_params* prm, const float* g
   ra = RevArgs{};
   ra.tgt = fa.tgt; ra.m_valid = pt.n_valid; ra.rmin = fa.rmin; ra.cur = fa.cur; ra.sstart = psx.start.as<uint32_t>(); ra.gs = psx.g;
   ra.n_valid = psx.n_valid; ra.corr_p = fa.corr_p; ra.nrm = fa.nrm;
+  ra.rnn = nullptr;
+  if (reciprocal && ctx->want_rnn) { CK(ctx->rnn.ensure((size_t)std::max(m, 1) * sizeof(int32_t))); ra.rnn = ctx->rnn.as<int32_t>(); }
   ra.partials = fa.partials; ra.st = d_st; ra.log = d_log; ra.grid = fused_grid_rev(pt.n_valid); ra.per = fused_rev_chunks(pt.n_valid);
   return MVR_OK;
 }

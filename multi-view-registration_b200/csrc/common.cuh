@@ -28,15 +28,6 @@ struct IndexDev {
   int n_valid;   // finite points (they occupy sorted positions [0, n_valid))
 };
 
-// Query points sorted by cell (shift = 6: `start` is a full cell table) or only by 4 x 4 x 4-cell brick
-// (shift = 0: `start` has one entry per brick); pts[k].w = bits(original index).  Same grid as the
-// candidate index it is searched against.
-struct QueryDev {
-  const float4* pts;
-  const uint32_t* start;
-  int shift;
-};
-
 // Row-major uniform grid of the per-align index (pair_index.cu): nx x ny x nz cells, x fastest,
 // cell_a = clamp(floor((p_a - o_a) * inv_cell), 0, n_a - 1).
 struct PairGrid {

@@ -1,4 +1,4 @@
-// icp.cu -- per-iteration ICP kernels (the search itself is in search.cu): estimator sums (K6 point-to-point 3x3 cross-covariance, K9 point-to-plane 6x6 normal equations)
+// icp.cu -- per-iteration ICP kernels (the search itself is in pair_search.cuh): estimator sums (K6 point-to-point 3x3 cross-covariance, K9 point-to-plane 6x6 normal equations)
 // with the solve and the convergence test in the reduction's last block, fitness reduction (K8) and
 // order-preserving correspondence compaction.
 //
@@ -454,7 +454,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, MVR_REV_MINBLOCKS * (256 / FUSE
     NnBest b{__uint_as_float(r), 0x7fffffff, -1};
     pg_search<MVR_PG_UNROLL>(a.gs, a.sstart, a.cur, a.n_valid, t.x, t.y, t.z, ux, uy, uz, dev, stretch, MVR_INF, b, seg);
     if (b.pos < 0) ++missed;
-    s_p[k] = (b.pos >= 0 && __ldg(a.corr_p + b.pos) == j) ? b.pos : -1;   // mutual, or the nearest source point chose another target
+    const int mutual = (b.pos >= 0 && __ldg(a.corr_p + b.pos) == j) ? b.pos : -1;   // or the nearest source point chose another target
+    s_p[k] = mutual;
+    if (a.rnn) a.rnn[j] = mutual;
   }
   if (missed) atomicAdd((unsigned long long*)&st->dbg[2], (unsigned long long)missed);   // must stay 0: a chooser was not found again
 
@@ -609,23 +611,23 @@ cudaError_t launch_reduce_fitness(const int32_t* idx, const float* d2, int n, do
   return cudaGetLastError();
 }
 
-__global__ void __launch_bounds__(256) k_resolve_corr(const int32_t* __restrict__ corr_p, const int32_t* __restrict__ rnn,
-                                                      const float4* __restrict__ tgt, int n, int32_t* __restrict__ corr_j) {
+__global__ void __launch_bounds__(256) k_resolve_pairs(const float4* __restrict__ src, int n_valid, const int32_t* __restrict__ corr_p,
+                                                       const int32_t* __restrict__ rnn, const float4* __restrict__ tgt,
+                                                       int32_t* __restrict__ corr_j, float* __restrict__ corr_d2) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= n_valid) return;
   const int p = __ldg(corr_p + i);
-  int j = -1;
-  if (p >= 0) {
-    j = __float_as_int(__ldg(tgt + p).w);
-    if (rnn && __ldg(rnn + p) != i) j = -2 - j;
-  }
-  corr_j[i] = j;
+  if (p < 0 || (rnn && __ldg(rnn + p) != i)) return;
+  const float4 s = __ldg(src + i), t = __ldg(tgt + p);
+  const int o = __float_as_int(s.w);
+  corr_j[o] = __float_as_int(t.w);
+  corr_d2[o] = d2_pinned(s.x, s.y, s.z, t.x, t.y, t.z);
 }
 
-cudaError_t launch_resolve_corr(const int32_t* corr_p, const int32_t* rnn, const float4* tgt_sorted, int n, int32_t* corr_j,
-                                cudaStream_t s) {
-  if (n <= 0) return cudaSuccess;
-  k_resolve_corr<<<(n + 255) / 256, 256, 0, s>>>(corr_p, rnn, tgt_sorted, n, corr_j); count_launch();
+cudaError_t launch_resolve_pairs(const float4* src_sorted, int n_valid, const int32_t* corr_p, const int32_t* rnn, const float4* tgt_sorted,
+                                 int32_t* corr_j, float* corr_d2, cudaStream_t s) {
+  if (n_valid <= 0) return cudaSuccess;
+  k_resolve_pairs<<<(n_valid + 255) / 256, 256, 0, s>>>(src_sorted, n_valid, corr_p, rnn, tgt_sorted, corr_j, corr_d2); count_launch();
   return cudaGetLastError();
 }
 

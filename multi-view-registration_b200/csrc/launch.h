@@ -42,25 +42,6 @@ cudaError_t launch_gather_sorted(const float4* pts, const uint32_t* perm, int n,
 // start[c] = first sorted position with key >= c, for c in [0, 1 << 3*bits].
 cudaError_t launch_cell_table(const uint32_t* sorted_keys, int n, int bits, uint32_t* start, cudaStream_t s);
 
-// ---- search.cu -----------------------------------------------------------------------------
-// Brick-tiled search (see search.cu).  Queries and candidates are binned in the SAME grid (bits >= 3).
-// list_bricks: list[0..*count) = occupied 4x4x4-cell bricks of a sorted cloud; *next (nullable) is zeroed.
-cudaError_t launch_list_bricks(const uint32_t* start, int bits, int shift, uint32_t* list, uint32_t* count, uint32_t* next,
-                               const int* d_done, cudaStream_t s);
-cudaError_t launch_fill_u32(uint32_t* p, size_t n, uint32_t v, cudaStream_t s);
-// Exact un-gated 1-NN; results at the query's original index.
-cudaError_t launch_brick_nn(QueryDev q, int nq, IndexDev c, const uint32_t* bricks, const uint32_t* n_bricks, int32_t* out_idx,
-                            float* out_d2, cudaStream_t s);
-// Forward correspondences source -> target with gate: corr_p[i] = sorted position of the matched target
-// point (-1 none), corr_d2[i] = float d2; rmin[p] (nullable) = min d2 bits over the source points that
-// chose target position p (must hold +inf bits on entry).
-cudaError_t launch_brick_forward(QueryDev q, int nq, IndexDev c, const uint32_t* bricks, const uint32_t* n_bricks, double max2,
-                                 float max_d2f, int32_t* corr_p, float* corr_d2, uint32_t* rmin, const int* d_done, cudaStream_t s);
-// Reciprocal half: for every target position p with rmin[p] < inf, rnn[p] = original index of the
-// nearest source point (lowest index on ties); rmin[p] is reset to +inf bits.
-cudaError_t launch_brick_reverse(QueryDev q, int nq, IndexDev c, const uint32_t* bricks, const uint32_t* n_bricks, uint32_t* rmin,
-                                 int32_t* rnn, const int* d_done, cudaStream_t s);
-
 // ---- bin.cu --------------------------------------------------------------------------------
 // Counting sort of a (moving) cloud by grid cell: see bin.cu.  counters has cells+1 entries (the last
 // one collects non-finite points) and must be zero on entry (k_scan_cells re-zeroes it); start gets
@@ -123,6 +104,7 @@ cudaError_t launch_pair_count(const float4* in, int n, const Mat4f* guess, PairG
                               uint32_t* counters, cudaStream_t s);
 cudaError_t launch_pair_scatter(const float4* in, int n, const Mat4f* guess, const uint32_t* keys, const uint32_t* rank, const uint32_t* start,
                                 float4* tmp, cudaStream_t s);
+cudaError_t launch_fill_u32(uint32_t* p, size_t n, uint32_t v, cudaStream_t s);
 // sorted[k] = {moved point, bits(original index)}; copy (nullable) gets the same.
 cudaError_t launch_pair_rerank(const float4* tmp, int n, const uint32_t* keys, const uint32_t* start, float4* sorted, float4* copy,
                                cudaStream_t s);
@@ -154,6 +136,7 @@ struct RevArgs {
   PairGrid gs;
   int n_valid;
   const int32_t* corr_p;
+  int32_t* rnn;            // nullable: [target sorted position] sorted position of its mutual source partner, -1 none (chosen targets only)
   const float4* nrm;
   double* partials;
   IcpState* st;
@@ -179,10 +162,12 @@ cudaError_t launch_icp_reverse(const RevBatch& batch, int pairs, int max_grid, i
 // by_w = true: the queries were sorted by cell and carry their original index in .w, results by original index.
 cudaError_t launch_pair_nn(const float4* q, int n, bool by_w, const float4* tgt_sorted, const uint32_t* tstart, PairGrid g, int m_valid,
                            int32_t* out_idx, float* out_d2, cudaStream_t s);
-// corr_j[i] = original index of the matched target point, -1 = none, -2-j = passed the gate but failed
-// the reciprocal test (the layout launch_compact_corr consumes).
-cudaError_t launch_resolve_corr(const int32_t* corr_p, const int32_t* rnn, const float4* tgt_sorted, int n, int32_t* corr_j,
-                                cudaStream_t s);
+// The correspondences of one fused iteration by ORIGINAL source index (what launch_compact_corr consumes): for every
+// finite source point (sorted position i, .w = original index) matched to target position p = corr_p[i] and, when rnn
+// is given, mutual (rnn[p] == i): corr_j[orig] = original index of the target point, corr_d2[orig] = their pinned
+// distance.  corr_j must be pre-filled with -1.
+cudaError_t launch_resolve_pairs(const float4* src_sorted, int n_valid, const int32_t* corr_p, const int32_t* rnn, const float4* tgt_sorted,
+                                 int32_t* corr_j, float* corr_d2, cudaStream_t s);
 // out = float(st->fin) * in   (the aligned cloud icp.align returns)
 cudaError_t launch_transform_final(const float4* in, float4* out, int n, const IcpState* st, cudaStream_t s);
 // sum and count of d2[i] with idx[i] >= 0 and d2 <= max_range  (getFitnessScore); out[0]=sum, out[1]=count

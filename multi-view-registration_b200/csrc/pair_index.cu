@@ -61,6 +61,18 @@ __global__ void __launch_bounds__(256) k_pair_rerank(const float4* __restrict__ 
   if (copy) copy[s + r] = p;
 }
 
+__global__ void k_fill_u32(uint32_t* __restrict__ p, size_t n, uint32_t v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+cudaError_t launch_fill_u32(uint32_t* p, size_t n, uint32_t v, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  const size_t want = (n + 255) / 256;
+  const int blocks = (int)(want < (size_t)(148 * 8) ? want : (size_t)(148 * 8));
+  k_fill_u32<<<blocks, 256, 0, s>>>(p, n, v); count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_pair_count(const float4* in, int n, const Mat4f* guess, PairGrid g, uint32_t cells, uint32_t* keys, uint32_t* rank,
                               uint32_t* counters, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
