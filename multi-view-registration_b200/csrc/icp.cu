@@ -477,15 +477,15 @@ __global__ void __launch_bounds__(FUSED_THREADS, MVR_REV_MINBLOCKS * (256 / FUSE
 }
 
 // Chunks of 256 target points per block of the reverse half: enough for its compacted list to fill whole rounds of
-// 256 searches (about half of the target points are chosen).  Measured on B200 (same box; 24 x 200k pairs in groups of
-// 8 / one 200k pair alone): 1 chunk 33.9 ms / 2.32 ms, 2 chunks 30.0 / 2.18, 4 chunks 29.1 / 2.50, 8 chunks
-// 30.7 / 3.10 -- two chunks, four once a cloud fills the GPU on its own.  A pure function of the cloud size, so that the
-// block partition, and with it the order of the sums, does not depend on what else runs in the batch.
+// 256 searches (about half of the target points are chosen).  Measured on B200 (same box; 24 x 200k pairs per launch /
+// one 200k pair alone): 2 chunks 25.3 ms / 2.06 ms, 3 chunks 24.1 / 2.08, 4 chunks 24.0 / 2.23 -- three chunks, four once
+// a cloud fills the GPU on its own.  A pure function of the cloud size, so that the block partition, and with it the
+// order of the sums, does not depend on what else runs in the batch.
 int fused_rev_chunks(int items) {
 #ifdef MVR_REV_CHUNKS
   return MVR_REV_CHUNKS;
 #else
-  return items >= 400000 ? 4 : 2;
+  return items >= 400000 ? 4 : 3;
 #endif
 }
 int fused_grid_rev(int items) {
