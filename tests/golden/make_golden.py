@@ -63,5 +63,48 @@ def main():
     print("golden vectors written to", HERE)
 
 
+def lum_fixture():
+    """LUM relaxation (host/lum.cpp lumRelax): point pairs of a 5-view graph (ring + one chord), noisy, and the corrections
+    that minimise sum |X_s a - X_t b|^2 with X_0 = I, found by scipy.optimize.least_squares on the explicit residuals --
+    an implementation that shares nothing with the moment-based Gauss-Newton of the library."""
+    from scipy.optimize import least_squares
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(20261018)
+    V = 5
+
+    def rigid(rot, trans):
+        T = np.eye(4)
+        T[:3, :3] = Rotation.from_rotvec(rot * rng.standard_normal(3)).as_matrix()
+        T[:3, 3] = trans * rng.standard_normal(3)
+        return T
+
+    def apply(T, p):
+        return p @ T[:3, :3].T + T[:3, 3]
+
+    disp = [np.eye(4)] + [rigid(0.02, 1.0) for _ in range(V - 1)]
+    edges = [(0, 1), (1, 2), (2, 3), (3, 4), (4, 0), (1, 3)]
+    A, B = [], []
+    for (s, t) in edges:
+        p = rng.standard_normal((150, 3)) * 45 + [0, 0, 900]
+        A.append(apply(disp[s], p) + 0.25 * rng.standard_normal(p.shape))
+        B.append(apply(disp[t], p) + 0.25 * rng.standard_normal(p.shape))
+
+    def pose(x6):
+        T = np.eye(4)
+        T[:3, :3] = Rotation.from_rotvec(x6[:3]).as_matrix()
+        T[:3, 3] = x6[3:]
+        return T
+
+    def resid(x):
+        Xs = [np.eye(4)] + [pose(x[6 * k:6 * k + 6]) for k in range(V - 1)]
+        return np.concatenate([(apply(Xs[s], a) - apply(Xs[t], b)).ravel() for (s, t), a, b in zip(edges, A, B)])
+
+    sol = least_squares(resid, np.zeros(6 * (V - 1)), xtol=1e-15, ftol=1e-15, gtol=1e-15)
+    X = np.stack([np.eye(4)] + [pose(sol.x[6 * k:6 * k + 6]) for k in range(V - 1)])
+    np.savez_compressed(os.path.join(HERE, "lum.npz"), src=np.array([e[0] for e in edges], dtype=np.int32),
+                        tgt=np.array([e[1] for e in edges], dtype=np.int32), a=np.stack(A), b=np.stack(B), X=X, cost=2.0 * sol.cost)
+
+
 if __name__ == "__main__":
     main()
+    lum_fixture()

@@ -346,3 +346,16 @@ def test_points_asc_format(mvr, tmp_path):
     f = tmp_path / "points.asc"
     mvr.points_save_asc(f, pts)
     assert f.read_text() == "1.500000 0.000000 900.000000 255 128 0\n-2.250000 3.000000 901.500000 1 2 3\n"
+
+
+def test_lum_relax_golden(mvr):
+    """tests/golden/lum.npz: explicit point pairs of a 5-view graph and the minimiser scipy.optimize.least_squares found
+    (tests/golden/make_golden.py lum_fixture); the library sees the pairs only through their moments."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "lum.npz"))
+    edges = [mvr.PairMoments.from_pairs(a, b, origin=[0, 0, 900]) for a, b in zip(g["a"], g["b"])]
+    X = mvr.lum_relax(edges, g["src"], g["tgt"], len(g["X"]), 16)
+    for v in range(len(g["X"])):
+        np.testing.assert_allclose(X[v], g["X"][v], atol=2e-6)   # the accuracy scipy stopped at
+    cost = sum((((a @ X[s][:3, :3].T + X[s][:3, 3]) - (b @ X[t][:3, :3].T + X[t][:3, 3])) ** 2).sum()
+               for s, t, a, b in zip(g["src"], g["tgt"], g["a"], g["b"]))
+    assert abs(cost - float(g["cost"])) <= 1e-9 * float(g["cost"])
