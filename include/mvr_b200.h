@@ -103,6 +103,9 @@ enum { MVR_K_MORTON = 0, MVR_K_SORT = 1, MVR_K_TABLE = 2, MVR_K_NN = 3, MVR_K_CO
 const char* mvr_version(void);
 /* Number of CUDA kernels this library has launched in the calling process (all contexts). */
 uint64_t mvr_kernel_launch_count(void);
+/* Bytes an align moves between host and device besides the clouds: the per-align loop state (copied in once, read back
+ * once per batch of iterations) and one per-iteration log record (read back after the align). */
+void mvr_transfer_sizes(size_t* state_bytes, size_t* log_record_bytes);
 const char* mvr_status_string(int status);
 void mvr_icp_params_default(mvr_icp_params* p);
 

@@ -145,6 +145,8 @@ def lib():
     L.mvr_version.restype = C.c_char_p
     L.mvr_kernel_launch_count.restype = C.c_uint64
     L.mvr_status_string.restype = C.c_char_p
+    L.mvr_transfer_sizes.argtypes = [C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    L.mvr_transfer_sizes.restype = None
     L.mvr_status_string.argtypes = [C.c_int]
     L.mvr_icp_params_default.argtypes = [C.POINTER(IcpParams)]
     L.mvr_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
@@ -209,6 +211,22 @@ def lib():
 
 def kernel_launch_count():
     return int(lib().mvr_kernel_launch_count())
+
+
+def _transfer_sizes():
+    a, b = C.c_size_t(0), C.c_size_t(0)
+    lib().mvr_transfer_sizes(C.byref(a), C.byref(b))
+    return int(a.value), int(b.value)
+
+
+def icp_state_bytes():
+    """Bytes of the per-align loop state an align copies in and reads back."""
+    return _transfer_sizes()[0]
+
+
+def icp_log_record_bytes():
+    """Bytes of one per-iteration log record read back after an align."""
+    return _transfer_sizes()[1]
 
 
 def default_params(**kw):

@@ -489,6 +489,11 @@ const char* mvr_version(void) { return "mvr_b200 0.1 (sm_100a)"; }
 
 uint64_t mvr_kernel_launch_count(void) { return (uint64_t)launch_count(); }
 
+void mvr_transfer_sizes(size_t* state_bytes, size_t* log_record_bytes) {
+  if (state_bytes) *state_bytes = sizeof(IcpState);
+  if (log_record_bytes) *log_record_bytes = sizeof(IterRec);
+}
+
 const char* mvr_status_string(int s) {
   switch (s) {
     case MVR_OK: return "ok";

@@ -7,7 +7,13 @@ exchange of ~100 B per pair: NCCL on GPUs, gloo in the CPU tests), and every ran
 No point data crosses ranks."""
 import numpy as np
 
-REC = 24   # floats per pair record: pose[16] (column-major), n_corr, mse, iterations, status, queries_lo, queries_hi, pad, pad
+# One pair record = the C struct mvr_pair_record of include/mvr_b200.h (96 bytes, no padding): what a rank contributes to
+# the all-gather.  Carried as raw bytes, so n_corr (int32), mse (double) and the query count (uint64) arrive exactly
+# as the single-GPU path reports them.
+RECORD = np.dtype([("pose", np.float32, 16), ("n_corr", np.int32), ("iterations", np.int32), ("status", np.int32), ("pad", np.int32),
+                   ("mse", np.float64), ("nn_queries", np.uint64)])
+REC = RECORD.itemsize   # bytes per pair record
+assert REC == 96
 
 
 def pair_range(rank, world, n_pairs):
@@ -20,52 +26,61 @@ def views_needed(p0, p1, n_views):
 
 def pack_reports(reports, p0, p1):
     """reports: list indexed by pair (dicts with pose 4x4, n_corr, mse, iterations, status, nn_queries)."""
-    out = np.zeros((p1 - p0, REC), dtype=np.float32)
+    out = np.zeros(p1 - p0, dtype=RECORD)
     for k, p in enumerate(range(p0, p1)):
         r = reports[p]
-        out[k, :16] = np.ascontiguousarray(np.asarray(r["pose"], dtype=np.float32).T).reshape(16)
-        out[k, 16] = r["n_corr"]
-        out[k, 17] = r["mse"]
-        out[k, 18] = r["iterations"]
-        out[k, 19] = r["status"]
-        q = int(r.get("nn_queries", 0))
-        out[k, 20] = q & 0xFFFFFF          # float32 holds 24 bits exactly
-        out[k, 21] = (q >> 24) & 0xFFFFFF
+        out[k]["pose"] = np.ascontiguousarray(np.asarray(r["pose"], dtype=np.float32).T).reshape(16)   # column-major
+        out[k]["n_corr"] = r["n_corr"]
+        out[k]["iterations"] = r["iterations"]
+        out[k]["status"] = r["status"]
+        out[k]["mse"] = r["mse"]
+        out[k]["nn_queries"] = int(r.get("nn_queries", 0))
     return out
 
 
 def unpack_records(rec):
-    rec = np.asarray(rec, dtype=np.float32).reshape(-1, REC)
-    out = []
-    for r in rec:
-        out.append(dict(pose=r[:16].reshape(4, 4).T.copy(), n_corr=int(r[16]), mse=float(r[17]), iterations=int(r[18]),
-                        status=int(r[19]), nn_queries=int(r[20]) | (int(r[21]) << 24)))
-    return out
+    rec = np.asarray(rec).view(RECORD).reshape(-1)
+    return [dict(pose=r["pose"].reshape(4, 4).T.copy(), n_corr=int(r["n_corr"]), mse=float(r["mse"]), iterations=int(r["iterations"]),
+                 status=int(r["status"]), nn_queries=int(r["nn_queries"])) for r in rec]
+
+
+def pose_checksum(allrec):
+    """Hash of the bit patterns of every gathered pair pose (plus n_corr and mse): equal checksums = bit-identical results,
+    whatever the number of ranks."""
+    import hashlib
+    rec = np.asarray(allrec).view(RECORD).reshape(-1)
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(rec["pose"]).tobytes())
+    h.update(np.ascontiguousarray(rec["n_corr"]).tobytes())
+    h.update(np.ascontiguousarray(rec["mse"]).tobytes())
+    return h.hexdigest()[:16]
 
 
 def gather_records(mine, rank, world, n_pairs, dist=None, device=None):
-    """All-gather the per-pair records: `mine` = (p1 - p0) x REC float32 of this rank -> n_pairs x REC on every rank.
+    """All-gather the per-pair records: `mine` = the (p1 - p0) RECORDs of this rank -> n_pairs RECORDs on every rank.
     `dist` = torch.distributed (initialised) when world > 1."""
+    mine = np.ascontiguousarray(np.asarray(mine).view(RECORD).reshape(-1))
     if world == 1:
-        return np.asarray(mine, dtype=np.float32).reshape(n_pairs, REC)
+        assert len(mine) == n_pairs
+        return mine
     import torch
     block = max(pair_range(r, world, n_pairs)[1] - pair_range(r, world, n_pairs)[0] for r in range(world))
-    pad = torch.zeros(block * REC, dtype=torch.float32)
-    flat = torch.from_numpy(np.ascontiguousarray(mine, dtype=np.float32).reshape(-1))
+    pad = torch.zeros(block * REC, dtype=torch.uint8)
+    flat = torch.from_numpy(mine.view(np.uint8).reshape(-1).copy())
     pad[:flat.numel()] = flat
     pad = pad.to(device) if device is not None else pad
-    out = torch.empty(world * block * REC, dtype=torch.float32, device=pad.device)
+    out = torch.empty(world * block * REC, dtype=torch.uint8, device=pad.device)
     if hasattr(dist, "all_gather_into_tensor") and pad.is_cuda:
         dist.all_gather_into_tensor(out, pad)          # one exchange, one device-to-host read
     else:                                              # gloo (CPU tests)
         parts = [torch.zeros_like(pad) for _ in range(world)]
         dist.all_gather(parts, pad)
         out = torch.cat(parts)
-    host = out.cpu().numpy().reshape(world, block, REC)
+    host = out.cpu().numpy().reshape(world, block * REC)
     rows = []
     for r in range(world):
         a, b = pair_range(r, world, n_pairs)
-        rows.append(host[r, :b - a])
+        rows.append(host[r, :(b - a) * REC].copy().view(RECORD))
     return np.concatenate(rows, axis=0)
 
 
