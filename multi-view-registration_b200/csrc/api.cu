@@ -80,12 +80,15 @@ struct ProfRec { int kind; cudaEvent_t a, b; double bytes, units; };
 // Per-align row-major index of one cloud (pair_index.cu).
 struct PairIndex {
   DevBuf sorted, start, s0;   // points by cell (the source's move in place), cell table, source binning-time copy
+  DevBuf gocc, gmask;         // gate mask of a target index (pair_index.cu) and its undilated occupancy words
+  float gm_gate = -1.f;       // the gate (float d2, rounded up) the mask was built for; < 0: none
+  int gm_stride = 0;
   PairGrid g{};
   uint32_t cells = 0;
   int n_valid = 0;
   uint64_t gen = 0;
   bool valid = false;
-  void release() { sorted.release(); start.release(); s0.release(); valid = false; }
+  void release() { sorted.release(); start.release(); s0.release(); gocc.release(); gmask.release(); gm_gate = -1.f; valid = false; }
 };
 
 }  // namespace
@@ -463,7 +466,28 @@ int build_pair_index(mvr_ctx* ctx, PairIndex& ix, const float4* pts, int n, int 
   if (ordered)
     CK(launch_pair_rerank(ctx->pmoved.as<float4>(), n, ctx->pkeys.as<uint32_t>(), ix.start.as<uint32_t>(), ix.sorted.as<float4>(),
                           keep_s0 ? ix.s0.as<float4>() : nullptr, ctx->stream));
-  ix.g = g; ix.cells = cells; ix.n_valid = n - n_bad; ix.valid = true;
+  ix.g = g; ix.cells = cells; ix.n_valid = n - n_bad; ix.valid = true; ix.gm_gate = -1.f;
+  return MVR_OK;
+}
+
+// The gate mask of target index ix for gate max_d2f (float d2, rounded up); without one (no gate, or a gate many cells
+// wide) the forward half searches every point.  Cells more than D apart in an axis are >= D cells apart along it; the
+// rounding of grid_t on the query and on the target point is absorbed by `slack` cells.
+int ensure_gate_mask(mvr_ctx* ctx, PairIndex& ix, float max_d2f) {
+  if (!(max_d2f < 3.0e38f) || ix.n_valid <= 0) { ix.gm_gate = -1.f; return MVR_OK; }
+  if (ix.gm_gate == max_d2f) return MVR_OK;
+  const double slack = 2.0 * ((double)MVR_CELL_MARGIN + 1.0e-6 * (double)std::max(ix.g.nx, std::max(ix.g.ny, ix.g.nz)));
+  const double need = std::sqrt((double)max_d2f) * (1.0 + 1.0e-5) / (double)ix.g.cell_lo + slack;
+  const int D = (int)std::ceil(need);
+  ix.gm_gate = -1.f;
+  if (D < 1 || D > 6) return MVR_OK;
+  const int wstride = (ix.g.nx + 31) / 32;
+  const size_t words = (size_t)ix.g.ny * ix.g.nz * wstride;
+  CK(ix.gocc.ensure(words * sizeof(uint32_t)));
+  CK(ix.gmask.ensure(words * sizeof(uint32_t)));
+  CK(launch_gate_mask(ix.start.as<uint32_t>(), ix.g, wstride, D, ix.gocc.as<uint32_t>(), ix.gmask.as<uint32_t>(), ctx->stream));
+  ix.gm_stride = wstride;
+  ix.gm_gate = max_d2f;
   return MVR_OK;
 }
 
@@ -836,7 +860,8 @@ static int align_prepare(mvr_ctx* ctx, const mvr_icp_params* prm, const float* g
     const PairGrid gs = make_pair_grid(lo, hi, pair_cell_edge(ctx, s, max_dist), &cells);
     Mat4f Gm;
     std::memcpy(Gm.m, G, sizeof(Gm.m));
-    if ((rc = build_pair_index(ctx, ctx->ps, s.pts, n, s.n_bad, &Gm, gs, cells, reciprocal))) return rc;
+    if ((rc = build_pair_index(ctx, ctx->ps, s.pts, n, s.n_bad, &Gm, gs, cells, false))) return rc;
+    for (int a = 0; a < 3; ++a) { ctx->h_state->box[a] = lo[a]; ctx->h_state->box[3 + a] = hi[a]; }   // kept across the memset below
   }
   const PairIndex &pt = ctx->pt, &psx = ctx->ps;
   CK(ctx->corr_p.ensure((size_t)std::max(n, 1) * sizeof(int32_t)));
@@ -854,7 +879,17 @@ static int align_prepare(mvr_ctx* ctx, const mvr_icp_params* prm, const float* g
 
   // initial state: the guess has been applied while binning the source; it is the start of `fin`
   IcpState& h = *ctx->h_state;
+  double sbox[6];
+  for (int a = 0; a < 6; ++a) sbox[a] = h.box[a];
   std::memset(&h, 0, sizeof(h));
+  // frame bookkeeping of the static source index: the box the guessed source was binned in (the pinned float transform
+  // rounds each coordinate by < 1e-3 of it), no drift yet
+  for (int a = 0; a < 3; ++a) {
+    const double pad = 1e-3 + 1e-5 * std::max(std::fabs(sbox[a]), std::fabs(sbox[3 + a]));
+    h.box[a] = sbox[a] - pad; h.box[3 + a] = sbox[3 + a] + pad;
+    h.babs[a] = std::max(std::fabs(h.box[a]), std::fabs(h.box[3 + a]));
+  }
+  h.devd = 0.0; h.dev = 0.0f;
   for (int k = 0; k < 16; ++k) { h.delta[k] = (k % 5 == 0) ? 1.f : 0.f; h.fin[k] = G[k]; h.cum[k] = (k % 5 == 0) ? 1.0 : 0.0; }
   for (int k = 0; k < 12; ++k) h.cinv[k] = (k % 5 == 0) ? 1.0 : 0.0;
   h.stretch = 1.0f;
@@ -877,10 +912,12 @@ static int align_prepare(mvr_ctx* ctx, const mvr_icp_params* prm, const float* g
 
   FwdArgs& fa = ctx->fa;
   fa = FwdArgs{};
-  fa.cur = psx.sorted.as<float4>(); fa.s0 = reciprocal ? psx.s0.as<float4>() : nullptr; fa.n_valid = psx.n_valid;
+  fa.cur = psx.sorted.as<float4>(); fa.n_valid = psx.n_valid;
   fa.tgt = pt.sorted.as<float4>(); fa.tstart = pt.start.as<uint32_t>(); fa.gt = pt.g; fa.m_valid = pt.n_valid;
   fa.corr_p = ctx->corr_p.as<int32_t>(); fa.rmin = reciprocal ? ctx->rmin.as<uint32_t>() : nullptr;
   fa.max2 = max_dist * max_dist; fa.max_d2f = gate_float(max_dist);
+  if ((rc = ensure_gate_mask(ctx, ctx->pt, fa.max_d2f))) return rc;
+  fa.gmask = ctx->pt.gm_gate >= 0.f ? ctx->pt.gmask.as<uint32_t>() : nullptr; fa.gm_stride = ctx->pt.gm_stride;
   fa.nrm = p2l ? ctx->normals.as<float4>() : nullptr;
   fa.partials = ctx->partials.as<double>(); fa.st = d_st; fa.log = d_log; fa.grid = fused_grid(psx.n_valid);
   RevArgs& ra = ctx->ra;
@@ -1121,7 +1158,7 @@ int mvr_pair_moments_compute_batch(mvr_ctx* const* ctxs, int count, double max_d
 }
 
 double mvr_debug_value(mvr_ctx* ctx, int k) {
-  if (!ctx || !ctx->h_state || k < 0 || k >= 4) return 0.0;
+  if (!ctx || !ctx->h_state || k < 0 || k >= 8) return 0.0;
   return (double)ctx->h_state->dbg[k];
 }
 

@@ -10,6 +10,9 @@
 // iteration: the host only enqueues iterations and reads the state back when a batch has run.
 #include "launch.h"
 #include "pair_search.cuh"
+#ifdef MVR_TS_TILE
+#include "tile_search.cuh"
+#endif
 #include "small_solve.h"
 
 // candidates evaluated per trip of the flat scan = independent 16-byte loads in flight per thread (measured: 8 > 4 > 2)
@@ -147,8 +150,41 @@ __device__ __forceinline__ void icp_advance_frame(IcpState* st, const double (&T
   const double eta = sqrt(eta2);
   // not a rigid motion any more (cannot happen with the estimators here): make every bound vacuous
   st->stretch = (eta < 0.5 && det > 0) ? (float)(1.0 / sqrt(1.0 - eta)) * 1.000001f + 1.0e-7f : 1.0e6f;
-  st->dev_bits = 0u;
   st->n_gate = 0u;
+
+  // How far the chain of in-place float transforms can have drifted from cum * (binning-time position) once the
+  // pending increment Td has been applied (k_icp_forward does that at the start of the next iteration):
+  //   cur' = fl(Td cur) = Td cur + e,  cum' = Td cum   =>   cur' - cum' s0 = A_Td (cur - cum s0) + e,
+  // so dev' <= ||A_Td||_2 dev + |e|.  One pinned transform rounds every term at most four times (xform_pinned: product,
+  // three sums), so per axis |e_r| <= 4.1 u (sum_j |Td_rj| B_j + |Td_r3|) with u = 2^-24 and B_j >= |coordinate j| of
+  // every point before the step; ||A_Td||_2 <= sqrt(1 + ||A_Td^T A_Td - I||_F).
+  const double u4 = 4.1 * 5.9604644775390625e-8;
+  double e2 = 0, etaT2 = 0;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const double er = u4 * (fabs(Td[r]) * st->babs[0] + fabs(Td[4 + r]) * st->babs[1] + fabs(Td[8 + r]) * st->babs[2] + fabs(Td[12 + r])) + 1.0e-30;
+    e2 += er * er;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double g = Td[i * 4 + 0] * Td[j * 4 + 0] + Td[i * 4 + 1] * Td[j * 4 + 1] + Td[i * 4 + 2] * Td[j * 4 + 2] - ((i == j) ? 1.0 : 0.0);
+      etaT2 += g * g;
+    }
+  const double devn = st->devd * sqrt(1.0 + sqrt(etaT2)) * (1.0 + 1.0e-9) + sqrt(e2) * (1.0 + 1.0e-9);
+  st->devd = devn;
+  st->dev = __double2float_ru(devn) * 1.000001f;
+  // the moved cloud lies in cum' * (binning box) widened by dev'
+  double bn[3] = {0, 0, 0};
+#pragma unroll
+  for (int c8 = 0; c8 < 8; ++c8) {
+    const double px = st->box[(c8 & 1) ? 3 : 0], py = st->box[(c8 & 2) ? 4 : 1], pz = st->box[(c8 & 4) ? 5 : 2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) bn[r] = fmax(bn[r], fabs(C[r] * px + C[4 + r] * py + C[8 + r] * pz + C[12 + r]));
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) st->babs[r] = (bn[r] + devn) * (1.0 + 1.0e-6) + 1.0e-3;
 }
 
 // The tail of one ICP iteration, run by one thread: estimate the increment from the sums, compose it
@@ -314,8 +350,31 @@ __device__ __forceinline__ void acc_pair(double (&v)[NV], float4 s, float4 t, co
 }
 
 // Phase A of both kernels is the search (registers: the query, the running best, grid geometry); phase B
-// re-reads the matches the block found and accumulates the estimator sums (registers: 18-30 doubles).  The
-// two never overlap, so the kernel's register budget is the larger of the two, not their sum.
+// re-reads the matches and accumulates the estimator sums (registers: 18-30 doubles).  The two never overlap, so a
+// kernel's register budget is the larger of the two, not their sum.
+// The seed of source point i: last iteration's neighbour is a real candidate and usually still the answer.
+__device__ __forceinline__ void fwd_seed(const FwdArgs& a, int i, const float4 p, NnBest& b) {
+  b = NnBest{MVR_INF, 0x7fffffff, -1};
+  const int j0 = a.corr_p[i];
+  if (j0 >= 0) {
+    const float4 t = __ldg(a.tgt + j0);
+    b.d2 = d2_pinned(p.x, p.y, p.z, t.x, t.y, t.z); b.idx = __float_as_int(t.w); b.pos = j0;
+  }
+}
+
+template <bool RECIP>
+__device__ __forceinline__ void fwd_commit(const FwdArgs& a, int i, const NnBest& b, unsigned int& ngate) {
+  const bool keep = b.pos >= 0 && !((double)b.d2 > a.max2);   // PCL: if (distance > max_dist_sqr) continue;
+  a.corr_p[i] = keep ? b.pos : -1;
+  if (keep) {
+    ++ngate;
+    if (RECIP) atomicMin(a.rmin + b.pos, __float_as_uint(b.d2));
+  }
+}
+
+#ifdef MVR_TS_TILE
+#include "icp_tile.cuh"
+#else
 template <bool RECIP, int EST>
 __global__ void __launch_bounds__(FUSED_THREADS, (RECIP ? MVR_FWD_MINBLOCKS : MVR_FWD1_MINBLOCKS) * (256 / FUSED_THREADS)) k_icp_forward(const __grid_constant__ FwdBatch batch, int first) {
   // this pair's arguments: parameter space -> shared memory (a dynamically indexed parameter would be copied to
@@ -336,7 +395,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, (RECIP ? MVR_FWD_MINBLOCKS : MV
 #pragma unroll
     for (int k = 0; k < 16; ++k) M.m[k] = st->delta[k];
   }
-  float devmax = 0.0f;
   unsigned int ngate = 0;
   for (int i = blockIdx.x * FUSED_THREADS + threadIdx.x; i < a.n_valid; i += stride) {
     float4 p = a.cur[i];
@@ -346,37 +404,22 @@ __global__ void __launch_bounds__(FUSED_THREADS, (RECIP ? MVR_FWD_MINBLOCKS : MV
       p.w = w;
       a.cur[i] = p;
     }
-    if (RECIP) {
-      // how far the float chain of in-place transforms has drifted from cum * (binning-time position)
-      const float4 s = __ldg(a.s0 + i);
-      const double ex = st->cum[0] * s.x + st->cum[4] * s.y + st->cum[8] * s.z + st->cum[12] - (double)p.x;
-      const double ey = st->cum[1] * s.x + st->cum[5] * s.y + st->cum[9] * s.z + st->cum[13] - (double)p.y;
-      const double ez = st->cum[2] * s.x + st->cum[6] * s.y + st->cum[10] * s.z + st->cum[14] - (double)p.z;
-      devmax = fmaxf(devmax, __double2float_ru(ex * ex + ey * ey + ez * ez));   // squared; one float sqrt per thread below
-    }
-    NnBest b{MVR_INF, 0x7fffffff, -1};
-    const int j0 = a.corr_p[i];
-    if (j0 >= 0) {   // seed: last iteration's neighbour is a real candidate and usually still the answer
-      const float4 t = __ldg(a.tgt + j0);
-      b.d2 = d2_pinned(p.x, p.y, p.z, t.x, t.y, t.z); b.idx = __float_as_int(t.w); b.pos = j0;
+    NnBest b;
+    fwd_seed(a, i, p, b);
+    // no partner inside the gate so far: one bit says whether the target has anything within the gate of p's cell
+    if (a.gmask && !(b.d2 <= a.max_d2f)) {
+      const int cx = pg_cell(grid_t(p.x, a.gt.ox, a.gt.inv_cell), a.gt.nx), cy = pg_cell(grid_t(p.y, a.gt.oy, a.gt.inv_cell), a.gt.ny),
+                cz = pg_cell(grid_t(p.z, a.gt.oz, a.gt.inv_cell), a.gt.nz);
+      const uint32_t wd = __ldg(a.gmask + ((size_t)cz * a.gt.ny + cy) * a.gm_stride + (cx >> 5));
+      if (!((wd >> (cx & 31)) & 1u)) { a.corr_p[i] = -1; continue; }
     }
     pg_search<MVR_PG_UNROLL>(a.gt, a.tstart, a.tgt, a.m_valid, p.x, p.y, p.z, p.x, p.y, p.z, 0.0f, 1.0f, a.max_d2f, b, seg);
-    const bool keep = b.pos >= 0 && !((double)b.d2 > a.max2);   // PCL: if (distance > max_dist_sqr) continue;
-    a.corr_p[i] = keep ? b.pos : -1;
-    if (keep) {
-      ++ngate;
-      if (RECIP) atomicMin(a.rmin + b.pos, __float_as_uint(b.d2));
-    }
+    fwd_commit<RECIP>(a, i, b, ngate);
   }
   if (RECIP) {
     // warp-level: no block barrier, a warp that is done is done
-    devmax = sqrtf(devmax) * 1.000001f;   // a double sqrt per point costs ~70 instructions; the maximum of the squares needs one
-    const unsigned int wd = __reduce_max_sync(0xffffffffu, __float_as_uint(devmax));   // non-negative floats order like their bits
     const unsigned int wg = __reduce_add_sync(0xffffffffu, ngate);
-    if ((threadIdx.x & 31) == 0) {
-      if (wd) atomicMax(&st->dev_bits, wd);
-      if (wg) atomicAdd(&st->n_gate, wg);
-    }
+    if ((threadIdx.x & 31) == 0 && wg) atomicAdd(&st->n_gate, wg);
   } else {
     // phase B: every thread revisits exactly the points it searched (its own writes, no barrier needed)
     const double ox = st->ox, oy = st->oy, oz = st->oz;
@@ -399,7 +442,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, (RECIP ? MVR_FWD_MINBLOCKS : MV
 // of its `per` chunks of 256 target points (in order, deterministic) into a list in shared memory, every thread then
 // searches its entries of the list, and sums over its own mutual pairs afterwards (phase B needs no barrier: a thread
 // revisits exactly the entries it searched, so a warp that is done does not wait for the slowest one of the block).
-constexpr int REV_MAX_CHUNKS = 4;
+#ifndef MVR_REV_MAX_CHUNKS
+#define MVR_REV_MAX_CHUNKS 4
+#endif
+constexpr int REV_MAX_CHUNKS = MVR_REV_MAX_CHUNKS;
 template <int EST>
 __global__ void __launch_bounds__(FUSED_THREADS, MVR_REV_MINBLOCKS * (256 / FUSED_THREADS)) k_icp_reverse(const __grid_constant__ RevBatch batch) {
   __shared__ RevArgs s_args;
@@ -412,7 +458,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, MVR_REV_MINBLOCKS * (256 / FUSE
   if (st->done) return;
   __shared__ uint2 s_seg[PG_SEGS * PG_STRIDE];
   __shared__ int s_q[REV_MAX_CHUNKS * FUSED_THREADS];   // the block's chosen target points (sorted positions), in order
-  __shared__ int s_p[REV_MAX_CHUNKS * FUSED_THREADS];   // their mutual partner (sorted source position), -1 none
+  __shared__ int s_p[REV_MAX_CHUNKS * FUSED_THREADS];   // in: bits of the nearest chooser's d2; out: the mutual partner (sorted source position), -1 none
   __shared__ int s_wcnt[FUSED_WARPS];
   uint2* seg = s_seg + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -424,26 +470,29 @@ __global__ void __launch_bounds__(FUSED_THREADS, MVR_REV_MINBLOCKS * (256 / FUSE
     const int c = blockIdx.x * a.per + cc;
     if (c >= chunks) break;
     const int j = c * FUSED_THREADS + threadIdx.x;
-    const bool chosen = j < a.m_valid && a.rmin[j] != 0x7f800000u;
+    uint32_t r = 0x7f800000u;
+    if (j < a.m_valid) {
+      r = a.rmin[j];
+      if (r != 0x7f800000u) a.rmin[j] = 0x7f800000u;   // re-armed for the next iteration
+    }
+    const bool chosen = r != 0x7f800000u;
     const unsigned int bal = __ballot_sync(0xffffffffu, chosen);
     if (lane == 0) s_wcnt[warp] = __popc(bal);
     __syncthreads();
     int ofs = qn, tot = 0;
 #pragma unroll
     for (int w = 0; w < FUSED_WARPS; ++w) { const int n = s_wcnt[w]; if (w < warp) ofs += n; tot += n; }
-    if (chosen) s_q[ofs + __popc(bal & ((1u << lane) - 1u))] = j;
+    if (chosen) { const int k = ofs + __popc(bal & ((1u << lane) - 1u)); s_q[k] = j; s_p[k] = (int)r; }
     qn += tot;
     __syncthreads();
   }
 
   // ---- phase A: the searches
   const float stretch = st->stretch;
-  const float dev0 = __uint_as_float(st->dev_bits) * 1.000001f;
+  const float dev0 = st->dev;
   unsigned int missed = 0;
   for (int k = threadIdx.x; k < qn; k += FUSED_THREADS) {
     const int j = s_q[k];
-    const uint32_t r = a.rmin[j];
-    a.rmin[j] = 0x7f800000u;          // re-armed for the next iteration
     const float4 t = __ldg(a.tgt + j);
     // the query in the frame the source was binned in
     const float ux = (float)(st->cinv[0] * t.x + st->cinv[1] * t.y + st->cinv[2] * t.z + st->cinv[3]);
@@ -451,7 +500,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, MVR_REV_MINBLOCKS * (256 / FUSE
     const float uz = (float)(st->cinv[8] * t.x + st->cinv[9] * t.y + st->cinv[10] * t.z + st->cinv[11]);
     const float dev = dev0 + 1.0e-6f * fmaxf(fabsf(ux), fmaxf(fabsf(uy), fabsf(uz)));
     // a chooser sits at exactly this distance: the lexicographic minimum (d2, index) over all source points is found
-    NnBest b{__uint_as_float(r), 0x7fffffff, -1};
+    NnBest b{__uint_as_float((uint32_t)s_p[k]), 0x7fffffff, -1};
     pg_search<MVR_PG_UNROLL>(a.gs, a.sstart, a.cur, a.n_valid, t.x, t.y, t.z, ux, uy, uz, dev, stretch, MVR_INF, b, seg);
     if (b.pos < 0) ++missed;
     const int mutual = (b.pos >= 0 && __ldg(a.corr_p + b.pos) == j) ? b.pos : -1;   // or the nearest source point chose another target
@@ -475,6 +524,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, MVR_REV_MINBLOCKS * (256 / FUSE
   }
   reduce_and_finish<NV>(v, a.partials, st, a.log, a.grid);
 }
+#endif   // MVR_TS_TILE
 
 // Chunks of 256 target points per block of the reverse half: enough for its compacted list to fill whole rounds of
 // 256 searches (about half of the target points are chosen).  Measured on B200 (same box; 24 x 200k pairs per launch /
@@ -485,7 +535,12 @@ int fused_rev_chunks(int items) {
 #ifdef MVR_REV_CHUNKS
   return MVR_REV_CHUNKS;
 #else
+#ifdef MVR_TS_TILE
+  (void)items;
+  return 2;   // about half of the target points are chosen: two chunks fill one tile of 256 searches
+#else
   return items >= 400000 ? 4 : 3;
+#endif
 #endif
 }
 int fused_grid_rev(int items) {

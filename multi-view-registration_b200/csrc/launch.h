@@ -80,13 +80,19 @@ struct IcpState {
   int iter, done, reason, status, n_corr;
   int max_iter, fixed, min_corr, p2l, recip, n_src;
   unsigned int ticket;    // blocks of the running reduction that have finished
-  long long dbg[4];       // diagnostics: [0] clock cycles spent in the serial solve, [1] solves, [2] reciprocal searches that lost their chooser (must be 0)
+  long long dbg[8];       // diagnostics: [0] clock cycles spent in the serial solve, [1] solves, [2] reciprocal searches that lost their chooser (must be 0),
+                          // [3] forward queries answered by the per-thread fallback, [4] forward rounds whose tile did not fit,
+                          // [5] / [6] the same for the reciprocal half, [7] forward queries settled by the gate mask
   // frame bookkeeping of the static source index (pair_index.cu / pair_search.cuh)
   double cum[16];         // increments applied since the source was binned, incl. the pending `delta`, column-major
   double cinv[12];        // its affine inverse, rows {A^-1 | -A^-1 b}
   float stretch;          // >= ||A^-1||_2
-  unsigned int dev_bits;  // float bits of max |cur - cum * s0| over the source points, measured by k_icp_forward
+  float dev;              // >= |cur - cum * s0| for every source point (s0 = its binning-time position): a bound on the rounding
+                          // of the chain of in-place float transforms, advanced analytically by the solve (icp_advance_frame)
   unsigned int n_gate;    // forward matches that passed the gate in the running iteration
+  double devd;            // the same bound in double
+  double box[6];          // box (lo xyz, hi xyz) that held the source when it was binned
+  double babs[3];         // >= |coordinate| per axis of every CURRENT source point
 };
 
 // ---- fused iteration (icp.cu) + per-align index (pair_index.cu) ---------------------------------
@@ -105,13 +111,14 @@ cudaError_t launch_pair_count(const float4* in, int n, const Mat4f* guess, PairG
 cudaError_t launch_pair_scatter(const float4* in, int n, const Mat4f* guess, const uint32_t* keys, const uint32_t* rank, const uint32_t* start,
                                 float4* tmp, cudaStream_t s);
 cudaError_t launch_fill_u32(uint32_t* p, size_t n, uint32_t v, cudaStream_t s);
+// Gate mask of an index (pair_index.cu): occ and mask hold ny * nz * wstride words, wstride = ceil(nx / 32); D = dilation in cells.
+cudaError_t launch_gate_mask(const uint32_t* start, PairGrid g, int wstride, int D, uint32_t* occ, uint32_t* mask, cudaStream_t s);
 // sorted[k] = {moved point, bits(original index)}; copy (nullable) gets the same.
 cudaError_t launch_pair_rerank(const float4* tmp, int n, const uint32_t* keys, const uint32_t* start, float4* sorted, float4* copy,
                                cudaStream_t s);
 
 struct FwdArgs {
   float4* cur;             // source, sorted by binning cell, current coordinates (updated in place), .w = original index
-  const float4* s0;        // the same points at binning time (reciprocal only)
   int n_valid;             // finite source points = sorted positions [0, n_valid)
   const float4* tgt;       // target, sorted by cell
   const uint32_t* tstart;
@@ -121,6 +128,8 @@ struct FwdArgs {
   uint32_t* rmin;          // [target sorted position] min d2 bits over its choosers (reciprocal only; +inf bits on entry)
   double max2;             // gate, exact (PCL compares in double)
   float max_d2f;           // gate rounded up to float: bounds the search
+  const uint32_t* gmask;   // nullable: gate mask of the target grid, bit x of word [(z * ny + y) * gm_stride + x / 32] =
+  int gm_stride;           //   "some target point lies within the gate of cell (x, y, z)" (pair_index.cu)
   const float4* nrm;       // target normals by ORIGINAL index (point-to-plane only)
   double* partials;        // max(grid of the forward half, grid of the reverse half) x REDUCE_MAX_VALS
   IcpState* st;

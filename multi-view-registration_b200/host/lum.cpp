@@ -10,7 +10,9 @@
 //
 // refineAxisFromPoses: Registrator::refineAxis (mvr/src/registrator.cpp:402-455) with math_solvers::least_squares
 // (mvr/src/math_solvers.cpp:24-39; LAPACK dgels there, Householder QR here).
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "registrator.h"
@@ -140,12 +142,14 @@ void se3_adjoint(const Matrix4d& T, double* Ad) {
     }
 }
 
-// Dense SPD solve (Cholesky), A row-major n x n, overwritten.
-bool chol_solve(std::vector<double>& A, std::vector<double>& b, int n) {
+// SPD solve (Cholesky), A row-major n x n, overwritten.  band: A(i, j) = 0 for |i - j| > band (n - 1 for a dense matrix);
+// the factor of a banded matrix keeps the band, so a chain-structured system costs O(n band^2) instead of O(n^3).
+bool chol_solve(std::vector<double>& A, std::vector<double>& b, int n, int band) {
+  if (band < 0 || band > n - 1) band = n - 1;
   for (int i = 0; i < n; ++i)
-    for (int j = 0; j <= i; ++j) {
+    for (int j = std::max(0, i - band); j <= i; ++j) {
       double s = A[(size_t)i * n + j];
-      for (int k = 0; k < j; ++k) s -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
+      for (int k = std::max(0, i - band); k < j; ++k) s -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
       if (i == j) {
         if (!(s > 0)) return false;
         A[(size_t)i * n + i] = std::sqrt(s);
@@ -155,12 +159,12 @@ bool chol_solve(std::vector<double>& A, std::vector<double>& b, int n) {
     }
   for (int i = 0; i < n; ++i) {
     double s = b[(size_t)i];
-    for (int k = 0; k < i; ++k) s -= A[(size_t)i * n + k] * b[(size_t)k];
+    for (int k = std::max(0, i - band); k < i; ++k) s -= A[(size_t)i * n + k] * b[(size_t)k];
     b[(size_t)i] = s / A[(size_t)i * n + i];
   }
   for (int i = n - 1; i >= 0; --i) {
     double s = b[(size_t)i];
-    for (int k = i + 1; k < n; ++k) s -= A[(size_t)k * n + i] * b[(size_t)k];
+    for (int k = i + 1; k <= std::min(n - 1, i + band); ++k) s -= A[(size_t)k * n + i] * b[(size_t)k];
     b[(size_t)i] = s / A[(size_t)i * n + i];
   }
   return true;
@@ -198,8 +202,13 @@ int ringClose(const std::vector<Matrix4d>& rel_in, const std::vector<double>& we
   for (double w : weight) wmax = std::fmax(wmax, w);
   if (!(wmax > 0)) return MVR_OK;
   const int n = 6 * (V - 1);
+  // With vertex 0 fixed the ring's unknowns 1 .. V-1 form a CHAIN (the edges 0 -> 1 and V-1 -> 0 touch one unknown
+  // each): the normal equations are block tridiagonal with 6 x 6 blocks, half bandwidth 11.
+  const int band = 11;
+  std::vector<double> H((size_t)n * n, 0.0), g((size_t)n, 0.0), Hd, gd;
   for (int it = 0; it < iterations; ++it) {
-    std::vector<double> H((size_t)n * n, 0.0), g((size_t)n, 0.0);
+    std::fill(H.begin(), H.end(), 0.0);
+    std::fill(g.begin(), g.end(), 0.0);
     double cost = 0;
     for (int p = 0; p < V; ++p) {
       const double w = weight[(size_t)p] / wmax;
@@ -249,9 +258,9 @@ int ringClose(const std::vector<Matrix4d>& rel_in, const std::vector<double>& we
     if (!(dmax > 0) || !std::isfinite(dmax)) break;
     bool solved = false;
     for (double lambda = 1e-12 * dmax; lambda <= 1e3 * dmax; lambda *= 1e3) {
-      std::vector<double> Hd(H), gd(g);
+      Hd = H; gd = g;
       for (int i = 0; i < n; ++i) Hd[(size_t)i * n + i] += lambda;
-      if (chol_solve(Hd, gd, n)) { g.swap(gd); solved = true; break; }
+      if (chol_solve(Hd, gd, n, band)) { g.swap(gd); solved = true; break; }
     }
     if (!solved) return MVR_ERR_NOT_SPD;
     double step = 0;
@@ -417,6 +426,10 @@ int lumRelax(const std::vector<mvr_pair_moments>& edges_in, const int* src, cons
   Matrix4d S = identity4d(), Si = identity4d();
   for (int k = 0; k < 3; ++k) { S.m[12 + k] = origin[k]; Si.m[12 + k] = -origin[k]; }
   const int n = 6 * (V - 1);
+  // half bandwidth of the normal equations: vertex 0 carries no unknowns, so a ring is a chain (block tridiagonal)
+  int band = 5;
+  for (size_t e = 0; e < es.size(); ++e)
+    if (es[e] > 0 && et[e] > 0) band = std::max(band, 6 * std::abs(es[e] - et[e]) + 5);
   std::vector<mvr_pair_moments> cur;
   double cost = graph_cost(base, es.data(), et.data(), X, origin, &cur);
   double lambda = 0.0;
@@ -448,7 +461,7 @@ int lumRelax(const std::vector<mvr_pair_moments>& edges_in, const int* src, cons
     for (int attempt = 0; attempt < 12 && !accepted; ++attempt) {
       std::vector<double> Hd(H), x(g);
       for (int i = 0; i < n; ++i) { Hd[(size_t)i * n + i] += lambda * std::fmax(H[(size_t)i * n + i], 1e-12 * dmax) + 1e-14 * dmax; x[(size_t)i] = -x[(size_t)i]; }
-      if (!chol_solve(Hd, x, n)) { lambda = lambda > 0 ? lambda * 10.0 : 1e-6; continue; }
+      if (!chol_solve(Hd, x, n, band)) { lambda = lambda > 0 ? lambda * 10.0 : 1e-6; continue; }
       std::vector<Matrix4d> Xn(X);
       step = 0;
       for (int v = 1; v < V; ++v) {
