@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-pairs", type=int, default=2, help="pairs the cpu_baseline leg aligns (0 = skip)")
     ap.add_argument("--cpu-reps", type=int, default=3, help="repetitions of the CPU sample (the minimum is reported)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--single-process", action="store_true",
+                    help="N GPUs from ONE process through mvr_register_turntable_multi (one host thread per GPU, ncclAllGather inside the "
+                         "C ABI); the default for --gpus N > 1 when not launched by torchrun")
     ap.add_argument("--streams", type=int, default=1, help="GPU contexts created up front (the driver grows the pool to one per pair)")
     return ap.parse_args()
 
@@ -472,10 +475,87 @@ def run_native(a):
         dist.destroy_process_group()
 
 
+def run_single_process(a):
+    """--gpus N from one process: the multi-GPU entry point of the C ABI (what a C++ caller such as the reference, itself one
+    process, would use).  Same workload, same JSON line; timing = host clock around the call (it returns after the exchange
+    and the host loop closure), device time per GPU from CUDA events inside the library."""
+    import torch
+    import mvr_b200
+    import mvr_b200.synth as synth
+    import mvr_b200.ring as ring
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback")
+    G = a.gpus
+    if torch.cuda.device_count() < G:
+        raise SystemExit("bench.py: %d GPUs requested, %d visible" % (G, torch.cuda.device_count()))
+    V, n = a.views, a.points
+    views, poses = synth.turntable_sequence(V, n)
+    init = view_init_poses(a, poses)
+    hv = [torch.from_numpy(p).pin_memory() for p in views]
+    host_list = [t.numpy() for t in hv]
+    icp = mvr_b200.default_params(max_iterations=a.iters, max_dist=a.max_dist, reciprocal=a.reciprocal, fixed_iterations=1)
+    tp = mvr_b200.turntable_params(pivot=synth.PIVOT, axis=synth.AXIS, icp=icp, repeat_times=1, mode=mvr_b200.RING_PAIRS,
+                                   loop_closure=1, lum_iterations=16)
+    m = mvr_b200.MultiRegistrator(range(G))
+    m.upload(host_list, init)
+    flush = [torch.empty(256 << 20, dtype=torch.uint8, device="cuda:%d" % g) for g in range(G)]
+
+    def sync_all():
+        for g in range(G):
+            torch.cuda.synchronize(g)
+
+    def timed(resident, steps):
+        tot, dev_ms, q, last = 0.0, 0.0, 0, None
+        for _ in range(steps):
+            for f in flush:
+                f.fill_(1)
+            sync_all()
+            t0 = time.perf_counter()
+            got, reps, recs, ms = m.register_turntable(host_list, tp, init_poses=init, use_resident=resident)
+            tot += (time.perf_counter() - t0) * 1e3
+            dev_ms += float(ms.max())
+            q += sum(r["nn_queries"] for r in reps)
+            last = (got, reps, recs)
+        return tot, dev_ms, q, last
+
+    sampler = ClockSampler(0)
+    for _ in range(a.warmup):
+        m.register_turntable(host_list, tp, init_poses=init, use_resident=True)
+    l0 = mvr_b200.kernel_launch_count()
+    w0 = time.time()
+    ms, dms, q, last = timed(True, a.steps)
+    w1 = time.time()
+    launches = mvr_b200.kernel_launch_count() - l0
+    clocks = sampler.stop(w0, w1)
+    e2e = None
+    if not a.no_e2e:
+        for _ in range(max(1, min(a.warmup, 2))):
+            m.register_turntable(host_list, tp, init_poses=init, use_resident=False)
+        ms_e, _, q_e, _ = timed(False, a.steps)
+        state_b, log_b = mvr_b200.icp_state_bytes(), mvr_b200.icp_log_record_bytes()
+        nviews = sum(len(ring.views_needed(*ring.pair_range(r, G, V), V)) for r in range(G))
+        e2e = {"value": q_e / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e / a.steps,
+               "h2d_bytes_per_step": int(nviews * n * 16 + V * state_b + V * ring.REC),
+               "d2h_bytes_per_step": int(V * (state_b + log_b * a.iters) + nviews * 28 + G * V * ring.REC)}
+    got, reps, recs = last
+    out = {
+        "metric": METRIC, "value": q / (ms * 1e-3), "unit": UNIT, "n_gpus": G, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, G), "registration_ms": ms / a.steps, "device_ms_max_per_step": dms / a.steps, "e2e": e2e,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": None, "cpu_baseline": None,
+        "pose_checksum": ring.pose_checksum(recs), "pairs_per_launch": min(24, -(-V // G)),
+        "launch": "single process: mvr_register_turntable_multi (one host thread per GPU, ncclAllGather of the pair records inside the C ABI)",
+    }
+    print(json.dumps(out))
+    m.close()
+
+
 def main():
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.single_process or (a.gpus > 1 and "WORLD_SIZE" not in os.environ):
+        run_single_process(a)
     else:
         run_native(a)
 

@@ -36,7 +36,8 @@ typedef enum {
   MVR_ERR_CUDA = 3,
   MVR_ERR_NO_INPUT = 4,                /* target/source not set */
   MVR_ERR_NOT_SPD = 5,                 /* point-to-plane normal equations not positive definite */
-  MVR_ERR_ALLOC = 6
+  MVR_ERR_ALLOC = 6,
+  MVR_ERR_NCCL = 7                     /* NCCL missing or a collective failed (multi-GPU entry points) */
 } mvr_status;
 
 typedef enum { MVR_CLOUD_TARGET = 0, MVR_CLOUD_SOURCE = 1 } mvr_cloud;
@@ -293,6 +294,42 @@ int mvr_pairwise_align(mvr_registrator* r, const mvr_view* source, const mvr_vie
  * gather).  reports: one per pair (ring: V entries indexed by pair; accumulate: V-1 entries, views 1..V-1). */
 int mvr_register_turntable(mvr_registrator* r, const mvr_view* views, int n_views, const mvr_turntable_params* prm,
                            float* poses, mvr_pair_report* reports);
+/* -- the same entry point over several GPUs of one node ----------------------------------------------------------
+ * The reference is one process (its registration runs on one pool thread, mvr/src/registrator.cpp:606, 696); what shards
+ * is the ring of neighbour pairs (the edges of :640-651 / :482-487).  One call, inside: one host thread per GPU aligns a
+ * contiguous block of the ring's pairs on its GPU (it uploads only the views it needs; point data never crosses GPUs),
+ * the ranks exchange their pair records with ONE ncclAllGather (96 bytes per pair, NVLink), the ring is closed on the
+ * host.  Results do not depend on the number of GPUs (same pair poses, bit for bit).  NCCL is bound at run time
+ * (libnccl.so.2; override with the environment variable MVR_NCCL_LIB): MVR_ERR_NCCL if it is missing or fails. */
+typedef struct mvr_multi mvr_multi;
+/* What a rank contributes to the exchange, one per pair (no padding: 96 bytes). */
+typedef struct {
+  float pose[16];          /* relative pose source -> target frame, column-major */
+  int32_t n_correspondences, iterations, status, reserved;
+  double mse;
+  uint64_t nn_queries;
+} mvr_pair_record;
+/* devices: n_devices distinct CUDA device ordinals (NULL: 0 .. n_devices - 1).  Creates one registrator per GPU and,
+ * for n_devices > 1, the NCCL communicators (ncclCommInitAll). */
+int mvr_multi_create(const int* devices, int n_devices, mvr_multi** out);
+int mvr_multi_destroy(mvr_multi* m);
+const char* mvr_multi_last_error(mvr_multi* m);
+int mvr_multi_devices(mvr_multi* m);
+/* The GPU contexts of rank `rank` (owned by the handle): profiling switches and kernel statistics. */
+int mvr_multi_contexts(mvr_multi* m, int rank);
+mvr_ctx* mvr_multi_context(mvr_multi* m, int rank, int slot);
+/* The block of ring pairs rank `rank` of `n_ranks` aligns: [begin, end) = [rank * n / n_ranks, (rank + 1) * n / n_ranks). */
+void mvr_multi_pair_range(int rank, int n_ranks, int n_pairs, int* pair_begin, int* pair_end);
+/* Make the (host) views resident: every GPU gets a copy of the views its block of pairs needs.  Later calls with
+ * use_resident = 1 align those copies and skip the host-to-device transfer. */
+int mvr_multi_upload(mvr_multi* m, const mvr_view* views, int n_views);
+/* views: n_views host views (init_pose as for mvr_register_turntable); prm->mode must be MVR_REGISTER_RING_PAIRS,
+ * pair_begin / pair_end are ignored.  poses: n_views x float[16] absolute poses after the loop closure; reports
+ * (nullable): n_views pair reports; records (nullable): the n_views gathered pair records as exchanged; device_ms
+ * (nullable): per GPU, the device time of its part including the exchange (CUDA events). */
+int mvr_register_turntable_multi(mvr_multi* m, const mvr_view* views, int n_views, const mvr_turntable_params* prm, int use_resident,
+                                 float* poses, mvr_pair_report* reports, mvr_pair_record* records, double* device_ms);
+
 /* Registrator::computeError (mvr/src/registrator.cpp:466-515): reciprocal correspondences (gate max_distance) between
  * neighbouring registered views (i, i + 1) and (V - 1, 0), each view posed by its init_pose first (getTransformedPoints).
  * Pair k: counts[k] correspondences with mean squared distance mean_d2[k]; arrays hold n_views entries. */

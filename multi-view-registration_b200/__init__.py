@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("MVR_B200_LIB") or os.path.join(_HERE, "libmvr_b200.so
 
 K_NAMES = ["morton", "sort", "table", "nn", "corr", "reduce", "transform", "normals"]
 K_COUNT = 8
-(OK, ERR_BAD_ARG, ERR_TOO_FEW, ERR_CUDA, ERR_NO_INPUT, ERR_NOT_SPD, ERR_ALLOC) = range(7)
+(OK, ERR_BAD_ARG, ERR_TOO_FEW, ERR_CUDA, ERR_NO_INPUT, ERR_NOT_SPD, ERR_ALLOC, ERR_NCCL) = range(8)
 TARGET, SOURCE = 0, 1
 POINT_TO_POINT, POINT_TO_PLANE = 0, 1
 
@@ -112,6 +112,12 @@ class ViewDesc(C.Structure):
     _fields_ = [("xyzw", C.c_void_p), ("n", C.c_size_t), ("on_device", C.c_int), ("init_pose", C.POINTER(C.c_double))]
 
 
+class PairRecord(C.Structure):
+    """mvr_pair_record: what a rank contributes to the all-gather (96 bytes)."""
+    _fields_ = [("pose", C.c_float * 16), ("n_correspondences", C.c_int32), ("iterations", C.c_int32), ("status", C.c_int32),
+                ("reserved", C.c_int32), ("mse", C.c_double), ("nn_queries", C.c_uint64)]
+
+
 class PairReport(C.Structure):
     _fields_ = [
         ("source_view", C.c_int),
@@ -191,6 +197,19 @@ def lib():
     L.mvr_registrator_streams.argtypes = [vp]
     L.mvr_pairwise_align.argtypes = [vp, C.POINTER(ViewDesc), C.POINTER(ViewDesc), C.POINTER(IcpParams), fp, fp, C.POINTER(IcpReport)]
     L.mvr_register_turntable.argtypes = [vp, C.POINTER(ViewDesc), C.c_int, C.POINTER(TurntableParams), fp, C.POINTER(PairReport)]
+    L.mvr_multi_create.argtypes = [ip, C.c_int, C.POINTER(vp)]
+    L.mvr_multi_destroy.argtypes = [vp]
+    L.mvr_multi_last_error.argtypes = [vp]
+    L.mvr_multi_last_error.restype = C.c_char_p
+    L.mvr_multi_devices.argtypes = [vp]
+    L.mvr_multi_contexts.argtypes = [vp, C.c_int]
+    L.mvr_multi_context.argtypes = [vp, C.c_int, C.c_int]
+    L.mvr_multi_context.restype = vp
+    L.mvr_multi_pair_range.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.mvr_multi_pair_range.restype = None
+    L.mvr_multi_upload.argtypes = [vp, C.POINTER(ViewDesc), C.c_int]
+    L.mvr_register_turntable_multi.argtypes = [vp, C.POINTER(ViewDesc), C.c_int, C.POINTER(TurntableParams), C.c_int, fp, C.POINTER(PairReport),
+                                               C.POINTER(PairRecord), dp]
     L.mvr_compute_error.argtypes = [vp, C.POINTER(ViewDesc), C.c_int, C.c_double, C.POINTER(C.c_size_t), dp, C.POINTER(C.c_int)]
     L.mvr_ring_close.argtypes = [fp, dp, C.c_int, C.c_int, C.c_int, dp, C.c_double, fp]
     L.mvr_get_bbox.argtypes = [vp, C.c_int, fp, fp]
@@ -686,3 +705,56 @@ class Registrator:
                         gpu_ms=reps[k].gpu_ms, nn_queries=int(reps[k].nn_queries), pose=pose_to_numpy(reps[k].pose[:]))
                    for k in range(n_rep)]
         return [pose_to_numpy(poses[k]) for k in range(V)], reports
+
+
+class MultiRegistrator:
+    """mvr_multi: the multi-view-register entry point over several GPUs of one node, inside the C ABI (one host thread per
+    GPU, one ncclAllGather of the pair records, host loop closure)."""
+
+    def __init__(self, devices):
+        devs = np.ascontiguousarray(np.asarray(list(devices), dtype=np.int32))
+        self._h = C.c_void_p()
+        rc = lib().mvr_multi_create(_ip(devs), len(devs), C.byref(self._h))
+        if rc != OK:
+            raise MvrError(rc, "mvr_multi_create failed (%s)" % lib().mvr_status_string(rc).decode())
+        self.n = len(devs)
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().mvr_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != OK:
+            raise MvrError(rc, (lib().mvr_multi_last_error(self._h) or b"").decode())
+
+    def contexts(self, rank):
+        """The (borrowed) Contexts of one rank."""
+        return [Context(_borrowed=lib().mvr_multi_context(self._h, int(rank), k)) for k in range(int(lib().mvr_multi_contexts(self._h, int(rank))))]
+
+    def upload(self, views, init_poses=None):
+        arr, keep = Registrator._views(views, init_poses)
+        self._ck(lib().mvr_multi_upload(self._h, arr, len(views)))
+
+    def register_turntable(self, views, params, init_poses=None, use_resident=False):
+        """Returns (poses, reports, records as a numpy array of ring.RECORD, per-device ms)."""
+        from . import ring
+        V = len(views)
+        arr, keep = Registrator._views(views, init_poses)
+        poses = np.empty((max(V, 1), 16), dtype=np.float32)
+        reps = (PairReport * max(V, 1))()
+        recs = (PairRecord * max(V, 1))()
+        ms = np.zeros(self.n, dtype=np.float64)
+        self._ck(lib().mvr_register_turntable_multi(self._h, arr, V, C.byref(params), 1 if use_resident else 0, _fp(poses), reps, recs, _dp(ms)))
+        reports = [dict(source_view=reps[k].source_view, target_view=reps[k].target_view, status=reps[k].status,
+                        iterations=reps[k].iterations, n_corr=reps[k].n_correspondences, mse=reps[k].mse,
+                        nn_queries=int(reps[k].nn_queries), pose=pose_to_numpy(reps[k].pose[:])) for k in range(V)]
+        records = np.frombuffer(bytes(recs), dtype=ring.RECORD, count=V).copy()
+        return [pose_to_numpy(poses[k]) for k in range(V)], reports, records, ms

@@ -14,7 +14,7 @@ HOST = os.path.join(HERE, "host")
 LIB = os.path.join(HERE, "libmvr_b200.so")
 
 CU_SOURCES = ["index.cu", "bin.cu", "pair_index.cu", "cell_nn.cu", "icp.cu", "normals.cu", "api.cu"]
-HOST_SOURCES = ["registrator.cpp", "lum.cpp", "capi.cpp"]
+HOST_SOURCES = ["registrator.cpp", "lum.cpp", "capi.cpp", "multi.cpp"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
@@ -58,7 +58,7 @@ def build(force=False, verbose=False, out=None):
     if out is None and not force and not stale():
         return LIB
     extra = os.environ.get("MVR_NVCC_DEFS", "").split()   # development: e.g. MVR_NVCC_DEFS="-DMVR_BS_THREADS=64"
-    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-shared", "-o", out or LIB, "-x", "cu"] + sources()
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-shared", "-o", out or LIB, "-x", "cu"] + sources() + ["-ldl"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
         print(" ".join(cmd))

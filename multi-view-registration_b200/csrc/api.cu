@@ -527,6 +527,7 @@ const char* mvr_status_string(int s) {
     case MVR_ERR_NO_INPUT: return "input cloud not set";
     case MVR_ERR_NOT_SPD: return "normal equations not positive definite";
     case MVR_ERR_ALLOC: return "allocation failed";
+    case MVR_ERR_NCCL: return "NCCL unavailable or a collective failed";
     default: return "unknown status";
   }
 }

@@ -78,6 +78,9 @@ class Registrator {
   const std::string& lastError() const { return err_; }
   int streams() const { return (int)ctx_.size(); }
   mvr_ctx* context(int slot) const { return (slot >= 0 && slot < (int)ctx_.size()) ? ctx_[(size_t)slot] : nullptr; }
+  // half the largest extent of the target cloud last given to context 0 (pair 0's target = view 0 in the ring mode):
+  // the length scale of the loop closure, the same whatever the sharding
+  double lastTargetRadius() const { return objectRadius(0); }
 
   // axis.txt state (mvr/src/registrator.cpp:258-328): defaults pivot (0,0,0), normal (0,-1,0) as in :86-87.
   void setPivotPoint(double x, double y, double z) { pivot_[0] = x; pivot_[1] = y; pivot_[2] = z; }

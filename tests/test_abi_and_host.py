@@ -359,3 +359,27 @@ def test_lum_relax_golden(mvr):
     cost = sum((((a @ X[s][:3, :3].T + X[s][:3, 3]) - (b @ X[t][:3, :3].T + X[t][:3, 3])) ** 2).sum()
                for s, t, a, b in zip(g["src"], g["tgt"], g["a"], g["b"]))
     assert abs(cost - float(g["cost"])) <= 1e-9 * float(g["cost"])
+
+
+def test_pair_record_layout_matches_the_header(mvr):
+    """mvr_pair_record is exchanged as raw bytes: the ctypes mirror, the numpy dtype of ring.py and the C struct are all 96 bytes
+    with the same field offsets."""
+    import ctypes
+    import mvr_b200.ring as ring
+    assert ctypes.sizeof(mvr.PairRecord) == ring.REC == 96
+    for name, np_name in (("pose", "pose"), ("n_correspondences", "n_corr"), ("iterations", "iterations"), ("status", "status"),
+                          ("mse", "mse"), ("nn_queries", "nn_queries")):
+        assert getattr(mvr.PairRecord, name).offset == ring.RECORD.fields[np_name][1]
+    for rank, world, n in ((0, 1, 24), (3, 8, 24), (7, 8, 24), (1, 5, 7)):
+        a, b = ctypes.c_int(0), ctypes.c_int(0)
+        mvr.lib().mvr_multi_pair_range(rank, world, n, ctypes.byref(a), ctypes.byref(b))
+        assert (a.value, b.value) == ring.pair_range(rank, world, n)
+
+
+def test_multi_create_without_gpu_fails_loudly(mvr):
+    import ctypes
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    h = ctypes.c_void_p()
+    assert mvr.lib().mvr_multi_create(None, 2, ctypes.byref(h)) == mvr.ERR_CUDA and not h.value

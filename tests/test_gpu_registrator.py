@@ -263,3 +263,35 @@ def test_compute_error_matches_oracle(mvr, orc, synth, seq):
         assert cnt == len(q)
         assert abs(msd - float(d2.astype(np.float64).mean())) <= 1e-9 * msd
     reg.close()
+
+
+def test_multi_gpu_entry_point_matches_the_single_gpu_driver(mvr, synth):
+    """mvr_register_turntable_multi (one host thread per GPU, ncclAllGather of the pair records, host loop closure) returns,
+    whatever the number of GPUs, bit for bit the pair poses of mvr_register_turntable on one GPU."""
+    import torch
+    import mvr_b200.ring as ring
+    V, n = 8, 20_000
+    views, poses = synth.turntable_sequence(V, n)
+    E = synth.perturbation()
+    init = [(poses[v] @ E) if v % 2 else poses[v].copy() for v in range(V)]
+    icp = mvr.default_params(max_iterations=10, max_dist=4.0, reciprocal=1, fixed_iterations=1)
+    tp = mvr.turntable_params(pivot=synth.PIVOT, axis=synth.AXIS, icp=icp, repeat_times=1, mode=mvr.RING_PAIRS, loop_closure=1, lum_iterations=16)
+    reg = mvr.Registrator(0, 1)
+    one_poses, one_reps = reg.register_turntable(views, tp, init_poses=init)
+    reg.close()
+    want = ring.pose_checksum(ring.pack_reports(one_reps, 0, V))
+    counts = [1] + [g for g in (2, 4, 8) if g <= torch.cuda.device_count()]
+    for g in counts:
+        m = mvr.MultiRegistrator(range(g))
+        got_poses, reps, recs, ms = m.register_turntable(views, tp, init_poses=init)
+        assert ring.pose_checksum(recs) == want, "%d GPUs: pair records differ from the single-GPU run" % g
+        for a, b in zip(reps, one_reps):
+            assert np.array_equal(a["pose"], b["pose"]) and a["n_corr"] == b["n_corr"] and a["mse"] == b["mse"] and a["nn_queries"] == b["nn_queries"]
+        for a, b in zip(got_poses, one_poses):
+            assert np.array_equal(a, b)
+        # resident views: the same again without the upload
+        m.upload(views, init)
+        got2, reps2, recs2, _ = m.register_turntable(views, tp, init_poses=init, use_resident=True)
+        assert ring.pose_checksum(recs2) == want
+        assert len(ms) == g and all(x > 0 for x in ms)
+        m.close()
