@@ -48,6 +48,11 @@ def parse_args():
     ap.add_argument("--cpu-sample-pairs", type=int, default=2, help="pairs the cpu_baseline leg aligns (0 = skip)")
     ap.add_argument("--cpu-reps", type=int, default=3, help="repetitions of the CPU sample (the minimum is reported)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="registration", choices=["registration", "nn_sweep"],
+                    help="registration: BASELINE configs[1]/[2] (the default, the driver's line); nn_sweep: configs[4], exact NN of 10k..16M "
+                         "queries against a 1M-point target")
+    ap.add_argument("--nn-target", type=int, default=1_000_000)
+    ap.add_argument("--nn-queries", type=int, default=16_000_000, help="queries of the headline step of the nn_sweep workload")
     ap.add_argument("--single-process", action="store_true",
                     help="N GPUs from ONE process through mvr_register_turntable_multi (one host thread per GPU, ncclAllGather inside the "
                          "C ABI); the default for --gpus N > 1 when not launched by torchrun")
@@ -550,8 +555,191 @@ def run_single_process(a):
     m.close()
 
 
+NN_METRIC = "nn_queries_per_s (exact 1-NN of N queries vs a 1M-point target grid; ms_per_step = one pass over the queries)"
+NN_SIZES = [10_000, 31_600, 100_000, 316_000, 1_000_000, 3_160_000, 10_000_000, 16_000_000]
+
+
+def nn_config(a):
+    return {"workload": "NN-query sweep: %d-point target (full bumpy sphere), queries = target distribution + 0.5 mm noise; headline step = %d "
+                        "queries in random order, un-gated exact 1-NN" % (a.nn_target, a.nn_queries),
+            "target_points": a.nn_target, "queries": a.nn_queries, "order": "random",
+            "l2": "queries + results of the headline step are 384 MB (> 126 MB L2): no flush needed"}
+
+
+def nn_cpu(a, tgt, q, threads):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    oracle.build()
+    oracle.set_num_threads(threads)
+    tree = oracle.KdTree(tgt)
+    best = None
+    for _ in range(max(a.cpu_reps, 1)):
+        t0 = time.perf_counter()
+        tree.query(q)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return len(q) / best, best, oracle.num_threads()
+
+
+def run_nn_reference(a):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import mvr_b200.synth as synth
+    ns = min(a.nn_queries, 2_000_000)
+    tgt, q = synth.nn_sweep_case(a.nn_target, ns, order="random")
+    val, sec, cores = nn_cpu(a, tgt, q, host_threads())
+    v1, s1, _ = nn_cpu(a, tgt, q[:200_000], 1)
+    print(json.dumps({
+        "impl": "reference", "metric": NN_METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * a.nn_queries / val, "ms_per_step_is": "extrapolated from the sampled rate", "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": nn_config(a),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "seconds": sec, "min_of": max(a.cpu_reps, 1),
+                         "sample": "first %d queries of the headline step (kd-tree build excluded)" % ns,
+                         "single_thread": {"value": v1, "unit": UNIT, "cores": 1, "seconds": s1, "sample": "first 200000 queries"}},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the oracle's exact kd-tree 1-NN (FLANN's role in the reference's PCL path), OpenMP over the queries"}))
+
+
+def run_nn_sweep(a):
+    """BASELINE configs[4]: exact NN-query throughput against a 1M-point target, 10k .. 16M queries in random and in cell-sorted
+    order.  The headline step is the largest random-order batch; every GPU of a multi-GPU run answers its own share of the
+    queries against a replicated index (no collective: "scaling": "weak" per GPU is not used -- total work is fixed)."""
+    import torch
+    import torch.distributed as dist
+    import mvr_b200
+    import mvr_b200.synth as synth
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = mvr_b200.Context(local)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)   # CUDA events of torch then bracket the library's work
+    m = a.nn_target
+    tgt, qall = synth.nn_sweep_case(m, a.nn_queries, order="random")
+    ctx.set_target(tgt)
+    lo, hi = (rank * a.nn_queries) // world, ((rank + 1) * a.nn_queries) // world
+    q = qall[lo:hi]
+    nq = len(q)
+    dq = torch.from_numpy(q).to(dev)
+    hq = torch.from_numpy(q).pin_memory()
+    di = torch.empty(nq, dtype=torch.int32, device=dev); dd = torch.empty(nq, dtype=torch.float32, device=dev)
+    hi_ = np.empty(nq, dtype=np.int32); hd = np.empty(nq, dtype=np.float32)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(steps, host):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        tot = 0.0
+        barrier()
+        for _ in range(steps):
+            e0.record()
+            if host:
+                i2, d2 = ctx.nn_query(hq.numpy())
+            else:
+                ctx.nn_query_device(dq.data_ptr(), nq, di.data_ptr(), dd.data_ptr())
+            e1.record(); e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        barrier()
+        return tot
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    for _ in range(a.warmup):
+        ctx.nn_query_device(dq.data_ptr(), nq, di.data_ptr(), dd.data_ptr())
+    torch.cuda.synchronize()
+    l0 = mvr_b200.kernel_launch_count()
+    w0 = time.time()
+    ms = allmax(timed(a.steps, False))
+    w1 = time.time()
+    launches = mvr_b200.kernel_launch_count() - l0
+    clocks = sampler.stop(w0, w1) if sampler else None
+    value = a.nn_queries * a.steps / (ms * 1e-3)
+    e2e = None
+    if not a.no_e2e:
+        timed(1, True)
+        ms_e = allmax(timed(max(1, a.steps // 2), True))
+        e2e = {"value": a.nn_queries * max(1, a.steps // 2) / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e / max(1, a.steps // 2),
+               "h2d_bytes_per_step": int(a.nn_queries * 16), "d2h_bytes_per_step": int(a.nn_queries * 8)}
+    # ---- roofline of the NN kernel (per-kernel CUDA events inside the library) + the sweep over batch sizes (rank 0)
+    roof, sweep, parity, cpu = None, None, None, None
+    if rank == 0:
+        ctx.set_profiling(True)
+        ctx.kernel_stats(reset=True)
+        ctx.nn_query_device(dq.data_ptr(), nq, di.data_ptr(), dd.data_ptr()); ctx.synchronize()
+        st = ctx.kernel_stats(reset=True)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        nn = st["nn"]
+        ach = nn["bytes"] / (nn["ms"] * 1e-3) / 1e9 if nn["ms"] > 0 else 0.0
+        tot_ms = sum(v["ms"] for v in st.values())
+        roof = {"bound": "hbm", "kernel": "k_cell_nn (exact 1-NN of cell-sorted queries, warp-cooperative)" if nq >= 8 * m else "k_warp_nn (one warp per query)",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                "bytes_per_launch": nn["bytes"] / max(nn["launches"], 1), "avg_launch_us": 1e3 * nn["ms"] / max(nn["launches"], 1),
+                "algorithmic_bytes": "24 B per query + 16 B per target point", "share_of_kernel_time": nn["ms"] / tot_ms if tot_ms > 0 else None,
+                "per_kernel_ms": {k: round(v["ms"], 4) for k, v in st.items() if v["launches"]}}
+        ctx.set_profiling(False)
+        sweep = []
+        for order in ("random", "morton"):
+            _, qo = synth.nn_sweep_case(m, a.nn_queries, order=order) if order == "morton" else (None, qall)
+            dqo = torch.from_numpy(qo).to(dev)
+            for n1 in [s_ for s_ in NN_SIZES if s_ <= a.nn_queries]:
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                best = None
+                for rep in range(4):
+                    e0.record()
+                    ctx.nn_query_device(dqo.data_ptr(), n1, di.data_ptr(), dd.data_ptr())
+                    e1.record(); e1.synchronize()
+                    t = e0.elapsed_time(e1)
+                    best = t if (best is None or (rep > 0 and t < best)) else best
+                sweep.append({"queries": n1, "order": order, "ms": best, "gqps": n1 / best / 1e6})
+            del dqo
+        # parity gate: the first 200k answers of the headline step against the oracle's kd-tree, bit for bit
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle
+        oracle.build()
+        ctx.nn_query_device(dq.data_ptr(), nq, di.data_ptr(), dd.data_ptr()); ctx.synchronize()
+        ns = min(nq, 200_000)
+        oi, od = oracle.nn_kdtree(tgt, q[:ns])
+        parity = {"against": "CPU oracle kd-tree, first %d queries of the headline step" % ns,
+                  "indices_equal": bool(np.array_equal(di[:ns].cpu().numpy(), oi)),
+                  "d2_bits_equal": bool(np.array_equal(dd[:ns].cpu().numpy().view(np.uint32), od.view(np.uint32)))}
+        if a.cpu_sample_pairs > 0:
+            ncs = min(nq, 2_000_000)
+            val, sec, cores = nn_cpu(a, tgt, q[:ncs], host_threads())
+            v1, s1, _ = nn_cpu(a, tgt, q[:200_000], 1)
+            cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "seconds": sec, "min_of": max(a.cpu_reps, 1),
+                   "sample": "first %d queries of the headline step (kd-tree build excluded)" % ncs,
+                   "single_thread": {"value": v1, "unit": UNIT, "cores": 1, "seconds": s1, "sample": "first 200000 queries"}}
+        print(json.dumps({
+            "metric": NN_METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": nn_config(a),
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity, "sweep": sweep}))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     a = parse_args()
+    if a.workload == "nn_sweep":
+        return run_nn_reference(a) if a.impl == "reference" else run_nn_sweep(a)
     if a.impl == "reference":
         run_reference(a)
     elif a.single_process or (a.gpus > 1 and "WORLD_SIZE" not in os.environ):

@@ -130,6 +130,11 @@ int mvr_ctx_set_index_options(mvr_ctx* ctx, float cell_edge, int max_bits);
  * the warp-cooperative pass is used, with about `points_per_cell` target points per occupied grid cell (default 8).
  * Results do not depend on either. */
 int mvr_ctx_set_nn_options(mvr_ctx* ctx, double points_per_cell, double dense_ratio);
+/* Which kernel answers mvr_nn_query / mvr_fitness_score (results are identical; a tuning and A/B aid):
+ * AUTO = one warp per query up to 131072 queries, the per-thread row walk above (queries sorted by cell from 256k on), the
+ * cell-cooperative pass from dense_ratio queries per target point on; WARP / THREAD / CELL force one of them. */
+typedef enum { MVR_NN_AUTO = 0, MVR_NN_WARP = 1, MVR_NN_THREAD = 2, MVR_NN_CELL = 3 } mvr_nn_mode;
+int mvr_ctx_set_nn_mode(mvr_ctx* ctx, int mode);
 
 /* -- inputs: icp.setInputTarget / icp.setInputSource (mvr/src/registrator.cpp:566-567, 776-777,
  *    913-914) and CorrespondenceEstimation::setInputSource/Target (:497-498, 645-646).

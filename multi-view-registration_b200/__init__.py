@@ -18,6 +18,7 @@ K_NAMES = ["morton", "sort", "table", "nn", "corr", "reduce", "transform", "norm
 K_COUNT = 8
 (OK, ERR_BAD_ARG, ERR_TOO_FEW, ERR_CUDA, ERR_NO_INPUT, ERR_NOT_SPD, ERR_ALLOC, ERR_NCCL) = range(8)
 TARGET, SOURCE = 0, 1
+NN_AUTO, NN_WARP, NN_THREAD, NN_CELL = 0, 1, 2, 3
 POINT_TO_POINT, POINT_TO_PLANE = 0, 1
 
 
@@ -168,6 +169,7 @@ def lib():
     L.mvr_ctx_set_index_options.argtypes = [vp, C.c_float, C.c_int]
     L.mvr_ctx_set_batch_group.argtypes = [vp, C.c_int]
     L.mvr_ctx_set_nn_options.argtypes = [vp, C.c_double, C.c_double]
+    L.mvr_ctx_set_nn_mode.argtypes = [vp, C.c_int]
     for name in ("mvr_set_target", "mvr_set_source", "mvr_set_target_device", "mvr_set_source_device", "mvr_set_target_normals"):
         getattr(L, name).argtypes = [vp, vp, C.c_size_t]
     L.mvr_index_build.argtypes = [vp, C.c_int, C.POINTER(Grid)]
@@ -346,6 +348,10 @@ class Context:
     def set_nn_options(self, points_per_cell=8.0, dense_ratio=8.0):
         """NN-query tuning: dense_ratio = queries per target point from which the warp-cooperative pass runs (0: never)."""
         self._ck(lib().mvr_ctx_set_nn_options(self._h, float(points_per_cell), float(dense_ratio)))
+
+    def set_nn_mode(self, mode):
+        """NN_AUTO / NN_WARP / NN_THREAD / NN_CELL: which kernel answers nn_query (identical results)."""
+        self._ck(lib().mvr_ctx_set_nn_mode(self._h, int(mode)))
 
     def set_batch_group(self, pairs):
         """Pairs per kernel launch of the batches this context leads (1..24)."""

@@ -104,6 +104,7 @@ struct mvr_ctx {
   PairIndex nt, nq;              // target / query index of the dense NN pass (cell_nn.cu)
   double nn_ppc = 8.0;           // its target points per occupied cell
   double nn_dense_ratio = 8.0;   // queries per target point from which the dense pass is used (0: never)
+  int nn_mode = MVR_NN_AUTO;     // mvr_ctx_set_nn_mode
   FwdArgs fa{}; RevArgs ra{};    // kernel arguments of the prepared align
   bool want_rnn = false;         // the next prepared align also records the mutual partners (mvr_correspondences)
   int group_pairs = 24;          // pairs per launch of a batch led by this context (mvr_ctx_set_batch_group)
@@ -361,8 +362,9 @@ int nn_pass_dense(mvr_ctx* ctx, const float4* q, int n, int32_t* d_idx, float* d
 
 // Exact un-gated NN of n device points in the target index; results at the queries' original index.
 int nn_pass(mvr_ctx* ctx, const float4* q, int n, int32_t* d_idx, float* d_d2) {
-  if (ctx->nn_dense_ratio > 0 && (double)n >= ctx->nn_dense_ratio * (double)std::max(ctx->tgt.n - ctx->tgt.n_bad, 1))
-    return nn_pass_dense(ctx, q, n, d_idx, d_d2);
+  const bool dense = ctx->nn_mode == MVR_NN_CELL ||
+                     (ctx->nn_mode == MVR_NN_AUTO && ctx->nn_dense_ratio > 0 && (double)n >= ctx->nn_dense_ratio * (double)std::max(ctx->tgt.n - ctx->tgt.n_bad, 1));
+  if (dense) return nn_pass_dense(ctx, q, n, d_idx, d_d2);
   // The row walk of pair_search.cuh on the target's per-align index: small batches as they come, large ones sorted by
   // cell first (locality).  It also gets through the empty space around far queries quickly, which a cell-by-cell ring
   // expansion does not.
@@ -375,9 +377,18 @@ int nn_pass(mvr_ctx* ctx, const float4* q, int n, int32_t* d_idx, float* d_d2) {
     if ((rc = build_pair_index(ctx, pt, t.pts, t.n, t.n_bad, nullptr, gt, cells, false))) return rc;
     pt.gen = t.gen;
   }
+  ProfScope ps(ctx, MVR_K_NN, 24.0 * n + 16.0 * t.n, (double)n);
+  // Measured on B200 (1M-point target; profiles/r02_nn_kernels.log): one warp per query answers 10k queries in 20 us against 87 us
+  // for the per-thread walk and wins up to ~130k queries; above that its 32 lanes per query cap it at 2 G queries/s and the
+  // per-thread walk (queries sorted by cell from 256k on) takes over, until the cell-cooperative pass wins at >= 8 queries per
+  // target point.
+  if (ctx->nn_mode == MVR_NN_WARP || (ctx->nn_mode == MVR_NN_AUTO && n <= 131072)) {
+    // one warp per query, queries as they come (cell_nn.cu): no serial chain of dependent loads per query
+    CK(launch_warp_nn(q, n, pt.sorted.as<float4>(), pt.start.as<uint32_t>(), pt.g, pt.n_valid, d_idx, d_d2, ctx->stream));
+    return MVR_OK;
+  }
   const bool sorted = n > 262144;
   if (sorted && (rc = build_pair_index(ctx, ctx->nq, q, n, 0, nullptr, pt.g, pt.cells, false, false))) return rc;
-  ProfScope ps(ctx, MVR_K_NN, 24.0 * n + 16.0 * t.n, (double)n);
   CK(launch_pair_nn(sorted ? ctx->nq.sorted.as<float4>() : q, n, sorted, pt.sorted.as<float4>(), pt.start.as<uint32_t>(), pt.g, pt.n_valid, d_idx,
                     d_d2, ctx->stream));
   return MVR_OK;
@@ -635,6 +646,12 @@ int mvr_ctx_set_nn_options(mvr_ctx* ctx, double points_per_cell, double dense_ra
   ctx->nn_ppc = points_per_cell;
   ctx->nn_dense_ratio = dense_ratio;
   ctx->nt.valid = false;
+  return MVR_OK;
+}
+
+int mvr_ctx_set_nn_mode(mvr_ctx* ctx, int mode) {
+  if (!ctx || mode < MVR_NN_AUTO || mode > MVR_NN_CELL) return MVR_ERR_BAD_ARG;
+  ctx->nn_mode = mode;
   return MVR_OK;
 }
 

@@ -153,6 +153,111 @@ __global__ void __launch_bounds__(CN_THREADS, MVR_CN_MINBLOCKS) k_cell_nn(CellNn
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// One WARP per query: exact un-gated 1-NN of queries in any order, for batches too small (or too sparse) to be worth
+// sorting.  A per-thread search is a serial chain of dependent loads (cell table -> points, row after row: ~100 us for a
+// batch that fits one wave, whatever its size); here the 32 lanes of a warp share ONE query: each lane fetches the table
+// entries of one row of the cube of cells [c - h, c + h]^3 around the query's cell, the lanes then split the candidates of
+// all rows evenly among themselves, and a 64-bit shuffle reduction of (d2 bits, index) keys picks the lexicographic minimum.
+// The cube doubles (h = 1, 2, 4, ...) until the best distance is provably smaller than anything outside it -- for a
+// query near the surface the first cube settles it: two dependent load round trips per query instead of dozens.
+// Getting through empty space (a query tens of cells from the cloud) costs two table loads per row, 32 rows at a time.
+// ---------------------------------------------------------------------------------------------
+constexpr int WN_THREADS = 256;
+constexpr int WN_WARPS = WN_THREADS / 32;
+
+__global__ void __launch_bounds__(WN_THREADS, 4) k_warp_nn(const float4* __restrict__ q, int n, const float4* __restrict__ tgt,
+                                                           const uint32_t* __restrict__ tstart, PairGrid g, int m_valid,
+                                                           int32_t* __restrict__ out_idx, float* __restrict__ out_d2) {
+  const int lane = threadIdx.x & 31;
+  const int nwarps = gridDim.x * WN_WARPS;
+  const float cell2 = g.cell_lo * g.cell_lo * MVR_REL_SHRINK;
+  const int rowlen = g.nx, slab = g.nx * g.ny;
+  for (int i = blockIdx.x * WN_WARPS + (threadIdx.x >> 5); i < n; i += nwarps) {
+    const float4 p = __ldg(q + i);
+    if (!finite3(p) || m_valid <= 0) {
+      if (lane == 0) { out_idx[i] = -1; out_d2[i] = MVR_INF; }
+      continue;
+    }
+    const float tx = grid_t(p.x, g.ox, g.inv_cell), ty = grid_t(p.y, g.oy, g.inv_cell), tz = grid_t(p.z, g.oz, g.inv_cell);
+    const int cx = pg_cell(tx, g.nx), cy = pg_cell(ty, g.ny), cz = pg_cell(tz, g.nz);
+    const float margin = MVR_CELL_MARGIN + 1.0e-6f * fmaxf(fabsf(tx), fmaxf(fabsf(ty), fabsf(tz)));
+    unsigned long long bkey = 0x7f8000007fffffffull;   // (+inf, INT_MAX)
+    for (int h = 1;; h <<= 1) {
+      const int x0 = max(cx - h, 0), x1 = min(cx + h, g.nx - 1);
+      const int y0 = max(cy - h, 0), y1 = min(cy + h, g.ny - 1);
+      const int z0 = max(cz - h, 0), z1 = min(cz + h, g.nz - 1);
+      const int ny_c = y1 - y0 + 1, rows = ny_c * (z1 - z0 + 1);
+      for (int r0 = 0; r0 < rows; r0 += 32) {
+        // lane -> row: its run of sorted positions
+        uint32_t rs = 0, len = 0;
+        const int r = r0 + lane;
+        if (r < rows) {
+          const int y = y0 + r % ny_c, z = z0 + r / ny_c;
+          // (the inner cube is scanned again when h doubles: duplicates never win, and the work is a geometric series)
+          const uint32_t* row = tstart + (size_t)z * slab + (size_t)y * rowlen;
+          rs = __ldg(row + x0);
+          len = __ldg(row + x1 + 1) - rs;
+        }
+        // the lanes split the candidates of the 32 runs evenly: candidate c of the concatenation belongs to the run whose
+        // inclusive prefix first exceeds c
+        uint32_t incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        for (uint32_t c0 = 0; c0 < total; c0 += 32u) {
+          const uint32_t c = c0 + (uint32_t)lane;
+          // run of candidate c: the number of runs whose inclusive prefix is <= c (binary search over the lanes' prefixes)
+          int lo = 0;
+#pragma unroll
+          for (int step = 16; step > 0; step >>= 1) {
+            const uint32_t pv = __shfl_sync(0xffffffffu, incl, lo + step - 1);
+            if (pv <= c) lo += step;
+          }
+          const int src = min(lo, 31);
+          const uint32_t s_rs = __shfl_sync(0xffffffffu, rs, src), s_in = __shfl_sync(0xffffffffu, incl, src), s_len = __shfl_sync(0xffffffffu, len, src);
+          if (c < total) {
+            const uint32_t k = s_rs + (c - (s_in - s_len));
+            const float4 t = __ldg(tgt + k);
+            const float d = d2_pinned(p.x, p.y, p.z, t.x, t.y, t.z);
+            const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)__float_as_uint(t.w);
+            if (key < bkey) bkey = key;
+          }
+        }
+      }
+      // the warp's best so far
+      unsigned long long wkey = bkey;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, wkey, o);
+        if (other < wkey) wkey = other;
+      }
+      bkey = wkey;
+      // is the cube enough?  Everything outside it is farther than u cells away along some axis.
+      const float u = fminf(cn_face(tx, cx, g.nx, h), fminf(cn_face(ty, cy, g.ny, h), cn_face(tz, cz, g.nz, h)));
+      if (u == MVR_INF) break;   // the cube is the whole grid
+      const float bu = fmaxf(u - margin, 0.0f);
+      if (__uint_as_float((uint32_t)(bkey >> 32)) < bu * bu * cell2) break;
+    }
+    if (lane == 0) {
+      const int idx = (int)(uint32_t)bkey;
+      out_idx[i] = idx == 0x7fffffff ? -1 : idx;
+      out_d2[i] = idx == 0x7fffffff ? MVR_INF : __uint_as_float((uint32_t)(bkey >> 32));
+    }
+  }
+}
+
+cudaError_t launch_warp_nn(const float4* q, int n, const float4* tgt_sorted, const uint32_t* tstart, PairGrid g, int m_valid, int32_t* out_idx,
+                           float* out_d2, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  const int blocks = std::min((n + WN_WARPS - 1) / WN_WARPS, 148 * 8 * 16);
+  k_warp_nn<<<blocks, WN_THREADS, 0, s>>>(q, n, tgt_sorted, tstart, g, m_valid, out_idx, out_d2); count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_cell_nn(const float4* q_sorted, int nq, const uint32_t* d_nq_valid, const float4* tgt_sorted, const uint32_t* tstart, PairGrid g,
                            int m_valid, int32_t* out_idx, float* out_d2, cudaStream_t s) {
   if (nq <= 0) return cudaSuccess;

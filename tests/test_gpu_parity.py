@@ -261,6 +261,33 @@ def test_pair_moments_without_correspondences(ctx, mvr):
     assert m.n == 0 and m.d2 == 0
 
 
+@pytest.mark.parametrize("mode", ["WARP", "THREAD", "CELL"])
+def test_nn_every_kernel_bit_exact(mvr, orc, synth, mode):
+    """The three NN kernels (one warp per query, per-thread row walk, cell-cooperative) against the oracle: queries near the
+    surface, far from the cloud (tens of cells of empty space), outside the grid, non-finite, and exact ties."""
+    c = mvr.Context(0)
+    c.set_nn_mode(getattr(mvr, "NN_" + mode))
+    tgt, q = synth.nn_sweep_case(60_000, 30_000, seed=77)
+    rng = np.random.default_rng(5)
+    far = q[:2000].copy(); far[:, :3] += rng.normal(size=(2000, 3)).astype(np.float32) * 60.0     # far from the surface, some outside the grid
+    dup = tgt[rng.integers(0, len(tgt), 3000)].copy()                                              # exactly on target points (d2 = 0)
+    tgt2 = np.concatenate([tgt, tgt[:5000]])                                                       # duplicated target points: ties -> lowest index
+    bad = q[:10].copy(); bad[::2, 0] = np.nan; bad[1::2, 2] = np.inf
+    qq = np.concatenate([q, far, dup, bad])
+    c.set_target(tgt2)
+    idx, d2 = c.nn_query(qq)
+    ok = np.isfinite(qq[:, :3]).all(axis=1)
+    oi, od = orc.nn_kdtree(tgt2, qq[ok])
+    assert np.array_equal(idx[ok], oi)
+    assert np.array_equal(d2[ok].view(np.uint32), od.view(np.uint32))
+    assert np.all(idx[~ok] == -1) and np.all(np.isinf(d2[~ok]))
+    # a one-point target and an all-far batch
+    c.set_target(tgt[:1])
+    idx, d2 = c.nn_query(qq[ok][:5000])
+    assert np.all(idx == 0)
+    c.close()
+
+
 # ---- ICP -------------------------------------------------------------------------------------------
 def _pair(synth, n, n_views=24):
     tgt, Tt = synth.turntable_view(0, n_views, n)
