@@ -249,8 +249,9 @@ typedef enum {
                                    the growing model, then refineAxis (mvr/src/registrator.cpp:746-842, 877-990) */
   MVR_REGISTER_ICP = 2,         /* registrationICP: views in the order 1, V-1, 2, V-2, .. against the growing model,
                                    the whole pass repeated repeat_times (mvr/src/registrator.cpp:517-588) */
-  MVR_REGISTER_LUM = 3          /* registrationLUM: ring relaxation from reciprocal correspondences of the posed
-                                   views, max(1, max_iterations / 16) outer loops (mvr/src/registrator.cpp:611-678) */
+  MVR_REGISTER_LUM = 3          /* registrationLUM: max(1, max_iterations / 16) outer loops of { pose every view, reciprocal
+                                   correspondences of the ring edges, 16 sweeps of pcl::registration::LUM (mvr_lum_compute),
+                                   pose <- T pose } (mvr/src/registrator.cpp:611-678) */
 } mvr_register_mode;
 
 typedef struct {
@@ -353,6 +354,15 @@ int mvr_ring_close(const float* rel_poses, const double* weights, int n_views, i
  * in the world frame (mvr_pair_moments_transform).  poses: V x double[16] column-major corrections. */
 int mvr_lum_relax(const mvr_pair_moments* edges, const int* src, const int* tgt, int n_edges, int n_views, int iterations,
                   double* poses);
+/* pcl::registration::LUM::compute() as the reference runs it (lum.setMaxIterations(16); lum.compute(); lum.getTransformation(v),
+ * mvr/src/registrator.cpp:630-656), on correspondence moments instead of point lists: vertex poses (x, y, z, roll, pitch,
+ * yaw), vertex 0 fixed; per sweep PCL's computeEdge (M'M, M'Z, s^2 of the pairs compounded onto the current poses), the dense
+ * 6 (V - 1) system G X = B, pose_v -= incidenceCorrection(pose_v)^-1 X_v; stops early when the summed update norm is
+ * <= convergence_threshold (V - 1) (PCL default 0).  edges[e]: moments of edge src[e] -> tgt[e] with BOTH clouds in the
+ * common frame the vertices were added in (a = source point, b = target point).  poses6 (nullable): V x 6;
+ * transforms (nullable): V x double[16] column-major = pcl::getTransformation(pose_v). */
+int mvr_lum_compute(const mvr_pair_moments* edges, const int* src, const int* tgt, int n_edges, int n_views, int iterations,
+                    double convergence_threshold, double* poses6, double* transforms);
 /* Re-express moments under the rigid map p -> pose * p (double[16] column-major); the new origin is
  * new_origin (nullable: keep pose * old origin). */
 void mvr_pair_moments_transform(const mvr_pair_moments* in, const double* pose, const double* new_origin, mvr_pair_moments* out);

@@ -224,6 +224,7 @@ def lib():
     L.mvr_merge_registered.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), dp, ip, C.c_int, C.c_int, vp, C.POINTER(C.c_size_t)]
     L.mvr_pair_moments_compute.argtypes = [vp, C.c_double, C.c_int, fp, C.POINTER(PairMoments)]
     L.mvr_lum_relax.argtypes = [C.POINTER(PairMoments), ip, ip, C.c_int, C.c_int, C.c_int, dp]
+    L.mvr_lum_compute.argtypes = [C.POINTER(PairMoments), ip, ip, C.c_int, C.c_int, C.c_int, C.c_double, dp, dp]
     L.mvr_pair_moments_transform.argtypes = [C.POINTER(PairMoments), dp, dp, C.POINTER(PairMoments)]
     L.mvr_pair_moments_transform.restype = None
     _lib = L
@@ -613,6 +614,20 @@ def lum_relax(edges, src, tgt, n_views, iterations=16):
     if rc != OK:
         raise MvrError(rc, lib().mvr_status_string(rc).decode())
     return [out[k].reshape(4, 4).T.copy() for k in range(n_views)]
+
+
+def lum_compute(edges, src, tgt, n_views, iterations=16, convergence_threshold=0.0):
+    """pcl::registration::LUM::compute() on moments: returns (poses V x 6, transforms list of V 4x4 float64)."""
+    E = len(edges)
+    arr = (PairMoments * max(E, 1))(*edges)
+    s = np.ascontiguousarray(np.asarray(src, dtype=np.int32))
+    t = np.ascontiguousarray(np.asarray(tgt, dtype=np.int32))
+    p6 = np.zeros((n_views, 6), dtype=np.float64)
+    X = np.zeros((n_views, 16), dtype=np.float64)
+    rc = lib().mvr_lum_compute(arr, _ip(s), _ip(t), E, int(n_views), int(iterations), float(convergence_threshold), _dp(p6), _dp(X))
+    if rc != OK:
+        raise MvrError(rc, "mvr_lum_compute failed")
+    return p6, [X[v].reshape(4, 4).T.copy() for v in range(n_views)]
 
 
 def refine_axis(poses, pivot, axis):

@@ -199,6 +199,19 @@ int mvr_lum_relax(const mvr_pair_moments* edges, const int* src, const int* tgt,
   return MVR_OK;
 }
 
+int mvr_lum_compute(const mvr_pair_moments* edges, const int* src, const int* tgt, int n_edges, int n_views, int iterations,
+                    double convergence_threshold, double* poses6, double* transforms) {
+  if (n_edges < 0 || n_views < 1 || (!poses6 && !transforms) || (n_edges && (!edges || !src || !tgt))) return MVR_ERR_BAD_ARG;
+  std::vector<mvr_pair_moments> e(edges, edges + n_edges);
+  std::vector<double> p6;
+  std::vector<Matrix4d> X;
+  const int rc = lumComputePcl(e, src, tgt, n_views, iterations > 0 ? iterations : 5, convergence_threshold, p6, X);   // PCL default: 5 sweeps
+  if (rc) return rc;
+  if (poses6) std::memcpy(poses6, p6.data(), (size_t)n_views * 6 * sizeof(double));
+  if (transforms) for (int v = 0; v < n_views; ++v) std::memcpy(transforms + 16 * v, X[(size_t)v].m, sizeof(X[(size_t)v].m));
+  return MVR_OK;
+}
+
 void mvr_pair_moments_transform(const mvr_pair_moments* in, const double* pose, const double* new_origin, mvr_pair_moments* out) {
   if (!in || !pose || !out) return;
   Matrix4d P;

@@ -404,6 +404,174 @@ void momentsTransform(const mvr_pair_moments& in, const Matrix4d& pose, const do
   out.d2 = in.d2;   // a common rigid motion keeps every distance: carry the measured sum
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// pcl::registration::LUM::compute() itself, on moments.
+//
+// What the reference runs (mvr/src/registrator.cpp:627-663; PCL's registration/impl/lum.hpp): vertices carry a
+// 6-vector pose (x, y, z, roll, pitch, yaw), vertex 0 fixed; per sweep every edge is re-linearised (computeEdge) with both
+// clouds compounded onto their current poses -- per correspondence the averaged point m = (s + t) / 2 and the difference
+// d = s - t enter M'M = sum M_k^T M_k and M'Z = sum M_k^T d_k, M_k = [ I | e_x x m, e_z x m, e_y x m ], then
+// D = (M'M)^-1 M'Z, s^2 = sum |d_k - M_k D|^2, cinv = M'M / s^2, cinvd = M'Z / s^2 --, the dense system G X = B over the
+// 6 (V - 1) unknowns is solved and every pose moves by -incidenceCorrection(pose)^-1 X_v.
+// Every sum computeEdge takes over the correspondences is a linear function of the pairs' first and second moments:
+//   sum m = (Sa + Sb) / 2,  sum m m^T = (Saa + Sab + Sba + Sbb) / 4,  sum d = Sa - Sb,  sum m x d = sum t x s (the
+//   antisymmetric part of Sba),  sum |d|^2 = tr Saa - 2 tr Sba + tr Sbb,  s^2 = sum |d|^2 - D . M'Z,
+// and the moments of the COMPOUNDED pairs follow from those of the raw pairs (moments_apply): the sweeps below are PCL's,
+// on 30 doubles per edge (GPU-reduced, mvr_pair_moments) instead of the point lists.  PCL runs them in float32; here
+// double.  oracle/lum_oracle.py restates the same procedure on the points themselves.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+// pcl::getTransformation(x, y, z, roll, pitch, yaw) = Translation * Rz(yaw) * Ry(pitch) * Rx(roll)
+Matrix4d pcl_transformation(const double* p) {
+  const double cr = std::cos(p[3]), sr = std::sin(p[3]), cp = std::cos(p[4]), sp = std::sin(p[4]), cy = std::cos(p[5]), sy = std::sin(p[5]);
+  const double R[9] = {cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr,
+                       sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr,
+                       -sp,     cp * sr,                cp * cr};
+  return from_Rt(R, p);
+}
+
+// LUM::incidenceCorrection (row-major 6 x 6)
+void incidence_correction(const double* p, double* H) {
+  const double cx = std::cos(p[3]), sx = std::sin(p[3]), cy = std::cos(p[4]), sy = std::sin(p[4]);
+  for (int k = 0; k < 36; ++k) H[k] = (k % 7 == 0) ? 1.0 : 0.0;
+  H[0 * 6 + 4] = p[1] * sx - p[2] * cx;
+  H[0 * 6 + 5] = p[1] * cx * cy + p[2] * sx * cy;
+  H[1 * 6 + 3] = p[2];
+  H[1 * 6 + 4] = -p[0] * sx;
+  H[1 * 6 + 5] = -p[0] * cx * cy + p[2] * sy;
+  H[2 * 6 + 3] = -p[1];
+  H[2 * 6 + 4] = p[0] * cx;
+  H[2 * 6 + 5] = -p[0] * sx * cy - p[1] * sy;
+  H[3 * 6 + 5] = sy;
+  H[4 * 6 + 4] = sx;
+  H[4 * 6 + 5] = cx * cy;
+  H[5 * 6 + 4] = cx;
+  H[5 * 6 + 5] = -sx * cy;
+}
+
+// Gaussian elimination with partial pivoting, A (n x n row-major) and b overwritten; false if singular.
+bool lu_solve(double* A, double* b, int n) {
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < n; ++r) if (std::fabs(A[r * n + c]) > std::fabs(A[piv * n + c])) piv = r;
+    if (!(std::fabs(A[piv * n + c]) > 0)) return false;
+    if (piv != c) { for (int k = 0; k < n; ++k) std::swap(A[c * n + k], A[piv * n + k]); std::swap(b[c], b[piv]); }
+    for (int r = c + 1; r < n; ++r) {
+      const double f = A[r * n + c] / A[c * n + c];
+      if (f == 0) continue;
+      for (int k = c; k < n; ++k) A[r * n + k] -= f * A[c * n + k];
+      b[r] -= f * b[c];
+    }
+  }
+  for (int r = n - 1; r >= 0; --r) {
+    double x = b[r];
+    for (int k = r + 1; k < n; ++k) x -= A[r * n + k] * b[k];
+    b[r] = x / A[r * n + r];
+  }
+  return true;
+}
+
+// computeEdge from the moments of the compounded pairs (absolute coordinates: origin 0).  false: the edge carries no information.
+bool pcl_edge(const mvr_pair_moments& m, double* cinv /* 36 */, double* cinvd /* 6 */) {
+  for (int k = 0; k < 36; ++k) cinv[k] = 0;
+  for (int k = 0; k < 6; ++k) cinvd[k] = 0;
+  if (!(m.n >= 3)) return false;
+  double Saa[9], Sbb[9], Smm[9];
+  sym_to_full(m.saa, Saa);
+  sym_to_full(m.sbb, Sbb);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) Smm[i * 3 + j] = 0.25 * (Saa[i * 3 + j] + Sbb[i * 3 + j] + m.sba[i * 3 + j] + m.sba[j * 3 + i]);
+  const double mx = 0.5 * (m.sa[0] + m.sb[0]), my = 0.5 * (m.sa[1] + m.sb[1]), mz = 0.5 * (m.sa[2] + m.sb[2]);
+  double MM[36];
+  for (int k = 0; k < 36; ++k) MM[k] = 0;
+  MM[0 * 6 + 4] = -my; MM[0 * 6 + 5] = mz;
+  MM[1 * 6 + 3] = -mz; MM[1 * 6 + 4] = mx;
+  MM[2 * 6 + 3] = my;  MM[2 * 6 + 5] = -mx;
+  MM[3 * 6 + 4] = -Smm[0 * 3 + 2]; MM[3 * 6 + 5] = -Smm[0 * 3 + 1]; MM[4 * 6 + 5] = -Smm[1 * 3 + 2];
+  MM[3 * 6 + 3] = Smm[4] + Smm[8]; MM[4 * 6 + 4] = Smm[0] + Smm[4]; MM[5 * 6 + 5] = Smm[0] + Smm[8];
+  MM[0] = MM[7] = MM[14] = m.n;
+  for (int i = 0; i < 6; ++i)
+    for (int j = i + 1; j < 6; ++j) MM[j * 6 + i] = MM[i * 6 + j];
+  // sum m x d = sum t x s: component x = sum (t_y s_z - t_z s_y), Sba[r][c] = sum t_r s_c
+  const double MZ[6] = {m.sa[0] - m.sb[0], m.sa[1] - m.sb[1], m.sa[2] - m.sb[2],
+                        m.sba[1 * 3 + 2] - m.sba[2 * 3 + 1],    // sum (m_y d_z - m_z d_y)
+                        m.sba[0 * 3 + 1] - m.sba[1 * 3 + 0],    // sum (m_x d_y - m_y d_x)
+                        m.sba[2 * 3 + 0] - m.sba[0 * 3 + 2]};   // sum (m_z d_x - m_x d_z)
+  double A[36], D[6];
+  std::memcpy(A, MM, sizeof(A));
+  std::memcpy(D, MZ, sizeof(D));
+  if (!lu_solve(A, D, 6)) return false;
+  const double dd = (m.saa[0] + m.saa[3] + m.saa[5]) + (m.sbb[0] + m.sbb[3] + m.sbb[5]) - 2.0 * (m.sba[0] + m.sba[4] + m.sba[8]);
+  double ss = dd;
+  for (int k = 0; k < 6; ++k) ss -= D[k] * MZ[k];
+  if (!(ss >= 0.0000000000001) || !std::isfinite(ss)) return false;   // PCL: "limitations of computation due to linearization"
+  for (int k = 0; k < 36; ++k) cinv[k] = MM[k] / ss;
+  for (int k = 0; k < 6; ++k) cinvd[k] = MZ[k] / ss;
+  return true;
+}
+
+}  // namespace
+
+int lumComputePcl(const std::vector<mvr_pair_moments>& edges, const int* src, const int* tgt, int V, int iterations, double convergence_threshold,
+                  std::vector<double>& poses6, std::vector<Matrix4d>& X) {
+  poses6.assign((size_t)std::max(V, 1) * 6, 0.0);
+  X.assign((size_t)std::max(V, 1), identity4d());
+  const int E = (int)edges.size();
+  if (V < 2) return MVR_OK;
+  for (int e = 0; e < E; ++e)
+    if (src[e] < 0 || src[e] >= V || tgt[e] < 0 || tgt[e] >= V || src[e] == tgt[e]) return MVR_ERR_BAD_ARG;
+  const int n = 6 * (V - 1);
+  const double zero[3] = {0, 0, 0};
+  std::vector<double> G((size_t)n * n), B((size_t)n), cinv((size_t)E * 36), cinvd((size_t)E * 6);
+  for (int it = 0; it < iterations; ++it) {
+    for (int e = 0; e < E; ++e) {
+      mvr_pair_moments m;
+      moments_apply(edges[(size_t)e], pcl_transformation(&poses6[(size_t)src[e] * 6]), pcl_transformation(&poses6[(size_t)tgt[e] * 6]), zero, m);
+      pcl_edge(m, &cinv[(size_t)e * 36], &cinvd[(size_t)e * 6]);
+    }
+    std::fill(G.begin(), G.end(), 0.0);
+    std::fill(B.begin(), B.end(), 0.0);
+    // PCL walks vertex pairs (vi, vj) and takes the forward edge if there is one, else the backward edge
+    for (int vi = 1; vi < V; ++vi)
+      for (int vj = 0; vj < V; ++vj) {
+        int e_use = -1;
+        double sign = 1.0;
+        for (int e = 0; e < E && e_use < 0; ++e) if (src[e] == vi && tgt[e] == vj) e_use = e;
+        if (e_use < 0) { for (int e = 0; e < E && e_use < 0; ++e) if (src[e] == vj && tgt[e] == vi) e_use = e; sign = -1.0; }
+        if (e_use < 0) continue;
+        const double* C = &cinv[(size_t)e_use * 36];
+        for (int i = 0; i < 6; ++i) {
+          for (int j = 0; j < 6; ++j) {
+            if (vj > 0) G[(size_t)(6 * (vi - 1) + i) * n + 6 * (vj - 1) + j] = -C[i * 6 + j];
+            G[(size_t)(6 * (vi - 1) + i) * n + 6 * (vi - 1) + j] += C[i * 6 + j];
+          }
+          B[(size_t)6 * (vi - 1) + i] += sign * cinvd[(size_t)e_use * 6 + i];
+        }
+      }
+    // G X = B (PCL: colPivHouseholderQr).  A vertex without information has a zero block: a vanishing ridge keeps it where it is.
+    double dmax = 0;
+    for (int i = 0; i < n; ++i) dmax = std::fmax(dmax, std::fabs(G[(size_t)i * n + i]));
+    if (!(dmax > 0) || !std::isfinite(dmax)) break;
+    std::vector<double> A(G), x(B);
+    for (int i = 0; i < n; ++i) if (!(A[(size_t)i * n + i] > 1e-14 * dmax)) A[(size_t)i * n + i] += 1e-14 * dmax;
+    if (!lu_solve(A.data(), x.data(), n)) return MVR_ERR_NOT_SPD;
+    double sum = 0;
+    for (int v = 1; v < V; ++v) {
+      double H[36], d[6];
+      incidence_correction(&poses6[(size_t)v * 6], H);
+      for (int k = 0; k < 6; ++k) d[k] = x[(size_t)6 * (v - 1) + k];
+      if (!lu_solve(H, d, 6)) return MVR_ERR_NOT_SPD;
+      double nrm = 0;
+      for (int k = 0; k < 6; ++k) { poses6[(size_t)v * 6 + k] -= d[k]; nrm += d[k] * d[k]; }
+      sum += std::sqrt(nrm);
+    }
+    if (sum <= convergence_threshold * (double)(V - 1)) break;
+  }
+  for (int v = 0; v < V; ++v) X[(size_t)v] = pcl_transformation(&poses6[(size_t)v * 6]);
+  return MVR_OK;
+}
+
 int lumRelax(const std::vector<mvr_pair_moments>& edges_in, const int* src, const int* tgt, int V, int iterations, std::vector<Matrix4d>& X) {
   X.assign((size_t)std::max(V, 1), identity4d());
   const int E = (int)edges_in.size();

@@ -506,10 +506,11 @@ int Registrator::uploadViews(const std::vector<View>& views, const std::vector<i
 
 int Registrator::registrationLUM(std::vector<View>& views, int max_iterations, double max_distance) {
   // mvr/src/registrator.cpp:611-678: every view gets its turntable pose, then max(1, max_iterations / 16) outer
-  // loops of { reciprocal correspondences on the ring edges i -> (i + 1) % V (:640-651), lum.compute() with 16
-  // sweeps (:630, 653), pose <- lum_T * pose (:655-661) }.  The correspondences of all edges are reduced on the GPU
-  // to their moments in one batch (edge k lives in context k, every view is uploaded once and shared between the two
-  // edges it belongs to); the relaxation itself is host work on 30 doubles per edge (lum.cpp).
+  // loops of { every view posed into the common frame (getTransformedPoints, :636-637), reciprocal correspondences of the
+  // ring edges i -> (i + 1) % V between the POSED clouds (:640-651), lum.compute() with 16 sweeps (:630, 653),
+  // pose <- lum_T * pose (:655-661) }.  The posing and the correspondences run on the GPU, every edge's pairs are reduced
+  // there to their moments in one batch (edge k lives in context k; a posed view is shared between the two edges it
+  // belongs to), and pcl::registration::LUM's sweeps run on those 30 doubles per edge (lumComputePcl, lum.cpp).
   if (!ok()) return fail(MVR_ERR_CUDA, "no GPU context");
   const int V = (int)views.size();
   if (V < 2) return MVR_OK;
@@ -525,41 +526,41 @@ int Registrator::registrationLUM(std::vector<View>& views, int max_iterations, d
   for (int v = 0; v < V; ++v) all.push_back(v);
   std::vector<const float*> dview;
   if ((rc = uploadViews(views, all, dview))) return rc;
-  // edge i: target = view i + 1 (measured once), source = view i = the target of edge i - 1 (shared)
+  cudaSetDevice(device_);
+  std::vector<DeviceCloud> posed((size_t)V);
+  for (int v = 0; v < V; ++v) if (!posed[(size_t)v].ensure(std::max<size_t>(views[(size_t)v].size, 1))) return fail(MVR_ERR_ALLOC, "posed view buffer");
   std::vector<mvr_ctx*> cs((size_t)E);
-  for (int i = 0; i < E; ++i) {
-    cs[(size_t)i] = ctx_[(size_t)i];
-    if ((rc = mvr_set_target_device(cs[(size_t)i], dview[(size_t)et[(size_t)i]], views[(size_t)et[(size_t)i]].size))) return fail(rc, mvr_last_error(cs[(size_t)i]));
-  }
-  for (int i = 0; i < E; ++i) {
-    const int j = (i - 1 + E) % E;   // the edge whose target is view i
-    if (E > 1 && et[(size_t)j] == es[(size_t)i]) rc = mvr_cloud_share(cs[(size_t)i], MVR_CLOUD_SOURCE, cs[(size_t)j], MVR_CLOUD_TARGET);
-    else rc = mvr_set_source_device(cs[(size_t)i], dview[(size_t)es[(size_t)i]], views[(size_t)es[(size_t)i]].size);
-    if (rc) return fail(rc, mvr_last_error(cs[(size_t)i]));
-  }
-  std::vector<float> guesses((size_t)E * 16);
-  std::vector<mvr_pair_moments> mom((size_t)E), edges((size_t)E);
+  for (int i = 0; i < E; ++i) cs[(size_t)i] = ctx_[(size_t)i];
+  std::vector<mvr_pair_moments> mom((size_t)E);
   std::vector<int> st((size_t)E, 0);
   for (int loop = 0; loop < outer; ++loop) {
+    // transformed_cloud = getTransformedPoints(view): double math narrowed to float, in the common frame
+    for (int v = 0; v < V; ++v)
+      if (views[(size_t)v].size && (rc = mvr_apply_pose_device(ctx_[0], dview[(size_t)v], views[(size_t)v].size, 16, views[(size_t)v].pose.m, posed[(size_t)v].p)))
+        return fail(rc, mvr_last_error(ctx_[0]));
+    // edge i: target = posed view i + 1 (measured once), source = posed view i = the target of edge i - 1 (shared)
+    for (int i = 0; i < E; ++i)
+      if ((rc = mvr_set_target_device(cs[(size_t)i], posed[(size_t)et[(size_t)i]].p, views[(size_t)et[(size_t)i]].size))) return fail(rc, mvr_last_error(cs[(size_t)i]));
     for (int i = 0; i < E; ++i) {
-      // the source posed into the target's sensor frame; the moments come back in that frame and move to the world with pose_t
-      const Matrix4f g = toFloat(multiply(inverseRigid(views[(size_t)et[(size_t)i]].pose), views[(size_t)es[(size_t)i]].pose));
-      std::memcpy(&guesses[(size_t)i * 16], g.m, sizeof(g.m));
+      const int j = (i - 1 + E) % E;   // the edge whose target is view i
+      if (E > 1 && et[(size_t)j] == es[(size_t)i]) rc = mvr_cloud_share(cs[(size_t)i], MVR_CLOUD_SOURCE, cs[(size_t)j], MVR_CLOUD_TARGET);
+      else rc = mvr_set_source_device(cs[(size_t)i], posed[(size_t)es[(size_t)i]].p, views[(size_t)es[(size_t)i]].size);
+      if (rc) return fail(rc, mvr_last_error(cs[(size_t)i]));
     }
-    if ((rc = mvr_pair_moments_compute_batch(cs.data(), E, max_distance, 1, guesses.data(), mom.data(), st.data()))) return fail(rc, mvr_last_error(cs[0]));
+    if ((rc = mvr_pair_moments_compute_batch(cs.data(), E, max_distance, 1, nullptr, mom.data(), st.data()))) return fail(rc, mvr_last_error(cs[0]));
     for (int i = 0; i < E; ++i) {
-      if (st[(size_t)i] == MVR_ERR_NO_INPUT) { edges[(size_t)i] = mvr_pair_moments{}; continue; }   // an empty view: no information
+      if (st[(size_t)i] == MVR_ERR_NO_INPUT) { mom[(size_t)i] = mvr_pair_moments{}; continue; }   // an empty view: no information
       if (st[(size_t)i]) return fail(st[(size_t)i], mvr_last_error(cs[(size_t)i]));
-      momentsTransform(mom[(size_t)i], views[(size_t)et[(size_t)i]].pose, nullptr, edges[(size_t)i]);
     }
+    std::vector<double> poses6;
     std::vector<Matrix4d> X;
-    rc = lumRelax(edges, es.data(), et.data(), V, lum_max_iterations, X);
+    rc = lumComputePcl(mom, es.data(), et.data(), V, lum_max_iterations, 0.0, poses6, X);
     if (std::getenv("MVR_DEBUG_LUM")) {
       double c = 0, n = 0;
-      for (const mvr_pair_moments& e : edges) { c += e.d2; n += e.n; }
+      for (const mvr_pair_moments& e : mom) { c += e.d2; n += e.n; }
       std::fprintf(stderr, "[lum] loop %d rc %d pairs %.0f mean d2 %.6f\n", loop, rc, n, n > 0 ? c / n : 0.0);
     }
-    if (rc) return fail(rc, "relaxation failed");
+    if (rc) return fail(rc, "LUM failed");
     for (int v = 0; v < V; ++v) views[(size_t)v].pose = multiply(X[(size_t)v], views[(size_t)v].pose);   // pose <- lum_T * pose
   }
   refineAxis(views);

@@ -155,6 +155,10 @@ bool savePointsAsc(const char* path, const void* rich_points48, size_t n);
 // LUM relaxation on correspondence moments (host): see lum.cpp.  edges[e] joins views src[e] -> tgt[e], sums in
 // the common world frame; X = rigid corrections, X[0] = identity.
 void momentsTransform(const mvr_pair_moments& in, const Matrix4d& pose, const double* new_origin, mvr_pair_moments& out);
+// pcl::registration::LUM::compute() on moments (lum.cpp): `iterations` sweeps of PCL's linearised update, vertex 0 fixed.
+// poses6: V x (x, y, z, roll, pitch, yaw); X: V transforms = lum.getTransformation(v).  Moments in ONE common frame.
+int lumComputePcl(const std::vector<mvr_pair_moments>& edges, const int* src, const int* tgt, int n_views, int iterations,
+                  double convergence_threshold, std::vector<double>& poses6, std::vector<Matrix4d>& X);
 int lumRelax(const std::vector<mvr_pair_moments>& edges, const int* src, const int* tgt, int n_views, int iterations,
              std::vector<Matrix4d>& X);
 // least squares min |A x - b| for a tall dense A (rows x cols, row-major): math_solvers::least_squares

@@ -383,3 +383,84 @@ def test_multi_create_without_gpu_fails_loudly(mvr):
         pytest.skip("needs a box without a GPU")
     h = ctypes.c_void_p()
     assert mvr.lib().mvr_multi_create(None, 2, ctypes.byref(h)) == mvr.ERR_CUDA and not h.value
+
+
+def _lum_ring(orc, synth, V=6, n=6000):
+    views, poses = synth.turntable_sequence(V, n)
+    E = synth.perturbation()
+    init = [(poses[v] @ E) if v % 2 else poses[v].copy() for v in range(V)]
+    clouds = [orc.apply_pose_double(views[v], init[v]) for v in range(V)]
+    edges = []
+    for i in range(V):
+        s, t = i, (i + 1) % V
+        iq, im, _ = orc.correspondences(clouds[s], clouds[t], 4.0, True)
+        edges.append((s, t, iq, im))
+    return views, poses, init, clouds, edges
+
+
+def test_lum_oracle_edge_model_is_the_exact_linearisation(orc):
+    """The restated computeEdge / incidenceCorrection pair (oracle/lum_oracle.py) is Borrmann et al.'s linearisation: for
+    R = Rx Ry Rz the Jacobian of a compounded point with respect to (x, y, z, roll, pitch, yaw) equals M(point) * H(pose)."""
+    import lum_oracle as L
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        p = np.concatenate([rng.normal(size=3) * 5, rng.normal(size=3) * 0.4])
+        x = rng.normal(size=3) * 50
+
+        def f(q):
+            ca, sa, cb, sb, cc, sc = np.cos(q[3]), np.sin(q[3]), np.cos(q[4]), np.sin(q[4]), np.cos(q[5]), np.sin(q[5])
+            Rx = np.array([[1, 0, 0], [0, ca, -sa], [0, sa, ca]]); Ry = np.array([[cb, 0, sb], [0, 1, 0], [-sb, 0, cb]])
+            Rz = np.array([[cc, -sc, 0], [sc, cc, 0], [0, 0, 1]])
+            return Rx @ Ry @ Rz @ x + q[:3]
+        J = np.stack([(f(p + 1e-6 * e) - f(p - 1e-6 * e)) / 2e-6 for e in np.eye(6)], axis=1)
+        a = f(p)
+        M = np.array([[1, 0, 0, 0, -a[1], a[2]], [0, 1, 0, -a[2], a[0], 0], [0, 0, 1, a[1], 0, -a[0]]])
+        assert np.abs(J - M @ L.incidence_correction(p)).max() < 1e-6 * np.abs(J).max()
+    # pcl::getTransformation is Translation * Rz(yaw) * Ry(pitch) * Rx(roll)
+    T = L.get_transformation([1, 2, 3, 0.1, 0.2, 0.3])
+    from scipy.spatial.transform import Rotation
+    assert np.allclose(T[:3, :3], Rotation.from_euler("ZYX", [0.3, 0.2, 0.1]).as_matrix()) and np.allclose(T[:3, 3], [1, 2, 3])
+
+
+def test_lum_compute_on_moments_equals_the_point_level_oracle(mvr, orc, synth):
+    """mvr_lum_compute (pcl::registration::LUM's sweeps on 30 doubles per edge) against oracle/lum_oracle.py, which walks the
+    correspondence lists like PCL's computeEdge: poses after 1, 5 and 16 sweeps agree to rounding; and the sweeps close the
+    ring (the drift of the perturbed poses shrinks)."""
+    import lum_oracle as L
+    views, poses, init, clouds, edges = _lum_ring(orc, synth)
+    V = len(views)
+    mom = [mvr.PairMoments.from_pairs(clouds[s][iq, :3], clouds[t][im, :3], origin=clouds[t][:, :3].mean(axis=0).astype(np.float64))
+           for (s, t, iq, im) in edges]
+    for sweeps in (1, 5, 16):
+        p6, X = mvr.lum_compute(mom, [e[0] for e in edges], [e[1] for e in edges], V, sweeps)
+        o6, OX = L.lum_compute(clouds, edges, max_iterations=sweeps)
+        # absolute coordinates of ~900 mm make M'M ill-conditioned: rounding level here is ~1e-8 mm / ~1e-11 rad
+        assert np.abs(p6[:, :3] - o6[:, :3]).max() < 1e-6 and np.abs(p6[:, 3:] - o6[:, 3:]).max() < 1e-9
+        for a, b in zip(X, OX):
+            assert np.abs(a - b).max() < 1e-6
+    assert np.all(p6[0] == 0)   # vertex 0 is the reference
+    # one edge without correspondences, one view without edges: no information, the rest still solves
+    mom2 = list(mom); mom2[2] = mvr.PairMoments()
+    p6b, _ = mvr.lum_compute(mom2, [e[0] for e in edges], [e[1] for e in edges], V, 4)
+    o6b, _ = L.lum_compute(clouds, [e if k != 2 else (e[0], e[1], e[2][:0], e[3][:0]) for k, e in enumerate(edges)], max_iterations=4)
+    assert np.abs(p6b[:, :3] - o6b[:, :3]).max() < 1e-6 and np.abs(p6b[:, 3:] - o6b[:, 3:]).max() < 1e-9
+
+
+def test_registration_lum_oracle_loop_reduces_drift(orc, synth):
+    """The reference's registrationLUM loop restated on the CPU (oracle/lum_oracle.registration_lum): the ring error against the
+    true poses falls with the number of outer loops."""
+    import lum_oracle as L
+    views, poses, init, _, _ = _lum_ring(orc, synth, n=6000)
+    V = len(views)
+
+    def err(P):
+        out = 0.0
+        for v in range(V):
+            R = (np.linalg.inv(P[0]) @ P[v])[:3, :3] @ (np.linalg.inv(poses[0]) @ poses[v])[:3, :3].T
+            w = 0.5 * np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+            out = max(out, float(np.arcsin(min(1.0, np.linalg.norm(w)))))
+        return out
+    e0 = err(init)
+    e4 = err(L.registration_lum(views, init, 64, 4.0, orc.correspondences, orc.apply_pose_double))
+    e10 = err(L.registration_lum(views, init, 160, 4.0, orc.correspondences, orc.apply_pose_double))
+    assert e10 < e4 < e0 and e10 < 0.75 * e0

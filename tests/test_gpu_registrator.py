@@ -177,35 +177,28 @@ def test_registration_lum_reduces_ring_error(mvr, synth, seq):
         got, _ = reg.register_turntable(views, tp, init_poses=init)
         reg.close()
         errs.append(max(rot_angle(np.linalg.inv(got[0]) @ got[v], np.linalg.inv(poses[0]) @ poses[v]) for v in range(V)))
-    assert before > 0.02 and errs[0] > errs[1] > errs[2] and errs[2] < 0.6 * before
+    assert before > 0.02 and errs[1] > errs[2] and errs[2] < 0.6 * before and errs[0] < 1.05 * before
 
 
 def test_registration_lum_matches_the_oracle_loop(mvr, orc, synth, seq):
-    """The same loop with the oracle's correspondences and numpy moments (tests/test_abi_and_host.py runs it on the
-    CPU): poses agree after 3 outer loops."""
+    """registrationLUM on the GPU (posing, reciprocal correspondences and their moments on the device, pcl::registration::LUM's
+    sweeps on the moments) against the reference's loop restated on the CPU (oracle/lum_oracle.registration_lum: the oracle's
+    correspondences, PCL's computeEdge over the point lists): poses after 1 and 3 outer loops within the north star's bars
+    (1e-5 rad, 1e-6 relative translation); measured gap reported in the assertion message."""
+    import lum_oracle
     V, n, views, poses, init = seq
-    icp = mvr.default_params(max_iterations=48, max_dist=4.0)
-    tp = mvr.turntable_params(pivot=synth.PIVOT, axis=synth.AXIS, icp=icp, mode=mvr.LUM)
-    reg = mvr.Registrator(0, 1)
-    got, _ = reg.register_turntable(views, tp, init_poses=init)
-    reg.close()
-    P = [np.array(T, dtype=np.float64) for T in init]
-    for loop in range(3):
-        edges = []
-        for i in range(V):
-            s, t = i, (i + 1) % V
-            guess = (np.linalg.inv(P[t]) @ P[s]).astype(np.float32)
-            a = orc.transform(views[s], guess)
-            q, m, _ = orc.correspondences(a, views[t], 4.0, True)
-            lo, hi = views[t][:, :3].min(0).astype(np.float64), views[t][:, :3].max(0).astype(np.float64)
-            mom = mvr.PairMoments.from_pairs(a[q, :3], views[t][m, :3], origin=0.5 * (lo + hi))
-            edges.append(mvr.pair_moments_transform(mom, P[t]))
-        X = mvr.lum_relax(edges, list(range(V)), [(i + 1) % V for i in range(V)], V, 16)
-        P = [X[v] @ P[v] for v in range(V)]
-    for v in range(V):
-        # a handful of borderline pairs may differ (the guesses agree to float rounding only): poses to ~1e-5
-        assert rot_angle(got[v], P[v]) < 5e-5
-        assert np.linalg.norm(got[v][:3, 3].astype(np.float64) - P[v][:3, 3]) < 5e-2
+    for loops in (1, 3):
+        icp = mvr.default_params(max_iterations=16 * loops, max_dist=4.0)
+        tp = mvr.turntable_params(pivot=synth.PIVOT, axis=synth.AXIS, icp=icp, mode=mvr.LUM)
+        reg = mvr.Registrator(0, 1)
+        got, _ = reg.register_turntable(views, tp, init_poses=init)
+        reg.close()
+        P = lum_oracle.registration_lum(views, init, 16 * loops, 4.0, orc.correspondences, orc.apply_pose_double)
+        for v in range(V):
+            ang = rot_angle(got[v], P[v])
+            dt = np.linalg.norm(got[v][:3, 3].astype(np.float64) - P[v][:3, 3]) / max(np.linalg.norm(P[v][:3, 3]), 1e-12)
+            # got is float32 (the ABI's pose type): 6e-8 relative on its own
+            assert ang < 1e-5 and dt < 1e-6, "view %d after %d loop(s): %.3g rad, %.3g relative translation" % (v, loops, ang, dt)
 
 
 def test_merge_registered_matches_reference_arithmetic(mvr, synth):
