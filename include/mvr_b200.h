@@ -390,6 +390,15 @@ int mvr_points_save_asc(const char* path, const void* rich_points, size_t n);
 int mvr_merge_registered(mvr_ctx* ctx, const void* const* views, const size_t* counts, const double* poses, const int* registered,
                          int n_views, int full_matrix_normals, void* out, size_t* out_count);
 
+/* PointCloud::denoise(segment_threshold, triangle_length) (mvr/src/point_cloud.cpp:423-466, called per view by
+ * Registrator::registration, mvr/src/registrator.cpp:719-744): the points whose connected component -- edges join points at most
+ * triangle_length apart; the reference takes them from a Delaunay triangulation, whose short edges have the same components as
+ * this radius graph -- has at least segment_threshold members.  points: n host records of stride_bytes (x, y, z first; 16 or
+ * 48).  kept_index (n entries): the indices of the kept points in the reference's output order (components by their smallest
+ * point index, points by index); non-finite points are singletons.  noise_count (nullable): the reference's noise_points_num_. */
+int mvr_denoise(mvr_ctx* ctx, const void* points, size_t n, size_t stride_bytes, int segment_threshold, double triangle_length,
+                int32_t* kept_index, size_t* kept_count, size_t* noise_count);
+
 #ifdef __cplusplus
 }
 #endif

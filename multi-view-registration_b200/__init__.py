@@ -181,6 +181,7 @@ def lib():
     L.mvr_icp_align_batch.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(IcpParams), fp, fp, C.POINTER(IcpReport), ip]
     L.mvr_icp_get_iterations.argtypes = [vp, C.POINTER(IcpIteration), C.c_int, C.POINTER(C.c_int)]
     L.mvr_fitness_score.argtypes = [vp, C.c_double, C.POINTER(C.c_double)]
+    L.mvr_denoise.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, C.c_double, ip, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.mvr_estimate_normals.argtypes = [vp, C.c_int, C.c_int, fp, fp, ip]
     dp = C.POINTER(C.c_double)
     L.mvr_apply_pose.argtypes = [vp, vp, C.c_size_t, C.c_size_t, dp, fp]
@@ -476,6 +477,17 @@ class Context:
         self._ck(lib().mvr_estimate_normals(self._h, int(which), int(k), _fp(vp), _fp(out), _ip(nbr) if nbr is not None else None))
         return (out, nbr) if want_neighbours else out
 
+
+    def denoise(self, pts, segment_threshold=10, triangle_length=2.5):
+        """PointCloud::denoise: (indices of the kept points in the reference's output order, number of noise points).
+        pts: n x 4 float32 (PointXYZ) or a RICH_POINT array (48-byte records)."""
+        a = np.ascontiguousarray(pts)
+        n = len(a)
+        stride = a.dtype.itemsize if a.dtype.fields else a.strides[0]
+        keep = np.empty(max(n, 1), dtype=np.int32)
+        cnt, noise = C.c_size_t(0), C.c_size_t(0)
+        self._ck(lib().mvr_denoise(self._h, a.ctypes.data, n, stride, int(segment_threshold), float(triangle_length), _ip(keep), C.byref(cnt), C.byref(noise)))
+        return keep[:cnt.value].copy(), int(noise.value)
 
     def apply_pose(self, pts, pose):
         """PointCloud::getTransformedPoints: pts (n x k float32, xyz first) -> n x 4 float32, pose 4x4 double."""

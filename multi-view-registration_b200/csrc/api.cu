@@ -1279,6 +1279,55 @@ int mvr_copy_aligned_device(mvr_ctx* ctx, float* d_out) {
   return MVR_OK;
 }
 
+int mvr_denoise(mvr_ctx* ctx, const void* points, size_t n, size_t stride_bytes, int segment_threshold, double triangle_length,
+                int32_t* kept_index, size_t* kept_count, size_t* noise_count) {
+  if (!ctx || !kept_count || (n && (!points || !kept_index))) return MVR_ERR_BAD_ARG;
+  if (stride_bytes < 12 || stride_bytes % 4 != 0) return fail(ctx, MVR_ERR_BAD_ARG, "stride must be a multiple of 4 and >= 12");
+  if (!(triangle_length > 0) || !std::isfinite(triangle_length)) return fail(ctx, MVR_ERR_BAD_ARG, "triangle_length must be positive");
+  if (n > (size_t)INT_MAX / 4) return fail(ctx, MVR_ERR_BAD_ARG, "cloud too large");
+  cudaSetDevice(ctx->device);
+  *kept_count = 0;
+  if (noise_count) *noise_count = 0;
+  if (n == 0) return MVR_OK;
+  const int ni = (int)n;
+  // the points as PointXYZ records on the device (identity pose: getTransformedPoints' narrowing of x, y, z only)
+  CK(ctx->scratch.ensure(n * stride_bytes));
+  CK(ctx->qtmp.ensure(n * sizeof(float4)));
+  CK(cudaMemcpyAsync(ctx->scratch.p, points, n * stride_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  const double I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  CK(launch_apply_pose(ctx->scratch.p, stride_bytes, ni, I16, ctx->qtmp.as<float4>(), ctx->stream));
+  // grid with cell edge = the edge threshold: every neighbour within it sits in the 27 cells around a point
+  Cloud tmp;
+  tmp.pts = ctx->qtmp.as<float4>(); tmp.n = ni;
+  int rc = cloud_bbox(ctx, tmp);
+  if (rc) return rc;
+  uint32_t cells = 0;
+  const PairGrid g = make_pair_grid(tmp.lo, tmp.hi, triangle_length * 1.0001, &cells);
+  if ((double)g.cell_lo < triangle_length) return fail(ctx, MVR_ERR_BAD_ARG, "cloud too large for this edge length (grid capped)");
+  PairIndex& ix = ctx->nq;
+  if ((rc = build_pair_index(ctx, ix, tmp.pts, ni, tmp.n_bad, nullptr, g, cells, false, false))) return rc;
+  // parent | count | keys | vals | keys_alt | vals_alt | hist | n_noise
+  const size_t nb = (size_t)radix_num_blocks(ni) * 256;
+  CK(ctx->itmp.ensure(((size_t)6 * n + nb + 16) * sizeof(uint32_t)));
+  uint32_t* parent = ctx->itmp.as<uint32_t>();
+  uint32_t *count = parent + n, *keys = count + n, *vals = keys + n, *keys_alt = vals + n, *vals_alt = keys_alt + n, *hist = vals_alt + n, *d_noise = hist + nb;
+  CK(cudaMemsetAsync(d_noise, 0, sizeof(uint32_t), ctx->stream));
+  CK(launch_denoise_components(ix.sorted.as<float4>(), ix.start.as<uint32_t>(), g, ni, ix.n_valid, triangle_length, parent, count, ctx->stream));
+  CK(launch_denoise_keys(parent, count, ni, (uint32_t)std::max(segment_threshold, 0), keys, vals, d_noise, ctx->stream));
+  uint32_t *ko = nullptr, *vo = nullptr;
+  SortScratch sc{keys_alt, vals_alt, hist};
+  CK(launch_radix_sort(keys, vals, ni, 32, sc, &ko, &vo, ctx->stream));   // stable: components by root, points by index
+  CK(cudaMemcpyAsync(ctx->h_small, d_noise, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const size_t noise = ctx->h_small[0], kept = n - noise;
+  if (kept) CK(cudaMemcpyAsync(kept_index, vo, kept * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *kept_count = kept;
+  if (noise_count) *noise_count = noise;
+  ctx->nq.valid = false;
+  return MVR_OK;
+}
+
 int mvr_estimate_normals(mvr_ctx* ctx, int which, int k, const float viewpoint[3], float* out, int32_t* neighbours) {
   if (!ctx || !out || (which != MVR_CLOUD_TARGET && which != MVR_CLOUD_SOURCE)) return MVR_ERR_BAD_ARG;
   if (k < 3 || k > 32) return fail(ctx, MVR_ERR_BAD_ARG, "k must be in 3..32");

@@ -202,6 +202,15 @@ cudaError_t launch_cell_nn(const float4* q_sorted, int nq, const uint32_t* d_nq_
 cudaError_t launch_warp_nn(const float4* q, int n, const float4* tgt_sorted, const uint32_t* tstart, PairGrid g, int m_valid, int32_t* out_idx,
                            float* out_d2, cudaStream_t s);
 
+// ---- denoise.cu ----------------------------------------------------------------------------
+// Connected components of the radius graph (edge iff distance <= threshold) over an index whose cell edge is >= threshold:
+// parent[i] = smallest point index of i's component, count[root] = its size (n entries each, original indices).
+cudaError_t launch_denoise_components(const float4* sorted, const uint32_t* start, PairGrid g, int n, int n_valid, double threshold,
+                                      uint32_t* parent, uint32_t* count, cudaStream_t s);
+// keys[i] = root of a kept point (component size >= segment_threshold), 0xffffffff of a dropped one; vals[i] = i; *n_noise += dropped.
+cudaError_t launch_denoise_keys(const uint32_t* parent, const uint32_t* count, int n, uint32_t segment_threshold, uint32_t* keys, uint32_t* vals,
+                                uint32_t* n_noise, cudaStream_t s);
+
 // ---- normals.cu ----------------------------------------------------------------------------
 cudaError_t launch_normals(IndexDev ix, const float4* pts_orig, int n, int k, float3 viewpoint, float4* out_nxyzc,
                            int32_t* out_nbr, cudaStream_t s);

@@ -567,6 +567,26 @@ int Registrator::registrationLUM(std::vector<View>& views, int max_iterations, d
   return MVR_OK;
 }
 
+int Registrator::registration(std::vector<View>& views, int segment_threshold, double triangle_length, std::vector<std::vector<int32_t> >& kept) {
+  if (!ok()) return fail(MVR_ERR_CUDA, "no GPU context");
+  const int V = (int)views.size();
+  kept.assign((size_t)V, std::vector<int32_t>());
+  for (int v = 0; v < V; ++v) {
+    View& w = views[(size_t)v];
+    w.view = v;
+    if (w.on_device) return fail(MVR_ERR_BAD_ARG, "registration: host views only");
+    kept[(size_t)v].resize(std::max<size_t>(w.size, 1));
+    size_t cnt = 0;
+    const int rc = mvr_denoise(ctx_[0], w.points, w.size, sizeof(PointXYZ), segment_threshold, triangle_length, kept[(size_t)v].data(), &cnt, nullptr);
+    if (rc) return fail(rc, mvr_last_error(ctx_[0]));
+    kept[(size_t)v].resize(cnt);
+    initRotation(w, V);
+    w.registered = true;
+  }
+  refineAxis(views);
+  return MVR_OK;
+}
+
 int Registrator::refineAxis(const std::vector<View>& views) {
   std::vector<Matrix4d> poses;
   for (size_t i = 1; i < views.size(); ++i)

@@ -108,6 +108,10 @@ class Registrator {
                             double transformation_epsilon, double euclidean_fitness_epsilon,
                             std::vector<mvr_pair_report>* reports = nullptr);
   int registrationLUM(std::vector<View>& views, int max_iterations, double max_distance);
+  // registration(object, segment_threshold) (mvr/src/registrator.cpp:719-744): every view is denoised (PointCloud::denoise with
+  // ParameterManager's triangle length, default 2.5), gets its turntable pose and counts as registered; then refineAxis.  The
+  // views' buffers are the caller's: kept[v] receives the indices of view v's surviving points in the reference's output order.
+  int registration(std::vector<View>& views, int segment_threshold, double triangle_length, std::vector<std::vector<int32_t> >& kept);
   // One LUM edge: reciprocal correspondences source -> target under `guess` (source in the target's frame),
   // reduced on the GPU to their moments (target frame).
   int edgeMoments(const View& source, const View& target, double max_distance, const Matrix4f& guess, int slot, mvr_pair_moments& out);

@@ -284,3 +284,30 @@ def estimate_normals(pts, k, viewpoint=(0.0, 0.0, 0.0), want_neighbours=False):
     nbr = np.empty((len(pts), k), dtype=np.int32) if want_neighbours else None
     lib().orc_estimate_normals(_f(pts), len(pts), int(k), _f(vp), _f(out), _i(nbr) if nbr is not None else None)
     return (out, nbr) if want_neighbours else out
+
+
+def denoise(pts, segment_threshold=10, triangle_length=2.5):
+    """PointCloud::denoise (mvr/src/point_cloud.cpp:423-466) restated: connected components of the graph of point pairs at
+    most triangle_length apart (the reference takes the edges from a CGAL Delaunay triangulation, :469-497; its short edges
+    contain the short edges of the Euclidean minimum spanning tree, so the components are those of this radius graph),
+    components smaller than segment_threshold dropped, output order = components by their smallest point index (the order
+    boost::connected_components discovers them), points by index (:441-447).  Returns (kept indices, number of noise points).
+    scipy does the neighbour search (cKDTree.query_pairs) and the labelling."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    from scipy.spatial import cKDTree
+    p = np.ascontiguousarray(np.asarray(pts)[:, :3], dtype=np.float64)
+    n = len(p)
+    if n == 0:
+        return np.zeros(0, dtype=np.int32), 0
+    ok = np.isfinite(p).all(axis=1)
+    idx = np.flatnonzero(ok)
+    pairs = cKDTree(p[ok]).query_pairs(float(triangle_length), output_type="ndarray") if len(idx) else np.zeros((0, 2), dtype=np.int64)
+    g = coo_matrix((np.ones(len(pairs), dtype=np.int8), (idx[pairs[:, 0]], idx[pairs[:, 1]])), shape=(n, n))
+    _, label = connected_components(g, directed=False)
+    size = np.bincount(label, minlength=label.max() + 1)
+    first = np.full(label.max() + 1, n, dtype=np.int64)
+    np.minimum.at(first, label, np.arange(n))
+    keep = np.flatnonzero(size[label] >= segment_threshold)
+    order = np.lexsort((keep, first[label[keep]]))
+    return keep[order].astype(np.int32), int(n - len(keep))

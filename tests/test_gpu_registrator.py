@@ -288,3 +288,37 @@ def test_multi_gpu_entry_point_matches_the_single_gpu_driver(mvr, synth):
         assert ring.pose_checksum(recs2) == want
         assert len(ms) == g and all(x > 0 for x in ms)
         m.close()
+
+
+def test_denoise_matches_the_oracle(mvr, orc, synth):
+    """PointCloud::denoise (mvr/src/point_cloud.cpp:423-466): kept indices, in the reference's output order, equal the oracle's
+    (scipy neighbour pairs + connected components) -- a scan plus isolated specks, 16-byte and 48-byte records, thresholds."""
+    rng = np.random.default_rng(21)
+    scan, _ = synth.turntable_view(2, 12, 40_000)
+    lo, hi = scan[:, :3].min(axis=0), scan[:, :3].max(axis=0)
+    specks = []
+    for k in range(60):   # small clusters floating off the surface: 1 .. 14 points each
+        c = lo + rng.random(3) * (hi - lo) + np.array([0, 0, 60.0])
+        specks.append(c + rng.normal(size=(1 + k % 14, 3)) * 0.4)
+    specks = np.concatenate(specks).astype(np.float32)
+    pts = np.ones((len(scan) + len(specks), 4), dtype=np.float32)
+    pts[:len(scan), :3] = scan[:, :3]; pts[len(scan):, :3] = specks
+    pts = pts[rng.permutation(len(pts))]
+    c = mvr.Context(0)
+    for thr, length in ((10, 2.5), (3, 2.5), (10, 1.0), (1, 0.5)):
+        keep, noise = c.denoise(pts, thr, length)
+        okeep, onoise = orc.denoise(pts, thr, length)
+        assert noise == onoise and np.array_equal(keep, okeep), "segment_threshold %d, triangle_length %g" % (thr, length)
+    keep, noise = c.denoise(pts, 10, 2.5)
+    assert 0 < noise < 1000 and len(keep) + noise == len(pts)
+    # PointXYZRGBNormal records, a non-finite point, the empty cloud
+    rich = np.zeros(len(pts), dtype=mvr.RICH_POINT)
+    rich["x"], rich["y"], rich["z"] = pts[:, 0], pts[:, 1], pts[:, 2]
+    rich["x"][5] = np.nan
+    k2, n2 = c.denoise(rich, 10, 2.5)
+    p2 = pts.copy(); p2[5, 0] = np.nan
+    ok2, on2 = orc.denoise(p2, 10, 2.5)
+    assert n2 == on2 and np.array_equal(k2, ok2) and 5 not in k2
+    k0, n0 = c.denoise(pts[:0], 10, 2.5)
+    assert len(k0) == 0 and n0 == 0
+    c.close()
