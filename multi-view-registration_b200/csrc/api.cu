@@ -1312,8 +1312,8 @@ int mvr_denoise(mvr_ctx* ctx, const void* points, size_t n, size_t stride_bytes,
   uint32_t* parent = ctx->itmp.as<uint32_t>();
   uint32_t *count = parent + n, *keys = count + n, *vals = keys + n, *keys_alt = vals + n, *vals_alt = keys_alt + n, *hist = vals_alt + n, *d_noise = hist + nb;
   CK(cudaMemsetAsync(d_noise, 0, sizeof(uint32_t), ctx->stream));
-  CK(launch_denoise_components(ix.sorted.as<float4>(), ix.start.as<uint32_t>(), g, ni, ix.n_valid, triangle_length, parent, count, ctx->stream));
-  CK(launch_denoise_keys(parent, count, ni, (uint32_t)std::max(segment_threshold, 0), keys, vals, d_noise, ctx->stream));
+  CK(launch_denoise_components(ix.sorted.as<float4>(), ix.start.as<uint32_t>(), g, ni, ix.n_valid, triangle_length, parent, keys, count, ctx->stream));
+  CK(launch_denoise_keys(count, ni, (uint32_t)std::max(segment_threshold, 0), keys, vals, d_noise, ctx->stream));
   uint32_t *ko = nullptr, *vo = nullptr;
   SortScratch sc{keys_alt, vals_alt, hist};
   CK(launch_radix_sort(keys, vals, ni, 32, sc, &ko, &vo, ctx->stream));   // stable: components by root, points by index

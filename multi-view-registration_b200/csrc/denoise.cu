@@ -65,20 +65,22 @@ __global__ void __launch_bounds__(128) k_dn_edges(const float4* __restrict__ sor
     }
 }
 
-__global__ void __launch_bounds__(256) k_dn_count(uint32_t* __restrict__ parent, uint32_t* __restrict__ count, int n) {
+// root[i] goes to its own array: parent[i] may still be rewritten (to an ancestor that is not the root) by the path halving
+// of another thread's find that passes through i.
+__global__ void __launch_bounds__(256) k_dn_count(uint32_t* __restrict__ parent, uint32_t* __restrict__ root, uint32_t* __restrict__ count, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t r = dn_find(parent, (uint32_t)i);
-  parent[i] = r;
+  root[i] = r;
   atomicAdd(count + r, 1u);
 }
 
-// key = root for a kept point, 0xffffffff for a dropped one; val = point index
-__global__ void __launch_bounds__(256) k_dn_keys(const uint32_t* __restrict__ parent, const uint32_t* __restrict__ count, int n, uint32_t threshold,
+// in: keys[i] = root of point i; out: key = root for a kept point, 0xffffffff for a dropped one; val = point index
+__global__ void __launch_bounds__(256) k_dn_keys(const uint32_t* __restrict__ count, int n, uint32_t threshold,
                                                  uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ n_noise) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint32_t r = parent[i];
+  const uint32_t r = keys[i];
   const bool keep = count[r] >= threshold;
   keys[i] = keep ? r : 0xffffffffu;
   vals[i] = (uint32_t)i;
@@ -87,18 +89,18 @@ __global__ void __launch_bounds__(256) k_dn_keys(const uint32_t* __restrict__ pa
 }
 
 cudaError_t launch_denoise_components(const float4* sorted, const uint32_t* start, PairGrid g, int n, int n_valid, double threshold,
-                                      uint32_t* parent, uint32_t* count, cudaStream_t s) {
+                                      uint32_t* parent, uint32_t* root, uint32_t* count, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   k_dn_init<<<(n + 255) / 256, 256, 0, s>>>(parent, count, n); count_launch();
   if (n_valid > 0) { k_dn_edges<<<(n_valid + 127) / 128, 128, 0, s>>>(sorted, start, g, n_valid, threshold, parent); count_launch(); }
-  k_dn_count<<<(n + 255) / 256, 256, 0, s>>>(parent, count, n); count_launch();
+  k_dn_count<<<(n + 255) / 256, 256, 0, s>>>(parent, root, count, n); count_launch();
   return cudaGetLastError();
 }
 
-cudaError_t launch_denoise_keys(const uint32_t* parent, const uint32_t* count, int n, uint32_t segment_threshold, uint32_t* keys, uint32_t* vals,
+cudaError_t launch_denoise_keys(const uint32_t* count, int n, uint32_t segment_threshold, uint32_t* keys, uint32_t* vals,
                                 uint32_t* n_noise, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  k_dn_keys<<<(n + 255) / 256, 256, 0, s>>>(parent, count, n, segment_threshold, keys, vals, n_noise); count_launch();
+  k_dn_keys<<<(n + 255) / 256, 256, 0, s>>>(count, n, segment_threshold, keys, vals, n_noise); count_launch();
   return cudaGetLastError();
 }
 

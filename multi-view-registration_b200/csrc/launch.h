@@ -204,11 +204,12 @@ cudaError_t launch_warp_nn(const float4* q, int n, const float4* tgt_sorted, con
 
 // ---- denoise.cu ----------------------------------------------------------------------------
 // Connected components of the radius graph (edge iff distance <= threshold) over an index whose cell edge is >= threshold:
-// parent[i] = smallest point index of i's component, count[root] = its size (n entries each, original indices).
+// root[i] = smallest point index of i's component, count[root] = its size (n entries each, original indices); parent = scratch.
 cudaError_t launch_denoise_components(const float4* sorted, const uint32_t* start, PairGrid g, int n, int n_valid, double threshold,
-                                      uint32_t* parent, uint32_t* count, cudaStream_t s);
-// keys[i] = root of a kept point (component size >= segment_threshold), 0xffffffff of a dropped one; vals[i] = i; *n_noise += dropped.
-cudaError_t launch_denoise_keys(const uint32_t* parent, const uint32_t* count, int n, uint32_t segment_threshold, uint32_t* keys, uint32_t* vals,
+                                      uint32_t* parent, uint32_t* root, uint32_t* count, cudaStream_t s);
+// in: keys[i] = root[i].  out: keys[i] = root of a kept point (component size >= segment_threshold), 0xffffffff of a dropped one;
+// vals[i] = i; *n_noise += dropped.
+cudaError_t launch_denoise_keys(const uint32_t* count, int n, uint32_t segment_threshold, uint32_t* keys, uint32_t* vals,
                                 uint32_t* n_noise, cudaStream_t s);
 
 // ---- normals.cu ----------------------------------------------------------------------------
