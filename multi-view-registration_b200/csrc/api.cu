@@ -1336,12 +1336,14 @@ int mvr_estimate_normals(mvr_ctx* ctx, int which, int k, const float viewpoint[3
   if (c.gen == 0) return fail(ctx, MVR_ERR_NO_INPUT, "cloud not set");
   const int n = c.n;
   if (n == 0) return MVR_OK;
-  if (!c.index_valid || c.index_gen != c.gen) {
-    // kNN wants about k points in the 27-neighbourhood: ~k/4 per occupied cell on a surface
-    double e = ctx->cell_edge_opt > 0 ? ctx->cell_edge_opt : density_cell_edge(c.lo, c.hi, n - c.n_bad, std::max(2.0, k / 4.0));
-    int rc = bin_index(ctx, c, const_cast<float4*>(c.pts), make_grid(c.lo, c.hi, e, ctx->max_bits_opt), nullptr, nullptr);
-    if (rc) return rc;
-  }
+  // the cell edge is ~1.25 x the expected distance of the k-th neighbour on a surface of the cloud's density: the 27 cells around
+  // a point then hold its k neighbours and prove it (the k-th distance is below one cell) for nearly every point
+  const double e = ctx->cell_edge_opt > 0 ? ctx->cell_edge_opt : density_cell_edge(c.lo, c.hi, n - c.n_bad, std::max(2.0, k / 3.0));
+  uint32_t cells = 0;
+  const PairGrid g = make_pair_grid(c.lo, c.hi, e, &cells);
+  PairIndex& ix = ctx->nq;
+  int rc = build_pair_index(ctx, ix, c.pts, n, c.n_bad, nullptr, g, cells, false, false);
+  if (rc) return rc;
   float3 vp = viewpoint ? make_float3(viewpoint[0], viewpoint[1], viewpoint[2]) : make_float3(0.f, 0.f, 0.f);
   DevBuf& nb = which == MVR_CLOUD_TARGET ? ctx->normals : ctx->qtmp;
   CK(nb.ensure((size_t)n * sizeof(float4)));
@@ -1349,8 +1351,9 @@ int mvr_estimate_normals(mvr_ctx* ctx, int which, int k, const float viewpoint[3
   if (neighbours) { CK(ctx->itmp.ensure((size_t)n * k * sizeof(int32_t))); dn = ctx->itmp.as<int32_t>(); }
   {
     ProfScope ps(ctx, MVR_K_NORMALS, 32.0 * n, n);
-    CK(launch_normals(c.dev(), c.pts, n, k, vp, nb.as<float4>(), dn, ctx->stream));
+    CK(launch_normals(ix.sorted.as<float4>(), ix.start.as<uint32_t>(), g, n, ix.n_valid, k, vp, nb.as<float4>(), dn, ctx->stream));
   }
+  ix.valid = false;
   CK(cudaMemcpyAsync(out, nb.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
   if (neighbours) CK(cudaMemcpyAsync(neighbours, dn, (size_t)n * k * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));

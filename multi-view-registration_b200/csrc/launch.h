@@ -213,7 +213,9 @@ cudaError_t launch_denoise_keys(const uint32_t* count, int n, uint32_t segment_t
                                 uint32_t* n_noise, cudaStream_t s);
 
 // ---- normals.cu ----------------------------------------------------------------------------
-cudaError_t launch_normals(IndexDev ix, const float4* pts_orig, int n, int k, float3 viewpoint, float4* out_nxyzc,
+// sorted / start / g: a row-major index of the cloud (pair_index.cu; the order inside a cell does not matter), n points of which
+// the first n_valid sorted positions are finite.  out_nxyzc / out_nbr are indexed by ORIGINAL point index.
+cudaError_t launch_normals(const float4* sorted, const uint32_t* start, PairGrid g, int n, int n_valid, int k, float3 viewpoint, float4* out_nxyzc,
                            int32_t* out_nbr, cudaStream_t s);
 
 }  // namespace mvr
