@@ -135,6 +135,10 @@ int mvr_ctx_set_nn_options(mvr_ctx* ctx, double points_per_cell, double dense_ra
  * cell-cooperative pass from dense_ratio queries per target point on; WARP / THREAD / CELL force one of them. */
 typedef enum { MVR_NN_AUTO = 0, MVR_NN_WARP = 1, MVR_NN_THREAD = 2, MVR_NN_CELL = 3 } mvr_nn_mode;
 int mvr_ctx_set_nn_mode(mvr_ctx* ctx, int mode);
+/* Gate mask of the target index (default off): one bit per grid cell, "some target point lies within the gate of this cell".
+ * With it a source point without a partner inside the gate is settled by one load instead of a gate-wide search; worth its
+ * build time (two small kernels per target) when a large part of the source has no partner.  Results are identical. */
+int mvr_ctx_set_gate_mask(mvr_ctx* ctx, int on);
 
 /* -- inputs: icp.setInputTarget / icp.setInputSource (mvr/src/registrator.cpp:566-567, 776-777,
  *    913-914) and CorrespondenceEstimation::setInputSource/Target (:497-498, 645-646).

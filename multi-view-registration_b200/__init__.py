@@ -170,6 +170,7 @@ def lib():
     L.mvr_ctx_set_batch_group.argtypes = [vp, C.c_int]
     L.mvr_ctx_set_nn_options.argtypes = [vp, C.c_double, C.c_double]
     L.mvr_ctx_set_nn_mode.argtypes = [vp, C.c_int]
+    L.mvr_ctx_set_gate_mask.argtypes = [vp, C.c_int]
     for name in ("mvr_set_target", "mvr_set_source", "mvr_set_target_device", "mvr_set_source_device", "mvr_set_target_normals"):
         getattr(L, name).argtypes = [vp, vp, C.c_size_t]
     L.mvr_index_build.argtypes = [vp, C.c_int, C.POINTER(Grid)]
@@ -354,6 +355,9 @@ class Context:
     def set_nn_mode(self, mode):
         """NN_AUTO / NN_WARP / NN_THREAD / NN_CELL: which kernel answers nn_query (identical results)."""
         self._ck(lib().mvr_ctx_set_nn_mode(self._h, int(mode)))
+
+    def set_gate_mask(self, on):
+        self._ck(lib().mvr_ctx_set_gate_mask(self._h, 1 if on else 0))
 
     def set_batch_group(self, pairs):
         """Pairs per kernel launch of the batches this context leads (1..24)."""

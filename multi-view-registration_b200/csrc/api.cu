@@ -13,11 +13,17 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mvr_b200.h"
 #include "launch.h"
 #include "small_solve.h"
+
+// x cells per y/z cell edge of the per-align indices of the fused ICP iteration (pair_search.cuh); measured in DESIGN.md section 7
+#ifndef MVR_PG_XRATIO
+#define MVR_PG_XRATIO 2
+#endif
 
 using namespace mvr;
 
@@ -105,6 +111,7 @@ struct mvr_ctx {
   double nn_ppc = 8.0;           // its target points per occupied cell
   double nn_dense_ratio = 8.0;   // queries per target point from which the dense pass is used (0: never)
   int nn_mode = MVR_NN_AUTO;     // mvr_ctx_set_nn_mode
+  bool gate_mask = false;        // mvr_ctx_set_gate_mask
   FwdArgs fa{}; RevArgs ra{};    // kernel arguments of the prepared align
   bool want_rnn = false;         // the next prepared align also records the mutual partners (mvr_correspondences)
   int group_pairs = 24;          // pairs per launch of a batch led by this context (mvr_ctx_set_batch_group)
@@ -301,7 +308,7 @@ int bin_index(mvr_ctx* ctx, Cloud& c, float4* pts, const mvr_grid& g, const floa
     CK(c.counters.ensure((cells + 1) * sizeof(uint32_t)));
     CK(cudaMemsetAsync(c.counters.p, 0, c.counters.cap, ctx->stream));   // k_scan_cells keeps them zero afterwards
   }
-  const size_t tiles = (size_t)scan_num_tiles(cells + 1);
+  const size_t tiles = (size_t)scan_num_tiles(cells + 1) + 1;   // + the ticket word
   if (tiles * sizeof(unsigned long long) > ctx->tiles.cap) {
     CK(ctx->tiles.ensure(tiles * sizeof(unsigned long long)));
     CK(cudaMemsetAsync(ctx->tiles.p, 0, ctx->tiles.cap, ctx->stream));
@@ -333,7 +340,7 @@ mvr_grid auto_grid(mvr_ctx* ctx, const Cloud& c) {
   return make_grid(c.lo, c.hi, e, ctx->max_bits_opt);
 }
 
-PairGrid make_pair_grid(const float lo[3], const float hi[3], double e, uint32_t* cells_out);
+PairGrid make_pair_grid(const float lo[3], const float hi[3], double e, uint32_t* cells_out, int xr = 1);
 bool same_pair_grid(const PairGrid& a, const PairGrid& b);
 int build_pair_index(mvr_ctx* ctx, PairIndex& ix, const float4* pts, int n, int n_bad, const Mat4f* guess, const PairGrid& g,
                      uint32_t cells, bool keep_s0, bool ordered = true);
@@ -371,7 +378,7 @@ int nn_pass(mvr_ctx* ctx, const float4* q, int n, int32_t* d_idx, float* d_d2) {
   Cloud& t = ctx->tgt;
   PairIndex& pt = ctx->pt;
   int rc;
-  if (!(pt.valid && pt.gen == t.gen)) {
+  if (!(pt.valid && pt.gen == t.gen && pt.g.xr == 1.0f)) {   // the NN kernels take isotropic cells
     uint32_t cells = 0;
     const PairGrid gt = make_pair_grid(t.lo, t.hi, pair_cell_edge(ctx, t, INFINITY), &cells);
     if ((rc = build_pair_index(ctx, pt, t.pts, t.n, t.n_bad, nullptr, gt, cells, false))) return rc;
@@ -415,9 +422,11 @@ double pair_cell_edge(mvr_ctx* ctx, const Cloud& c, double max_dist) {
   return (m2 < 1e30) ? std::min(std::max(0.5 * max_dist * 1.002, e_lo), e_hi) : density_cell_edge(c.lo, c.hi, nv, 6.0);
 }
 
-// Grid over the box [lo, hi] padded by one cell; the edge grows until the table fits max_cells.
-PairGrid make_pair_grid(const float lo[3], const float hi[3], double e, uint32_t* cells_out) {
+// Grid over the box [lo, hi] padded by one cell; the edge grows until the table fits max_cells.  xr (1, 2, 4 or 8): x cells
+// per y/z cell edge.
+PairGrid make_pair_grid(const float lo[3], const float hi[3], double e, uint32_t* cells_out, int xr) {
   const double max_cells = 16.0 * 1024 * 1024;
+  if (xr != 1 && xr != 2 && xr != 4 && xr != 8) xr = 1;
   double ext[3];
   for (int a = 0; a < 3; ++a) {
     ext[a] = (double)hi[a] - (double)lo[a];
@@ -427,8 +436,13 @@ PairGrid make_pair_grid(const float lo[3], const float hi[3], double e, uint32_t
   int n[3];
   for (;;) {
     double tot = 1;
-    for (int a = 0; a < 3; ++a) { n[a] = (int)std::min(4096.0, std::floor(ext[a] / e) + 3.0); tot *= n[a]; }
+    for (int a = 0; a < 3; ++a) {
+      const int r = a == 0 ? xr : 1;
+      n[a] = (int)std::min(4096.0 * r, std::floor(ext[a] / (e / r)) + 3.0 * r);
+      tot *= n[a];
+    }
     if (tot <= max_cells) break;
+    if (xr > 1) { xr /= 2; continue; }   // a coarser x first, then larger cells
     e *= 1.25;
   }
   PairGrid g;
@@ -439,6 +453,8 @@ PairGrid make_pair_grid(const float lo[3], const float hi[3], double e, uint32_t
   g.inv_cell = (float)(1.0 / e);
   g.cell_lo = std::nextafterf((float)((1.0 / (double)g.inv_cell) * (1.0 - 1e-6)), 0.0f);
   g.nx = n[0]; g.ny = n[1]; g.nz = n[2];
+  g.xr = (float)xr;
+  g.inv_cell_x = g.inv_cell * g.xr;
   *cells_out = (uint32_t)n[0] * (uint32_t)n[1] * (uint32_t)n[2];
   return g;
 }
@@ -461,7 +477,7 @@ int build_pair_index(mvr_ctx* ctx, PairIndex& ix, const float4* pts, int n, int 
     CK(ctx->pcount.ensure(((size_t)cells + 1) * sizeof(uint32_t)));
     CK(cudaMemsetAsync(ctx->pcount.p, 0, ctx->pcount.cap, ctx->stream));   // k_scan_cells keeps the counters zero afterwards
   }
-  const size_t tiles = (size_t)scan_num_tiles((size_t)cells + 1);
+  const size_t tiles = (size_t)scan_num_tiles((size_t)cells + 1) + 1;   // + the ticket word
   if (tiles * sizeof(unsigned long long) > ctx->tiles.cap) {
     CK(ctx->tiles.ensure(tiles * sizeof(unsigned long long)));
     CK(cudaMemsetAsync(ctx->tiles.p, 0, ctx->tiles.cap, ctx->stream));
@@ -485,18 +501,22 @@ int build_pair_index(mvr_ctx* ctx, PairIndex& ix, const float4* pts, int n, int 
 // wide) the forward half searches every point.  Cells more than D apart in an axis are >= D cells apart along it; the
 // rounding of grid_t on the query and on the target point is absorbed by `slack` cells.
 int ensure_gate_mask(mvr_ctx* ctx, PairIndex& ix, float max_d2f) {
-  if (!(max_d2f < 3.0e38f) || ix.n_valid <= 0) { ix.gm_gate = -1.f; return MVR_OK; }
+  // Off unless asked for (mvr_ctx_set_gate_mask): on the bench workload (neighbouring views of a 24-view turntable, ~4 % of the
+  // source points beyond the gate) the mask saves 0.03 ms over 22 iterations and costs 0.2 ms to build for 24 targets
+  // (profiles/r02_iteration_ab.log); it pays when a large part of the source has no partner (little overlap).
+  if (!ctx->gate_mask || !(max_d2f < 3.0e38f) || ix.n_valid <= 0) { ix.gm_gate = -1.f; return MVR_OK; }
   if (ix.gm_gate == max_d2f) return MVR_OK;
   const double slack = 2.0 * ((double)MVR_CELL_MARGIN + 1.0e-6 * (double)std::max(ix.g.nx, std::max(ix.g.ny, ix.g.nz)));
   const double need = std::sqrt((double)max_d2f) * (1.0 + 1.0e-5) / (double)ix.g.cell_lo + slack;
   const int D = (int)std::ceil(need);
+  const int Dx = (int)std::ceil(need * (double)ix.g.xr);
   ix.gm_gate = -1.f;
-  if (D < 1 || D > 6) return MVR_OK;
+  if (D < 1 || D > 6 || Dx > 31) return MVR_OK;
   const int wstride = (ix.g.nx + 31) / 32;
   const size_t words = (size_t)ix.g.ny * ix.g.nz * wstride;
   CK(ix.gocc.ensure(words * sizeof(uint32_t)));
   CK(ix.gmask.ensure(words * sizeof(uint32_t)));
-  CK(launch_gate_mask(ix.start.as<uint32_t>(), ix.g, wstride, D, ix.gocc.as<uint32_t>(), ix.gmask.as<uint32_t>(), ctx->stream));
+  CK(launch_gate_mask(ix.start.as<uint32_t>(), ix.g, wstride, D, Dx, ix.gocc.as<uint32_t>(), ix.gmask.as<uint32_t>(), ctx->stream));
   ix.gm_stride = wstride;
   ix.gm_gate = max_d2f;
   return MVR_OK;
@@ -508,6 +528,20 @@ int ensure_pinned(mvr_ctx* ctx) {
   if (!ctx->h_state) CK(cudaMallocHost((void**)&ctx->h_state, sizeof(IcpState)));
   if (!ctx->h_log) CK(cudaMallocHost((void**)&ctx->h_log, ICP_MAX_LOG * sizeof(IterRec)));
   return MVR_OK;
+}
+
+// fn(k) for k in [0, n) on up to MVR_HOST_THREADS (environment, default 6) host threads; the calling thread takes part.
+template <class F>
+void parallel_for(int n, F fn) {
+  static const int max_threads = [] { const char* e = std::getenv("MVR_HOST_THREADS"); const int v = e ? std::atoi(e) : 6; return v < 1 ? 1 : (v > 64 ? 64 : v); }();
+  const int nt = std::min(max_threads, n);
+  if (nt <= 1) { for (int k = 0; k < n; ++k) fn(k); return; }
+  std::atomic<int> next{0};
+  auto work = [&] { for (int k = next.fetch_add(1); k < n; k = next.fetch_add(1)) fn(k); };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nt; ++t) th.emplace_back(work);
+  work();
+  for (std::thread& t : th) t.join();
 }
 
 // Algorithmic bytes of one iteration's correspondence search: each query read once
@@ -649,6 +683,13 @@ int mvr_ctx_set_nn_options(mvr_ctx* ctx, double points_per_cell, double dense_ra
   return MVR_OK;
 }
 
+int mvr_ctx_set_gate_mask(mvr_ctx* ctx, int on) {
+  if (!ctx) return MVR_ERR_BAD_ARG;
+  ctx->gate_mask = on != 0;
+  ctx->pt.gm_gate = -1.f;
+  return MVR_OK;
+}
+
 int mvr_ctx_set_nn_mode(mvr_ctx* ctx, int mode) {
   if (!ctx || mode < MVR_NN_AUTO || mode > MVR_NN_CELL) return MVR_ERR_BAD_ARG;
   ctx->nn_mode = mode;
@@ -776,6 +817,7 @@ int mvr_nn_query(mvr_ctx* ctx, const float* q, size_t n, int32_t* idx, float* d2
 }
 
 static int align_prepare(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, int est);
+
 static int align_run(mvr_ctx* const* ctxs, int count, const mvr_icp_params* prm, int est);
 
 int mvr_correspondences(mvr_ctx* ctx, double max_dist, int reciprocal, int32_t* iq, int32_t* im, float* dist, size_t* count) {
@@ -854,7 +896,7 @@ static int align_prepare(mvr_ctx* ctx, const mvr_icp_params* prm, const float* g
   int rc = MVR_OK;
   {
     uint32_t cells = 0;
-    const PairGrid gt = make_pair_grid(ctx->tgt.lo, ctx->tgt.hi, pair_cell_edge(ctx, ctx->tgt, max_dist), &cells);
+    const PairGrid gt = make_pair_grid(ctx->tgt.lo, ctx->tgt.hi, pair_cell_edge(ctx, ctx->tgt, max_dist), &cells, MVR_PG_XRATIO);
     PairIndex& pt = ctx->pt;
     if (!(pt.valid && pt.gen == ctx->tgt.gen && same_pair_grid(pt.g, gt))) {
       if ((rc = build_pair_index(ctx, pt, ctx->tgt.pts, m, ctx->tgt.n_bad, nullptr, gt, cells, false))) return rc;
@@ -875,7 +917,7 @@ static int align_prepare(mvr_ctx* ctx, const mvr_icp_params* prm, const float* g
     for (int a = 0; a < 3; ++a) if (!(lo[a] <= hi[a])) { lo[a] = 0.f; hi[a] = 0.f; }
     uint32_t cells = 0;
     // the cell edge follows the source's own density (its box as given: a rigid guess keeps the surface area)
-    const PairGrid gs = make_pair_grid(lo, hi, pair_cell_edge(ctx, s, max_dist), &cells);
+    const PairGrid gs = make_pair_grid(lo, hi, pair_cell_edge(ctx, s, max_dist), &cells, MVR_PG_XRATIO);
     Mat4f Gm;
     std::memcpy(Gm.m, G, sizeof(Gm.m));
     if ((rc = build_pair_index(ctx, ctx->ps, s.pts, n, s.n_bad, &Gm, gs, cells, false))) return rc;
@@ -1085,10 +1127,11 @@ int mvr_icp_align_batch(mvr_ctx* const* ctxs, int count, const mvr_icp_params* p
   const bool timing = std::getenv("MVR_DEBUG_TIMING") != nullptr;
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t0 = now();
-  for (int k = 0; k < count; ++k) {
-    statuses[k] = align_prepare(ctxs[k], prm, guesses ? guesses + 16 * k : nullptr, est);
+  // every pair's preparation (index builds, initial state: ~14 small launches on the pair's own stream) is enqueued by a few
+  // host threads at once: one thread spends ~50 us per pair on launch calls alone
+  parallel_for(count, [&](int k) { statuses[k] = align_prepare(ctxs[k], prm, guesses ? guesses + 16 * k : nullptr, est); });
+  for (int k = 0; k < count; ++k)
     if (statuses[k] == MVR_OK) { ok.push_back(ctxs[k]); slot.push_back(k); }
-  }
   if (ok.empty()) return MVR_OK;
   const double t1 = now();
   int rc = align_run(ok.data(), (int)ok.size(), prm, est);
@@ -1155,11 +1198,12 @@ int mvr_pair_moments_compute_batch(mvr_ctx* const* ctxs, int count, double max_d
   one.min_correspondences = 1;
   std::vector<mvr_ctx*> ok;
   std::vector<int> slot;
-  for (int k = 0; k < count; ++k) {
+  parallel_for(count, [&](int k) {
     std::memset(out + k, 0, sizeof(mvr_pair_moments));
     statuses[k] = align_prepare(ctxs[k], &one, guesses ? guesses + 16 * k : nullptr, EST_MOM);
+  });
+  for (int k = 0; k < count; ++k)
     if (statuses[k] == MVR_OK) { ok.push_back(ctxs[k]); slot.push_back(k); }
-  }
   if (ok.empty()) return MVR_OK;
   int rc = align_run(ok.data(), (int)ok.size(), &one, EST_MOM);
   if (rc) { if (ok[0] != ctxs[0]) ctxs[0]->err = ok[0]->err; return rc; }

@@ -42,31 +42,45 @@ __global__ void __launch_bounds__(256) k_transform_bin(float4* __restrict__ pts,
 }
 
 // ---------------------------------------------------------------------------------------------
-// single-pass exclusive scan (Merrill & Garland decoupled look-back), 2048 counters per tile.
+// single-pass exclusive scan (Merrill & Garland decoupled look-back), 8192 counters per tile.
 // tile_state[t] = (epoch*4 + flag) << 32 | value, flag 1 = tile aggregate, 2 = inclusive prefix;
 // words written under an older epoch read as "not ready", so the array never needs clearing.
 // ---------------------------------------------------------------------------------------------
 constexpr int SC_THREADS = 256;
-constexpr int SC_ITEMS = 8;
+constexpr int SC_ITEMS = 32;   // counters per thread: the prefix travels down the tiles 32 tiles per look-back round trip, so a
+                               // tile is made large (8192 counters) -- with 2048 a 1.7M-cell table took 25 us, latency all of it
 constexpr int SC_TILE = SC_THREADS * SC_ITEMS;
 
 int scan_num_tiles(size_t len) { return (int)((len + SC_TILE - 1) / SC_TILE); }
 
+// tile_state[0] is the ticket counter of the launch (tiles are handed out in the order blocks START, so a tile never waits
+// for a predecessor that has not been scheduled yet; the block that draws the last ticket resets the counter for the next
+// launch); tile t's state word lives at tile_state[1 + t].
 __global__ void __launch_bounds__(SC_THREADS) k_scan_cells(uint32_t* __restrict__ counters, uint32_t* __restrict__ start, uint32_t len,
                                                            unsigned long long* __restrict__ tile_state, uint32_t epoch,
                                                            const int* __restrict__ done) {
   if (done && *done) return;
   __shared__ uint32_t warp_sums[SC_THREADS / 32];
-  __shared__ uint32_t s_prefix;
-  const uint32_t tile = blockIdx.x;
+  __shared__ uint32_t s_prefix, s_tile;
+  if (threadIdx.x == 0) {
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(tile_state);
+    const unsigned int t = atomicAdd(ticket, 1u);
+    if (t == gridDim.x - 1) *ticket = 0u;   // every ticket of this launch has been drawn
+    s_tile = t;
+  }
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  volatile unsigned long long* st = tile_state + 1;
   const uint32_t base = tile * SC_TILE + threadIdx.x * SC_ITEMS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t v[SC_ITEMS];
   if (base + SC_ITEMS <= len) {
-    uint4 a = *reinterpret_cast<const uint4*>(counters + base), b = *reinterpret_cast<const uint4*>(counters + base + 4);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    *reinterpret_cast<uint4*>(counters + base) = make_uint4(0, 0, 0, 0);
-    *reinterpret_cast<uint4*>(counters + base + 4) = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < SC_ITEMS; k += 4) {
+      const uint4 a = *reinterpret_cast<const uint4*>(counters + base + k);
+      v[k] = a.x; v[k + 1] = a.y; v[k + 2] = a.z; v[k + 3] = a.w;
+      *reinterpret_cast<uint4*>(counters + base + k) = make_uint4(0, 0, 0, 0);
+    }
   } else {
 #pragma unroll
     for (int k = 0; k < SC_ITEMS; ++k) {
@@ -92,7 +106,6 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_cells(uint32_t* __restrict_
 
   const unsigned long long tag = (unsigned long long)epoch << 34;
   if (warp == 0) {
-    volatile unsigned long long* st = tile_state;
     if (tile == 0) {
       if (lane == 0) { st[0] = tag | (2ull << 32) | agg; s_prefix = 0; }
     } else {
@@ -129,11 +142,12 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_cells(uint32_t* __restrict_
   __syncthreads();
   uint32_t run = s_prefix + texcl;
   if (base + SC_ITEMS <= len) {
-    uint4 a, b;
-    a.x = run; run += v[0]; a.y = run; run += v[1]; a.z = run; run += v[2]; a.w = run; run += v[3];
-    b.x = run; run += v[4]; b.y = run; run += v[5]; b.z = run; run += v[6]; b.w = run; run += v[7];
-    *reinterpret_cast<uint4*>(start + base) = a;
-    *reinterpret_cast<uint4*>(start + base + 4) = b;
+#pragma unroll
+    for (int k = 0; k < SC_ITEMS; k += 4) {
+      uint4 a;
+      a.x = run; run += v[k]; a.y = run; run += v[k + 1]; a.z = run; run += v[k + 2]; a.w = run; run += v[k + 3];
+      *reinterpret_cast<uint4*>(start + base + k) = a;
+    }
   } else {
 #pragma unroll
     for (int k = 0; k < SC_ITEMS; ++k) {

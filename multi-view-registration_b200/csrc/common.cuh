@@ -30,11 +30,16 @@ struct IndexDev {
 
 // Row-major uniform grid of the per-align index (pair_index.cu): nx x ny x nz cells, x fastest,
 // cell_a = clamp(floor((p_a - o_a) * inv_cell), 0, n_a - 1).
+// Cells may be FINER along x (xr cells per y/z cell edge, xr = 1, 2, 4 or 8): the points of a (y, z) row are one contiguous run
+// whatever the x resolution, so a finer x only narrows the run a ball query reads -- the same two table loads per row, fewer
+// candidates (the fused ICP iteration uses xr = MVR_PG_XRATIO; every other user of the grid builds it with xr = 1).
 struct PairGrid {
   float ox, oy, oz;
-  float inv_cell;
-  float cell_lo;   // a float strictly below the true cell edge
+  float inv_cell;     // y and z: cells per unit length
+  float cell_lo;      // a float strictly below the true y/z cell edge
   int nx, ny, nz;
+  float inv_cell_x;   // x: cells per unit length = inv_cell * xr (exact: xr is a power of two)
+  float xr;
 };
 
 struct Mat4f { float m[16]; };  // column-major

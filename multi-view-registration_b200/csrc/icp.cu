@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (RECIP ? MVR_FWD_MINBLOCKS : MV
     fwd_seed(a, i, p, b);
     // no partner inside the gate so far: one bit says whether the target has anything within the gate of p's cell
     if (a.gmask && !(b.d2 <= a.max_d2f)) {
-      const int cx = pg_cell(grid_t(p.x, a.gt.ox, a.gt.inv_cell), a.gt.nx), cy = pg_cell(grid_t(p.y, a.gt.oy, a.gt.inv_cell), a.gt.ny),
+      const int cx = pg_cell(grid_t(p.x, a.gt.ox, a.gt.inv_cell_x), a.gt.nx), cy = pg_cell(grid_t(p.y, a.gt.oy, a.gt.inv_cell), a.gt.ny),
                 cz = pg_cell(grid_t(p.z, a.gt.oz, a.gt.inv_cell), a.gt.nz);
       const uint32_t wd = __ldg(a.gmask + ((size_t)cz * a.gt.ny + cy) * a.gm_stride + (cx >> 5));
       if (!((wd >> (cx & 31)) & 1u)) { a.corr_p[i] = -1; continue; }

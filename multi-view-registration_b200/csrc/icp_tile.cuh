@@ -6,6 +6,9 @@
 // the per-thread row walk, every candidate costs more than in registers, and the staging phases (ten block barriers, two
 // block scans, eight-lane row loops) add ~39 warp-instructions per query.  Included from icp.cu inside namespace mvr.
 #pragma once
+#if defined(MVR_PG_XRATIO) && MVR_PG_XRATIO != 1
+#error "the tile-search experiment assumes isotropic grid cells: build with -DMVR_PG_XRATIO=1"
+#endif
 
 template <bool RECIP, int EST>
 __global__ void __launch_bounds__(FUSED_THREADS, (RECIP ? MVR_FWD_MINBLOCKS : MVR_FWD1_MINBLOCKS) * (256 / FUSED_THREADS)) k_icp_forward(const __grid_constant__ FwdBatch batch, int first) {

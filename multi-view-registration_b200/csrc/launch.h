@@ -111,8 +111,9 @@ cudaError_t launch_pair_count(const float4* in, int n, const Mat4f* guess, PairG
 cudaError_t launch_pair_scatter(const float4* in, int n, const Mat4f* guess, const uint32_t* keys, const uint32_t* rank, const uint32_t* start,
                                 float4* tmp, cudaStream_t s);
 cudaError_t launch_fill_u32(uint32_t* p, size_t n, uint32_t v, cudaStream_t s);
-// Gate mask of an index (pair_index.cu): occ and mask hold ny * nz * wstride words, wstride = ceil(nx / 32); D = dilation in cells.
-cudaError_t launch_gate_mask(const uint32_t* start, PairGrid g, int wstride, int D, uint32_t* occ, uint32_t* mask, cudaStream_t s);
+// Gate mask of an index (pair_index.cu): occ and mask hold ny * nz * wstride words, wstride = ceil(nx / 32); D / Dx = dilation in
+// y-z / x cells.
+cudaError_t launch_gate_mask(const uint32_t* start, PairGrid g, int wstride, int D, int Dx, uint32_t* occ, uint32_t* mask, cudaStream_t s);
 // sorted[k] = {moved point, bits(original index)}; copy (nullable) gets the same.
 cudaError_t launch_pair_rerank(const float4* tmp, int n, const uint32_t* keys, const uint32_t* start, float4* sorted, float4* copy,
                                cudaStream_t s);

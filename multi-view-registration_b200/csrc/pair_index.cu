@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) k_pair_rerank(const float4* __restrict__ 
 
 // ---------------------------------------------------------------------------------------------
 // Gate mask of a target index: bit x of word [(z * ny + y) * wstride + x / 32] is set when some target point lies in a
-// cell within D cells (Chebyshev) of cell (x, y, z).  Cells that differ by more than D in some axis are at least D cells
+// cell within D cells in y and z and Dx cells in x of cell (x, y, z).  Cells that differ by more than D in some axis are at least D cells
 // apart along it, so with D cell >= gate a CLEAR bit proves that a query filed in that cell has no target point within the
 // gate: pcl's "if (distance > max_dist_sqr) continue"  without a search.  The part of a turntable view the
 // neighbouring view does not cover is settled by one load per point and iteration.
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) k_gate_occ(const uint32_t* __restrict__ s
   occ[w] = bits;
 }
 
-__global__ void __launch_bounds__(256) k_gate_dilate(const uint32_t* __restrict__ occ, PairGrid g, int wstride, int D, size_t words, uint32_t* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_gate_dilate(const uint32_t* __restrict__ occ, PairGrid g, int wstride, int D, int Dx, size_t words, uint32_t* __restrict__ out) {
   const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= words) return;
   const int xw = (int)(w % (size_t)wstride);
@@ -98,18 +98,18 @@ __global__ void __launch_bounds__(256) k_gate_dilate(const uint32_t* __restrict_
       const uint32_t* r = occ + ((size_t)zz * g.ny + yy) * wstride;
       const uint32_t cur = __ldg(r + xw), prev = xw > 0 ? __ldg(r + xw - 1) : 0u, next = xw + 1 < wstride ? __ldg(r + xw + 1) : 0u;
       uint32_t v = cur;
-      for (int k = 1; k <= D; ++k) v |= (cur << k) | (cur >> k) | (prev >> (32 - k)) | (next << (32 - k));
+      for (int k = 1; k <= Dx; ++k) v |= (cur << k) | (cur >> k) | (prev >> (32 - k)) | (next << (32 - k));
       acc |= v;
     }
   out[w] = acc;
 }
 
-cudaError_t launch_gate_mask(const uint32_t* start, PairGrid g, int wstride, int D, uint32_t* occ, uint32_t* mask, cudaStream_t s) {
+cudaError_t launch_gate_mask(const uint32_t* start, PairGrid g, int wstride, int D, int Dx, uint32_t* occ, uint32_t* mask, cudaStream_t s) {
   const size_t words = (size_t)g.ny * g.nz * wstride;
-  if (words == 0 || D < 1 || D > 31) return cudaErrorInvalidValue;
+  if (words == 0 || D < 1 || Dx < 1 || Dx > 31) return cudaErrorInvalidValue;
   const unsigned blocks = (unsigned)((words + 255) / 256);
   k_gate_occ<<<blocks, 256, 0, s>>>(start, g, wstride, words, occ); count_launch();
-  k_gate_dilate<<<blocks, 256, 0, s>>>(occ, g, wstride, D, words, mask); count_launch();
+  k_gate_dilate<<<blocks, 256, 0, s>>>(occ, g, wstride, D, Dx, words, mask); count_launch();
   return cudaGetLastError();
 }
 

@@ -37,7 +37,7 @@ __device__ __forceinline__ int pg_cell(float t, int n) { return (int)fminf(fmaxf
 
 // Row-major cell of a finite point.
 __device__ __forceinline__ uint32_t pg_key(float4 p, const PairGrid& g) {
-  const int cx = pg_cell(grid_t(p.x, g.ox, g.inv_cell), g.nx);
+  const int cx = pg_cell(grid_t(p.x, g.ox, g.inv_cell_x), g.nx);
   const int cy = pg_cell(grid_t(p.y, g.oy, g.inv_cell), g.ny);
   const int cz = pg_cell(grid_t(p.z, g.oz, g.inv_cell), g.nz);
   return (uint32_t)((cz * g.ny + cy) * g.nx + cx);
@@ -118,9 +118,13 @@ __device__ __forceinline__ void pg_search(const PairGrid& g, const uint32_t* __r
                                           int n_valid, float qx, float qy, float qz, float ux, float uy, float uz, float dev,
                                           float stretch, float gate, NnBest& b, uint2* __restrict__ seg) {
   if (n_valid <= 0) return;
-  const float tx = grid_t(ux, g.ox, g.inv_cell), ty = grid_t(uy, g.oy, g.inv_cell), tz = grid_t(uz, g.oz, g.inv_cell);
+  const float tx = grid_t(ux, g.ox, g.inv_cell_x), ty = grid_t(uy, g.oy, g.inv_cell), tz = grid_t(uz, g.oz, g.inv_cell);
   const int cx = pg_cell(tx, g.nx), cy = pg_cell(ty, g.ny), cz = pg_cell(tz, g.nz);
-  const float margin = MVR_CELL_MARGIN + 1.0e-6f * fmaxf(fabsf(tx), fmaxf(fabsf(ty), fabsf(tz))) + dev * stretch * g.inv_cell * 1.000001f;
+  // margins in cells of the respective axis (x cells are xr times finer)
+  const float margin = MVR_CELL_MARGIN + 1.0e-6f * fmaxf(fabsf(ty), fabsf(tz)) + dev * stretch * g.inv_cell * 1.000001f;
+  const float margin_x = MVR_CELL_MARGIN + 1.0e-6f * fabsf(tx) + dev * stretch * g.inv_cell_x * 1.000001f;
+  const float rscale_x = stretch * g.inv_cell_x * 1.000001f;
+  const int xri = (int)g.xr;
   const float cell2 = g.cell_lo * g.cell_lo * MVR_REL_SHRINK / (stretch * stretch * 1.000001f);
   const float inv_cell2 = 1.000002f / cell2;
   const float rscale = stretch * g.inv_cell * 1.000001f;
@@ -131,7 +135,7 @@ __device__ __forceinline__ void pg_search(const PairGrid& g, const uint32_t* __r
   if (!(lim < MVR_INF)) {
     // no bound at all (un-gated first iteration): grow a cube of cells until it holds a point
     for (int R = 1;; R <<= 1) {
-      const int x0 = max(cx - R, 0), x1 = min(cx + R, g.nx - 1);
+      const int x0 = max(cx - R * xri, 0), x1 = min(cx + R * xri, g.nx - 1);
       const int y0 = max(cy - R, 0), y1 = min(cy + R, g.ny - 1);
       const int z0 = max(cz - R, 0), z1 = min(cz + R, g.nz - 1);
       for (int z = z0; z <= z1; ++z)
@@ -149,14 +153,16 @@ __device__ __forceinline__ void pg_search(const PairGrid& g, const uint32_t* __r
   float rc = sqrtf(lim) * rscale + margin;
   if (rc > 1.25f) {
     // loose bound: the own row usually tightens it for all the others
-    const int x0 = (int)fminf(fmaxf(floorf(tx - rc), 0.0f), fx), x1 = (int)fminf(fmaxf(floorf(tx + rc), 0.0f), fx);
+    const float rcx = sqrtf(lim) * rscale_x + margin_x;
+    const int x0 = (int)fminf(fmaxf(floorf(tx - rcx), 0.0f), fx), x1 = (int)fminf(fmaxf(floorf(tx + rcx), 0.0f), fx);
     const uint32_t* row = start + (size_t)cz * slab + (size_t)cy * rowlen;
     pg_scan(pts, __ldg(row + x0), __ldg(row + x1 + 1), qx, qy, qz, b);
     lim = fminf(b.d2, gate);
     rc = sqrtf(lim) * rscale + margin;
     own_done = true;   // [x0, x1] of the own row covers whatever the tighter ball still needs there
   }
-  const int x0 = (int)fminf(fmaxf(floorf(tx - rc), 0.0f), fx), x1 = (int)fminf(fmaxf(floorf(tx + rc), 0.0f), fx);
+  const float rcx = sqrtf(lim) * rscale_x + margin_x;
+  const int x0 = (int)fminf(fmaxf(floorf(tx - rcx), 0.0f), fx), x1 = (int)fminf(fmaxf(floorf(tx + rcx), 0.0f), fx);
   const int y0 = (int)fminf(fmaxf(floorf(ty - rc), 0.0f), fy), y1 = (int)fminf(fmaxf(floorf(ty + rc), 0.0f), fy);
   const int z0 = (int)fminf(fmaxf(floorf(tz - rc), 0.0f), fz), z1 = (int)fminf(fmaxf(floorf(tz + rc), 0.0f), fz);
 
@@ -171,7 +177,7 @@ __device__ __forceinline__ void pg_search(const PairGrid& g, const uint32_t* __r
       if (!(eyz * cell2 > lim) && !(own_done && y == cy && z == cz)) {
         // x extent of the ball inside this row
         const float rem = fmaxf(lim * inv_cell2 - eyz, 0.0f);
-        const float rx = sqrtf(rem) * 1.000001f + margin + margin;
+        const float rx = sqrtf(rem) * 1.000001f * g.xr + margin_x + margin_x;   // sqrt(rem) is in y/z cells
         const int xa = max(x0, (int)fminf(fmaxf(floorf(tx - rx), 0.0f), fx));
         const int xb = min(x1, (int)fminf(fmaxf(floorf(tx + rx), 0.0f), fx));
         const uint32_t* row = start + (size_t)z * slab + (size_t)y * rowlen;

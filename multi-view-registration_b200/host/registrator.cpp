@@ -400,13 +400,29 @@ int Registrator::multiViewRegister(std::vector<View>& views, const mvr_turntable
   std::vector<uint64_t> queries((size_t)P, 0);
   std::vector<double> ms((size_t)P, 0.0);
   std::vector<mvr_icp_report> rep((size_t)P);
+  // every pair's target: the cloud's bounding box is measured on the device and read back (one stream round trip per view);
+  // a few host threads issue them at once
+  std::vector<int> set_rc((size_t)P, MVR_OK);
+  {
+    std::atomic<int> next{0};
+    auto work = [&] {
+      for (int k = next.fetch_add(1); k < P; k = next.fetch_add(1)) {
+        const int p = p0 + k;
+        set_rc[(size_t)k] = mvr_set_target_device(ctx_[(size_t)k], dview[(size_t)(p % V)], views[(size_t)p].size);
+      }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < std::min(P, 6); ++t) th.emplace_back(work);
+    work();
+    for (std::thread& t : th) t.join();
+  }
   for (int k = 0; k < P; ++k) {
     const int p = p0 + k;
     const View& tgt = views[(size_t)p];
     const View& src = views[(size_t)((p + 1) % V)];
     mvr_ctx* c = ctx_[(size_t)k];
     cs[(size_t)k] = c;
-    if ((rc = mvr_set_target_device(c, dview[(size_t)(p % V)], tgt.size))) return fail(rc, mvr_last_error(c));
+    if ((rc = set_rc[(size_t)k])) return fail(rc, mvr_last_error(c));
     radius[(size_t)p] = objectRadius(k);
     // initial guess: where the turntable says the source sits in the target's frame
     const Matrix4f g = toFloat(multiply(inverseRigid(tgt.pose), src.pose));

@@ -320,6 +320,28 @@ def test_icp_fixed_iterations_matches_oracle_per_iteration(ctx, orc, mvr, synth,
     assert np.array_equal(r["cloud"], orc.transform(src, r["final"]))
 
 
+def test_icp_gate_mask_changes_nothing(mvr, orc, synth):
+    """The optional gate mask of the target (one bit per cell: anything within the gate?) only skips searches that cannot
+    find a partner: every iteration's correspondences and the pose are bit-identical with and without it, for a pair with
+    little overlap (views three steps apart) and for a gate of several cells."""
+    tgt, Tt = synth.turntable_view(0, 12, 30_000)
+    src, Ts = synth.turntable_view(3, 12, 30_000)
+    guess = (synth.perturbation() @ np.linalg.inv(Tt) @ Ts).astype(np.float32)
+    for max_dist, recip in ((4.0, 1), (4.0, 0), (9.0, 1)):
+        p = mvr.default_params(max_iterations=8, max_dist=max_dist, reciprocal=recip, fixed_iterations=1)
+        got = []
+        for on in (False, True):
+            c = mvr.Context(0)
+            c.set_gate_mask(on)
+            c.set_target(tgt); c.set_source(src)
+            got.append(c.icp_align(p, guess=guess, n_source=len(src)))
+            c.close()
+        a, b = got
+        assert [x["n_corr"] for x in a["log"]] == [x["n_corr"] for x in b["log"]] and np.array_equal(a["final"], b["final"]) and a["mse"] == b["mse"]
+        o = orc.icp_align(src, tgt, orc.make_params(max_iterations=8, max_dist=max_dist, reciprocal=bool(recip), fixed_iterations=True), guess=guess)
+        assert [x["n_corr"] for x in b["log"]] == [x["n_corr"] for x in o["log"]]
+
+
 def test_icp_align_batch_equals_separate_aligns(mvr, synth):
     """mvr_icp_align_batch: pairs of different sizes advancing in lock-step (one launch per iteration half for all of
     them) return exactly what one mvr_icp_align per pair returns; criteria stop each pair on its own."""
