@@ -282,6 +282,9 @@ typedef struct {
   float pose[16];                /* ring mode: relative pose source -> target frame; accumulate: view -> model frame */
 } mvr_pair_report;
 
+/* One line of the reference's fitness_scores.txt (mvr/src/registrator.cpp:880-925): getFitnessScore() after repeat `repeat` of view `view`. */
+typedef struct { int view; int repeat; double score; } mvr_fitness_record;
+
 void mvr_turntable_params_default(mvr_turntable_params* p);
 /* Registrator::getRotationMatrix (mvr/src/registrator.cpp:331-342): T(pivot) R(axis, angle) T(-pivot), double[16]
  * column-major; and the angle PointCloud::initRotation gives view v of V (mvr/src/point_cloud.cpp:400-413). */
@@ -343,6 +346,8 @@ int mvr_register_turntable_multi(mvr_multi* m, const mvr_view* views, int n_view
 /* Registrator::computeError (mvr/src/registrator.cpp:466-515): reciprocal correspondences (gate max_distance) between
  * neighbouring registered views (i, i + 1) and (V - 1, 0), each view posed by its init_pose first (getTransformedPoints).
  * Pair k: counts[k] correspondences with mean squared distance mean_d2[k]; arrays hold n_views entries. */
+/* The fitness scores of the last MVR_REGISTER_ACCUMULATE / MVR_REGISTER_ICP run, one per view and repeat (out nullable: count only). */
+int mvr_registrator_get_fitness_log(mvr_registrator* r, mvr_fitness_record* out, int max_records, int* count);
 int mvr_compute_error(mvr_registrator* r, const mvr_view* views, int n_views, double max_distance, size_t* counts, double* mean_d2,
                       int* n_pairs);
 /* Host-side loop closure over gathered ring pairs: rel[p] = pose of view (p+1)%V in view p's frame, w[p] its

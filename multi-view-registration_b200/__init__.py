@@ -119,6 +119,10 @@ class PairRecord(C.Structure):
                 ("reserved", C.c_int32), ("mse", C.c_double), ("nn_queries", C.c_uint64)]
 
 
+class FitnessRecord(C.Structure):
+    _fields_ = [("view", C.c_int), ("repeat", C.c_int), ("score", C.c_double)]
+
+
 class PairReport(C.Structure):
     _fields_ = [
         ("source_view", C.c_int),
@@ -214,6 +218,7 @@ def lib():
     L.mvr_multi_upload.argtypes = [vp, C.POINTER(ViewDesc), C.c_int]
     L.mvr_register_turntable_multi.argtypes = [vp, C.POINTER(ViewDesc), C.c_int, C.POINTER(TurntableParams), C.c_int, fp, C.POINTER(PairReport),
                                                C.POINTER(PairRecord), dp]
+    L.mvr_registrator_get_fitness_log.argtypes = [vp, C.POINTER(FitnessRecord), C.c_int, C.POINTER(C.c_int)]
     L.mvr_compute_error.argtypes = [vp, C.POINTER(ViewDesc), C.c_int, C.c_double, C.POINTER(C.c_size_t), dp, C.POINTER(C.c_int)]
     L.mvr_ring_close.argtypes = [fp, dp, C.c_int, C.c_int, C.c_int, dp, C.c_double, fp]
     L.mvr_get_bbox.argtypes = [vp, C.c_int, fp, fp]
@@ -714,6 +719,14 @@ class Registrator:
             raise MvrError(rc, (lib().mvr_registrator_last_error(self._h) or b"").decode())
         return dict(status=rc, final=pose_to_numpy(fin), iterations=rep.iterations, n_corr=rep.n_correspondences, mse=rep.mse,
                     gpu_ms=rep.gpu_ms, nn_queries=int(rep.nn_queries))
+
+    def fitness_log(self):
+        """[(view, repeat, getFitnessScore())] of the last accumulative registration (the reference's fitness_scores.txt)."""
+        n = C.c_int(0)
+        lib().mvr_registrator_get_fitness_log(self._h, None, 0, C.byref(n))
+        arr = (FitnessRecord * max(n.value, 1))()
+        lib().mvr_registrator_get_fitness_log(self._h, arr, n.value, C.byref(n))
+        return [(arr[k].view, arr[k].repeat, arr[k].score) for k in range(n.value)]
 
     def compute_error(self, views, poses, max_distance):
         """Registrator::computeError: [(count, mean squared distance)] of the reciprocal correspondences of neighbouring views."""

@@ -1,5 +1,6 @@
 // capi.cpp -- extern "C" face of the host driver (declared in include/mvr_b200.h): the entry points a
 // maintainer binds under the reference's Registrator slots.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -150,6 +151,18 @@ int mvr_register_turntable(mvr_registrator* r, const mvr_view* views, int n_view
       std::memcpy(poses + 16 * k, f.m, sizeof(f.m));
     }
   return rc;
+}
+
+int mvr_registrator_get_fitness_log(mvr_registrator* r, mvr_fitness_record* out, int max_records, int* count) {
+  if (!r || !count) return MVR_ERR_BAD_ARG;
+  const std::vector<mvr_fitness_record>& log = r->reg->fitnessLog();
+  int n = (int)log.size();
+  if (out) {
+    n = std::min(n, std::max(max_records, 0));
+    if (n) std::memcpy(out, log.data(), (size_t)n * sizeof(mvr_fitness_record));
+  }
+  *count = n;
+  return MVR_OK;
 }
 
 int mvr_compute_error(mvr_registrator* r, const mvr_view* views, int n_views, double max_distance, size_t* counts, double* mean_d2,

@@ -256,7 +256,7 @@ AlignResult Registrator::pairwiseAlign(const View& source, const View& target, c
 // times, against the model accumulated so far; its pose is composed with each result; the aligned points join
 // the model (mvr/src/registrator.cpp:562-577 and 909-983).
 int Registrator::accumulate(std::vector<View>& views, const std::vector<int>& order, const mvr_icp_params& icp, int repeat_times,
-                            bool want_fitness, std::vector<mvr_pair_report>* reports) {
+                            bool want_fitness, std::vector<mvr_pair_report>* reports, bool per_view_axis) {
   if (!ok()) return fail(MVR_ERR_CUDA, "no GPU context");
   if (views.empty()) return MVR_OK;
   cudaSetDevice(device_);
@@ -284,8 +284,13 @@ int Registrator::accumulate(std::vector<View>& views, const std::vector<int>& or
   model_n = views[0].size;
   views[0].registered = true;
   if (reports) reports->clear();
+  fitness_log_.clear();
+  const int V = (int)views.size();
   for (int vi : order) {
     View& v = views[(size_t)vi];
+    // automaticRegistration gives a view its turntable pose when its turn comes (initRotation, mvr/src/registrator.cpp:766), i.e.
+    // about the axis as refined from the views registered so far (:986)
+    if (per_view_axis) initRotation(v, V);
     if (!src.ensure(std::max<size_t>(v.size, 1))) return fail(MVR_ERR_ALLOC, "source buffer");
     if ((rc = upload_posed(v, src.p))) return fail(rc, "source upload");
     if ((rc = mvr_set_target_device(c, model.p, model_n))) return fail(rc, mvr_last_error(c));
@@ -306,12 +311,15 @@ int Registrator::accumulate(std::vector<View>& views, const std::vector<int>& or
       v.pose = multiply(toDouble(fin), v.pose);
       v.pose_is_identity = false;
       if ((rc = mvr_copy_aligned_device(c, src.p))) return fail(rc, mvr_last_error(c));
-    }
-    if (want_fitness) {
-      double f = -1;
-      if (mvr_fitness_score(c, DBL_MAX, &f) == MVR_OK) last.fitness = f;
+      if (want_fitness) {
+        // the reference prints / logs icp_.getFitnessScore() after EVERY repeat (mvr/src/registrator.cpp:923-925, 1015); the score
+        // here is that of the aligned cloud (SURVEY.md A9 on the reference's double application of `final`)
+        double f = -1;
+        if (mvr_fitness_score(c, DBL_MAX, &f) == MVR_OK) { last.fitness = f; mvr_fitness_record fr{v.view, r, f}; fitness_log_.push_back(fr); }
+      }
     }
     v.registered = true;
+    if (per_view_axis) refineAxis(views);   // :836, 986: the axis follows every newly registered view
     // *target += transformed_source
     if (cudaMemcpyAsync(model.p + model_n * 4, src.p, v.size * 16, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
       return fail(MVR_ERR_CUDA, "model append");
@@ -356,7 +364,7 @@ int Registrator::automaticRegistration(std::vector<View>& views, int max_iterati
   // The reference collects transformation_epsilon but never applies it to icp_; kept so.
   (void)transformation_epsilon;
   const int V = (int)views.size();
-  for (int v = 0; v < V; ++v) { views[(size_t)v].view = v; initRotation(views[(size_t)v], V); }
+  for (int v = 0; v < V; ++v) views[(size_t)v].view = v;       // initRotation when the view's turn comes (accumulate)
   mvr_icp_params icp;
   mvr_icp_params_default(&icp);
   icp.use_reciprocal_correspondences = 1;                       // :768, 901
@@ -365,9 +373,12 @@ int Registrator::automaticRegistration(std::vector<View>& views, int max_iterati
   icp.euclidean_fitness_epsilon = euclidean_fitness_epsilon;    // :771, 904
   std::vector<int> order;
   for (int v = 1; v < V; ++v) order.push_back(v);               // views 1..V-1 against the growing model
-  int rc = accumulate(views, order, icp, repeat_times, true, reports);
-  if (rc == MVR_OK) refineAxis(views);                           // :836, 986
-  return rc;
+  // What is kept of the reference's flow: every view aligned repeat_times against the model grown so far, the fitness score
+  // after every repeat, refineAxis after every view (so later views start from the refined axis).  What is dropped: the
+  // reference re-runs the whole prefix 1..k from scratch for every k (automaticRegistrationICP inside the while loop, :753-757,
+  // O(V^2) aligns whose results the next pass overwrites) and then indexes point_clouds_ out of range (:760-766 after the
+  // clear at :985); DESIGN.md section 6 lists this.
+  return accumulate(views, order, icp, repeat_times, true, reports, true);
 }
 
 int Registrator::multiViewRegister(std::vector<View>& views, const mvr_turntable_params& prm, std::vector<mvr_pair_report>& reports) {

@@ -116,6 +116,8 @@ class Registrator {
   // reduced on the GPU to their moments (target frame).
   int edgeMoments(const View& source, const View& target, double max_distance, const Matrix4f& guess, int slot, mvr_pair_moments& out);
   int refineAxis(const std::vector<View>& views);
+  // the fitness scores the reference logs to fitness_scores.txt (mvr/src/registrator.cpp:880-925): one per view and repeat
+  const std::vector<mvr_fitness_record>& fitnessLog() const { return fitness_log_; }
   // computeError (mvr/src/registrator.cpp:466-515): reciprocal correspondences of neighbouring registered views;
   // returns per pair (count, mean squared distance).
   int computeError(std::vector<View>& views, double max_distance, std::vector<std::pair<size_t, double> >& out);
@@ -126,7 +128,8 @@ class Registrator {
 
  private:
   int accumulate(std::vector<View>& views, const std::vector<int>& order, const mvr_icp_params& icp, int repeat_times,
-                 bool want_fitness, std::vector<mvr_pair_report>* reports);
+                 bool want_fitness, std::vector<mvr_pair_report>* reports, bool per_view_axis = false);
+  std::vector<mvr_fitness_record> fitness_log_;   // getFitnessScore() after every repeat of the last accumulative registration
   int ensureContexts(int n);             // grow the context pool to n (batched aligns use one context per pair)
   // device pointers of the listed views: device views as given, host views uploaded once into view_cache_
   int uploadViews(const std::vector<View>& views, const std::vector<int>& which, std::vector<const float*>& dview);

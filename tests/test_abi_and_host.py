@@ -464,3 +464,31 @@ def test_registration_lum_oracle_loop_reduces_drift(orc, synth):
     e4 = err(L.registration_lum(views, init, 64, 4.0, orc.correspondences, orc.apply_pose_double))
     e10 = err(L.registration_lum(views, init, 160, 4.0, orc.correspondences, orc.apply_pose_double))
     assert e10 < e4 < e0 and e10 < 0.75 * e0
+
+
+def _build_adapter_check(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "adapter_check")
+    libdir = os.path.join(ROOT, "multi-view-registration_b200")
+    cmd = ["g++", "-std=c++11", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "tests", "mock_pcl"),
+           os.path.join(ROOT, "tests", "adapter_check.cpp"), "-o", exe, os.path.join(libdir, "libmvr_b200.so"), "-Wl,-rpath," + libdir]
+    for d in ("/usr/local/cuda/lib64", "/usr/local/cuda/targets/x86_64-linux/lib"):
+        if os.path.isdir(d):
+            cmd += ["-L" + d, "-Wl,-rpath," + d]
+    r = subprocess.run(cmd + ["-lcudart"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_pcl_adapter_header_compiles_and_links(mvr, tmp_path):
+    """include/mvr_pcl_adapter.hpp (the GpuICP / GpuCorrespondenceEstimation classes a maintainer puts under
+    mvr/include/registrator.h:91 and mvr/src/registrator.cpp:496, 551, 644) is real C++: compiled against stand-in PCL / Eigen
+    declarations and linked with the library; without a GPU its constructor fails loudly."""
+    import subprocess
+    import torch
+    mvr.lib()
+    exe = _build_adapter_check(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    if not torch.cuda.is_available():
+        assert "no usable CUDA device" in out.stdout

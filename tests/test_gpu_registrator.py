@@ -1,5 +1,7 @@
 """GPU parity of the C++ registration driver (host/registrator.cpp behind the C ABI) against the CPU oracle
 replaying the reference's workflows (mvr/src/registrator.cpp:517-588, 746-842, 877-990) step by step."""
+import os
+
 import numpy as np
 import pytest
 
@@ -146,6 +148,40 @@ def test_automatic_registration_matches_oracle(mvr, orc, synth, seq):
         assert_pose_close(got[v], want[v], scale=max(1.0, float(np.linalg.norm(want[v][:3, 3]))))
     assert [r["source_view"] for r in reps] == [1, 2, 3] and all(r["fitness"] > 0 for r in reps)
     reg.close()
+
+
+def test_automatic_registration_axis_follows_every_view_and_logs_every_repeat(mvr, orc, synth, seq):
+    """automaticRegistration as kept from the reference (mvr/src/registrator.cpp:746-842, 877-990): a view gets its turntable
+    pose when its turn comes, from the axis as refined (refineAxis, :836 / :986) over the views registered so far; the fitness
+    score is logged after EVERY repeat (:923-925).  Replayed here with the oracle's ICP and the host's refine_axis."""
+    V, n, views, poses, _ = seq
+    V = 4
+    icp = mvr.default_params(max_iterations=5, max_dist=4.0, reciprocal=1, fixed_iterations=1)
+    tp = mvr.turntable_params(pivot=synth.PIVOT, axis=synth.AXIS, icp=icp, repeat_times=2, mode=mvr.ACCUMULATE)
+    reg = mvr.Registrator(0, 1)
+    got, reps = reg.register_turntable(views[:V], tp)          # no initial poses: PointCloud::initRotation at each view's turn
+    log = reg.fitness_log()
+    reg.close()
+    assert [(v, r) for v, r, _ in log] == [(v, r) for v in range(1, V) for r in range(2)]
+    op = orc.make_params(max_iterations=5, max_dist=4.0, reciprocal=True, fixed_iterations=True)
+    pivot, axis = np.array(synth.PIVOT, dtype=np.float64), np.array(synth.AXIS, dtype=np.float64)
+    pose = [np.eye(4) for _ in range(V)]
+    model = orc.apply_pose_double(views[0], pose[0])
+    scores = []
+    for v in range(1, V):
+        pose[v] = mvr.turntable_rotation(pivot, axis, mvr.turntable_view_angle(v, V))
+        src = orc.apply_pose_double(views[v], pose[v])
+        for r in range(2):
+            o = orc.icp_align(src, model, op)
+            pose[v] = o["final"].astype(np.float64) @ pose[v]
+            src = o["cloud"]
+            scores.append(orc.fitness_score(src, model))
+        model = np.concatenate([model, src])
+        pivot, axis = mvr.refine_axis([pose[k] for k in range(1, v + 1)], pivot, axis)
+    for v in range(V):
+        assert_pose_close(got[v], pose[v], scale=max(1.0, float(np.linalg.norm(pose[v][:3, 3]))))
+    for (_, _, f), want in zip(log, scores):
+        assert abs(f - want) <= 1e-9 * want
 
 
 def test_registration_icp_order_and_reference_settings(mvr, orc, synth, seq):
@@ -322,3 +358,16 @@ def test_denoise_matches_the_oracle(mvr, orc, synth):
     k0, n0 = c.denoise(pts[:0], 10, 2.5)
     assert len(k0) == 0 and n0 == 0
     c.close()
+
+
+def test_pcl_adapter_runs_icp_through_the_pcl_shaped_classes(mvr, tmp_path):
+    """The adapter header's GpuICP / GpuCorrespondenceEstimation (include/mvr_pcl_adapter.hpp) drive a small align on the GPU."""
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_abi_and_host import _build_adapter_check
+    exe = _build_adapter_check(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.startswith("gpu ok: iterations 3"), out.stdout + out.stderr
+    tx = float(out.stdout.split("tx")[1].split()[0])
+    assert 0.2 < tx < 0.4      # the target is the source shifted by 0.3 along x
