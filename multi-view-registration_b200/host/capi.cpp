@@ -131,8 +131,6 @@ int mvr_register_turntable(mvr_registrator* r, const mvr_view* views, int n_view
   std::vector<mvr_pair_report> rep;
   int rc;
   if (prm->mode == MVR_REGISTER_ACCUMULATE) {
-    const int V = n_views;
-    for (int k = 0; k < V; ++k) reg.initRotation(v[(size_t)k], V);
     mvr_icp_params icp = prm->icp;
     // automaticRegistration's shape: views 1..V-1 in order against the growing model, repeat_times aligns each
     rc = reg.automaticRegistration(v, icp.max_iterations, prm->repeat_times, icp.max_correspondence_distance,

@@ -181,7 +181,7 @@ def test_automatic_registration_axis_follows_every_view_and_logs_every_repeat(mv
     for v in range(V):
         assert_pose_close(got[v], pose[v], scale=max(1.0, float(np.linalg.norm(pose[v][:3, 3]))))
     for (_, _, f), want in zip(log, scores):
-        assert abs(f - want) <= 1e-9 * want
+        assert abs(f - want) <= 1e-6 * want   # the replay refines the axis from float32 poses (mvr_refine_axis), the driver from doubles
 
 
 def test_registration_icp_order_and_reference_settings(mvr, orc, synth, seq):
