@@ -70,7 +70,7 @@ typedef struct {
   int reason;             /* mvr_reason */
   int n_correspondences;  /* size of the last correspondence set */
   double mse;             /* mean squared distance of the last correspondence set */
-  double gpu_ms;          /* device time of the align (CUDA events on the context stream) */
+  double gpu_ms;          /* device time of the align (CUDA events on the context stream); in a batch: the batch's time / its pairs */
   uint64_t nn_queries;    /* nearest-neighbour queries answered (forward + reciprocal) */
 } mvr_icp_report;
 
@@ -121,7 +121,9 @@ void* mvr_ctx_get_stream(mvr_ctx* ctx);
 const char* mvr_last_error(mvr_ctx* ctx);
 int mvr_ctx_set_profiling(mvr_ctx* ctx, int on);
 int mvr_ctx_get_kernel_stats(mvr_ctx* ctx, mvr_kernel_stat* out /* [MVR_K_COUNT] */, int reset);
-/* Diagnostics of the last align (development aid): k = 0 clock cycles in the serial per-iteration solve, 1 solves. */
+/* Diagnostics of the last align (development aid): k = 0 clock cycles in the serial per-iteration solve, 1 solves, 2 reciprocal
+ * searches that lost their chooser (must be 0), 8 population of a grid cell too crowded to be ordered (0: none; mvr_last_error then
+ * carries a warning: thousands of duplicated or invalid points on one spot make the index build and the search crawl). */
 double mvr_debug_value(mvr_ctx* ctx, int k);
 /* Tuning knobs of the spatial index: cell edge (<= 0: automatic) and maximum bits per axis (1..10). */
 int mvr_ctx_set_index_options(mvr_ctx* ctx, float cell_edge, int max_bits);

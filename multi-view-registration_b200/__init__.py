@@ -346,6 +346,9 @@ class Context:
         return {K_NAMES[i]: dict(launches=int(arr[i].launches), ms=arr[i].ms, bytes=arr[i].bytes, units=arr[i].units)
                 for i in range(K_COUNT)}
 
+    def last_error(self):
+        return (lib().mvr_last_error(self._h) or b"").decode()
+
     def debug_value(self, k):
         return float(lib().mvr_debug_value(self._h, int(k)))
 

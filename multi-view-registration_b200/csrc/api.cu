@@ -116,6 +116,8 @@ struct mvr_ctx {
   bool want_rnn = false;         // the next prepared align also records the mutual partners (mvr_correspondences)
   int group_pairs = 24;          // pairs per launch of a batch led by this context (mvr_ctx_set_batch_group)
   DevBuf pkeys, pvals, pmoved, pcount;   // build scratch of the per-align indices: keys, arrival ranks, arrival-order records, cell counters
+  DevBuf crowded;                        // one word: population of the most crowded cell an index build could not rank (0: none)
+  uint32_t crowded_seen = 0;             // its value after the last align
   uint32_t scan_epoch = 1;
   IcpState* h_state = nullptr;   // pinned staging copy of the device IcpState
   IterRec* h_log = nullptr;      // pinned, ICP_MAX_LOG records
@@ -483,6 +485,7 @@ int build_pair_index(mvr_ctx* ctx, PairIndex& ix, const float4* pts, int n, int 
     CK(cudaMemsetAsync(ctx->tiles.p, 0, ctx->tiles.cap, ctx->stream));
   }
   ix.valid = false;
+  if (!ctx->crowded.p) { CK(ctx->crowded.ensure(64)); CK(cudaMemsetAsync(ctx->crowded.p, 0, 64, ctx->stream)); }
   ProfScope ps(ctx, MVR_K_SORT, (keep_s0 ? 48.0 : 32.0) * n + 8.0 * cells, n);
   CK(launch_pair_count(pts, n, guess, g, cells, ctx->pkeys.as<uint32_t>(), ctx->pvals.as<uint32_t>(), ctx->pcount.as<uint32_t>(), ctx->stream));
   CK(launch_scan_cells(ctx->pcount.as<uint32_t>(), ix.start.as<uint32_t>(), (size_t)cells + 1, ctx->tiles.as<unsigned long long>(),
@@ -492,7 +495,7 @@ int build_pair_index(mvr_ctx* ctx, PairIndex& ix, const float4* pts, int n, int 
                          ordered ? ctx->pmoved.as<float4>() : ix.sorted.as<float4>(), ctx->stream));
   if (ordered)
     CK(launch_pair_rerank(ctx->pmoved.as<float4>(), n, ctx->pkeys.as<uint32_t>(), ix.start.as<uint32_t>(), ix.sorted.as<float4>(),
-                          keep_s0 ? ix.s0.as<float4>() : nullptr, ctx->stream));
+                          keep_s0 ? ix.s0.as<float4>() : nullptr, ctx->crowded.as<uint32_t>(), ctx->stream));
   ix.g = g; ix.cells = cells; ix.n_valid = n - n_bad; ix.valid = true; ix.gm_gate = -1.f;
   return MVR_OK;
 }
@@ -618,7 +621,7 @@ int mvr_ctx_destroy(mvr_ctx* ctx) {
   ctx->pt.release(); ctx->ps.release(); ctx->nt.release(); ctx->nq.release();
   ctx->pkeys.release(); ctx->pvals.release(); ctx->pmoved.release(); ctx->pcount.release();
   DevBuf* bufs[] = {&ctx->cur, &ctx->corr_p, &ctx->rmin, &ctx->rnn, &ctx->corr_j, &ctx->corr_d2, &ctx->partials, &ctx->sums, &ctx->out_cloud, &ctx->qtmp,
-                    &ctx->itmp, &ctx->ftmp, &ctx->scratch, &ctx->misc, &ctx->tiles, &ctx->state, &ctx->log};
+                    &ctx->itmp, &ctx->ftmp, &ctx->scratch, &ctx->misc, &ctx->tiles, &ctx->state, &ctx->log, &ctx->crowded};
   for (DevBuf* b : bufs) b->release();
   if (ctx->h_sums) cudaFreeHost(ctx->h_sums);
   if (ctx->h_small) cudaFreeHost(ctx->h_small);
@@ -1062,11 +1065,15 @@ static int align_finish_enqueue(mvr_ctx* ctx, mvr_ctx* lead, float* out_xyzw) {
   const int n_log = std::min(h.iter, (int)ICP_MAX_LOG);
   if (n_log > 0) CK(cudaMemcpyAsync(ctx->h_log, ctx->log.p, (size_t)n_log * sizeof(IterRec), cudaMemcpyDeviceToHost, st));
   if (out_xyzw) CK(cudaMemcpyAsync(out_xyzw, ctx->out_cloud.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, st));
+  if (ctx->crowded.p) {   // the builds ran on ctx->stream, which `st` has waited for
+    CK(cudaMemcpyAsync(ctx->h_small + 8, ctx->crowded.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemsetAsync(ctx->crowded.p, 0, sizeof(uint32_t), st));
+  }
   return MVR_OK;
 }
 
 // After the lead stream has been synchronised.
-static int align_finish_collect(mvr_ctx* ctx, mvr_ctx* lead, float* out_pose, mvr_icp_report* report) {
+static int align_finish_collect(mvr_ctx* ctx, mvr_ctx* lead, float* out_pose, mvr_icp_report* report, int batch_pairs = 1) {
   const IcpState& h = *ctx->h_state;
   const int n_log = std::min(h.iter, (int)ICP_MAX_LOG);
   ctx->have_out = true;
@@ -1081,8 +1088,13 @@ static int align_finish_collect(mvr_ctx* ctx, mvr_ctx* lead, float* out_pose, mv
     float ms = 0.f;
     cudaEventElapsedTime(&ms, lead->ev_a, lead->ev_b);
     report->iterations = h.iter; report->converged = (h.done && h.status == 0) ? 1 : 0; report->reason = h.reason;
-    report->n_correspondences = h.n_corr; report->mse = h.cur_mse; report->gpu_ms = ms; report->nn_queries = h.queries;
+    report->n_correspondences = h.n_corr; report->mse = h.cur_mse; report->nn_queries = h.queries;
+    // pairs of a batch advance in lock-step and are not separable: each is given its share of the batch's device time
+    report->gpu_ms = (double)ms / (double)std::max(batch_pairs, 1);
   }
+  ctx->crowded_seen = ctx->crowded.p ? ctx->h_small[8] : 0u;
+  if (ctx->crowded_seen)
+    ctx->err = "warning: a grid cell holds " + std::to_string(ctx->crowded_seen) + " points (duplicates or clamped outliers?): index build and search slow down, sums over it lose their fixed order";
   if (h.status == MVR_ERR_TOO_FEW_CORRESPONDENCES) ctx->err = "not enough correspondences";
   if (h.status == MVR_ERR_NOT_SPD) ctx->err = "point-to-plane normal equations not positive definite";
   return h.status;
@@ -1141,7 +1153,7 @@ int mvr_icp_align_batch(mvr_ctx* const* ctxs, int count, const mvr_icp_params* p
   if (cudaStreamSynchronize(ok[0]->stream) != cudaSuccess) return fail(ctxs[0], MVR_ERR_CUDA, "batch tail failed");
   for (size_t j = 0; j < ok.size(); ++j) {
     const int k = slot[j];
-    if (statuses[k] == MVR_OK) statuses[k] = align_finish_collect(ok[j], ok[0], out_poses ? out_poses + 16 * k : nullptr, reports ? reports + k : nullptr);
+    if (statuses[k] == MVR_OK) statuses[k] = align_finish_collect(ok[j], ok[0], out_poses ? out_poses + 16 * k : nullptr, reports ? reports + k : nullptr, (int)ok.size());
   }
   return MVR_OK;
 }
@@ -1220,6 +1232,7 @@ int mvr_pair_moments_compute_batch(mvr_ctx* const* ctxs, int count, double max_d
 }
 
 double mvr_debug_value(mvr_ctx* ctx, int k) {
+  if (ctx && k == 8) return (double)ctx->crowded_seen;   // population of a cell too crowded to rank in the last align's index builds
   if (!ctx || !ctx->h_state || k < 0 || k >= 8) return 0.0;
   return (double)ctx->h_state->dbg[k];
 }

@@ -115,8 +115,10 @@ cudaError_t launch_fill_u32(uint32_t* p, size_t n, uint32_t v, cudaStream_t s);
 // y-z / x cells.
 cudaError_t launch_gate_mask(const uint32_t* start, PairGrid g, int wstride, int D, int Dx, uint32_t* occ, uint32_t* mask, cudaStream_t s);
 // sorted[k] = {moved point, bits(original index)}; copy (nullable) gets the same.
+// crowded (nullable, device word): raised (atomicMax) to the population of a cell too crowded to be ranked (its points keep
+// their arrival order).
 cudaError_t launch_pair_rerank(const float4* tmp, int n, const uint32_t* keys, const uint32_t* start, float4* sorted, float4* copy,
-                               cudaStream_t s);
+                               uint32_t* crowded, cudaStream_t s);
 
 struct FwdArgs {
   float4* cur;             // source, sorted by binning cell, current coordinates (updated in place), .w = original index

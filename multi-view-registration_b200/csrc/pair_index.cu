@@ -47,14 +47,25 @@ __global__ void __launch_bounds__(256) k_pair_scatter(const float4* __restrict__
   tmp[__ldg(start + __ldg(keys + i)) + __ldg(rank + i)] = p;
 }
 
+// A cell that holds more than RERANK_LIMIT points (duplicated or invalid returns piled on one spot, outliers clamped into a
+// boundary cell) would make the rank count below quadratic: its points keep their arrival order instead and the population is
+// reported through *crowded (searches stay exact; only the run-to-run order of sums over that cell's points is lost).
+constexpr uint32_t RERANK_LIMIT = 1024;
 __global__ void __launch_bounds__(256) k_pair_rerank(const float4* __restrict__ tmp, int n, const uint32_t* __restrict__ keys,
-                                                     const uint32_t* __restrict__ start, float4* __restrict__ sorted, float4* __restrict__ copy) {
+                                                     const uint32_t* __restrict__ start, float4* __restrict__ sorted, float4* __restrict__ copy,
+                                                     uint32_t* __restrict__ crowded) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const float4 p = __ldg(tmp + k);
   const uint32_t idx = __float_as_uint(p.w);
   const uint32_t key = __ldg(keys + idx);
   const uint32_t s = __ldg(start + key), e = __ldg(start + key + 1);
+  if (e - s > RERANK_LIMIT) {
+    sorted[k] = p;
+    if (copy) copy[k] = p;
+    if (crowded && (uint32_t)k == s) atomicMax(crowded, e - s);
+    return;
+  }
   uint32_t r = 0;
   for (uint32_t j = s; j < e; ++j) r += (__float_as_uint(__ldg(&tmp[j].w)) < idx) ? 1u : 0u;
   sorted[s + r] = p;
@@ -144,9 +155,9 @@ cudaError_t launch_pair_scatter(const float4* in, int n, const Mat4f* guess, con
 }
 
 cudaError_t launch_pair_rerank(const float4* tmp, int n, const uint32_t* keys, const uint32_t* start, float4* sorted, float4* copy,
-                               cudaStream_t s) {
+                               uint32_t* crowded, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  k_pair_rerank<<<(n + 255) / 256, 256, 0, s>>>(tmp, n, keys, start, sorted, copy); count_launch();
+  k_pair_rerank<<<(n + 255) / 256, 256, 0, s>>>(tmp, n, keys, start, sorted, copy, crowded); count_launch();
   return cudaGetLastError();
 }
 

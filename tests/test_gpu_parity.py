@@ -320,6 +320,25 @@ def test_icp_fixed_iterations_matches_oracle_per_iteration(ctx, orc, mvr, synth,
     assert np.array_equal(r["cloud"], orc.transform(src, r["final"]))
 
 
+def test_icp_crowded_cell_is_reported_and_stays_exact(ctx, orc, mvr, synth):
+    """Thousands of identical points (an invalid-return value repeated by a scanner) land in one grid cell: the index build no
+    longer ranks that cell (it would be quadratic), says so, and the correspondences stay those of the oracle."""
+    src, tgt, guess, _ = _pair(synth, 12_000)
+    tgt = tgt.copy(); src = src.copy()
+    tgt[:3000, :3] = tgt[5000, :3]        # 3000 copies of one target point
+    src[:2500, :3] = src[7000, :3]
+    ctx.set_target(tgt); ctx.set_source(src)
+    p = mvr.default_params(max_iterations=4, max_dist=4.0, reciprocal=1, fixed_iterations=1)
+    r = ctx.icp_align(p, guess=guess, n_source=len(src))
+    o = orc.icp_align(src, tgt, orc.make_params(max_iterations=4, max_dist=4.0, reciprocal=True, fixed_iterations=True), guess=guess)
+    assert [a["n_corr"] for a in r["log"]] == [b["n_corr"] for b in o["log"]]
+    assert ctx.debug_value(8) >= 2500 and "grid cell holds" in ctx.last_error()
+    src2, tgt2, guess2, _ = _pair(synth, 12_000)
+    ctx.set_target(tgt2); ctx.set_source(src2)
+    ctx.icp_align(p, guess=guess2, n_source=len(src2))
+    assert ctx.debug_value(8) == 0
+
+
 def test_icp_gate_mask_changes_nothing(mvr, orc, synth):
     """The optional gate mask of the target (one bit per cell: anything within the gate?) only skips searches that cannot
     find a partner: every iteration's correspondences and the pose are bit-identical with and without it, for a pair with
