@@ -72,7 +72,9 @@ constexpr int PG_STRIDE = FUSED_THREADS;
 // trip, so the trip count of a warp is the maximum over its lanes of the TOTAL number of candidates (not the sum over
 // rows of per-row maxima) and the loads of a trip overlap.  Past a segment's end the last point is simply evaluated
 // again: a duplicate never wins a strict lexicographic comparison.  (Measured on B200, same box: testing min(d) of a group against the best first, to skip the comparisons, was 9 % slower -- in
-// a warp some lane nearly always improves; 8 loads per trip
+// a warp some lane nearly always improves; handing a block's queries out again sorted by their candidate count, so that the
+// lanes of a warp scan lists of equal length, was 14 % slower (profiles/r02_work_sort_ab.log: three more block barriers and the
+// lanes no longer read neighbouring cells); 8 loads per trip
 // beat 4 by 2.5 % and 2 by 20 %; reading whole groups past the segment end into the next cells' points -- also exact --
 // was 3 % slower, as was dropping the per-row x narrowing for narrow boxes; guarding every candidate of a trip by its
 // own range test instead of re-reading the last point turned into divergent branches and was 70 % slower.)

@@ -16,7 +16,8 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 prev = 0.0
 for iters in [int(x) for x in os.environ.get("MVR_ITERS", "1,2,3,4,6,8,12,16,20,30").split(",")]:
     icp = mvr_b200.default_params(max_iterations=iters, max_dist=4.0, reciprocal=int(os.environ.get("MVR_RECIP", "1")), fixed_iterations=1)
-    tp = mvr_b200.turntable_params(pivot=synth.PIVOT, axis=synth.AXIS, icp=icp, repeat_times=1, mode=mvr_b200.RING_PAIRS, loop_closure=1, lum_iterations=16)
+    tp = mvr_b200.turntable_params(pivot=synth.PIVOT, axis=synth.AXIS, icp=icp, repeat_times=1, mode=mvr_b200.RING_PAIRS, loop_closure=1, lum_iterations=16,
+                                   pair_begin=0, pair_end=int(os.environ.get("MVR_PAIRS", "0")))
     ts = []
     for rep in range(4):
         flush.fill_(1); torch.cuda.synchronize()
