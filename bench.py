@@ -393,6 +393,10 @@ def run_native(a):
         avg_ms = c["ms"] / max(c["launches"], 1)
         bytes_per_launch = c["bytes"] / max(c["launches"], 1)
         ach = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+        # the same without the 36 B per source point of the per-iteration source re-index, which the reference's PCL path
+        # performs (SURVEY.md section 8d counts it as compulsory) and this implementation avoids with its static index
+        lean_bytes = (p1 - p0) * (40.0 * n + 16.0 * n)
+        ach_lean = lean_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
         total_kernel_ms = sum(v["ms"] for v in st.values())
         # DRAM traffic of the same launch pair from the committed ncu --set full capture (cold cache), if it was taken
         # with the same number of pairs per launch
@@ -411,6 +415,9 @@ def run_native(a):
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "bytes_per_launch": bytes_per_launch, "avg_launch_us": avg_ms * 1e3, "launches": c["launches"],
+                "algorithmic_bytes": "SURVEY.md section 8d, reciprocal fused iteration: 16 N + 16 M + 36 N (source re-index) + 16 N (reverse pass) "
+                                     "= 68 N + 16 M per pair and iteration, cell tables not counted; one launch pair serves pairs_per_launch pairs",
+                "achieved_without_reindex_bytes": ach_lean, "frac_without_reindex_bytes": ach_lean / peak,
                 "share_of_kernel_time": c["ms"] / total_kernel_ms if total_kernel_ms > 0 else None,
                 "pairs_per_launch": min(24, p1 - p0),
                 "per_kernel_ms": {k: round(v["ms"], 4) for k, v in st.items() if v["launches"]}}

@@ -81,7 +81,7 @@ struct Cloud {
   }
 };
 
-struct ProfRec { int kind; cudaEvent_t a, b; double bytes, units; };
+struct ProfRec { int kind; cudaEvent_t a, b; double bytes, units; int count; };
 
 // Per-align row-major index of one cloud (pair_index.cu).
 struct PairIndex {
@@ -160,9 +160,11 @@ cudaEvent_t get_event(mvr_ctx* ctx) {
 
 struct ProfScope {
   mvr_ctx* ctx; int idx;
-  ProfScope(mvr_ctx* c, int kind, double bytes, double units) : ctx(c), idx(-1) {
+  // count: launches (of the kernel family) the scope brackets -- the iterations of an align share ONE pair of events, so the
+  // measurement puts nothing between them
+  ProfScope(mvr_ctx* c, int kind, double bytes, double units, int count = 1) : ctx(c), idx(-1) {
     if (!c->profiling) return;
-    ProfRec r{kind, get_event(c), get_event(c), bytes, units};
+    ProfRec r{kind, get_event(c), get_event(c), bytes, units, count};
     cudaEventRecord(r.a, c->stream);
     c->prof.push_back(r);
     idx = (int)c->prof.size() - 1;
@@ -176,7 +178,7 @@ void prof_flush(mvr_ctx* ctx) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
       mvr_kernel_stat& s = ctx->stats[r.kind];
-      s.launches += 1; s.ms += ms; s.bytes += r.bytes; s.units += r.units;
+      s.launches += (uint64_t)r.count; s.ms += ms; s.bytes += r.bytes; s.units += r.units;
     }
     ctx->ev_pool.push_back(r.a); ctx->ev_pool.push_back(r.b);
   }
@@ -547,10 +549,6 @@ void parallel_for(int n, F fn) {
   for (std::thread& t : th) t.join();
 }
 
-// Algorithmic bytes of one iteration's correspondence search: each query read once
-// (16 B) and its result written once (8 B), each target point once (16 B); the reciprocal half reads
-// each source point once more as a candidate (16 B).  Cell-table entries are NOT counted (conservative).
-double corr_bytes(int n, int m, bool reciprocal) { return 24.0 * n + 16.0 * m + (reciprocal ? 16.0 * n : 0.0); }
 
 }  // namespace
 
@@ -1028,12 +1026,18 @@ static int align_run(mvr_ctx* const* ctxs, int count, const mvr_icp_params* prm,
     int first = 1;
     while (!done) {
       const int todo = std::min(batch, std::max(prm->max_iterations - enqueued, 1));
-      for (int it = 0; it < todo; ++it) {
-        // one scope = one iteration: forward search (+ transform), reciprocal search (+ sums, solve, criteria)
-        ProfScope ps(ctx, MVR_K_CORR, 24.0 * n_tot + 16.0 * m_tot + (reciprocal ? 16.0 * n_tot : 0.0), (double)n_tot);
-        CK(launch_icp_forward(fb, gn, gf, first, reciprocal, est, ctx->stream));
-        first = 0;
-        if (reciprocal) CK(launch_icp_reverse(rb, gn, gr, est, ctx->stream));
+      {
+        // one scope = `todo` iterations: forward search (+ transform), reciprocal search (+ sums, solve, criteria) each.
+        // Bytes per iteration as SURVEY.md section 8d counts them: every source and target point once (16 B each); with
+        // reciprocal correspondences the source re-index PCL performs per iteration (36 B per source point) and the reverse
+        // pass (16 B per source point) -- cell-table entries not counted.
+        const double per_it = 16.0 * n_tot + 16.0 * m_tot + (reciprocal ? 52.0 * n_tot : 0.0);
+        ProfScope ps(ctx, MVR_K_CORR, per_it * todo, (double)n_tot * todo, todo);
+        for (int it = 0; it < todo; ++it) {
+          CK(launch_icp_forward(fb, gn, gf, first, reciprocal, est, ctx->stream));
+          first = 0;
+          if (reciprocal) CK(launch_icp_reverse(rb, gn, gr, est, ctx->stream));
+        }
       }
       enqueued += todo;
       for (int k = 0; k < gn; ++k)
