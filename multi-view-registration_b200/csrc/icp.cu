@@ -526,6 +526,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, MVR_REV_MINBLOCKS * (256 / FUSE
 }
 #endif   // MVR_TS_TILE
 
+// (Tried in round 2 and dropped, profiles/r02_dynamic_items_ab.log: resident blocks drawing their chunks from a counter instead of
+// one block per chunk -- 12 % slower with 24 pairs per launch, no gain with 3.)
 // Chunks of 256 target points per block of the reverse half: enough for its compacted list to fill whole rounds of
 // 256 searches (about half of the target points are chosen).  Measured on B200 (same box; 24 x 200k pairs per launch /
 // one 200k pair alone): 2 chunks 25.3 ms / 2.06 ms, 3 chunks 24.1 / 2.08, 4 chunks 24.0 / 2.23 -- three chunks, four once
