@@ -368,12 +368,16 @@ def run_native(a):
         e2e = {"value": q_e / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e / a.steps,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
 
-    # ---- roofline of the dominant kernel: one extra untimed step, per-kernel CUDA events on every stream ----
+    # ---- roofline of the dominant kernels: one extra untimed step with the library's event bracket around the iterations ----
+    # In profiling mode the library finishes every pair's preparation (index builds) first, then records one CUDA event before
+    # the first and one after the last iteration launch of the rank's batch (all groups of pairs, which run concurrently on
+    # their own streams); every pair report carries its share of that span.
     ctxs = [reg.context(k) for k in range(reg.streams())]
     for c in ctxs:
         c.set_profiling(True)
         c.kernel_stats(reset=True)
-    step(False)
+    _, preps, _ = step(False)
+    iter_ms = sum(preps[p]["gpu_ms"] for p in range(p0, p1))
     st = {}
     for c in ctxs:
         for k, v in c.kernel_stats(reset=True).items():
@@ -389,38 +393,42 @@ def run_native(a):
         except OSError:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        c = st["corr"]
-        avg_ms = c["ms"] / max(c["launches"], 1)
-        bytes_per_launch = c["bytes"] / max(c["launches"], 1)
+        npairs = p1 - p0
+        avg_ms = iter_ms / max(a.iters, 1)                       # one iteration of every pair of the rank
+        recip = bool(a.reciprocal)
+        bytes_per_launch = npairs * (16.0 * n + 16.0 * n + (52.0 * n if recip else 0.0))     # SURVEY.md section 8d, N = M = n
         ach = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
         # the same without the 36 B per source point of the per-iteration source re-index, which the reference's PCL path
         # performs (SURVEY.md section 8d counts it as compulsory) and this implementation avoids with its static index
-        lean_bytes = (p1 - p0) * (40.0 * n + 16.0 * n)
+        lean_bytes = npairs * (24.0 * n + 16.0 * n + (16.0 * n if recip else 0.0))
         ach_lean = lean_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
-        total_kernel_ms = sum(v["ms"] for v in st.values())
-        # DRAM traffic of the same launch pair from the committed ncu --set full capture (cold cache), if it was taken
-        # with the same number of pairs per launch
+        # DRAM traffic of the same launches from the committed ncu --set full capture (cold cache), if it was taken with the
+        # same number of pairs
         traffic, traffic_src = None, None
         try:
             import glob, re
             caps = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_icp_fused_ncu_full.txt")))
             if caps:
                 m = re.search(r"one iteration of (\d+) pairs\): ([0-9.]+) MB", open(caps[-1]).read())
-                if m and int(m.group(1)) == min(24, p1 - p0):
+                if m and int(m.group(1)) == npairs:
                     traffic, traffic_src = float(m.group(2)) * 1e6, os.path.relpath(caps[-1], ROOT) + " (ncu --set full, caches flushed per replay)"
         except OSError:
             pass
+        group = max(1, (npairs + 3) // 4)
         roof = {"bound": "hbm", "kernel": "k_icp_forward + k_icp_reverse (one ICP iteration of every pair of the rank: forward search, reciprocal "
-                                          "search, estimator sums, solve; two launches serve the whole batch)",
+                                          "search, estimator sums, solve; a launch pair serves a group of %d pairs, the %d groups run concurrently)"
+                                          % (group, (npairs + group - 1) // group),
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                "bytes_per_launch": bytes_per_launch, "avg_launch_us": avg_ms * 1e3, "launches": c["launches"],
+                "bytes_per_launch": bytes_per_launch, "avg_launch_us": avg_ms * 1e3, "launches": a.iters,
+                "launch_unit": "one iteration of all %d pairs = %d concurrent launch pairs; duration = (CUDA-event span of the iterations) / %d"
+                               % (npairs, (npairs + group - 1) // group, a.iters),
                 "algorithmic_bytes": "SURVEY.md section 8d, reciprocal fused iteration: 16 N + 16 M + 36 N (source re-index) + 16 N (reverse pass) "
-                                     "= 68 N + 16 M per pair and iteration, cell tables not counted; one launch pair serves pairs_per_launch pairs",
+                                     "= 68 N + 16 M per pair and iteration, cell tables not counted",
                 "achieved_without_reindex_bytes": ach_lean, "frac_without_reindex_bytes": ach_lean / peak,
-                "share_of_kernel_time": c["ms"] / total_kernel_ms if total_kernel_ms > 0 else None,
-                "pairs_per_launch": min(24, p1 - p0),
-                "per_kernel_ms": {k: round(v["ms"], 4) for k, v in st.items() if v["launches"]}}
+                "share_of_step": iter_ms / (ms / a.steps) if ms > 0 else None,
+                "pairs_per_launch": group,
+                "per_kernel_ms": {k: round(v["ms"], 4) for k, v in st.items() if v["launches"] and k != "corr"}}
 
     # ---- accuracy summary (parity itself lives in tests/) ----
     acc = None
@@ -479,7 +487,7 @@ def run_native(a):
             "dtype": "f32", "data": "synthetic", "config": cfg,
             "registration_ms": ms / a.steps, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roof, "cpu_baseline": cpu, "accuracy": acc, "parity": parity, "pose_checksum": checksum,
-            "pairs_per_launch": min(24, p1 - p0),   # mvr_ctx_set_batch_group default: up to 24 pairs advance per launch
+            "pairs_per_launch": max(1, (p1 - p0 + 3) // 4),   # mvr_ctx_set_batch_group default: a quarter of the rank's pairs per launch, the groups run concurrently
         }
         print(json.dumps(out))
     reg.close()
@@ -555,7 +563,7 @@ def run_single_process(a):
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(a, G), "registration_ms": ms / a.steps, "device_ms_max_per_step": dms / a.steps, "e2e": e2e,
         "gpu_launches": int(launches), "clocks": clocks, "roofline": None, "cpu_baseline": None,
-        "pose_checksum": ring.pose_checksum(recs), "pairs_per_launch": min(24, -(-V // G)),
+        "pose_checksum": ring.pose_checksum(recs), "pairs_per_launch": max(1, (-(-V // G) + 3) // 4),
         "launch": "single process: mvr_register_turntable_multi (one host thread per GPU, ncclAllGather of the pair records inside the C ABI)",
     }
     print(json.dumps(out))

@@ -189,8 +189,9 @@ int mvr_icp_align(mvr_ctx* ctx, const mvr_icp_params* params, const float* guess
  * All contexts must live on one device; the work runs on the first context's stream. */
 int mvr_icp_align_batch(mvr_ctx* const* ctxs, int count, const mvr_icp_params* params, const float* guesses, float* out_poses,
                         mvr_icp_report* reports, int* statuses);
-/* Pairs per kernel launch of the batches this context leads (1..24, default 24): a group of pairs runs all its
- * iterations before the next group starts. */
+/* Pairs per kernel launch of the batches this context leads (1..24; 0 = automatic, the default: a quarter of the batch).  The
+ * pairs of a group advance in lock-step, one launch per iteration half; the groups of a batch run concurrently, each on the
+ * stream of its first context.  Results do not depend on the grouping. */
 int mvr_ctx_set_batch_group(mvr_ctx* ctx, int pairs);
 /* Per-iteration records of the last align (n_correspondences, mse, delta). */
 int mvr_icp_get_iterations(mvr_ctx* ctx, mvr_icp_iteration* out, int max_records, int* count);

@@ -114,7 +114,7 @@ struct mvr_ctx {
   bool gate_mask = false;        // mvr_ctx_set_gate_mask
   FwdArgs fa{}; RevArgs ra{};    // kernel arguments of the prepared align
   bool want_rnn = false;         // the next prepared align also records the mutual partners (mvr_correspondences)
-  int group_pairs = 24;          // pairs per launch of a batch led by this context (mvr_ctx_set_batch_group)
+  int group_pairs = 0;           // pairs per launch of a batch led by this context (mvr_ctx_set_batch_group); 0 = automatic
   DevBuf pkeys, pvals, pmoved, pcount;   // build scratch of the per-align indices: keys, arrival ranks, arrival-order records, cell counters
   DevBuf crowded;                        // one word: population of the most crowded cell an index build could not rank (0: none)
   uint32_t crowded_seen = 0;             // its value after the last align
@@ -698,7 +698,7 @@ int mvr_ctx_set_nn_mode(mvr_ctx* ctx, int mode) {
 }
 
 int mvr_ctx_set_batch_group(mvr_ctx* ctx, int pairs) {
-  if (!ctx || pairs < 1 || pairs > (int)FUSED_MAX_PAIRS) return MVR_ERR_BAD_ARG;
+  if (!ctx || pairs < 0 || pairs > (int)FUSED_MAX_PAIRS) return MVR_ERR_BAD_ARG;
   ctx->group_pairs = pairs;
   return MVR_OK;
 }
@@ -996,59 +996,96 @@ static int align_prepare(mvr_ctx* ctx, const mvr_icp_params* prm, const float* g
 // to completion before the next one starts.  Measured on B200 (24 x 200k pairs): groups of 6 / 8 / 12 / 24 pairs take
 // 28.3 / 27.7 / 26.8 / 25.3 ms -- fewer launch tails outweigh the L2 misses of a working set of 24 x 20 MB.
 static int align_run(mvr_ctx* const* ctxs, int count, const mvr_icp_params* prm, int est) {
-  mvr_ctx* ctx = ctxs[0];   // the lead: its stream carries the batch, CK() reports into it
+  mvr_ctx* ctx = ctxs[0];   // the lead: CK() reports into it, its ev_a .. ev_b bracket the iterations of the whole batch
   cudaSetDevice(ctx->device);
   const bool reciprocal = prm->use_reciprocal_correspondences != 0;
-  for (int k = 1; k < count; ++k) CK(cudaEventRecord(ctxs[k]->ev_b, ctxs[k]->stream));   // "context k is prepared"
-  CK(cudaEventRecord(ctx->ev_a, ctx->stream));
-  const int gsz = std::max(1, std::min(ctx->group_pairs, (int)FUSED_MAX_PAIRS));
+  // Groups of pairs advance in lock-step (one launch per iteration half serves a group); the groups themselves run
+  // CONCURRENTLY, each on the stream of its first context, so that one group's launch tails, its serial solve and the gaps
+  // between its dependent launches are filled by the others.  Measured on B200 (scripts/gpu_streams_vs_batch.py,
+  // profiles/r02_concurrent_groups.log): 24 pairs 22.5 ms as one group, 20.6-20.8 ms as 2 .. 8 groups; 12 pairs 12.1 -> 10.5 ms;
+  // 3 pairs 4.05 -> 3.3 ms.  Default: four groups (a group size set with mvr_ctx_set_batch_group is kept).
+  const int gsz = ctx->group_pairs > 0 ? std::min(ctx->group_pairs, (int)FUSED_MAX_PAIRS)
+                                       : std::max(1, std::min((count + 3) / 4, (int)FUSED_MAX_PAIRS));
+  struct Group {
+    int g0, gn, gf, gr, enqueued, first;
+    bool done;
+    long long n_tot, m_tot;
+    mvr_ctx* lead;
+    FwdBatch fb;
+    RevBatch rb;
+  };
+  std::vector<Group> groups;
   for (int g0 = 0; g0 < count; g0 += gsz) {
-    const int gn = std::min(gsz, count - g0);
-    FwdBatch fb{};
-    RevBatch rb{};
-    int gf = 1, gr = 1;
-    bool done = true;
-    long long n_tot = 0, m_tot = 0;
-    for (int k = 0; k < gn; ++k) {
+    Group g{};
+    g.g0 = g0; g.gn = std::min(gsz, count - g0); g.gf = 1; g.gr = 1; g.enqueued = 0; g.first = 1; g.done = true;
+    g.lead = ctxs[g0];
+    for (int k = 0; k < g.gn; ++k) {
       mvr_ctx* c = ctxs[g0 + k];
-      // the lead stream waits for the preparation of THIS group only: later groups' index builds (on their own
-      // streams) overlap with this group's iterations
-      if (c != ctx) CK(cudaStreamWaitEvent(ctx->stream, c->ev_b, 0));
-      fb.a[k] = c->fa; rb.a[k] = c->ra;
-      gf = std::max(gf, c->fa.grid); gr = std::max(gr, c->ra.grid);
-      if (!c->h_state->done) done = false;
-      n_tot += c->src.n; m_tot += c->tgt.n;
+      g.fb.a[k] = c->fa; g.rb.a[k] = c->ra;
+      g.gf = std::max(g.gf, c->fa.grid); g.gr = std::max(g.gr, c->ra.grid);
+      if (!c->h_state->done) g.done = false;
+      g.n_tot += c->src.n; g.m_tot += c->tgt.n;
     }
-    // Enqueue iterations in batches; after each batch read the states back.  Once a pair raises `done` its
-    // blocks of the remaining launches return immediately.
-    int enqueued = 0;
-    int batch = prm->fixed_iterations ? 64 : 2;
-    int first = 1;
-    while (!done) {
-      const int todo = std::min(batch, std::max(prm->max_iterations - enqueued, 1));
+    groups.push_back(g);
+  }
+  // a group's stream waits for the preparation (index builds, initial state: each on the pair's own stream) of its members
+  for (Group& g : groups)
+    for (int k = 1; k < g.gn; ++k) {
+      mvr_ctx* c = ctxs[g.g0 + k];
+      CK(cudaEventRecord(c->ev_b, c->stream));
+      CK(cudaStreamWaitEvent(g.lead->stream, c->ev_b, 0));
+    }
+  if (ctx->profiling)   // a clean bracket for the roofline measurement: nothing of the preparation inside ev_a .. ev_b
+    for (int k = 0; k < count; ++k) CK(cudaStreamSynchronize(ctxs[k]->stream));
+  CK(cudaEventRecord(ctx->ev_a, ctx->stream));
+  for (size_t gi = 1; gi < groups.size(); ++gi) CK(cudaStreamWaitEvent(groups[gi].lead->stream, ctx->ev_a, 0));
+  // Enqueue iterations in batches; after each batch read the states back.  Once a pair raises `done` its blocks of the
+  // remaining launches return immediately.
+  int batch = prm->fixed_iterations ? 64 : 2;
+  for (;;) {
+    bool any = false;
+    for (Group& g : groups) {
+      if (g.done) continue;
+      any = true;
+      const int todo = std::min(batch, std::max(prm->max_iterations - g.enqueued, 1));
       {
         // one scope = `todo` iterations: forward search (+ transform), reciprocal search (+ sums, solve, criteria) each.
         // Bytes per iteration as SURVEY.md section 8d counts them: every source and target point once (16 B each); with
         // reciprocal correspondences the source re-index PCL performs per iteration (36 B per source point) and the reverse
         // pass (16 B per source point) -- cell-table entries not counted.
-        const double per_it = 16.0 * n_tot + 16.0 * m_tot + (reciprocal ? 52.0 * n_tot : 0.0);
-        ProfScope ps(ctx, MVR_K_CORR, per_it * todo, (double)n_tot * todo, todo);
+        const double per_it = 16.0 * g.n_tot + 16.0 * g.m_tot + (reciprocal ? 52.0 * g.n_tot : 0.0);
+        ProfScope ps(g.lead, MVR_K_CORR, per_it * todo, (double)g.n_tot * todo, todo);
         for (int it = 0; it < todo; ++it) {
-          CK(launch_icp_forward(fb, gn, gf, first, reciprocal, est, ctx->stream));
-          first = 0;
-          if (reciprocal) CK(launch_icp_reverse(rb, gn, gr, est, ctx->stream));
+          CK(launch_icp_forward(g.fb, g.gn, g.gf, g.first, reciprocal, est, g.lead->stream));
+          g.first = 0;
+          if (reciprocal) CK(launch_icp_reverse(g.rb, g.gn, g.gr, est, g.lead->stream));
         }
       }
-      enqueued += todo;
-      for (int k = 0; k < gn; ++k)
-        CK(cudaMemcpyAsync(ctxs[g0 + k]->h_state, ctxs[g0 + k]->state.p, sizeof(IcpState), cudaMemcpyDeviceToHost, ctx->stream));
-      if (g0 + gn >= count || !prm->fixed_iterations) CK(cudaStreamSynchronize(ctx->stream));
-      done = true;
-      if (!prm->fixed_iterations)
-        for (int k = 0; k < gn; ++k) if (!ctxs[g0 + k]->h_state->done) done = false;
-      batch = std::min(batch * 2, 64);
-      if (prm->fixed_iterations && enqueued < prm->max_iterations) done = false;
+      g.enqueued += todo;
+      for (int k = 0; k < g.gn; ++k)
+        CK(cudaMemcpyAsync(ctxs[g.g0 + k]->h_state, ctxs[g.g0 + k]->state.p, sizeof(IcpState), cudaMemcpyDeviceToHost, g.lead->stream));
     }
+    if (!any) break;
+    bool more = false;
+    for (Group& g : groups) {
+      if (g.done) continue;
+      if (prm->fixed_iterations) {
+        g.done = g.enqueued >= prm->max_iterations;
+      } else {
+        CK(cudaStreamSynchronize(g.lead->stream));
+        g.done = true;
+        for (int k = 0; k < g.gn; ++k) if (!ctxs[g.g0 + k]->h_state->done) g.done = false;
+      }
+      if (!g.done) more = true;
+    }
+    if (!more) break;
+    batch = std::min(batch * 2, 64);
+  }
+  // the lead stream joins the groups: ev_b marks the end of every pair's iterations, and whatever follows on the lead stream
+  // (aligned clouds, logs) is ordered after all of them
+  for (size_t gi = 1; gi < groups.size(); ++gi) {
+    CK(cudaEventRecord(groups[gi].lead->ev_a, groups[gi].lead->stream));
+    CK(cudaStreamWaitEvent(ctx->stream, groups[gi].lead->ev_a, 0));
   }
   CK(cudaEventRecord(ctx->ev_b, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));

@@ -29,7 +29,7 @@ tot = sum(a[1] for a in agg.values())
 with open(os.path.join(P, "%s_ncu_launches_summary.txt" % rnd), "w") as f:
     f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 python bench.py --steps 2 --warmup 1 --no-e2e --cpu-sample-pairs 0\n")
     f.write("# per-launch times are cold-cache and serialised: the SHARE of a kernel is what compares with bench.py's live measurement\n")
-    f.write("# (bench.py roofline.share_of_kernel_time = %.3f for k_icp_forward + k_icp_reverse)\n" % (bench["roofline"]["share_of_kernel_time"] or 0))
+    f.write("# (bench.py roofline.share_of_step = %.3f: the CUDA-event span of the iterations / the step)\n" % (bench["roofline"].get("share_of_step") or 0))
     for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
         f.write("%-64s launches %5d  total %10.1f us  avg %8.2f us  share %.3f\n" % (k[:64], a[0], a[1], a[1] / a[0], a[1] / tot))
     icp = sum(a[1] for k, a in agg.items() if "k_icp_" in k)
@@ -48,11 +48,11 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
         "smsp__cycles_active.avg", "sm__cycles_elapsed.max"]
 traffic = 0.0
-pairs = bench["roofline"]["pairs_per_launch"]
+pairs = bench["config"]["pairs"]
 n = bench["config"]["points_per_view"]
 with open(os.path.join(P, "%s_icp_fused_ncu_full.txt" % rnd), "w") as f:
     f.write("# MVR_ITERS=30 ncu --set full --clock-control none --import-source on -k regex:k_icp_forward|k_icp_reverse -s 20 -c 1 python scripts/gpu_iter_profile.py\n")
-    f.write("# (two captures, one per kernel) one forward + one reverse launch of all 24 pairs (24 views x 200k points), iteration 21 of 30; caches flushed by ncu before each replay\n")
+    f.write("# (two captures, one per kernel; MVR batch group forced to 24) one forward + one reverse launch of all 24 pairs (24 views x 200k points), iteration 21 of 30; caches flushed by ncu before each replay\n")
     for which in ("fwd", "rev"):
         rep = os.path.join(G, "%s_%s.ncu-rep" % (tag, which))
         out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
