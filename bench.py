@@ -293,13 +293,21 @@ def run_native(a):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     import mvr_b200.ring as ring
 
+    # the view descriptors (pointers, sizes, initial poses) are marshalled once; every step passes the same buffers
+    bound_dev = reg.bind_views(dev_list, init)
+    bound_host = reg.bind_views(host_list, init)
+
     def step(host_buffers):
         """One registration: this rank's ring pairs through the C++ driver, gather of the per-pair results, host
-        loop closure over the whole ring.  Returns (queries of this rank, pair reports, absolute poses)."""
-        _, reps = reg.register_turntable(host_list if host_buffers else dev_list, tp, init_poses=init)
-        q = sum(reps[p]["nn_queries"] for p in range(p0, p1))
-        allrec = ring.gather_records(ring.pack_reports(reps, p0, p1), rank, world, V, dist=dist if world > 1 else None, device=dev)
-        abs_poses = ring.close_ring(allrec, synth.PIVOT, obj_radius)
+        loop closure over the whole ring.  Returns (queries of this rank, raw pair reports (numpy records), (absolute
+        poses, gathered records))."""
+        cposes, reps = reg.register_turntable(bound_host if host_buffers else bound_dev, tp, raw=True)
+        q = int(reps["nn_queries"][p0:p1].sum())
+        allrec = ring.gather_records(ring.records_from_reports(reps, p0, p1), rank, world, V, dist=dist if world > 1 else None, device=dev)
+        if world == 1:   # the driver had every pair and closed the ring itself (Registrator::multiViewRegister): its poses
+            abs_poses = cposes
+        else:
+            abs_poses = ring.close_ring(allrec, synth.PIVOT, obj_radius)
         return q, reps, (abs_poses, allrec)
 
     def timed(host_buffers, steps):
@@ -364,7 +372,7 @@ def run_native(a):
         # every view, and the gathered records
         state_b, log_b = mvr_b200.icp_state_bytes(), mvr_b200.icp_log_record_bytes()
         h2d = allsum(float(len(need) * n * 16 + (p1 - p0) * state_b))
-        d2h = allsum(float((p1 - p0) * (state_b + log_b * a.iters) + len(need) * 28 + V * ring.REC))
+        d2h = allsum(float((p1 - p0) * state_b + (p1 - p0) * 28 + V * ring.REC))   # (the iteration logs stay on the device until asked for)
         e2e = {"value": q_e / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e / a.steps,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
 
@@ -377,7 +385,7 @@ def run_native(a):
         c.set_profiling(True)
         c.kernel_stats(reset=True)
     _, preps, _ = step(False)
-    iter_ms = sum(preps[p]["gpu_ms"] for p in range(p0, p1))
+    iter_ms = float(preps["gpu_ms"][p0:p1].sum())
     st = {}
     for c in ctxs:
         for k, v in c.kernel_stats(reset=True).items():
@@ -434,7 +442,10 @@ def run_native(a):
     acc = None
     if rank == 0 and last:
         reps, (abs_poses, _) = last
-        r = reps[p0]
+        if world == 1:   # V x 16 column-major absolute poses of the driver -> relative to view 0
+            base_inv = np.linalg.inv(init[0])
+            abs_poses = [base_inv @ abs_poses[v].reshape(4, 4).T.astype(np.float64) for v in range(V)]
+        r = dict(pose=reps["pose"][p0].reshape(4, 4).T.copy(), mse=float(reps["mse"][p0]), n_corr=int(reps["n_correspondences"][p0]))
         dT = r["pose"].astype(np.float64) @ np.linalg.inv(truth0)
         w = 0.5 * np.array([dT[2, 1] - dT[1, 2], dT[0, 2] - dT[2, 0], dT[1, 0] - dT[0, 1]])
         worst = 0.0
@@ -460,7 +471,7 @@ def run_native(a):
             c.set_target(views[0]); c.set_source(views[1 % V])
             g = c.icp_align(icp, guess=(np.linalg.inv(init[0]) @ init[1 % V]).astype(np.float32), n_source=n)
             c.close()
-            rep0 = last[0][0]
+            rep0 = dict(pose=last[0]["pose"][0].reshape(4, 4).T.copy(), n_corr=int(last[0]["n_correspondences"][0]))
             dR = g["final"][:3, :3].astype(np.float64) @ o["final"][:3, :3].astype(np.float64).T
             w = 0.5 * np.array([dR[2, 1] - dR[1, 2], dR[0, 2] - dR[2, 0], dR[1, 0] - dR[0, 1]])
             tb = o["final"][:3, 3].astype(np.float64)

@@ -150,6 +150,9 @@ int mvr_set_target(mvr_ctx* ctx, const float* xyzw, size_t n);
 int mvr_set_source(mvr_ctx* ctx, const float* xyzw, size_t n);
 int mvr_set_target_device(mvr_ctx* ctx, const float* d_xyzw, size_t n);
 int mvr_set_source_device(mvr_ctx* ctx, const float* d_xyzw, size_t n);
+/* `count` device clouds at once (contexts of one device; which[k]: mvr_cloud): the same as mvr_set_target_device /
+ * mvr_set_source_device per cloud, but every bounding box is measured by one launch and read back by one copy. */
+int mvr_set_clouds_device(mvr_ctx* const* ctxs, const int* which, const float* const* d_xyzw, const size_t* n, int count);
 /* Give `dst` the cloud another context of the same device already holds (same device pointer, same bounding box:
  * nothing is copied or recomputed).  The points must stay alive and unchanged while `dst` uses them -- a view of a
  * turntable ring is the target of one pair and the source of the next. */

@@ -138,6 +138,19 @@ class PairReport(C.Structure):
     ]
 
 
+# numpy view of an array of PairReport
+REPORT = np.dtype([("source_view", "<i4"), ("target_view", "<i4"), ("status", "<i4"), ("iterations", "<i4"), ("n_correspondences", "<i4"),
+                   ("pad", "<i4"), ("mse", "<f8"), ("fitness", "<f8"), ("gpu_ms", "<f8"), ("nn_queries", "<u8"), ("pose", "<f4", (16,))])
+assert REPORT.itemsize == C.sizeof(PairReport)
+
+
+class BoundViews:
+    """Marshalled view descriptors (Registrator.bind_views)."""
+
+    def __init__(self, arr, keep, n, views):
+        self.arr, self.keep, self.n, self.views = arr, keep, n, views
+
+
 RING_PAIRS, ACCUMULATE, ICP_ORDER, LUM = 0, 1, 2, 3
 
 _lib = None
@@ -555,6 +568,21 @@ def ring_close(rel_poses, weights=None, relax=True, iterations=16, centre=None, 
     return [pose_to_numpy(out[k]) for k in range(V)]
 
 
+def ring_close_flat(rel16, weights, relax=True, iterations=16, centre=None, rot_scale=1.0):
+    """ring_close on V x 16 column-major float32 poses (as the pair records carry them); returns the V absolute poses as
+    4x4 numpy matrices."""
+    rel = np.ascontiguousarray(rel16, dtype=np.float32).reshape(-1, 16)
+    V = len(rel)
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+    out = np.empty((V, 16), dtype=np.float32)
+    cc = None if centre is None else np.ascontiguousarray(centre, dtype=np.float64)
+    rc = lib().mvr_ring_close(_fp(rel), _dp(w) if w is not None else None, V, int(bool(relax)), int(iterations),
+                              _dp(cc) if cc is not None else None, float(rot_scale), _fp(out))
+    if rc != OK:
+        raise MvrError(rc, lib().mvr_status_string(rc).decode())
+    return list(out.reshape(V, 4, 4).transpose(0, 2, 1).copy())
+
+
 # ---- persistence in the reference's text formats (transformation.txt, axis.txt, points.asc) ----------------------------
 RICH_POINT = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("pad0", "<f4"),
                        ("normal_x", "<f4"), ("normal_y", "<f4"), ("normal_z", "<f4"), ("pad1", "<f4"),
@@ -743,15 +771,27 @@ class Registrator:
             raise MvrError(rc, (lib().mvr_registrator_last_error(self._h) or b"").decode())
         return [(int(counts[k]), float(msd[k])) for k in range(n.value)]
 
-    def register_turntable(self, views, params, init_poses=None):
-        """Returns (poses: list of V 4x4 float32, reports: list of dict)."""
-        V = len(views)
+    def bind_views(self, views, init_poses=None):
+        """The view descriptors of a sequence, marshalled once: pass the result to register_turntable instead of the
+        lists when the same buffers are registered again and again (bench.py)."""
         arr, keep = self._views(views, init_poses)
+        return BoundViews(arr, keep, len(views), views)
+
+    def register_turntable(self, views, params, init_poses=None, raw=False):
+        """Returns (poses: list of V 4x4 float32, reports: list of dict); raw = True: (poses V x 16 float32 column-major,
+        reports as a numpy record array of REPORT) without per-pair Python objects."""
+        if isinstance(views, BoundViews):
+            V, arr, keep = views.n, views.arr, views.keep
+        else:
+            V = len(views)
+            arr, keep = self._views(views, init_poses)
         poses = np.empty((max(V, 1), 16), dtype=np.float32)
         reps = (PairReport * max(V, 1))()
         rc = lib().mvr_register_turntable(self._h, arr, V, C.byref(params), _fp(poses), reps)
         if rc != OK:
             raise MvrError(rc, (lib().mvr_registrator_last_error(self._h) or b"").decode())
+        if raw:
+            return poses, np.frombuffer(reps, dtype=REPORT, count=max(V, 1))
         n_rep = V if params.mode == RING_PAIRS else (0 if params.mode == LUM else max(V - 1, 0))
         reports = [dict(source_view=reps[k].source_view, target_view=reps[k].target_view, status=reps[k].status,
                         iterations=reps[k].iterations, n_corr=reps[k].n_correspondences, mse=reps[k].mse, fitness=reps[k].fitness,

@@ -115,10 +115,19 @@ struct mvr_ctx {
   FwdArgs fa{}; RevArgs ra{};    // kernel arguments of the prepared align
   bool want_rnn = false;         // the next prepared align also records the mutual partners (mvr_correspondences)
   int group_pairs = 0;           // pairs per launch of a batch led by this context (mvr_ctx_set_batch_group); 0 = automatic
-  DevBuf pkeys, pvals, pmoved, pcount;   // build scratch of the per-align indices: keys, arrival ranks, arrival-order records, cell counters
+  // build scratch of the per-align indices (keys, arrival ranks, arrival-order records, cell counters, scan tiles): two sets,
+  // so that the target and the source index of an align can be built by the same batched launches
+  struct BuildScratch { DevBuf keys, vals, moved, count, tiles; uint32_t epoch = 1; } bs[2];
+  // batched aligns led by this context: the pairs' IcpStates travel together (one copy each way)
+  DevBuf stage_dev;
+  IcpState* h_stage = nullptr;   // pinned, stage_cap records
+  int stage_cap = 0;
+  DevBuf bbox_dev;               // 7 words per cloud of a batched mvr_set_clouds_device
+  uint32_t* h_bbox = nullptr;    // pinned, BBOX_MAX_JOBS * 7 words
+  int log_pending = 0;           // records of the device log not fetched yet (mvr_icp_get_iterations fetches them)
+  bool out_pending = false;      // out_cloud has not been computed yet (materialize_out)
   DevBuf crowded;                        // one word: population of the most crowded cell an index build could not rank (0: none)
   uint32_t crowded_seen = 0;             // its value after the last align
-  uint32_t scan_epoch = 1;
   IcpState* h_state = nullptr;   // pinned staging copy of the device IcpState
   IterRec* h_log = nullptr;      // pinned, ICP_MAX_LOG records
   double* h_sums = nullptr;      // pinned, REDUCE_MAX_VALS
@@ -162,14 +171,15 @@ struct ProfScope {
   mvr_ctx* ctx; int idx;
   // count: launches (of the kernel family) the scope brackets -- the iterations of an align share ONE pair of events, so the
   // measurement puts nothing between them
-  ProfScope(mvr_ctx* c, int kind, double bytes, double units, int count = 1) : ctx(c), idx(-1) {
+  cudaStream_t st;
+  ProfScope(mvr_ctx* c, int kind, double bytes, double units, int count = 1, cudaStream_t stream = nullptr) : ctx(c), idx(-1), st(stream ? stream : c->stream) {
     if (!c->profiling) return;
     ProfRec r{kind, get_event(c), get_event(c), bytes, units, count};
-    cudaEventRecord(r.a, c->stream);
+    cudaEventRecord(r.a, st);
     c->prof.push_back(r);
     idx = (int)c->prof.size() - 1;
   }
-  ~ProfScope() { if (idx >= 0) cudaEventRecord(ctx->prof[idx].b, ctx->stream); }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(ctx->prof[idx].b, st); }
 };
 
 void prof_flush(mvr_ctx* ctx) {
@@ -297,48 +307,6 @@ int build_index(mvr_ctx* ctx, Cloud& c, const float4* pts, const mvr_grid& g) {
   return MVR_OK;
 }
 
-// (Re)index cloud c's points `pts` (n = c.n) in grid g with the counting sort of bin.cu.  d_delta
-// (nullable, device float[16]) is applied to pts in place first; d_done (nullable) skips the work on
-// the device once an align has converged.
-int bin_index(mvr_ctx* ctx, Cloud& c, float4* pts, const mvr_grid& g, const float* d_delta, const int* d_done) {
-  const int n = c.n;
-  const size_t cells = (size_t)1 << (3 * g.bits);
-  const size_t nn = (size_t)std::max(n, 1);
-  CK(c.keys.ensure(nn * sizeof(uint32_t)));
-  CK(c.vals.ensure(nn * sizeof(uint32_t)));
-  CK(c.sorted.ensure(nn * sizeof(float4)));
-  CK(c.table.ensure((cells + 2) * sizeof(uint32_t)));
-  if ((cells + 1) * sizeof(uint32_t) > c.counters.cap) {
-    CK(c.counters.ensure((cells + 1) * sizeof(uint32_t)));
-    CK(cudaMemsetAsync(c.counters.p, 0, c.counters.cap, ctx->stream));   // k_scan_cells keeps them zero afterwards
-  }
-  const size_t tiles = (size_t)scan_num_tiles(cells + 1) + 1;   // + the ticket word
-  if (tiles * sizeof(unsigned long long) > ctx->tiles.cap) {
-    CK(ctx->tiles.ensure(tiles * sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(ctx->tiles.p, 0, ctx->tiles.cap, ctx->stream));
-  }
-  c.grid = g;
-  c.gd = to_dev(g);
-  {
-    ProfScope ps(ctx, MVR_K_TRANSFORM, (d_delta ? 40.0 : 24.0) * n, n);
-    CK(launch_transform_bin(pts, n, d_delta, d_done, c.gd, c.keys.as<uint32_t>(), c.vals.as<uint32_t>(), c.counters.as<uint32_t>(), ctx->stream));
-  }
-  {
-    ProfScope ps(ctx, MVR_K_TABLE, 8.0 * (double)(cells + 1), (double)cells);
-    CK(launch_scan_cells(c.counters.as<uint32_t>(), c.table.as<uint32_t>(), cells + 1, ctx->tiles.as<unsigned long long>(),
-                         ctx->scan_epoch, d_done, ctx->stream));
-    ctx->scan_epoch = (ctx->scan_epoch % 0x3fffffffu) + 1;
-  }
-  {
-    ProfScope ps(ctx, MVR_K_SORT, 44.0 * n, n);
-    CK(launch_bin_scatter(pts, n, c.keys.as<uint32_t>(), c.vals.as<uint32_t>(), c.table.as<uint32_t>(), d_done, c.sorted.as<float4>(), ctx->stream));
-  }
-  c.index_valid = true;
-  c.exportable = false;
-  c.index_gen = c.gen;
-  return MVR_OK;
-}
-
 mvr_grid auto_grid(mvr_ctx* ctx, const Cloud& c) {
   double e = ctx->cell_edge_opt > 0 ? ctx->cell_edge_opt : density_cell_edge(c.lo, c.hi, c.n - c.n_bad, 6.0);
   return make_grid(c.lo, c.hi, e, ctx->max_bits_opt);
@@ -348,6 +316,9 @@ PairGrid make_pair_grid(const float lo[3], const float hi[3], double e, uint32_t
 bool same_pair_grid(const PairGrid& a, const PairGrid& b);
 int build_pair_index(mvr_ctx* ctx, PairIndex& ix, const float4* pts, int n, int n_bad, const Mat4f* guess, const PairGrid& g,
                      uint32_t cells, bool keep_s0, bool ordered = true);
+int plan_pair_index(mvr_ctx* ctx, PairIndex& ix, int slot, const float4* pts, int n, int n_bad, const Mat4f* guess, const PairGrid& g,
+                    uint32_t cells, bool ordered, cudaStream_t stream, BuildJob* job);
+int run_pair_builds(mvr_ctx* ctx, const BuildJob* jobs, int count, cudaStream_t stream);
 
 double pair_cell_edge(mvr_ctx* ctx, const Cloud& c, double max_dist);
 
@@ -465,47 +436,71 @@ PairGrid make_pair_grid(const float lo[3], const float hi[3], double e, uint32_t
 
 bool same_pair_grid(const PairGrid& a, const PairGrid& b) { return std::memcmp(&a, &b, sizeof(PairGrid)) == 0; }
 
-// Index `n` points (n_bad of them non-finite) in grid g; guess (nullable) is applied first (pinned float
-// transform); keep_s0: also keep a copy of the sorted binning-time coordinates.
-// ordered = false leaves the points of a cell in arrival order (queries: their results go out by original index).
-int build_pair_index(mvr_ctx* ctx, PairIndex& ix, const float4* pts, int n, int n_bad, const Mat4f* guess, const PairGrid& g,
-                     uint32_t cells, bool keep_s0, bool ordered) {
+// Plan the index of `n` points (n_bad of them non-finite) in grid g: buffers of ix and of scratch set `slot` (0 or 1) are
+// made ready (first-time zeroing on `stream`, the stream the build will run on) and the build is described in *job.
+// guess (nullable) is applied first (pinned float transform).  ordered = false leaves the points of a cell in arrival order
+// (queries: their results go out by original index).
+int plan_pair_index(mvr_ctx* ctx, PairIndex& ix, int slot, const float4* pts, int n, int n_bad, const Mat4f* guess, const PairGrid& g,
+                    uint32_t cells, bool ordered, cudaStream_t stream, BuildJob* job) {
+  mvr_ctx::BuildScratch& bs = ctx->bs[slot];
   const size_t nn = (size_t)std::max(n, 1);
-  CK(ctx->pkeys.ensure(nn * sizeof(uint32_t)));
-  CK(ctx->pvals.ensure(nn * sizeof(uint32_t)));
-  if (ordered) CK(ctx->pmoved.ensure(nn * sizeof(float4)));
+  CK(bs.keys.ensure(nn * sizeof(uint32_t)));
+  CK(bs.vals.ensure(nn * sizeof(uint32_t)));
+  if (ordered) CK(bs.moved.ensure(nn * sizeof(float4)));
   CK(ix.sorted.ensure(nn * sizeof(float4)));
   CK(ix.start.ensure(((size_t)cells + 2) * sizeof(uint32_t)));
-  if (keep_s0) CK(ix.s0.ensure(nn * sizeof(float4)));
-  if (((size_t)cells + 1) * sizeof(uint32_t) > ctx->pcount.cap) {
-    CK(ctx->pcount.ensure(((size_t)cells + 1) * sizeof(uint32_t)));
-    CK(cudaMemsetAsync(ctx->pcount.p, 0, ctx->pcount.cap, ctx->stream));   // k_scan_cells keeps the counters zero afterwards
+  if (((size_t)cells + 1) * sizeof(uint32_t) > bs.count.cap) {
+    CK(bs.count.ensure(((size_t)cells + 1) * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(bs.count.p, 0, bs.count.cap, stream));   // the scan keeps the counters zero afterwards
   }
-  const size_t tiles = (size_t)scan_num_tiles((size_t)cells + 1) + 1;   // + the ticket word
-  if (tiles * sizeof(unsigned long long) > ctx->tiles.cap) {
-    CK(ctx->tiles.ensure(tiles * sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(ctx->tiles.p, 0, ctx->tiles.cap, ctx->stream));
+  const int ntiles = scan_num_tiles((size_t)cells + 1);
+  const size_t tiles = (size_t)ntiles + 1;   // + the ticket word
+  if (tiles * sizeof(unsigned long long) > bs.tiles.cap) {
+    CK(bs.tiles.ensure(tiles * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(bs.tiles.p, 0, bs.tiles.cap, stream));
   }
-  ix.valid = false;
-  if (!ctx->crowded.p) { CK(ctx->crowded.ensure(64)); CK(cudaMemsetAsync(ctx->crowded.p, 0, 64, ctx->stream)); }
-  ProfScope ps(ctx, MVR_K_SORT, (keep_s0 ? 48.0 : 32.0) * n + 8.0 * cells, n);
-  CK(launch_pair_count(pts, n, guess, g, cells, ctx->pkeys.as<uint32_t>(), ctx->pvals.as<uint32_t>(), ctx->pcount.as<uint32_t>(), ctx->stream));
-  CK(launch_scan_cells(ctx->pcount.as<uint32_t>(), ix.start.as<uint32_t>(), (size_t)cells + 1, ctx->tiles.as<unsigned long long>(),
-                       ctx->scan_epoch, nullptr, ctx->stream));
-  ctx->scan_epoch = (ctx->scan_epoch % 0x3fffffffu) + 1;
-  CK(launch_pair_scatter(pts, n, guess, ctx->pkeys.as<uint32_t>(), ctx->pvals.as<uint32_t>(), ix.start.as<uint32_t>(),
-                         ordered ? ctx->pmoved.as<float4>() : ix.sorted.as<float4>(), ctx->stream));
-  if (ordered)
-    CK(launch_pair_rerank(ctx->pmoved.as<float4>(), n, ctx->pkeys.as<uint32_t>(), ix.start.as<uint32_t>(), ix.sorted.as<float4>(),
-                          keep_s0 ? ix.s0.as<float4>() : nullptr, ctx->crowded.as<uint32_t>(), ctx->stream));
+  if (!ctx->crowded.p) { CK(ctx->crowded.ensure(64)); CK(cudaMemsetAsync(ctx->crowded.p, 0, 64, stream)); }
+  BuildJob& j = *job;
+  j = BuildJob{};
+  j.in = pts; j.n = n; j.apply = guess ? 1 : 0;
+  if (guess) j.M = *guess;
+  j.g = g; j.cells = cells;
+  j.keys = bs.keys.as<uint32_t>(); j.rank = bs.vals.as<uint32_t>(); j.counters = bs.count.as<uint32_t>();
+  j.tiles = bs.tiles.as<unsigned long long>(); j.epoch = bs.epoch; j.ntiles = ntiles;
+  bs.epoch = (bs.epoch % 0x3fffffffu) + 1;
+  j.tmp = ordered ? bs.moved.as<float4>() : nullptr; j.sorted = ix.sorted.as<float4>(); j.start = ix.start.as<uint32_t>();
+  j.crowded = ctx->crowded.as<uint32_t>(); j.ordered = ordered ? 1 : 0;
   ix.g = g; ix.cells = cells; ix.n_valid = n - n_bad; ix.valid = true; ix.gm_gate = -1.f;
   return MVR_OK;
+}
+
+// The planned builds, four launches per BUILD_MAX_JOBS of them (pair_index.cu); ctx: where errors and the profile go.
+int run_pair_builds(mvr_ctx* ctx, const BuildJob* jobs, int count, cudaStream_t stream) {
+  for (int k0 = 0; k0 < count; k0 += BUILD_MAX_JOBS) {
+    const int c = std::min(count - k0, (int)BUILD_MAX_JOBS);
+    BuildBatch batch;
+    double bytes = 0, pts = 0;
+    for (int k = 0; k < c; ++k) { batch.j[k] = jobs[k0 + k]; bytes += 32.0 * jobs[k0 + k].n + 8.0 * jobs[k0 + k].cells; pts += jobs[k0 + k].n; }
+    ProfScope ps(ctx, MVR_K_SORT, bytes, pts, 1, stream);
+    CK(launch_pair_builds(batch, c, stream));
+  }
+  return MVR_OK;
+}
+
+int build_pair_index(mvr_ctx* ctx, PairIndex& ix, const float4* pts, int n, int n_bad, const Mat4f* guess, const PairGrid& g,
+                     uint32_t cells, bool keep_s0, bool ordered) {
+  (void)keep_s0;
+  BuildJob job;
+  ix.valid = false;
+  int rc = plan_pair_index(ctx, ix, &ix == &ctx->pt || &ix == &ctx->nt ? 0 : 1, pts, n, n_bad, guess, g, cells, ordered, ctx->stream, &job);
+  if (rc) { ix.valid = false; return rc; }
+  return run_pair_builds(ctx, &job, 1, ctx->stream);
 }
 
 // The gate mask of target index ix for gate max_d2f (float d2, rounded up); without one (no gate, or a gate many cells
 // wide) the forward half searches every point.  Cells more than D apart in an axis are >= D cells apart along it; the
 // rounding of grid_t on the query and on the target point is absorbed by `slack` cells.
-int ensure_gate_mask(mvr_ctx* ctx, PairIndex& ix, float max_d2f) {
+int ensure_gate_mask(mvr_ctx* ctx, PairIndex& ix, float max_d2f, cudaStream_t stream) {
   // Off unless asked for (mvr_ctx_set_gate_mask): on the bench workload (neighbouring views of a 24-view turntable, ~4 % of the
   // source points beyond the gate) the mask saves 0.03 ms over 22 iterations and costs 0.2 ms to build for 24 targets
   // (profiles/r02_iteration_ab.log); it pays when a large part of the source has no partner (little overlap).
@@ -521,7 +516,7 @@ int ensure_gate_mask(mvr_ctx* ctx, PairIndex& ix, float max_d2f) {
   const size_t words = (size_t)ix.g.ny * ix.g.nz * wstride;
   CK(ix.gocc.ensure(words * sizeof(uint32_t)));
   CK(ix.gmask.ensure(words * sizeof(uint32_t)));
-  CK(launch_gate_mask(ix.start.as<uint32_t>(), ix.g, wstride, D, Dx, ix.gocc.as<uint32_t>(), ix.gmask.as<uint32_t>(), ctx->stream));
+  CK(launch_gate_mask(ix.start.as<uint32_t>(), ix.g, wstride, D, Dx, ix.gocc.as<uint32_t>(), ix.gmask.as<uint32_t>(), stream));
   ix.gm_stride = wstride;
   ix.gm_gate = max_d2f;
   return MVR_OK;
@@ -617,7 +612,10 @@ int mvr_ctx_destroy(mvr_ctx* ctx) {
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   ctx->tgt.release(); ctx->src.release(); ctx->normals.release();
   ctx->pt.release(); ctx->ps.release(); ctx->nt.release(); ctx->nq.release();
-  ctx->pkeys.release(); ctx->pvals.release(); ctx->pmoved.release(); ctx->pcount.release();
+  for (auto& b : ctx->bs) { b.keys.release(); b.vals.release(); b.moved.release(); b.count.release(); b.tiles.release(); }
+  ctx->stage_dev.release(); ctx->bbox_dev.release();
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->h_bbox) cudaFreeHost(ctx->h_bbox);
   DevBuf* bufs[] = {&ctx->cur, &ctx->corr_p, &ctx->rmin, &ctx->rnn, &ctx->corr_j, &ctx->corr_d2, &ctx->partials, &ctx->sums, &ctx->out_cloud, &ctx->qtmp,
                     &ctx->itmp, &ctx->ftmp, &ctx->scratch, &ctx->misc, &ctx->tiles, &ctx->state, &ctx->log, &ctx->crowded};
   for (DevBuf* b : bufs) b->release();
@@ -728,6 +726,47 @@ int mvr_set_source_device(mvr_ctx* ctx, const float* d, size_t n) {
   return cloud_set(ctx, ctx->src, d, n, true);
 }
 
+// Many clouds at once: their bounding boxes are measured by ONE launch and read back by one copy (mvr_set_*_device pays a
+// stream round trip per cloud: ~25 us each, 0.6 ms for the 24 views of a turntable sequence).
+int mvr_set_clouds_device(mvr_ctx* const* ctxs, const int* which, const float* const* d_xyzw, const size_t* n, int count) {
+  if (count < 0 || (count && (!ctxs || !which || !d_xyzw || !n))) return MVR_ERR_BAD_ARG;
+  if (count == 0) return MVR_OK;
+  mvr_ctx* ctx = ctxs[0];
+  if (!ctx) return MVR_ERR_BAD_ARG;
+  for (int k = 0; k < count; ++k) {
+    if (!ctxs[k] || (which[k] != MVR_CLOUD_TARGET && which[k] != MVR_CLOUD_SOURCE)) return MVR_ERR_BAD_ARG;
+    if (ctxs[k]->device != ctx->device) return fail(ctx, MVR_ERR_BAD_ARG, "the contexts of a batch must share a device");
+    if (n[k] > (size_t)INT_MAX / 2) return fail(ctx, MVR_ERR_BAD_ARG, "cloud too large");
+    if (n[k] > 0 && !d_xyzw[k]) return fail(ctx, MVR_ERR_BAD_ARG, "null point pointer");
+  }
+  cudaSetDevice(ctx->device);
+  if (!ctx->h_bbox) CK(cudaMallocHost((void**)&ctx->h_bbox, (size_t)BBOX_MAX_JOBS * 7 * sizeof(uint32_t)));
+  CK(ctx->bbox_dev.ensure((size_t)BBOX_MAX_JOBS * 7 * sizeof(uint32_t)));
+  for (int k0 = 0; k0 < count; k0 += BBOX_MAX_JOBS) {
+    const int c = std::min(count - k0, (int)BBOX_MAX_JOBS);
+    BboxBatch bb;
+    for (int k = 0; k < c; ++k) { bb.j[k].pts = (const float4*)d_xyzw[k0 + k]; bb.j[k].n = (int)n[k0 + k]; bb.j[k].pad_ = 0; }
+    CK(launch_bbox_batch(bb, c, ctx->bbox_dev.as<uint32_t>(), ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_bbox, ctx->bbox_dev.p, (size_t)c * 7 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < c; ++k) {
+      mvr_ctx* m = ctxs[k0 + k];
+      Cloud& cl = which[k0 + k] == MVR_CLOUD_TARGET ? m->tgt : m->src;
+      if (which[k0 + k] == MVR_CLOUD_TARGET) m->has_normals = false; else { m->have_out = false; m->out_pending = false; }
+      cl.index_valid = false;
+      cl.gen++;
+      cl.n = (int)n[k0 + k];
+      cl.pts = (const float4*)d_xyzw[k0 + k];
+      const uint32_t* w = ctx->h_bbox + 7 * k;
+      for (int a = 0; a < 3; ++a) { cl.lo[a] = 0; cl.hi[a] = 0; }
+      cl.n_bad = cl.n > 0 ? (int)w[6] : 0;
+      if (cl.n > 0 && cl.n_bad < cl.n)
+        for (int a = 0; a < 3; ++a) { cl.lo[a] = bbox_decode(w[a]); cl.hi[a] = bbox_decode(w[3 + a]); }
+    }
+  }
+  return MVR_OK;
+}
+
 int mvr_cloud_share(mvr_ctx* dst, int which_dst, mvr_ctx* src, int which_src) {
   if (!dst || !src || (which_dst != MVR_CLOUD_TARGET && which_dst != MVR_CLOUD_SOURCE) ||
       (which_src != MVR_CLOUD_TARGET && which_src != MVR_CLOUD_SOURCE)) return MVR_ERR_BAD_ARG;
@@ -817,7 +856,15 @@ int mvr_nn_query(mvr_ctx* ctx, const float* q, size_t n, int32_t* idx, float* d2
   return MVR_OK;
 }
 
-static int align_prepare(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, int est);
+static int align_prepare_batch(mvr_ctx* const* ctxs, int count, const mvr_icp_params* prm, const float* guesses, int est, int* statuses,
+                               std::vector<mvr_ctx*>& ok, std::vector<int>& slot);
+static int align_prepare(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, int est) {
+  int st = MVR_OK;
+  std::vector<mvr_ctx*> ok;
+  std::vector<int> slot;
+  const int rc = align_prepare_batch(&ctx, 1, prm, guess, est, &st, ok, slot);
+  return rc ? rc : st;
+}
 
 static int align_run(mvr_ctx* const* ctxs, int count, const mvr_icp_params* prm, int est);
 
@@ -872,11 +919,14 @@ int mvr_correspondences(mvr_ctx* ctx, double max_dist, int reciprocal, int32_t* 
 // ---- the align behind mvr_icp_align, mvr_icp_align_batch and mvr_pair_moments_compute ------------------------------
 // An align is split in three so that many of them can advance in lock-step, ONE launch per iteration half for the
 // whole batch (a single 200k-point pair fills a fraction of a B200):
-//   align_prepare : per context, on its own stream -- per-align indices, initial state, kernel arguments;
-//   align_run     : the iterations of every context of the batch, on the first context's stream;
-//   align_finish  : per context -- aligned cloud, iteration log, report.
+//   align_plan / align_prepare_batch : per context on the host -- grids, buffers, initial state, kernel arguments; then for
+//                   the whole batch on the first context's stream -- every per-align index (four launches), the seeds,
+//                   gates and initial states (one launch);
+//   align_run     : the iterations of every context of the batch (groups of pairs, each group on the stream of its first context);
+//   align_finish  : per context -- report; the aligned cloud and the iteration log are produced when asked for.
 // est = EST_MOM accumulates second moments next to the point-to-point sums (those of the LAST iteration's pairs).
-static int align_prepare(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, int est) {
+// S: the stream the batch's preparation runs on; jobs: receives the index builds this align needs.
+static int align_plan(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, int est, cudaStream_t S, std::vector<BuildJob>& jobs) {
   cudaSetDevice(ctx->device);
   if (ctx->tgt.gen == 0 || ctx->src.gen == 0) return fail(ctx, MVR_ERR_NO_INPUT, "source/target not set");
   Cloud& s = ctx->src;
@@ -900,7 +950,10 @@ static int align_prepare(mvr_ctx* ctx, const mvr_icp_params* prm, const float* g
     const PairGrid gt = make_pair_grid(ctx->tgt.lo, ctx->tgt.hi, pair_cell_edge(ctx, ctx->tgt, max_dist), &cells, MVR_PG_XRATIO);
     PairIndex& pt = ctx->pt;
     if (!(pt.valid && pt.gen == ctx->tgt.gen && same_pair_grid(pt.g, gt))) {
-      if ((rc = build_pair_index(ctx, pt, ctx->tgt.pts, m, ctx->tgt.n_bad, nullptr, gt, cells, false))) return rc;
+      BuildJob job;
+      pt.valid = false;
+      if ((rc = plan_pair_index(ctx, pt, 0, ctx->tgt.pts, m, ctx->tgt.n_bad, nullptr, gt, cells, true, S, &job))) { pt.valid = false; return rc; }
+      jobs.push_back(job);
       pt.gen = ctx->tgt.gen;
     }
   }
@@ -921,18 +974,16 @@ static int align_prepare(mvr_ctx* ctx, const mvr_icp_params* prm, const float* g
     const PairGrid gs = make_pair_grid(lo, hi, pair_cell_edge(ctx, s, max_dist), &cells, MVR_PG_XRATIO);
     Mat4f Gm;
     std::memcpy(Gm.m, G, sizeof(Gm.m));
-    if ((rc = build_pair_index(ctx, ctx->ps, s.pts, n, s.n_bad, &Gm, gs, cells, false))) return rc;
+    BuildJob job;
+    ctx->ps.valid = false;
+    if ((rc = plan_pair_index(ctx, ctx->ps, 1, s.pts, n, s.n_bad, &Gm, gs, cells, true, S, &job))) { ctx->ps.valid = false; return rc; }
+    jobs.push_back(job);
     for (int a = 0; a < 3; ++a) { ctx->h_state->box[a] = lo[a]; ctx->h_state->box[3 + a] = hi[a]; }   // kept across the memset below
   }
   const PairIndex &pt = ctx->pt, &psx = ctx->ps;
-  CK(ctx->corr_p.ensure((size_t)std::max(n, 1) * sizeof(int32_t)));
-  CK(cudaMemsetAsync(ctx->corr_p.p, 0xff, (size_t)std::max(n, 1) * sizeof(int32_t), ctx->stream));   // -1: no seed yet
-  if (reciprocal) {
-    CK(ctx->rmin.ensure((size_t)std::max(m, 1) * sizeof(uint32_t)));
-    CK(launch_fill_u32(ctx->rmin.as<uint32_t>(), (size_t)std::max(m, 1), 0x7f800000u, ctx->stream));   // +inf: "chosen by nobody"
-  }
+  CK(ctx->corr_p.ensure((size_t)std::max(n, 1) * sizeof(int32_t)));   // seeds and gates are filled by launch_align_init
+  if (reciprocal) CK(ctx->rmin.ensure((size_t)std::max(m, 1) * sizeof(uint32_t)));
   CK(ctx->partials.ensure((size_t)std::max((int)FUSED_MAX_BLOCKS, fused_grid_rev(m)) * REDUCE_MAX_VALS * sizeof(double)));
-  CK(ctx->out_cloud.ensure((size_t)n * sizeof(float4)));
   CK(ctx->state.ensure(sizeof(IcpState)));
   CK(ctx->log.ensure((size_t)ICP_MAX_LOG * sizeof(IterRec)));
   IcpState* d_st = ctx->state.as<IcpState>();
@@ -967,9 +1018,9 @@ static int align_prepare(mvr_ctx* ctx, const mvr_icp_params* prm, const float* g
   h.min_corr = prm->min_correspondences > 0 ? prm->min_correspondences : 3;
   h.p2l = p2l; h.recip = reciprocal; h.n_src = n;
   if (prm->max_iterations <= 0) { h.done = 1; h.reason = MVR_REASON_ITERATIONS; }
-  CK(cudaMemcpyAsync(d_st, &h, sizeof(IcpState), cudaMemcpyHostToDevice, ctx->stream));
   ctx->iters.clear();
-  ctx->have_out = false;
+  ctx->log_pending = 0;
+  ctx->have_out = false; ctx->out_pending = false;
 
   FwdArgs& fa = ctx->fa;
   fa = FwdArgs{};
@@ -977,8 +1028,7 @@ static int align_prepare(mvr_ctx* ctx, const mvr_icp_params* prm, const float* g
   fa.tgt = pt.sorted.as<float4>(); fa.tstart = pt.start.as<uint32_t>(); fa.gt = pt.g; fa.m_valid = pt.n_valid;
   fa.corr_p = ctx->corr_p.as<int32_t>(); fa.rmin = reciprocal ? ctx->rmin.as<uint32_t>() : nullptr;
   fa.max2 = max_dist * max_dist; fa.max_d2f = gate_float(max_dist);
-  if ((rc = ensure_gate_mask(ctx, ctx->pt, fa.max_d2f))) return rc;
-  fa.gmask = ctx->pt.gm_gate >= 0.f ? ctx->pt.gmask.as<uint32_t>() : nullptr; fa.gm_stride = ctx->pt.gm_stride;
+  fa.gmask = nullptr; fa.gm_stride = 0;   // set by align_prepare_batch once the target index exists
   fa.nrm = p2l ? ctx->normals.as<float4>() : nullptr;
   fa.partials = ctx->partials.as<double>(); fa.st = d_st; fa.log = d_log; fa.grid = fused_grid(psx.n_valid);
   RevArgs& ra = ctx->ra;
@@ -988,6 +1038,77 @@ static int align_prepare(mvr_ctx* ctx, const mvr_icp_params* prm, const float* g
   ra.rnn = nullptr;
   if (reciprocal && ctx->want_rnn) { CK(ctx->rnn.ensure((size_t)std::max(m, 1) * sizeof(int32_t))); ra.rnn = ctx->rnn.as<int32_t>(); }
   ra.partials = fa.partials; ra.st = d_st; ra.log = d_log; ra.grid = fused_grid_rev(pt.n_valid); ra.per = fused_rev_chunks(pt.n_valid);
+  return MVR_OK;
+}
+
+// The contexts' pinned staging of a batch led by `lead`: room for `count` IcpStates on both sides.
+static int ensure_stage(mvr_ctx* lead, int count) {
+  mvr_ctx* ctx = lead;
+  if (count > lead->stage_cap) {
+    if (lead->h_stage) cudaFreeHost(lead->h_stage);
+    lead->h_stage = nullptr; lead->stage_cap = 0;
+    const int want = std::max(count + count / 2, 8);
+    CK(cudaMallocHost((void**)&lead->h_stage, (size_t)want * sizeof(IcpState)));
+    lead->stage_cap = want;
+  }
+  CK(lead->stage_dev.ensure((size_t)lead->stage_cap * sizeof(IcpState)));
+  return MVR_OK;
+}
+
+static InitJob init_job_of(mvr_ctx* c) {
+  InitJob j{};
+  j.corr_p = c->corr_p.as<int32_t>(); j.n = std::max(c->src.n, 1); j.m = std::max(c->tgt.n, 1);
+  j.rmin = c->fa.rmin; j.st = c->state.as<IcpState>(); j.crowded = c->crowded.as<uint32_t>();
+  return j;
+}
+
+// Prepare `count` aligns (same device): statuses[k] = the plan's verdict for context k; ok / slot = the contexts that go on
+// and their positions.  All device work -- index builds, seeds, gates, initial states -- is enqueued on the FIRST prepared
+// context's stream with a handful of launches whatever the batch size (24 ring pairs: 48 index builds in 4 launches; one
+// thread spent ~50 us per pair on launch calls alone when every pair prepared itself).
+static int align_prepare_batch(mvr_ctx* const* ctxs, int count, const mvr_icp_params* prm, const float* guesses, int est, int* statuses,
+                               std::vector<mvr_ctx*>& ok, std::vector<int>& slot) {
+  ok.clear(); slot.clear();
+  if (count <= 0) return MVR_OK;
+  mvr_ctx* lead = ctxs[0];
+  cudaStream_t S = lead->stream;
+  std::vector<std::vector<BuildJob>> jobs((size_t)count);
+  for (int k = 0; k < count; ++k) if (ensure_pinned(ctxs[k]) != MVR_OK) return MVR_ERR_CUDA;
+  // host side of every pair (grids, buffer checks, initial state): a few threads, no launches
+  parallel_for(count, [&](int k) { statuses[k] = align_plan(ctxs[k], prm, guesses ? guesses + 16 * k : nullptr, est, S, jobs[(size_t)k]); });
+  std::vector<BuildJob> all;
+  for (int k = 0; k < count; ++k) {
+    if (statuses[k] != MVR_OK) continue;
+    ok.push_back(ctxs[k]); slot.push_back(k);
+    all.insert(all.end(), jobs[(size_t)k].begin(), jobs[(size_t)k].end());
+  }
+  if (ok.empty()) return MVR_OK;
+  mvr_ctx* ctx = ok[0];   // CK() reports into it
+  if (ctx->stream != S) {   // the first context dropped out: keep stream order between the plans' first-time memsets and the builds
+    cudaEvent_t e = ctx->ev_b;
+    CK(cudaEventRecord(e, S));
+    S = ctx->stream;
+    CK(cudaStreamWaitEvent(S, e, 0));
+  }
+  int rc = run_pair_builds(ctx, all.data(), (int)all.size(), S);
+  if (rc) return rc;
+  const int P = (int)ok.size();
+  if ((rc = ensure_stage(ctx, P))) return rc;
+  for (int k0 = 0; k0 < P; k0 += BUILD_MAX_JOBS) {
+    const int c = std::min(P - k0, (int)BUILD_MAX_JOBS);
+    InitBatch ib;
+    for (int k = 0; k < c; ++k) {
+      mvr_ctx* m = ok[(size_t)(k0 + k)];
+      ib.j[k] = init_job_of(m);
+      std::memcpy(ctx->h_stage + k0 + k, m->h_state, sizeof(IcpState));
+    }
+    CK(cudaMemcpyAsync(ctx->stage_dev.as<IcpState>() + k0, ctx->h_stage + k0, (size_t)c * sizeof(IcpState), cudaMemcpyHostToDevice, S));
+    CK(launch_align_init(ib, c, ctx->stage_dev.as<IcpState>() + k0, S));
+  }
+  for (mvr_ctx* m : ok) {
+    if ((rc = ensure_gate_mask(m, m->pt, m->fa.max_d2f, S))) { ctx->err = m->err; return rc; }
+    m->fa.gmask = m->pt.gm_gate >= 0.f ? m->pt.gmask.as<uint32_t>() : nullptr; m->fa.gm_stride = m->pt.gm_stride;
+  }
   return MVR_OK;
 }
 
@@ -1008,7 +1129,7 @@ static int align_run(mvr_ctx* const* ctxs, int count, const mvr_icp_params* prm,
                                        : std::max(1, std::min((count + 3) / 4, (int)FUSED_MAX_PAIRS));
   struct Group {
     int g0, gn, gf, gr, enqueued, first;
-    bool done;
+    bool done, fetched;
     long long n_tot, m_tot;
     mvr_ctx* lead;
     FwdBatch fb;
@@ -1017,7 +1138,7 @@ static int align_run(mvr_ctx* const* ctxs, int count, const mvr_icp_params* prm,
   std::vector<Group> groups;
   for (int g0 = 0; g0 < count; g0 += gsz) {
     Group g{};
-    g.g0 = g0; g.gn = std::min(gsz, count - g0); g.gf = 1; g.gr = 1; g.enqueued = 0; g.first = 1; g.done = true;
+    g.g0 = g0; g.gn = std::min(gsz, count - g0); g.gf = 1; g.gr = 1; g.enqueued = 0; g.first = 1; g.done = true; g.fetched = true;
     g.lead = ctxs[g0];
     for (int k = 0; k < g.gn; ++k) {
       mvr_ctx* c = ctxs[g0 + k];
@@ -1028,17 +1149,24 @@ static int align_run(mvr_ctx* const* ctxs, int count, const mvr_icp_params* prm,
     }
     groups.push_back(g);
   }
-  // a group's stream waits for the preparation (index builds, initial state: each on the pair's own stream) of its members
-  for (Group& g : groups)
-    for (int k = 1; k < g.gn; ++k) {
-      mvr_ctx* c = ctxs[g.g0 + k];
-      CK(cudaEventRecord(c->ev_b, c->stream));
-      CK(cudaStreamWaitEvent(g.lead->stream, c->ev_b, 0));
-    }
-  if (ctx->profiling)   // a clean bracket for the roofline measurement: nothing of the preparation inside ev_a .. ev_b
-    for (int k = 0; k < count; ++k) CK(cudaStreamSynchronize(ctxs[k]->stream));
+  // the preparation of the whole batch (index builds, initial states) ran on the lead's stream: ev_a orders every group behind it
+  if (ctx->profiling) CK(cudaStreamSynchronize(ctx->stream));   // a clean bracket for the roofline measurement
+  int rc0 = ensure_stage(ctx, count);
+  if (rc0) return rc0;
   CK(cudaEventRecord(ctx->ev_a, ctx->stream));
   for (size_t gi = 1; gi < groups.size(); ++gi) CK(cudaStreamWaitEvent(groups[gi].lead->stream, ctx->ev_a, 0));
+  // staged states of a group -> its contexts (after the group's stream has been synchronised)
+  auto unpack = [&](Group& g) {
+    if (g.fetched) return;
+    g.fetched = true;
+    for (int k = 0; k < g.gn; ++k) {
+      mvr_ctx* c = ctxs[g.g0 + k];
+      std::memcpy(c->h_state, ctx->h_stage + g.g0 + k, sizeof(IcpState));
+      c->crowded_seen = std::max(c->crowded_seen, (uint32_t)c->h_state->dbg[3]);
+      c->h_state->dbg[3] = 0;
+    }
+  };
+  for (int k = 0; k < count; ++k) ctxs[k]->crowded_seen = 0;
   // Enqueue iterations in batches; after each batch read the states back.  Once a pair raises `done` its blocks of the
   // remaining launches return immediately.
   int batch = prm->fixed_iterations ? 64 : 2;
@@ -1062,8 +1190,16 @@ static int align_run(mvr_ctx* const* ctxs, int count, const mvr_icp_params* prm,
         }
       }
       g.enqueued += todo;
-      for (int k = 0; k < g.gn; ++k)
-        CK(cudaMemcpyAsync(ctxs[g.g0 + k]->h_state, ctxs[g.g0 + k]->state.p, sizeof(IcpState), cudaMemcpyDeviceToHost, g.lead->stream));
+      // the group's states come back together: one gather launch, one copy
+      for (int k0 = 0; k0 < g.gn; k0 += BUILD_MAX_JOBS) {
+        const int c = std::min(g.gn - k0, (int)BUILD_MAX_JOBS);
+        InitBatch ib;
+        for (int k = 0; k < c; ++k) ib.j[k] = init_job_of(ctxs[g.g0 + k0 + k]);
+        IcpState* d = ctx->stage_dev.as<IcpState>() + g.g0 + k0;
+        CK(launch_align_gather(ib, c, d, g.lead->stream));
+        CK(cudaMemcpyAsync(ctx->h_stage + g.g0 + k0, d, (size_t)c * sizeof(IcpState), cudaMemcpyDeviceToHost, g.lead->stream));
+      }
+      g.fetched = false;
     }
     if (!any) break;
     bool more = false;
@@ -1073,6 +1209,7 @@ static int align_run(mvr_ctx* const* ctxs, int count, const mvr_icp_params* prm,
         g.done = g.enqueued >= prm->max_iterations;
       } else {
         CK(cudaStreamSynchronize(g.lead->stream));
+        unpack(g);
         g.done = true;
         for (int k = 0; k < g.gn; ++k) if (!ctxs[g.g0 + k]->h_state->done) g.done = false;
       }
@@ -1089,41 +1226,47 @@ static int align_run(mvr_ctx* const* ctxs, int count, const mvr_icp_params* prm,
   }
   CK(cudaEventRecord(ctx->ev_b, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  for (Group& g : groups) unpack(g);
   return MVR_OK;
 }
 
-// lead: the context whose stream ran the batch (its ev_a .. ev_b bracket the iterations).  Split in two so that a
-// batch enqueues the tails of all its aligns before it waits once.
-static int align_finish_enqueue(mvr_ctx* ctx, mvr_ctx* lead, float* out_xyzw) {
-  const IcpState& h = *ctx->h_state;
+// The aligned cloud icp.align returns, out = float(final) * source: computed when somebody asks for it (a batch of ring pairs
+// never does), on the context's own stream -- the iterations are complete by the time an align returns.
+static int materialize_out(mvr_ctx* ctx) {
+  if (!ctx->have_out || !ctx->out_pending) return MVR_OK;
   const int n = ctx->src.n;
-  cudaStream_t st = lead->stream;
-  if (h.dbg[2] != 0) return fail(ctx, MVR_ERR_CUDA, "internal error: a reciprocal search lost its chooser (search bound violated)");
+  CK(ctx->out_cloud.ensure((size_t)std::max(n, 1) * sizeof(float4)));
   {
-    ProfScope ps(lead, MVR_K_TRANSFORM, 32.0 * n, n);
-    CK(launch_transform_final(ctx->src.pts, ctx->out_cloud.as<float4>(), n, ctx->state.as<IcpState>(), st));
+    ProfScope ps(ctx, MVR_K_TRANSFORM, 32.0 * n, n);
+    CK(launch_transform_final(ctx->src.pts, ctx->out_cloud.as<float4>(), n, ctx->state.as<IcpState>(), ctx->stream));
   }
-  const int n_log = std::min(h.iter, (int)ICP_MAX_LOG);
-  if (n_log > 0) CK(cudaMemcpyAsync(ctx->h_log, ctx->log.p, (size_t)n_log * sizeof(IterRec), cudaMemcpyDeviceToHost, st));
-  if (out_xyzw) CK(cudaMemcpyAsync(out_xyzw, ctx->out_cloud.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, st));
-  if (ctx->crowded.p) {   // the builds ran on ctx->stream, which `st` has waited for
-    CK(cudaMemcpyAsync(ctx->h_small + 8, ctx->crowded.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemsetAsync(ctx->crowded.p, 0, sizeof(uint32_t), st));
-  }
+  ctx->out_pending = false;
   return MVR_OK;
 }
 
-// After the lead stream has been synchronised.
-static int align_finish_collect(mvr_ctx* ctx, mvr_ctx* lead, float* out_pose, mvr_icp_report* report, int batch_pairs = 1) {
-  const IcpState& h = *ctx->h_state;
-  const int n_log = std::min(h.iter, (int)ICP_MAX_LOG);
-  ctx->have_out = true;
+// The iteration log of the last align, fetched from the device on first use.
+static int fetch_log(mvr_ctx* ctx) {
+  const int n_log = ctx->log_pending;
+  if (n_log <= 0) return MVR_OK;
+  ctx->log_pending = 0;
+  CK(cudaMemcpyAsync(ctx->h_log, ctx->log.p, (size_t)n_log * sizeof(IterRec), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   for (int k = 0; k < n_log; ++k) {
     mvr_icp_iteration rec;
     rec.iteration = ctx->h_log[k].iteration; rec.n_correspondences = ctx->h_log[k].n_corr; rec.mse = ctx->h_log[k].mse;
     std::memcpy(rec.delta, ctx->h_log[k].delta, sizeof(rec.delta));
     ctx->iters.push_back(rec);
   }
+  return MVR_OK;
+}
+
+// After align_run (which has synchronised): the report of one context.  lead: the context whose ev_a .. ev_b bracket the
+// iterations of the batch.
+static int align_finish_collect(mvr_ctx* ctx, mvr_ctx* lead, float* out_pose, mvr_icp_report* report, int batch_pairs = 1) {
+  const IcpState& h = *ctx->h_state;
+  if (h.dbg[2] != 0) return fail(ctx, MVR_ERR_CUDA, "internal error: a reciprocal search lost its chooser (search bound violated)");
+  ctx->have_out = true; ctx->out_pending = true;
+  ctx->log_pending = std::min(h.iter, (int)ICP_MAX_LOG);
   if (out_pose) for (int k = 0; k < 16; ++k) out_pose[k] = (float)h.fin[k];
   if (report) {
     float ms = 0.f;
@@ -1133,7 +1276,6 @@ static int align_finish_collect(mvr_ctx* ctx, mvr_ctx* lead, float* out_pose, mv
     // pairs of a batch advance in lock-step and are not separable: each is given its share of the batch's device time
     report->gpu_ms = (double)ms / (double)std::max(batch_pairs, 1);
   }
-  ctx->crowded_seen = ctx->crowded.p ? ctx->h_small[8] : 0u;
   if (ctx->crowded_seen)
     ctx->err = "warning: a grid cell holds " + std::to_string(ctx->crowded_seen) + " points (duplicates or clamped outliers?): index build and search slow down, sums over it lose their fixed order";
   if (h.status == MVR_ERR_TOO_FEW_CORRESPONDENCES) ctx->err = "not enough correspondences";
@@ -1142,10 +1284,14 @@ static int align_finish_collect(mvr_ctx* ctx, mvr_ctx* lead, float* out_pose, mv
 }
 
 static int align_finish(mvr_ctx* ctx, mvr_ctx* lead, float* out_pose, float* out_xyzw, mvr_icp_report* report) {
-  int rc = align_finish_enqueue(ctx, lead, out_xyzw);
-  if (rc) return rc;
-  CK(cudaStreamSynchronize(lead->stream));
-  return align_finish_collect(ctx, lead, out_pose, report);
+  const int status = align_finish_collect(ctx, lead, out_pose, report);
+  if (out_xyzw && ctx->have_out) {
+    int rc = materialize_out(ctx);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_xyzw, ctx->out_cloud.p, (size_t)ctx->src.n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return status;
 }
 
 static int icp_align_impl(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, float* out_pose, float* out_xyzw,
@@ -1180,21 +1326,16 @@ int mvr_icp_align_batch(mvr_ctx* const* ctxs, int count, const mvr_icp_params* p
   const bool timing = std::getenv("MVR_DEBUG_TIMING") != nullptr;
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t0 = now();
-  // every pair's preparation (index builds, initial state: ~14 small launches on the pair's own stream) is enqueued by a few
-  // host threads at once: one thread spends ~50 us per pair on launch calls alone
-  parallel_for(count, [&](int k) { statuses[k] = align_prepare(ctxs[k], prm, guesses ? guesses + 16 * k : nullptr, est); });
-  for (int k = 0; k < count; ++k)
-    if (statuses[k] == MVR_OK) { ok.push_back(ctxs[k]); slot.push_back(k); }
+  int rc = align_prepare_batch(ctxs, count, prm, guesses, est, statuses, ok, slot);
+  if (rc) { if (!ok.empty() && ok[0] != ctxs[0]) ctxs[0]->err = ok[0]->err; return rc; }
   if (ok.empty()) return MVR_OK;
   const double t1 = now();
-  int rc = align_run(ok.data(), (int)ok.size(), prm, est);
+  rc = align_run(ok.data(), (int)ok.size(), prm, est);
   if (timing) std::fprintf(stderr, "[timing]   prepare (host enqueue) %.3f ms, run %.3f ms\n", t1 - t0, now() - t1);
   if (rc) { if (ok[0] != ctxs[0]) ctxs[0]->err = ok[0]->err; return rc; }
-  for (size_t j = 0; j < ok.size(); ++j) statuses[slot[j]] = align_finish_enqueue(ok[j], ok[0], nullptr);
-  if (cudaStreamSynchronize(ok[0]->stream) != cudaSuccess) return fail(ctxs[0], MVR_ERR_CUDA, "batch tail failed");
   for (size_t j = 0; j < ok.size(); ++j) {
     const int k = slot[j];
-    if (statuses[k] == MVR_OK) statuses[k] = align_finish_collect(ok[j], ok[0], out_poses ? out_poses + 16 * k : nullptr, reports ? reports + k : nullptr, (int)ok.size());
+    statuses[k] = align_finish_collect(ok[j], ok[0], out_poses ? out_poses + 16 * k : nullptr, reports ? reports + k : nullptr, (int)ok.size());
   }
   return MVR_OK;
 }
@@ -1251,14 +1392,11 @@ int mvr_pair_moments_compute_batch(mvr_ctx* const* ctxs, int count, double max_d
   one.min_correspondences = 1;
   std::vector<mvr_ctx*> ok;
   std::vector<int> slot;
-  parallel_for(count, [&](int k) {
-    std::memset(out + k, 0, sizeof(mvr_pair_moments));
-    statuses[k] = align_prepare(ctxs[k], &one, guesses ? guesses + 16 * k : nullptr, EST_MOM);
-  });
-  for (int k = 0; k < count; ++k)
-    if (statuses[k] == MVR_OK) { ok.push_back(ctxs[k]); slot.push_back(k); }
+  for (int k = 0; k < count; ++k) std::memset(out + k, 0, sizeof(mvr_pair_moments));
+  int rc = align_prepare_batch(ctxs, count, &one, guesses, EST_MOM, statuses, ok, slot);
+  if (rc) { if (!ok.empty() && ok[0] != ctxs[0]) ctxs[0]->err = ok[0]->err; return rc; }
   if (ok.empty()) return MVR_OK;
-  int rc = align_run(ok.data(), (int)ok.size(), &one, EST_MOM);
+  rc = align_run(ok.data(), (int)ok.size(), &one, EST_MOM);
   if (rc) { if (ok[0] != ctxs[0]) ctxs[0]->err = ok[0]->err; return rc; }
   for (size_t j = 0; j < ok.size(); ++j) {
     const IcpState& h = *ok[j]->h_state;
@@ -1267,7 +1405,7 @@ int mvr_pair_moments_compute_batch(mvr_ctx* const* ctxs, int count, double max_d
     const bool have = h.status == MVR_OK;
     statuses[k] = (have || h.status == MVR_ERR_TOO_FEW_CORRESPONDENCES) ? MVR_OK : h.status;
     moments_from_state(h, have, out + k);
-    ok[j]->have_out = false;
+    ok[j]->have_out = false; ok[j]->out_pending = false;
   }
   return MVR_OK;
 }
@@ -1280,6 +1418,9 @@ double mvr_debug_value(mvr_ctx* ctx, int k) {
 
 int mvr_icp_get_iterations(mvr_ctx* ctx, mvr_icp_iteration* out, int max_records, int* count) {
   if (!ctx || !count) return MVR_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  int rcl = fetch_log(ctx);
+  if (rcl) return rcl;
   int c = (int)ctx->iters.size();
   if (out) {
     int m = std::min(c, std::max(max_records, 0));
@@ -1298,7 +1439,8 @@ int mvr_fitness_score(mvr_ctx* ctx, double max_range, double* score) {
   const int n = ctx->src.n;
   *score = DBL_MAX;
   if (n == 0 || ctx->tgt.n == 0) return MVR_OK;
-  int rc = MVR_OK;
+  int rc = materialize_out(ctx);
+  if (rc) return rc;
   const float4* cloud = ctx->have_out ? ctx->out_cloud.as<float4>() : ctx->src.pts;
   CK(ctx->itmp.ensure((size_t)n * sizeof(int32_t)));
   CK(ctx->ftmp.ensure((size_t)n * sizeof(float)));
@@ -1372,6 +1514,8 @@ int mvr_copy_aligned_device(mvr_ctx* ctx, float* d_out) {
   if (!ctx || !d_out) return MVR_ERR_BAD_ARG;
   cudaSetDevice(ctx->device);
   if (!ctx->have_out) return fail(ctx, MVR_ERR_NO_INPUT, "no align has run");
+  int rcm = materialize_out(ctx);
+  if (rcm) return rcm;
   if (ctx->src.n > 0) CK(cudaMemcpyAsync(d_out, ctx->out_cloud.p, (size_t)ctx->src.n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return MVR_OK;

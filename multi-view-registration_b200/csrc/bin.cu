@@ -56,10 +56,9 @@ int scan_num_tiles(size_t len) { return (int)((len + SC_TILE - 1) / SC_TILE); }
 // tile_state[0] is the ticket counter of the launch (tiles are handed out in the order blocks START, so a tile never waits
 // for a predecessor that has not been scheduled yet; the block that draws the last ticket resets the counter for the next
 // launch); tile t's state word lives at tile_state[1 + t].
-__global__ void __launch_bounds__(SC_THREADS) k_scan_cells(uint32_t* __restrict__ counters, uint32_t* __restrict__ start, uint32_t len,
-                                                           unsigned long long* __restrict__ tile_state, uint32_t epoch,
-                                                           const int* __restrict__ done) {
-  if (done && *done) return;
+// ntiles: tiles of this table; gridDim.x >= ntiles blocks draw tickets (a batched launch is as wide as its largest table).
+__device__ __forceinline__ void scan_tiles(uint32_t* __restrict__ counters, uint32_t* __restrict__ start, uint32_t len,
+                                           unsigned long long* __restrict__ tile_state, uint32_t epoch, uint32_t ntiles) {
   __shared__ uint32_t warp_sums[SC_THREADS / 32];
   __shared__ uint32_t s_prefix, s_tile;
   if (threadIdx.x == 0) {
@@ -70,6 +69,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_cells(uint32_t* __restrict_
   }
   __syncthreads();
   const uint32_t tile = s_tile;
+  if (tile >= ntiles) return;
   volatile unsigned long long* st = tile_state + 1;
   const uint32_t base = tile * SC_TILE + threadIdx.x * SC_ITEMS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -156,7 +156,28 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_cells(uint32_t* __restrict_
     }
   }
   // total after the last counter
-  if (tile == gridDim.x - 1 && threadIdx.x == SC_THREADS - 1) start[len] = s_prefix + agg;
+  if (tile == ntiles - 1 && threadIdx.x == SC_THREADS - 1) start[len] = s_prefix + agg;
+}
+
+__global__ void __launch_bounds__(SC_THREADS) k_scan_cells(uint32_t* __restrict__ counters, uint32_t* __restrict__ start, uint32_t len,
+                                                           unsigned long long* __restrict__ tile_state, uint32_t epoch,
+                                                           const int* __restrict__ done) {
+  if (done && *done) return;
+  scan_tiles(counters, start, len, tile_state, epoch, gridDim.x);
+}
+
+// The cell tables of every build of a batch in one launch (blockIdx.y = job, pair_index.cu).
+__global__ void __launch_bounds__(SC_THREADS) k_scan_cells_batch(const __grid_constant__ BuildBatch b) {
+  __shared__ uint32_t* s_counters;
+  __shared__ uint32_t* s_start;
+  __shared__ unsigned long long* s_tiles;
+  __shared__ uint32_t s_len, s_epoch, s_ntiles;
+  if (threadIdx.x == 0) {
+    const BuildJob& j = b.j[blockIdx.y];
+    s_counters = j.counters; s_start = j.start; s_tiles = j.tiles; s_len = j.cells + 1u; s_epoch = j.epoch; s_ntiles = (uint32_t)j.ntiles;
+  }
+  __syncthreads();
+  scan_tiles(s_counters, s_start, s_len, s_tiles, s_epoch, s_ntiles);
 }
 
 __global__ void __launch_bounds__(256) k_bin_scatter(const float4* __restrict__ pts, int n, const uint32_t* __restrict__ keys,
@@ -180,6 +201,12 @@ cudaError_t launch_transform_bin(float4* pts, int n, const float* d_delta, const
 cudaError_t launch_scan_cells(uint32_t* counters, uint32_t* start, size_t len, unsigned long long* tile_state, uint32_t epoch,
                               const int* d_done, cudaStream_t s) {
   k_scan_cells<<<scan_num_tiles(len), SC_THREADS, 0, s>>>(counters, start, (uint32_t)len, tile_state, epoch, d_done); count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scan_cells_batch(const BuildBatch& batch, int count, int max_tiles, cudaStream_t s) {
+  if (count <= 0 || max_tiles <= 0) return cudaSuccess;
+  k_scan_cells_batch<<<dim3((unsigned)max_tiles, (unsigned)count), SC_THREADS, 0, s>>>(batch); count_launch();
   return cudaGetLastError();
 }
 

@@ -8,6 +8,8 @@
 //   DefaultConvergenceCriteria.
 // The whole loop state lives in an IcpState on the device, so an align needs no host round trip per
 // iteration: the host only enqueues iterations and reads the state back when a batch has run.
+#include <algorithm>
+
 #include "launch.h"
 #include "pair_search.cuh"
 #ifdef MVR_TS_TILE
@@ -622,6 +624,52 @@ cudaError_t launch_pair_nn(const float4* q, int n, bool by_w, const float4* tgt_
   if (by_w) k_pair_nn<true><<<blocks, FUSED_THREADS, 0, s>>>(q, n, tgt_sorted, tstart, g, m_valid, out_idx, out_d2);
   else k_pair_nn<false><<<blocks, FUSED_THREADS, 0, s>>>(q, n, tgt_sorted, tstart, g, m_valid, out_idx, out_d2);
   count_launch();
+  return cudaGetLastError();
+}
+
+// ---- start / end of a batch of aligns (launch.h) ------------------------------------------------
+__global__ void __launch_bounds__(256) k_align_init(const __grid_constant__ InitBatch b, const IcpState* __restrict__ stage) {
+  const InitJob& j = b.j[blockIdx.y];
+  int32_t* __restrict__ corr_p = j.corr_p;
+  uint32_t* __restrict__ rmin = j.rmin;
+  const int n = j.n, m = rmin ? j.m : 0;
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) corr_p[i] = -1;           // no seed yet
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) rmin[i] = 0x7f800000u;   // +inf: "chosen by nobody"
+  if (blockIdx.x == 0) {
+    static_assert(sizeof(IcpState) % 4 == 0, "IcpState words");
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(stage + blockIdx.y);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(j.st);
+    for (int k = threadIdx.x; k < (int)(sizeof(IcpState) / 4); k += blockDim.x) dst[k] = src[k];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_align_gather(const __grid_constant__ InitBatch b, IcpState* __restrict__ stage) {
+  const InitJob& j = b.j[blockIdx.x];
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(j.st);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(stage + blockIdx.x);
+  for (int k = threadIdx.x; k < (int)(sizeof(IcpState) / 4); k += blockDim.x) dst[k] = src[k];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    stage[blockIdx.x].dbg[3] = j.crowded ? (long long)*j.crowded : 0ll;
+    if (j.crowded) *j.crowded = 0u;
+  }
+}
+
+cudaError_t launch_align_init(const InitBatch& batch, int count, const IcpState* stage, cudaStream_t s) {
+  if (count <= 0) return cudaSuccess;
+  if (count > BUILD_MAX_JOBS) return cudaErrorInvalidValue;
+  int items = 1;
+  for (int k = 0; k < count; ++k) items = std::max(items, std::max(batch.j[k].n, batch.j[k].rmin ? batch.j[k].m : 0));
+  const int blocks = std::max(1, std::min((items + 1023) / 1024, (148 * 8 + count - 1) / count));
+  k_align_init<<<dim3((unsigned)blocks, (unsigned)count), 256, 0, s>>>(batch, stage); count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_align_gather(const InitBatch& batch, int count, IcpState* stage, cudaStream_t s) {
+  if (count <= 0) return cudaSuccess;
+  if (count > BUILD_MAX_JOBS) return cudaErrorInvalidValue;
+  k_align_gather<<<(unsigned)count, 256, 0, s>>>(batch, stage); count_launch();
   return cudaGetLastError();
 }
 

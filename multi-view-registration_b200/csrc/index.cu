@@ -35,7 +35,7 @@ __global__ void k_bbox_init(uint32_t* out) {
   else if (t == 6) out[t] = 0u;             // non-finite count
 }
 
-__global__ void __launch_bounds__(256) k_bbox(const float4* __restrict__ pts, int n, uint32_t* out) {
+__device__ __forceinline__ void bbox_body(const float4* __restrict__ pts, int n, uint32_t* out) {
   float lo[3] = {MVR_INF, MVR_INF, MVR_INF}, hi[3] = {-MVR_INF, -MVR_INF, -MVR_INF};
   uint32_t bad = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -80,8 +80,33 @@ __global__ void __launch_bounds__(256) k_bbox(const float4* __restrict__ pts, in
   }
 }
 
+__global__ void __launch_bounds__(256) k_bbox(const float4* __restrict__ pts, int n, uint32_t* out) { bbox_body(pts, n, out); }
+
+// Every cloud of a batch in one launch (blockIdx.y = cloud); the seven words of each are initialised by k_bbox_init_batch.
+__global__ void k_bbox_init_batch(uint32_t* out, int count) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < 7 * count) out[t] = (t % 7 < 3) ? 0xffffffffu : 0u;
+}
+__global__ void __launch_bounds__(256) k_bbox_batch(const __grid_constant__ BboxBatch b, uint32_t* out) {
+  const BboxJob& j = b.j[blockIdx.y];
+  bbox_body(j.pts, j.n, out + 7 * blockIdx.y);
+}
+
 cudaError_t launch_bbox_init(uint32_t* out7, cudaStream_t s) {
   k_bbox_init<<<1, 32, 0, s>>>(out7); count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bbox_batch(const BboxBatch& batch, int count, uint32_t* out7, cudaStream_t s) {
+  if (count <= 0) return cudaSuccess;
+  if (count > BBOX_MAX_JOBS) return cudaErrorInvalidValue;
+  int max_n = 0;
+  for (int k = 0; k < count; ++k) max_n = max(max_n, batch.j[k].n);
+  k_bbox_init_batch<<<(7 * count + 255) / 256, 256, 0, s>>>(out7, count); count_launch();
+  if (max_n > 0) {
+    const int blocks = max(1, min((max_n + 1023) / 1024, (148 * 4 + count - 1) / count));
+    k_bbox_batch<<<dim3((unsigned)blocks, (unsigned)count), 256, 0, s>>>(batch, out7); count_launch();
+  }
   return cudaGetLastError();
 }
 

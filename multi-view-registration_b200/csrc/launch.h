@@ -18,6 +18,11 @@ unsigned long long launch_count();
 cudaError_t launch_bbox_init(uint32_t* out7, cudaStream_t s);
 cudaError_t launch_bbox(const float4* pts, int n, uint32_t* out7, cudaStream_t s);
 float bbox_decode(uint32_t enc);
+// The boxes of `count` clouds in one launch: out7[7 * k ..] of cloud k (initialised by the launcher).
+struct BboxJob { const float4* pts; int n; int pad_; };
+enum { BBOX_MAX_JOBS = 64 };
+struct BboxBatch { BboxJob j[BBOX_MAX_JOBS]; };
+cudaError_t launch_bbox_batch(const BboxBatch& batch, int count, uint32_t* out7, cudaStream_t s);
 
 // out[i] = float(M * in[i]) in double arithmetic; `in` records are `stride` bytes apart (x, y, z first).
 cudaError_t launch_apply_pose(const void* in, size_t stride, int n, const double* M16, float4* out, cudaStream_t s);
@@ -103,23 +108,36 @@ struct IcpState {
 enum { FUSED_THREADS = MVR_FUSED_THREADS, FUSED_WARPS = FUSED_THREADS / 32, FUSED_MAX_BLOCKS = 148 * 8 * (256 / FUSED_THREADS) };
 
 // Deterministic counting sort of a cloud by row-major cell (pair_index.cu): count (keys + arrival ranks; counters
-// has cells + 1 zeroed entries, the last one collects non-finite points), launch_scan_cells (bin.cu), scatter into
-// tmp in arrival order, rerank into ascending original index inside every cell.  guess (nullable) is applied to the
-// points first (pinned float transform).
-cudaError_t launch_pair_count(const float4* in, int n, const Mat4f* guess, PairGrid g, uint32_t cells, uint32_t* keys, uint32_t* rank,
-                              uint32_t* counters, cudaStream_t s);
-cudaError_t launch_pair_scatter(const float4* in, int n, const Mat4f* guess, const uint32_t* keys, const uint32_t* rank, const uint32_t* start,
-                                float4* tmp, cudaStream_t s);
+// has cells + 1 zeroed entries, the last one collects non-finite points), scan (bin.cu), scatter into tmp in arrival
+// order, rerank into ascending original index inside every cell.  A BuildJob describes one build; one launch per
+// phase serves every job of a BuildBatch (blockIdx.y = job).
+struct BuildJob {
+  const float4* in;              // n points; M is applied first when apply != 0 (pinned float transform)
+  int n, apply;
+  Mat4f M;
+  PairGrid g;
+  uint32_t cells;                // non-finite points get the sentinel key `cells`
+  uint32_t* keys;                // scratch, n
+  uint32_t* rank;                // scratch, n
+  uint32_t* counters;            // scratch, cells + 1, zero on entry and on exit
+  unsigned long long* tiles;     // scratch of the scan: ticket word + scan_num_tiles(cells + 1) state words
+  uint32_t epoch;                // of the scan (a different one per launch over the same tiles)
+  int ntiles;                    // scan_num_tiles(cells + 1)
+  float4* tmp;                   // scratch, n records in arrival order (ordered builds)
+  float4* sorted;                // out: {point, bits(original index)} by cell
+  uint32_t* start;               // out: cells + 2 entries
+  uint32_t* crowded;             // nullable device word: raised (atomicMax) to the population of a cell too crowded to be ranked
+  int ordered;                   // 0: the points of a cell stay in arrival order (queries: results go out by original index)
+  int pad_;
+};
+enum { BUILD_MAX_JOBS = 48 };
+struct BuildBatch { BuildJob j[BUILD_MAX_JOBS]; };
+cudaError_t launch_pair_builds(const BuildBatch& batch, int count, cudaStream_t s);
+cudaError_t launch_scan_cells_batch(const BuildBatch& batch, int count, int max_tiles, cudaStream_t s);
 cudaError_t launch_fill_u32(uint32_t* p, size_t n, uint32_t v, cudaStream_t s);
 // Gate mask of an index (pair_index.cu): occ and mask hold ny * nz * wstride words, wstride = ceil(nx / 32); D / Dx = dilation in
 // y-z / x cells.
 cudaError_t launch_gate_mask(const uint32_t* start, PairGrid g, int wstride, int D, int Dx, uint32_t* occ, uint32_t* mask, cudaStream_t s);
-// sorted[k] = {moved point, bits(original index)}; copy (nullable) gets the same.
-// crowded (nullable, device word): raised (atomicMax) to the population of a cell too crowded to be ranked (its points keep
-// their arrival order).
-cudaError_t launch_pair_rerank(const float4* tmp, int n, const uint32_t* keys, const uint32_t* start, float4* sorted, float4* copy,
-                               uint32_t* crowded, cudaStream_t s);
-
 struct FwdArgs {
   float4* cur;             // source, sorted by binning cell, current coordinates (updated in place), .w = original index
   int n_valid;             // finite source points = sorted positions [0, n_valid)
@@ -165,6 +183,13 @@ enum { EST_P2P = 0, EST_P2L = 1, EST_MOM = 2 /* point-to-point + second moments 
 enum { FUSED_MAX_PAIRS = 24 };
 struct FwdBatch { FwdArgs a[FUSED_MAX_PAIRS]; };
 struct RevBatch { RevArgs a[FUSED_MAX_PAIRS]; };
+// Start of a batch of aligns in one launch: per pair, corr_p <- -1 (no seed), rmin <- +inf bits (chosen by nobody; nullable),
+// *st <- stage[k] (the initial states, uploaded together).  End of a batch: stage[k] <- *st (dbg[3] of the copy = the pair's
+// crowded word, which is reset).
+struct InitJob { int32_t* corr_p; int n; int m; uint32_t* rmin; IcpState* st; uint32_t* crowded; };
+struct InitBatch { InitJob j[BUILD_MAX_JOBS]; };
+cudaError_t launch_align_init(const InitBatch& batch, int count, const IcpState* stage, cudaStream_t s);
+cudaError_t launch_align_gather(const InitBatch& batch, int count, IcpState* stage, cudaStream_t s);
 int fused_grid(int items);
 int fused_grid_rev(int items);   // blocks of the reverse half (not capped)
 int fused_rev_chunks(int items);

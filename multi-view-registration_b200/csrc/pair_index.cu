@@ -20,56 +20,68 @@
 //                    second copy s0 = its binning-time coordinates next to the coordinates that move.
 //
 // Algorithmic bytes per point: 16 read + 16 (32 with the s0 copy) written, + 8 B per cell.
+#include <algorithm>
+
 #include "launch.h"
 #include "pair_search.cuh"
 
 namespace mvr {
 
-__global__ void __launch_bounds__(256) k_pair_count(const float4* __restrict__ in, int n, Mat4f M, int apply, PairGrid g, uint32_t cells,
-                                                    uint32_t* __restrict__ keys, uint32_t* __restrict__ rank, uint32_t* __restrict__ counters) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float4 p = __ldg(in + i);
-  const bool ok = finite3(p);
-  if (apply && ok) p = xform_pinned(M, p);
-  const uint32_t key = ok ? pg_key(p, g) : cells;
-  keys[i] = key;
-  rank[i] = atomicAdd(counters + key, 1u);
+// One launch per phase serves EVERY build of a batch (blockIdx.y = job; the jobs travel by value in the kernel's
+// parameter space): a 24-pair registration builds 48 indices with 4 launches instead of 192.
+__device__ __forceinline__ const BuildJob& load_job(const BuildBatch& b, BuildJob& s_job) {
+  static_assert(sizeof(BuildJob) % 4 == 0 && sizeof(BuildJob) / 4 <= 256, "job block");
+  if (threadIdx.x < sizeof(BuildJob) / 4) ((uint32_t*)&s_job)[threadIdx.x] = ((const uint32_t*)&b.j[blockIdx.y])[threadIdx.x];
+  __syncthreads();
+  return s_job;
 }
 
-__global__ void __launch_bounds__(256) k_pair_scatter(const float4* __restrict__ in, int n, Mat4f M, int apply, const uint32_t* __restrict__ keys,
-                                                      const uint32_t* __restrict__ rank, const uint32_t* __restrict__ start, float4* __restrict__ tmp) {
+__global__ void __launch_bounds__(256) k_pair_count(const __grid_constant__ BuildBatch b) {
+  __shared__ BuildJob s_job;
+  const BuildJob& j = load_job(b, s_job);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float4 p = __ldg(in + i);
-  if (apply && finite3(p)) p = xform_pinned(M, p);   // the same pinned arithmetic as k_pair_count: the same point
+  if (i >= j.n) return;
+  float4 p = __ldg(j.in + i);
+  const bool ok = finite3(p);
+  if (j.apply && ok) p = xform_pinned(j.M, p);
+  const uint32_t key = ok ? pg_key(p, j.g) : j.cells;
+  j.keys[i] = key;
+  j.rank[i] = atomicAdd(j.counters + key, 1u);
+}
+
+__global__ void __launch_bounds__(256) k_pair_scatter(const __grid_constant__ BuildBatch b) {
+  __shared__ BuildJob s_job;
+  const BuildJob& j = load_job(b, s_job);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= j.n) return;
+  float4 p = __ldg(j.in + i);
+  if (j.apply && finite3(p)) p = xform_pinned(j.M, p);   // the same pinned arithmetic as k_pair_count: the same point
   p.w = __uint_as_float((uint32_t)i);
-  tmp[__ldg(start + __ldg(keys + i)) + __ldg(rank + i)] = p;
+  (j.ordered ? j.tmp : j.sorted)[__ldg(j.start + __ldg(j.keys + i)) + __ldg(j.rank + i)] = p;
 }
 
 // A cell that holds more than RERANK_LIMIT points (duplicated or invalid returns piled on one spot, outliers clamped into a
 // boundary cell) would make the rank count below quadratic: its points keep their arrival order instead and the population is
 // reported through *crowded (searches stay exact; only the run-to-run order of sums over that cell's points is lost).
 constexpr uint32_t RERANK_LIMIT = 1024;
-__global__ void __launch_bounds__(256) k_pair_rerank(const float4* __restrict__ tmp, int n, const uint32_t* __restrict__ keys,
-                                                     const uint32_t* __restrict__ start, float4* __restrict__ sorted, float4* __restrict__ copy,
-                                                     uint32_t* __restrict__ crowded) {
+__global__ void __launch_bounds__(256) k_pair_rerank(const __grid_constant__ BuildBatch b) {
+  __shared__ BuildJob s_job;
+  const BuildJob& j = load_job(b, s_job);
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
+  if (k >= j.n || !j.ordered) return;
+  const float4* __restrict__ tmp = j.tmp;
   const float4 p = __ldg(tmp + k);
   const uint32_t idx = __float_as_uint(p.w);
-  const uint32_t key = __ldg(keys + idx);
-  const uint32_t s = __ldg(start + key), e = __ldg(start + key + 1);
+  const uint32_t key = __ldg(j.keys + idx);
+  const uint32_t s = __ldg(j.start + key), e = __ldg(j.start + key + 1);
   if (e - s > RERANK_LIMIT) {
-    sorted[k] = p;
-    if (copy) copy[k] = p;
-    if (crowded && (uint32_t)k == s) atomicMax(crowded, e - s);
+    j.sorted[k] = p;
+    if (j.crowded && (uint32_t)k == s) atomicMax(j.crowded, e - s);
     return;
   }
   uint32_t r = 0;
-  for (uint32_t j = s; j < e; ++j) r += (__float_as_uint(__ldg(&tmp[j].w)) < idx) ? 1u : 0u;
-  sorted[s + r] = p;
-  if (copy) copy[s + r] = p;
+  for (uint32_t q = s; q < e; ++q) r += (__float_as_uint(__ldg(&tmp[q].w)) < idx) ? 1u : 0u;
+  j.sorted[s + r] = p;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -136,28 +148,22 @@ cudaError_t launch_fill_u32(uint32_t* p, size_t n, uint32_t v, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_pair_count(const float4* in, int n, const Mat4f* guess, PairGrid g, uint32_t cells, uint32_t* keys, uint32_t* rank,
-                              uint32_t* counters, cudaStream_t s) {
-  if (n <= 0) return cudaSuccess;
-  Mat4f M{};
-  if (guess) M = *guess;
-  k_pair_count<<<(n + 255) / 256, 256, 0, s>>>(in, n, M, guess ? 1 : 0, g, cells, keys, rank, counters); count_launch();
-  return cudaGetLastError();
-}
-
-cudaError_t launch_pair_scatter(const float4* in, int n, const Mat4f* guess, const uint32_t* keys, const uint32_t* rank, const uint32_t* start,
-                                float4* tmp, cudaStream_t s) {
-  if (n <= 0) return cudaSuccess;
-  Mat4f M{};
-  if (guess) M = *guess;
-  k_pair_scatter<<<(n + 255) / 256, 256, 0, s>>>(in, n, M, guess ? 1 : 0, keys, rank, start, tmp); count_launch();
-  return cudaGetLastError();
-}
-
-cudaError_t launch_pair_rerank(const float4* tmp, int n, const uint32_t* keys, const uint32_t* start, float4* sorted, float4* copy,
-                               uint32_t* crowded, cudaStream_t s) {
-  if (n <= 0) return cudaSuccess;
-  k_pair_rerank<<<(n + 255) / 256, 256, 0, s>>>(tmp, n, keys, start, sorted, copy, crowded); count_launch();
+// The four phases of `count` index builds (<= BUILD_MAX_JOBS) on stream s.
+cudaError_t launch_pair_builds(const BuildBatch& batch, int count, cudaStream_t s) {
+  if (count <= 0) return cudaSuccess;
+  if (count > BUILD_MAX_JOBS) return cudaErrorInvalidValue;
+  int max_n = 0, max_tiles = 0;
+  bool any_ordered = false;
+  for (int k = 0; k < count; ++k) {
+    max_n = std::max(max_n, batch.j[k].n);
+    max_tiles = std::max(max_tiles, batch.j[k].ntiles);
+    any_ordered = any_ordered || batch.j[k].ordered;
+  }
+  const dim3 gp((unsigned)std::max((max_n + 255) / 256, 1), (unsigned)count);
+  if (max_n > 0) { k_pair_count<<<gp, 256, 0, s>>>(batch); count_launch(); }
+  launch_scan_cells_batch(batch, count, max_tiles, s);
+  if (max_n > 0) { k_pair_scatter<<<gp, 256, 0, s>>>(batch); count_launch(); }
+  if (max_n > 0 && any_ordered) { k_pair_rerank<<<gp, 256, 0, s>>>(batch); count_launch(); }
   return cudaGetLastError();
 }
 

@@ -411,21 +411,15 @@ int Registrator::multiViewRegister(std::vector<View>& views, const mvr_turntable
   std::vector<uint64_t> queries((size_t)P, 0);
   std::vector<double> ms((size_t)P, 0.0);
   std::vector<mvr_icp_report> rep((size_t)P);
-  // every pair's target: the cloud's bounding box is measured on the device and read back (one stream round trip per view);
-  // a few host threads issue them at once
+  // every pair's target in one call: the bounding boxes of all views are measured by one launch and read back together
   std::vector<int> set_rc((size_t)P, MVR_OK);
   {
-    std::atomic<int> next{0};
-    auto work = [&] {
-      for (int k = next.fetch_add(1); k < P; k = next.fetch_add(1)) {
-        const int p = p0 + k;
-        set_rc[(size_t)k] = mvr_set_target_device(ctx_[(size_t)k], dview[(size_t)(p % V)], views[(size_t)p].size);
-      }
-    };
-    std::vector<std::thread> th;
-    for (int t = 1; t < std::min(P, 6); ++t) th.emplace_back(work);
-    work();
-    for (std::thread& t : th) t.join();
+    std::vector<mvr_ctx*> cc((size_t)P);
+    std::vector<int> which((size_t)P, MVR_CLOUD_TARGET);
+    std::vector<const float*> ptr((size_t)P);
+    std::vector<size_t> cnt((size_t)P);
+    for (int k = 0; k < P; ++k) { cc[(size_t)k] = ctx_[(size_t)k]; ptr[(size_t)k] = dview[(size_t)((p0 + k) % V)]; cnt[(size_t)k] = views[(size_t)(p0 + k)].size; }
+    if ((rc = mvr_set_clouds_device(cc.data(), which.data(), ptr.data(), cnt.data(), P))) return fail(rc, mvr_last_error(ctx_[0]));
   }
   for (int k = 0; k < P; ++k) {
     const int p = p0 + k;

@@ -38,6 +38,19 @@ def pack_reports(reports, p0, p1):
     return out
 
 
+def records_from_reports(reports, p0, p1):
+    """The same from the raw report array of Registrator.register_turntable(raw=True): no per-pair Python objects."""
+    r = reports[p0:p1]
+    out = np.zeros(p1 - p0, dtype=RECORD)
+    out["pose"] = r["pose"]
+    out["n_corr"] = r["n_correspondences"]
+    out["iterations"] = r["iterations"]
+    out["status"] = r["status"]
+    out["mse"] = r["mse"]
+    out["nn_queries"] = r["nn_queries"]
+    return out
+
+
 def unpack_records(rec):
     rec = np.asarray(rec).view(RECORD).reshape(-1)
     return [dict(pose=r["pose"].reshape(4, 4).T.copy(), n_corr=int(r["n_corr"]), mse=float(r["mse"]), iterations=int(r["iterations"]),
@@ -86,8 +99,7 @@ def gather_records(mine, rank, world, n_pairs, dist=None, device=None):
 
 def close_ring(allrec, centre, radius, relax=True, iterations=16):
     """Loop closure over the gathered records (every rank computes the same poses)."""
-    from . import ring_close
-    recs = unpack_records(allrec)
-    rel = [r["pose"] for r in recs]
-    w = [float(r["n_corr"]) if r["status"] == 0 else 0.0 for r in recs]
-    return ring_close(rel, w, relax=relax, iterations=iterations, centre=centre, rot_scale=radius)
+    from . import ring_close_flat
+    rec = np.asarray(allrec).view(RECORD).reshape(-1)
+    w = np.where(rec["status"] == 0, rec["n_corr"].astype(np.float64), 0.0)
+    return ring_close_flat(np.ascontiguousarray(rec["pose"]), w, relax=relax, iterations=iterations, centre=centre, rot_scale=radius)
