@@ -128,14 +128,15 @@ double mvr_debug_value(mvr_ctx* ctx, int k);
 /* Tuning knobs of the spatial index: cell edge (<= 0: automatic) and maximum bits per axis (1..10). */
 int mvr_ctx_set_index_options(mvr_ctx* ctx, float cell_edge, int max_bits);
 
-/* Tuning of mvr_nn_query / mvr_fitness_score: from `dense_ratio` queries per target point on (default 8; 0 = never)
- * the warp-cooperative pass is used, with about `points_per_cell` target points per occupied grid cell (default 8).
+/* Tuning of mvr_nn_query / mvr_fitness_score: large batches are sorted by the cells of a target grid with about
+ * `points_per_cell` target points per occupied cell (default 8).  dense_ratio is kept for compatibility (unused).
  * Results do not depend on either. */
 int mvr_ctx_set_nn_options(mvr_ctx* ctx, double points_per_cell, double dense_ratio);
 /* Which kernel answers mvr_nn_query / mvr_fitness_score (results are identical; a tuning and A/B aid):
- * AUTO = one warp per query up to 131072 queries, the per-thread row walk above (queries sorted by cell from 256k on), the
- * cell-cooperative pass from dense_ratio queries per target point on; WARP / THREAD / CELL force one of them. */
-typedef enum { MVR_NN_AUTO = 0, MVR_NN_WARP = 1, MVR_NN_THREAD = 2, MVR_NN_CELL = 3 } mvr_nn_mode;
+ * AUTO = one warp per query up to 131072 queries, the per-thread row walk up to 262144, above that the queries are sorted by
+ * cell and every query is seeded from its own cell (SEEDED); WARP / THREAD / CELL / SEEDED force one of them (CELL: the
+ * cell-cooperative scan of whole 27-cell neighbourhoods). */
+typedef enum { MVR_NN_AUTO = 0, MVR_NN_WARP = 1, MVR_NN_THREAD = 2, MVR_NN_CELL = 3, MVR_NN_SEEDED = 4 } mvr_nn_mode;
 int mvr_ctx_set_nn_mode(mvr_ctx* ctx, int mode);
 /* Gate mask of the target index (default off): one bit per grid cell, "some target point lies within the gate of this cell".
  * With it a source point without a partner inside the gate is settled by one load instead of a gate-wide search; worth its

@@ -18,7 +18,7 @@ K_NAMES = ["morton", "sort", "table", "nn", "corr", "reduce", "transform", "norm
 K_COUNT = 8
 (OK, ERR_BAD_ARG, ERR_TOO_FEW, ERR_CUDA, ERR_NO_INPUT, ERR_NOT_SPD, ERR_ALLOC, ERR_NCCL) = range(8)
 TARGET, SOURCE = 0, 1
-NN_AUTO, NN_WARP, NN_THREAD, NN_CELL = 0, 1, 2, 3
+NN_AUTO, NN_WARP, NN_THREAD, NN_CELL, NN_SEEDED = 0, 1, 2, 3, 4
 POINT_TO_POINT, POINT_TO_PLANE = 0, 1
 
 
@@ -235,6 +235,7 @@ def lib():
     L.mvr_compute_error.argtypes = [vp, C.POINTER(ViewDesc), C.c_int, C.c_double, C.POINTER(C.c_size_t), dp, C.POINTER(C.c_int)]
     L.mvr_ring_close.argtypes = [fp, dp, C.c_int, C.c_int, C.c_int, dp, C.c_double, fp]
     L.mvr_get_bbox.argtypes = [vp, C.c_int, fp, fp]
+    L.mvr_set_clouds_device.argtypes = [C.POINTER(vp), ip, C.POINTER(vp), C.POINTER(C.c_size_t), C.c_int]
     L.mvr_refine_axis.argtypes = [fp, C.c_int, dp, dp]
     L.mvr_transformation_load.argtypes = [C.c_char_p, dp]
     L.mvr_transformation_save.argtypes = [C.c_char_p, dp]
@@ -374,7 +375,7 @@ class Context:
         self._ck(lib().mvr_ctx_set_nn_options(self._h, float(points_per_cell), float(dense_ratio)))
 
     def set_nn_mode(self, mode):
-        """NN_AUTO / NN_WARP / NN_THREAD / NN_CELL: which kernel answers nn_query (identical results)."""
+        """NN_AUTO / NN_WARP / NN_THREAD / NN_CELL / NN_SEEDED: which kernel answers nn_query (identical results)."""
         self._ck(lib().mvr_ctx_set_nn_mode(self._h, int(mode)))
 
     def set_gate_mask(self, on):
@@ -488,6 +489,15 @@ class Context:
             self._ck(lib().mvr_merge_registered(self._h, ptrs, counts, _dp(P), _ip(reg) if reg is not None else None, V, int(bool(full_matrix_normals)),
                                                 out.ctypes.data, C.byref(total)))
         return out
+
+    def iterations(self):
+        """Per-iteration records of the last align of this context (also after a batched align)."""
+        cnt = C.c_int(0)
+        self._ck(lib().mvr_icp_get_iterations(self._h, None, 0, C.byref(cnt)))
+        recs = (IcpIteration * max(cnt.value, 1))()
+        self._ck(lib().mvr_icp_get_iterations(self._h, recs, cnt.value, C.byref(cnt)))
+        return [dict(iteration=recs[k].iteration, n_corr=recs[k].n_correspondences, mse=recs[k].mse,
+                     delta=pose_to_numpy(recs[k].delta[:])) for k in range(cnt.value)]
 
     def fitness_score(self, max_range=None):
         import sys
@@ -625,6 +635,21 @@ def points_save_asc(path, rich_points):
     rc = lib().mvr_points_save_asc(os.fsencode(path), a.ctypes.data, len(a))
     if rc != OK:
         raise MvrError(rc, "cannot write " + str(path))
+
+
+def set_clouds_device(contexts, which, ptrs, counts, keepalive=None):
+    """mvr_set_clouds_device: contexts[k] adopts the device cloud (ptrs[k], counts[k]) as its TARGET / SOURCE (which[k]); the
+    bounding boxes of all clouds are measured by one launch."""
+    n = len(contexts)
+    hs = (C.c_void_p * n)(*[c._h for c in contexts])
+    w = np.ascontiguousarray(which, dtype=np.int32)
+    pp = (C.c_void_p * n)(*[int(p) for p in ptrs])
+    cc = (C.c_size_t * n)(*[int(x) for x in counts])
+    for k, c in enumerate(contexts):
+        c._keep["tgt" if int(w[k]) == TARGET else "src"] = keepalive
+    rc = lib().mvr_set_clouds_device(hs, _ip(w), pp, cc, n)
+    if rc != OK:
+        raise MvrError(rc, contexts[0].last_error() if n else "")
 
 
 def icp_align_batch(contexts, params, guesses=None):

@@ -111,6 +111,7 @@ struct mvr_ctx {
   double nn_ppc = 8.0;           // its target points per occupied cell
   double nn_dense_ratio = 8.0;   // queries per target point from which the dense pass is used (0: never)
   int nn_mode = MVR_NN_AUTO;     // mvr_ctx_set_nn_mode
+  int nn_sorted_from = 262144;   // AUTO: batches larger than this are sorted by cell and answered by the seeded pass
   bool gate_mask = false;        // mvr_ctx_set_gate_mask
   FwdArgs fa{}; RevArgs ra{};    // kernel arguments of the prepared align
   bool want_rnn = false;         // the next prepared align also records the mutual partners (mvr_correspondences)
@@ -324,7 +325,7 @@ double pair_cell_edge(mvr_ctx* ctx, const Cloud& c, double max_dist);
 
 // Many queries per target point: target and queries counting-sorted by the cells of one row-major grid, then the
 // warp-cooperative scan of cell_nn.cu.
-int nn_pass_dense(mvr_ctx* ctx, const float4* q, int n, int32_t* d_idx, float* d_d2) {
+int nn_pass_dense(mvr_ctx* ctx, const float4* q, int n, int32_t* d_idx, float* d_d2, bool seeded) {
   Cloud& t = ctx->tgt;
   const int mv = t.n - t.n_bad;
   const double e = ctx->cell_edge_opt > 0 ? ctx->cell_edge_opt : density_cell_edge(t.lo, t.hi, mv, ctx->nn_ppc);
@@ -337,16 +338,21 @@ int nn_pass_dense(mvr_ctx* ctx, const float4* q, int n, int32_t* d_idx, float* d
   }
   if ((rc = build_pair_index(ctx, ctx->nq, q, n, 0, nullptr, g, cells, false, false))) return rc;
   ProfScope ps(ctx, MVR_K_NN, 24.0 * n + 16.0 * t.n, (double)n);
-  CK(launch_cell_nn(ctx->nq.sorted.as<float4>(), n, ctx->nq.start.as<uint32_t>() + cells, ctx->nt.sorted.as<float4>(),
-                    ctx->nt.start.as<uint32_t>(), g, mv, d_idx, d_d2, ctx->stream));
+  if (seeded)
+    CK(launch_seeded_nn(ctx->nq.sorted.as<float4>(), n, ctx->nq.start.as<uint32_t>() + cells, ctx->nt.sorted.as<float4>(),
+                        ctx->nt.start.as<uint32_t>(), g, mv, d_idx, d_d2, ctx->stream));
+  else
+    CK(launch_cell_nn(ctx->nq.sorted.as<float4>(), n, ctx->nq.start.as<uint32_t>() + cells, ctx->nt.sorted.as<float4>(),
+                      ctx->nt.start.as<uint32_t>(), g, mv, d_idx, d_d2, ctx->stream));
   return MVR_OK;
 }
 
 // Exact un-gated NN of n device points in the target index; results at the queries' original index.
 int nn_pass(mvr_ctx* ctx, const float4* q, int n, int32_t* d_idx, float* d_d2) {
-  const bool dense = ctx->nn_mode == MVR_NN_CELL ||
-                     (ctx->nn_mode == MVR_NN_AUTO && ctx->nn_dense_ratio > 0 && (double)n >= ctx->nn_dense_ratio * (double)std::max(ctx->tgt.n - ctx->tgt.n_bad, 1));
-  if (dense) return nn_pass_dense(ctx, q, n, d_idx, d_d2);
+  // queries sorted by the cells of the target's grid, then either every query seeded from its own cell (SEEDED; AUTO from
+  // nn_sorted_from queries on) or the cell-cooperative scan of whole neighbourhoods (CELL)
+  if (ctx->nn_mode == MVR_NN_CELL) return nn_pass_dense(ctx, q, n, d_idx, d_d2, false);
+  if (ctx->nn_mode == MVR_NN_SEEDED || (ctx->nn_mode == MVR_NN_AUTO && n > ctx->nn_sorted_from)) return nn_pass_dense(ctx, q, n, d_idx, d_d2, true);
   // The row walk of pair_search.cuh on the target's per-align index: small batches as they come, large ones sorted by
   // cell first (locality).  It also gets through the empty space around far queries quickly, which a cell-by-cell ring
   // expansion does not.
@@ -690,7 +696,7 @@ int mvr_ctx_set_gate_mask(mvr_ctx* ctx, int on) {
 }
 
 int mvr_ctx_set_nn_mode(mvr_ctx* ctx, int mode) {
-  if (!ctx || mode < MVR_NN_AUTO || mode > MVR_NN_CELL) return MVR_ERR_BAD_ARG;
+  if (!ctx || mode < MVR_NN_AUTO || mode > MVR_NN_SEEDED) return MVR_ERR_BAD_ARG;
   ctx->nn_mode = mode;
   return MVR_OK;
 }
@@ -1062,52 +1068,68 @@ static InitJob init_job_of(mvr_ctx* c) {
   return j;
 }
 
+// Pairs per lock-step group of a batch of `count` aligns led by `lead` (see align_run): a quarter of the batch unless
+// mvr_ctx_set_batch_group chose a size.
+static int batch_group_size(const mvr_ctx* lead, int count) {
+  return lead->group_pairs > 0 ? std::min(lead->group_pairs, (int)FUSED_MAX_PAIRS) : std::max(1, std::min((count + 3) / 4, (int)FUSED_MAX_PAIRS));
+}
+
 // Prepare `count` aligns (same device): statuses[k] = the plan's verdict for context k; ok / slot = the contexts that go on
-// and their positions.  All device work -- index builds, seeds, gates, initial states -- is enqueued on the FIRST prepared
-// context's stream with a handful of launches whatever the batch size (24 ring pairs: 48 index builds in 4 launches; one
-// thread spent ~50 us per pair on launch calls alone when every pair prepared itself).
+// and their positions.  The device work -- index builds, seeds, gates, initial states -- of every lock-step GROUP of pairs
+// (align_run) is enqueued on the group's stream with a handful of launches whatever the group size (24 ring pairs in four
+// groups: 48 index builds in 16 launches; one thread spent ~50 us per pair on launch calls alone when every pair prepared
+// itself), so one group's builds overlap the iterations of the groups that started before it.
 static int align_prepare_batch(mvr_ctx* const* ctxs, int count, const mvr_icp_params* prm, const float* guesses, int est, int* statuses,
                                std::vector<mvr_ctx*>& ok, std::vector<int>& slot) {
   ok.clear(); slot.clear();
   if (count <= 0) return MVR_OK;
-  mvr_ctx* lead = ctxs[0];
-  cudaStream_t S = lead->stream;
+  const int gsz0 = batch_group_size(ctxs[0], count);
   std::vector<std::vector<BuildJob>> jobs((size_t)count);
   for (int k = 0; k < count; ++k) if (ensure_pinned(ctxs[k]) != MVR_OK) return MVR_ERR_CUDA;
-  // host side of every pair (grids, buffer checks, initial state): a few threads, no launches
-  parallel_for(count, [&](int k) { statuses[k] = align_plan(ctxs[k], prm, guesses ? guesses + 16 * k : nullptr, est, S, jobs[(size_t)k]); });
-  std::vector<BuildJob> all;
-  for (int k = 0; k < count; ++k) {
-    if (statuses[k] != MVR_OK) continue;
-    ok.push_back(ctxs[k]); slot.push_back(k);
-    all.insert(all.end(), jobs[(size_t)k].begin(), jobs[(size_t)k].end());
-  }
+  // host side of every pair (grids, buffer checks, initial state): a few threads, no launches (first-time zeroing of a
+  // scratch buffer goes to the stream of the group the pair is expected in)
+  parallel_for(count, [&](int k) {
+    statuses[k] = align_plan(ctxs[k], prm, guesses ? guesses + 16 * k : nullptr, est, ctxs[(k / gsz0) * gsz0]->stream, jobs[(size_t)k]);
+  });
+  for (int k = 0; k < count; ++k)
+    if (statuses[k] == MVR_OK) { ok.push_back(ctxs[k]); slot.push_back(k); }
   if (ok.empty()) return MVR_OK;
   mvr_ctx* ctx = ok[0];   // CK() reports into it
-  if (ctx->stream != S) {   // the first context dropped out: keep stream order between the plans' first-time memsets and the builds
-    cudaEvent_t e = ctx->ev_b;
-    CK(cudaEventRecord(e, S));
-    S = ctx->stream;
-    CK(cudaStreamWaitEvent(S, e, 0));
-  }
-  int rc = run_pair_builds(ctx, all.data(), (int)all.size(), S);
-  if (rc) return rc;
   const int P = (int)ok.size();
-  if ((rc = ensure_stage(ctx, P))) return rc;
-  for (int k0 = 0; k0 < P; k0 += BUILD_MAX_JOBS) {
-    const int c = std::min(P - k0, (int)BUILD_MAX_JOBS);
-    InitBatch ib;
-    for (int k = 0; k < c; ++k) {
-      mvr_ctx* m = ok[(size_t)(k0 + k)];
-      ib.j[k] = init_job_of(m);
-      std::memcpy(ctx->h_stage + k0 + k, m->h_state, sizeof(IcpState));
+  const int gsz = batch_group_size(ctx, P);
+  if (P != count || gsz != gsz0) {
+    // a context dropped out: the groups are not the expected ones -- order every group's stream behind every stream a plan
+    // may have used (rare; only first-time zeroing is ever enqueued by a plan)
+    for (int k = 0; k < count; k += gsz0) {
+      cudaEvent_t e = ctxs[k]->ev_b;
+      CK(cudaEventRecord(e, ctxs[k]->stream));
+      for (int g0 = 0; g0 < P; g0 += gsz) CK(cudaStreamWaitEvent(ok[(size_t)g0]->stream, e, 0));
     }
-    CK(cudaMemcpyAsync(ctx->stage_dev.as<IcpState>() + k0, ctx->h_stage + k0, (size_t)c * sizeof(IcpState), cudaMemcpyHostToDevice, S));
-    CK(launch_align_init(ib, c, ctx->stage_dev.as<IcpState>() + k0, S));
   }
-  for (mvr_ctx* m : ok) {
-    if ((rc = ensure_gate_mask(m, m->pt, m->fa.max_d2f, S))) { ctx->err = m->err; return rc; }
-    m->fa.gmask = m->pt.gm_gate >= 0.f ? m->pt.gmask.as<uint32_t>() : nullptr; m->fa.gm_stride = m->pt.gm_stride;
+  int rc = ensure_stage(ctx, P);
+  if (rc) return rc;
+  for (int g0 = 0; g0 < P; g0 += gsz) {
+    const int gn = std::min(gsz, P - g0);
+    cudaStream_t S = ok[(size_t)g0]->stream;
+    std::vector<BuildJob> all;
+    for (int k = 0; k < gn; ++k) { const std::vector<BuildJob>& j = jobs[(size_t)slot[(size_t)(g0 + k)]]; all.insert(all.end(), j.begin(), j.end()); }
+    if ((rc = run_pair_builds(ctx, all.data(), (int)all.size(), S))) return rc;
+    for (int k0 = 0; k0 < gn; k0 += BUILD_MAX_JOBS) {
+      const int c = std::min(gn - k0, (int)BUILD_MAX_JOBS);
+      InitBatch ib;
+      for (int k = 0; k < c; ++k) {
+        mvr_ctx* m = ok[(size_t)(g0 + k0 + k)];
+        ib.j[k] = init_job_of(m);
+        std::memcpy(ctx->h_stage + g0 + k0 + k, m->h_state, sizeof(IcpState));
+      }
+      CK(cudaMemcpyAsync(ctx->stage_dev.as<IcpState>() + g0 + k0, ctx->h_stage + g0 + k0, (size_t)c * sizeof(IcpState), cudaMemcpyHostToDevice, S));
+      CK(launch_align_init(ib, c, ctx->stage_dev.as<IcpState>() + g0 + k0, S));
+    }
+    for (int k = 0; k < gn; ++k) {
+      mvr_ctx* m = ok[(size_t)(g0 + k)];
+      if ((rc = ensure_gate_mask(m, m->pt, m->fa.max_d2f, S))) { ctx->err = m->err; return rc; }
+      m->fa.gmask = m->pt.gm_gate >= 0.f ? m->pt.gmask.as<uint32_t>() : nullptr; m->fa.gm_stride = m->pt.gm_stride;
+    }
   }
   return MVR_OK;
 }
@@ -1125,8 +1147,7 @@ static int align_run(mvr_ctx* const* ctxs, int count, const mvr_icp_params* prm,
   // between its dependent launches are filled by the others.  Measured on B200 (scripts/gpu_streams_vs_batch.py,
   // profiles/r02_concurrent_groups.log): 24 pairs 22.5 ms as one group, 20.6-20.8 ms as 2 .. 8 groups; 12 pairs 12.1 -> 10.5 ms;
   // 3 pairs 4.05 -> 3.3 ms.  Default: four groups (a group size set with mvr_ctx_set_batch_group is kept).
-  const int gsz = ctx->group_pairs > 0 ? std::min(ctx->group_pairs, (int)FUSED_MAX_PAIRS)
-                                       : std::max(1, std::min((count + 3) / 4, (int)FUSED_MAX_PAIRS));
+  const int gsz = batch_group_size(ctx, count);
   struct Group {
     int g0, gn, gf, gr, enqueued, first;
     bool done, fetched;
@@ -1135,6 +1156,13 @@ static int align_run(mvr_ctx* const* ctxs, int count, const mvr_icp_params* prm,
     FwdBatch fb;
     RevBatch rb;
   };
+  // Source points per thread of the reciprocal forward half.  Measured on B200 (registration of 24 / 12 / 6 / 3 pairs of 200k
+  // points, ms): 1 point 21.4 / 10.84 / 5.75 / 3.85, 2 points 20.3 / 10.44 / 5.63 / 3.90, 4 points 19.85 / 10.26 / 5.77 / 4.37,
+  // 8 points 19.85, 16 points 20.1 -- about one point per 600k source points of the batch, at most four.
+  long long batch_points = 0;
+  for (int k = 0; k < count; ++k) batch_points += ctxs[k]->fa.n_valid;
+  static const int fwd_items_env = [] { const char* e = std::getenv("MVR_FWD_ITEMS"); return e ? std::atoi(e) : 0; }();
+  const int fwd_items = fwd_items_env > 0 ? fwd_items_env : (int)std::min<long long>(4, std::max<long long>(1, (batch_points + 300000) / 600000));
   std::vector<Group> groups;
   for (int g0 = 0; g0 < count; g0 += gsz) {
     Group g{};
@@ -1143,18 +1171,25 @@ static int align_run(mvr_ctx* const* ctxs, int count, const mvr_icp_params* prm,
     for (int k = 0; k < g.gn; ++k) {
       mvr_ctx* c = ctxs[g0 + k];
       g.fb.a[k] = c->fa; g.rb.a[k] = c->ra;
-      g.gf = std::max(g.gf, c->fa.grid); g.gr = std::max(g.gr, c->ra.grid);
+      // the reciprocal forward half sums nothing, so its block partition is free to follow the load: with enough pairs to fill
+      // the GPU several times over a thread takes `fwd_items` source points (fewer blocks, the per-block set-up amortised)
+      if (reciprocal && fwd_items > 1) g.fb.a[k].grid = std::max(1, (c->fa.n_valid + FUSED_THREADS * fwd_items - 1) / (FUSED_THREADS * fwd_items));
+      g.gf = std::max(g.gf, g.fb.a[k].grid); g.gr = std::max(g.gr, c->ra.grid);
       if (!c->h_state->done) g.done = false;
       g.n_tot += c->src.n; g.m_tot += c->tgt.n;
     }
     groups.push_back(g);
   }
-  // the preparation of the whole batch (index builds, initial states) ran on the lead's stream: ev_a orders every group behind it
-  if (ctx->profiling) CK(cudaStreamSynchronize(ctx->stream));   // a clean bracket for the roofline measurement
+  // every group's preparation (index builds, initial states) was enqueued on the group's own stream (align_prepare_batch)
   int rc0 = ensure_stage(ctx, count);
   if (rc0) return rc0;
-  CK(cudaEventRecord(ctx->ev_a, ctx->stream));
-  for (size_t gi = 1; gi < groups.size(); ++gi) CK(cudaStreamWaitEvent(groups[gi].lead->stream, ctx->ev_a, 0));
+  if (ctx->profiling) {   // a clean bracket for the roofline measurement: no build inside ev_a .. ev_b
+    for (Group& g : groups) CK(cudaStreamSynchronize(g.lead->stream));
+    CK(cudaEventRecord(ctx->ev_a, ctx->stream));
+    for (size_t gi = 1; gi < groups.size(); ++gi) CK(cudaStreamWaitEvent(groups[gi].lead->stream, ctx->ev_a, 0));
+  } else {
+    CK(cudaEventRecord(ctx->ev_a, ctx->stream));
+  }
   // staged states of a group -> its contexts (after the group's stream has been synchronised)
   auto unpack = [&](Group& g) {
     if (g.fetched) return;

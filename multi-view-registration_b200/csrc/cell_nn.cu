@@ -250,6 +250,66 @@ __global__ void __launch_bounds__(WN_THREADS, 4) k_warp_nn(const float4* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cell-sorted queries, one thread per query, SEEDED: the fused ICP iteration's search (pair_search.cuh) owes its speed to a
+// seed -- a real candidate near the query, so that the ball that provably holds the answer is about a cell wide.  Un-gated
+// queries have no previous iteration to take one from; sorted by cell they get one almost for free:
+//   1. every query scans the target points of ITS OWN cell (one table load pair, a handful of candidates);
+//   2. a query whose cell holds no target point (it sits beside the surface) borrows the best candidate of the nearest lane
+//      of its warp that has one -- the lanes of a warp are neighbours in cell order, and ANY real candidate is a valid seed;
+//   3. the seeded ball walk finishes the query exactly (lanes still without a seed start from the growing cube).
+// Against the cell-cooperative pass above (which evaluates the whole 27-cell neighbourhood, ~100 candidates per query) a
+// query evaluates ~30; against the unseeded per-thread walk it skips the 27-cell first cube.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FUSED_THREADS, 4) k_seeded_nn(const float4* __restrict__ q, int nq, const uint32_t* __restrict__ q_valid,
+                                                                const float4* __restrict__ tgt, const uint32_t* __restrict__ tstart, PairGrid g,
+                                                                int m_valid, int32_t* __restrict__ out_idx, float* __restrict__ out_d2) {
+  __shared__ uint2 s_seg[PG_SEGS * PG_STRIDE];
+  const int i = blockIdx.x * FUSED_THREADS + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int nq_valid = (int)__ldg(q_valid);
+  const float far2 = 4.0f / (g.inv_cell * g.inv_cell);   // (two cell edges)^2
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < nq) p = __ldg(q + i);
+  const bool fin = i < nq_valid && m_valid > 0;
+  NnBest b{MVR_INF, 0x7fffffff, -1};
+  if (fin) {
+    const int cx = pg_cell(grid_t(p.x, g.ox, g.inv_cell_x), g.nx), cy = pg_cell(grid_t(p.y, g.oy, g.inv_cell), g.ny),
+              cz = pg_cell(grid_t(p.z, g.oz, g.inv_cell), g.nz);
+    const uint32_t* row = tstart + ((size_t)cz * g.ny + cy) * g.nx;
+    pg_scan(tgt, __ldg(row + cx), __ldg(row + cx + 1), p.x, p.y, p.z, b);
+  }
+  const unsigned int have = __ballot_sync(0xffffffffu, fin && b.pos >= 0);
+  const unsigned int need = __ballot_sync(0xffffffffu, fin && b.pos < 0);
+  if (need && have) {
+    const unsigned int below = have & ((1u << lane) - 1u), above = lane < 31 ? (have & ~((2u << lane) - 1u)) : 0u;
+    const int lo = below ? 31 - __clz((int)below) : -1, hi = above ? __ffs((int)above) - 1 : -1;
+    const int src = lo < 0 ? hi : (hi < 0 ? lo : (lane - lo <= hi - lane ? lo : hi));
+    const int spos = __shfl_sync(0xffffffffu, b.pos, src < 0 ? lane : src);
+    if (fin && b.pos < 0 && spos >= 0) {
+      const float4 t = __ldg(tgt + spos);
+      const float d = d2_pinned(p.x, p.y, p.z, t.x, t.y, t.z);
+      // a far seed is worse than none: the ball walk visits every row inside its radius, the growing cube stops at the first
+      // cube that holds a point (lanes at the end of a row sit next to lanes of another row)
+      if (d <= far2) { b.d2 = d; b.idx = __float_as_int(t.w); b.pos = spos; }
+    }
+  }
+  if (fin) pg_search<8>(g, tstart, tgt, m_valid, p.x, p.y, p.z, p.x, p.y, p.z, 0.0f, 1.0f, MVR_INF, b, s_seg + threadIdx.x);
+  if (i < nq) {
+    const int o = __float_as_int(p.w);
+    out_idx[o] = b.pos >= 0 ? b.idx : -1;
+    out_d2[o] = b.pos >= 0 ? b.d2 : MVR_INF;
+  }
+}
+
+cudaError_t launch_seeded_nn(const float4* q_sorted, int nq, const uint32_t* d_nq_valid, const float4* tgt_sorted, const uint32_t* tstart, PairGrid g,
+                             int m_valid, int32_t* out_idx, float* out_d2, cudaStream_t s) {
+  if (nq <= 0) return cudaSuccess;
+  k_seeded_nn<<<(nq + FUSED_THREADS - 1) / FUSED_THREADS, FUSED_THREADS, 0, s>>>(q_sorted, nq, d_nq_valid, tgt_sorted, tstart, g, m_valid, out_idx, out_d2);
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_warp_nn(const float4* q, int n, const float4* tgt_sorted, const uint32_t* tstart, PairGrid g, int m_valid, int32_t* out_idx,
                            float* out_d2, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;

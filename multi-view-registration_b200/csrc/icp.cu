@@ -30,7 +30,7 @@
 #define MVR_REV_MINBLOCKS 4
 #endif
 #ifndef MVR_PG_UNROLL
-#define MVR_PG_UNROLL 8
+#define MVR_PG_UNROLL 6
 #endif
 
 namespace mvr {

@@ -226,6 +226,11 @@ cudaError_t launch_merge_rich(const void* in48, int n, const double* M16, int fu
 cudaError_t launch_cell_nn(const float4* q_sorted, int nq, const uint32_t* d_nq_valid, const float4* tgt_sorted, const uint32_t* tstart,
                            PairGrid g, int m_valid, int32_t* out_idx, float* out_d2, cudaStream_t s);
 
+// The same queries (sorted by the cells of g, finite ones first), one thread per query, seeded from the query's own cell or a
+// neighbouring lane (cell_nn.cu).  Results by original index.
+cudaError_t launch_seeded_nn(const float4* q_sorted, int nq, const uint32_t* d_nq_valid, const float4* tgt_sorted, const uint32_t* tstart,
+                             PairGrid g, int m_valid, int32_t* out_idx, float* out_d2, cudaStream_t s);
+
 // Exact un-gated 1-NN of queries in ANY order, one warp per query (small or sparse batches).  Results in query order.
 cudaError_t launch_warp_nn(const float4* q, int n, const float4* tgt_sorted, const uint32_t* tstart, PairGrid g, int m_valid, int32_t* out_idx,
                            float* out_d2, cudaStream_t s);

@@ -11,9 +11,10 @@ _, qm = synth.nn_sweep_case(m, 16_000_000, order="morton")
 ctx.set_target(tgt)
 for order, qq in (("random", q), ("morton", qm)):
     tq = torch.from_numpy(qq).cuda(); ti = torch.empty(len(qq), dtype=torch.int32, device="cuda"); td = torch.empty(len(qq), dtype=torch.float32, device="cuda")
-    for nq in (10_000, 100_000, 1_000_000, 4_000_000, 16_000_000):
+    for nq in [int(x) for x in os.environ.get("MVR_NQ", "10000,100000,1000000,4000000,16000000").split(",")]:
         ref = None
-        for mode, ppc in (("WARP", 8), ("THREAD", 8), ("CELL", 8), ("CELL", 4), ("CELL", 3), ("CELL", 2)):
+        for mode, ppc in (("WARP", 8), ("THREAD", 8), ("CELL", 8), ("SEEDED", 16), ("SEEDED", 8), ("SEEDED", 4), ("SEEDED", 2)):
+            if mode == "WARP" and nq > 1_000_000: continue
             ctx.set_nn_mode(getattr(mvr_b200, "NN_" + mode)); ctx.set_nn_options(ppc, 8.0)
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             best = 1e9

@@ -261,9 +261,9 @@ def test_pair_moments_without_correspondences(ctx, mvr):
     assert m.n == 0 and m.d2 == 0
 
 
-@pytest.mark.parametrize("mode", ["WARP", "THREAD", "CELL"])
+@pytest.mark.parametrize("mode", ["WARP", "THREAD", "CELL", "SEEDED"])
 def test_nn_every_kernel_bit_exact(mvr, orc, synth, mode):
-    """The three NN kernels (one warp per query, per-thread row walk, cell-cooperative) against the oracle: queries near the
+    """The four NN kernels (one warp per query, per-thread row walk, cell-cooperative, cell-sorted and seeded) against the oracle: queries near the
     surface, far from the cloud (tens of cells of empty space), outside the grid, non-finite, and exact ties."""
     c = mvr.Context(0)
     c.set_nn_mode(getattr(mvr, "NN_" + mode))
@@ -359,6 +359,43 @@ def test_icp_gate_mask_changes_nothing(mvr, orc, synth):
         assert [x["n_corr"] for x in a["log"]] == [x["n_corr"] for x in b["log"]] and np.array_equal(a["final"], b["final"]) and a["mse"] == b["mse"]
         o = orc.icp_align(src, tgt, orc.make_params(max_iterations=8, max_dist=max_dist, reciprocal=bool(recip), fixed_iterations=True), guess=guess)
         assert [x["n_corr"] for x in b["log"]] == [x["n_corr"] for x in o["log"]]
+
+
+def test_set_clouds_device_equals_per_cloud_calls(mvr, synth):
+    """mvr_set_clouds_device (every bounding box from one launch) leaves the contexts exactly as mvr_set_target_device /
+    mvr_set_source_device do: the same aligns come out bit for bit, non-finite points and an empty cloud included; the
+    iteration log and the aligned cloud, produced on demand, belong to the right align."""
+    import torch
+    clouds, ptrs = [], []
+    for k in range(4):
+        p, _ = synth.turntable_view(k, 12, 9_000 + 1_000 * k)
+        if k == 1:
+            p[5, 0] = np.nan; p[77, 2] = np.inf
+        clouds.append(torch.from_numpy(p).cuda())
+    empty = torch.zeros((0, 4), dtype=torch.float32, device="cuda")
+    prm = mvr.default_params(max_iterations=6, max_dist=4.0, reciprocal=1, fixed_iterations=1)
+    guesses = [(synth.perturbation() @ np.linalg.inv(synth.view_pose(k, 12)) @ synth.view_pose(k + 1, 12)).astype(np.float32) for k in range(3)]
+    a = [mvr.Context(0) for _ in range(3)]
+    b = [mvr.Context(0) for _ in range(3)]
+    for k in range(3):
+        a[k].set_target_device(clouds[k].data_ptr(), len(clouds[k]))
+        a[k].set_source_device(clouds[k + 1].data_ptr(), len(clouds[k + 1]))
+    mvr.set_clouds_device(b + b, [mvr.TARGET] * 3 + [mvr.SOURCE] * 3, [clouds[k].data_ptr() for k in range(3)] + [clouds[k + 1].data_ptr() for k in range(3)],
+                          [len(clouds[k]) for k in range(3)] + [len(clouds[k + 1]) for k in range(3)])
+    ra = [a[k].icp_align(prm, guess=guesses[k], n_source=len(clouds[k + 1])) for k in range(3)]
+    rb = mvr.icp_align_batch(b, prm, guesses)
+    for k in range(3):
+        assert ra[k]["status"] == rb[k]["status"] == 0
+        assert np.array_equal(ra[k]["final"], rb[k]["final"]) and ra[k]["n_corr"] == rb[k]["n_corr"] and ra[k]["mse"] == rb[k]["mse"]
+        la, lb = ra[k]["log"], b[k].iterations()
+        assert len(la) == len(lb) == 6
+        assert all(x["n_corr"] == y["n_corr"] and x["mse"] == y["mse"] and np.array_equal(x["delta"], y["delta"]) for x, y in zip(la, lb))
+        assert b[k].fitness_score() == a[k].fitness_score()
+    # an empty cloud through the batched call
+    mvr.set_clouds_device([b[0]], [mvr.SOURCE], [empty.data_ptr() or 0], [0])
+    assert mvr.icp_align_batch(b[:1], prm, guesses[:1])[0]["status"] == mvr.ERR_NO_INPUT
+    for c in a + b:
+        c.close()
 
 
 def test_icp_align_batch_equals_separate_aligns(mvr, synth):
