@@ -328,12 +328,48 @@ __device__ __forceinline__ void acc_p2l(double (&v)[REDUCE_P2L_VALS], float4 s, 
   v[28] += (double)d2;
 }
 
+// block_reduce_store + last_block_done in one: the block's partial is written, fenced and the ticket drawn by warp 0 alone
+// (the threads that wrote are the ones that fence), so the block's tail is two barriers instead of three and seven warps
+// skip the memory fence.  Same sums in the same order.
+template <int NV>
+__device__ __forceinline__ bool block_reduce_ticket(double (&v)[NV], double* __restrict__ partials, unsigned int* ticket, unsigned int nblk) {
+  __shared__ double sm[FUSED_WARPS][NV];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int a = 0; a < NV; ++a) {
+    double x = v[a];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) sm[warp][a] = x;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    static_assert(NV <= 32, "one warp writes the partial");
+    if (lane < NV) {
+      double x = 0;
+#pragma unroll
+      for (int w = 0; w < FUSED_WARPS; ++w) x += sm[w][lane];
+      partials[(size_t)blockIdx.x * REDUCE_MAX_VALS + lane] = x;
+      __threadfence();
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const unsigned int t = atomicAdd(ticket, 1u);
+      is_last = (t == nblk - 1);
+      if (is_last) *ticket = 0;
+    }
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
 // Block partials -> (last block) ordered total -> solve, compose, criteria.
 template <int NV>
 __device__ __forceinline__ void reduce_and_finish(double (&v)[NV], double* __restrict__ partials, IcpState* __restrict__ st,
                                                   IterRec* __restrict__ log, int nblk) {
-  block_reduce_store<NV, FUSED_WARPS>(v, partials);
-  if (!last_block_done(&st->ticket, (unsigned int)nblk)) return;
+  if (!block_reduce_ticket<NV>(v, partials, &st->ticket, (unsigned int)nblk)) return;
   ordered_total<NV>(partials, nblk, st->sums);
   if (threadIdx.x == 0) {
     const long long t0 = clock64();
