@@ -436,7 +436,8 @@ def run_native(a):
                 "achieved_without_reindex_bytes": ach_lean, "frac_without_reindex_bytes": ach_lean / peak,
                 "share_of_step": iter_ms / (ms / a.steps) if ms > 0 else None,
                 "pairs_per_launch": group,
-                "per_kernel_ms": {k: round(v["ms"], 4) for k, v in st.items() if v["launches"] and k != "corr"}}
+                "per_kernel_ms": {k: round(v["ms"], 4) for k, v in st.items() if v["launches"] and k != "corr"},
+                "per_kernel_ms_note": "CUDA-event spans of the concurrent groups of pairs, summed (index builds: each group's four launches on its own stream)"}
 
     # ---- accuracy summary (parity itself lives in tests/) ----
     acc = None

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -1149,7 +1150,7 @@ static int align_run(mvr_ctx* const* ctxs, int count, const mvr_icp_params* prm,
   // 3 pairs 4.05 -> 3.3 ms.  Default: four groups (a group size set with mvr_ctx_set_batch_group is kept).
   const int gsz = batch_group_size(ctx, count);
   struct Group {
-    int g0, gn, gf, gr, enqueued, first;
+    int g0, gn, gf, gr, enqueued, first, todo;
     bool done, fetched;
     long long n_tot, m_tot;
     mvr_ctx* lead;
@@ -1207,24 +1208,35 @@ static int align_run(mvr_ctx* const* ctxs, int count, const mvr_icp_params* prm,
   int batch = prm->fixed_iterations ? 64 : 2;
   for (;;) {
     bool any = false;
+    // The launches of the groups are enqueued ROUND-ROBIN, one iteration of every group at a time: a launch call costs the host
+    // ~5 us, so enqueueing one group's 60 launches first would start the next group 0.3 ms late (3 pairs on 3 streams: 105 us
+    // per iteration instead of ~80).
+    int todo_max = 0;
+    std::vector<std::unique_ptr<ProfScope>> scopes;
     for (Group& g : groups) {
+      g.todo = 0;
       if (g.done) continue;
       any = true;
-      const int todo = std::min(batch, std::max(prm->max_iterations - g.enqueued, 1));
-      {
-        // one scope = `todo` iterations: forward search (+ transform), reciprocal search (+ sums, solve, criteria) each.
-        // Bytes per iteration as SURVEY.md section 8d counts them: every source and target point once (16 B each); with
-        // reciprocal correspondences the source re-index PCL performs per iteration (36 B per source point) and the reverse
-        // pass (16 B per source point) -- cell-table entries not counted.
-        const double per_it = 16.0 * g.n_tot + 16.0 * g.m_tot + (reciprocal ? 52.0 * g.n_tot : 0.0);
-        ProfScope ps(g.lead, MVR_K_CORR, per_it * todo, (double)g.n_tot * todo, todo);
-        for (int it = 0; it < todo; ++it) {
-          CK(launch_icp_forward(g.fb, g.gn, g.gf, g.first, reciprocal, est, g.lead->stream));
-          g.first = 0;
-          if (reciprocal) CK(launch_icp_reverse(g.rb, g.gn, g.gr, est, g.lead->stream));
-        }
+      g.todo = std::min(batch, std::max(prm->max_iterations - g.enqueued, 1));
+      todo_max = std::max(todo_max, g.todo);
+      // one scope = `todo` iterations: forward search (+ transform), reciprocal search (+ sums, solve, criteria) each.
+      // Bytes per iteration as SURVEY.md section 8d counts them: every source and target point once (16 B each); with
+      // reciprocal correspondences the source re-index PCL performs per iteration (36 B per source point) and the reverse
+      // pass (16 B per source point) -- cell-table entries not counted.
+      const double per_it = 16.0 * g.n_tot + 16.0 * g.m_tot + (reciprocal ? 52.0 * g.n_tot : 0.0);
+      scopes.emplace_back(new ProfScope(g.lead, MVR_K_CORR, per_it * g.todo, (double)g.n_tot * g.todo, g.todo));
+    }
+    for (int it = 0; it < todo_max; ++it)
+      for (Group& g : groups) {
+        if (it >= g.todo) continue;
+        CK(launch_icp_forward(g.fb, g.gn, g.gf, g.first, reciprocal, est, g.lead->stream));
+        g.first = 0;
+        if (reciprocal) CK(launch_icp_reverse(g.rb, g.gn, g.gr, est, g.lead->stream));
       }
-      g.enqueued += todo;
+    scopes.clear();   // closes the brackets (each on its group's stream)
+    for (Group& g : groups) {
+      if (g.todo == 0) continue;
+      g.enqueued += g.todo;
       // the group's states come back together: one gather launch, one copy
       for (int k0 = 0; k0 < g.gn; k0 += BUILD_MAX_JOBS) {
         const int c = std::min(g.gn - k0, (int)BUILD_MAX_JOBS);
