@@ -69,6 +69,9 @@ def pose_checksum(allrec):
     return h.hexdigest()[:16]
 
 
+_GATHER_CACHE = {}
+
+
 def gather_records(mine, rank, world, n_pairs, dist=None, device=None):
     """All-gather the per-pair records: `mine` = the (p1 - p0) RECORDs of this rank -> n_pairs RECORDs on every rank.
     `dist` = torch.distributed (initialised) when world > 1."""
@@ -78,6 +81,27 @@ def gather_records(mine, rank, world, n_pairs, dist=None, device=None):
         return mine
     import torch
     block = max(pair_range(r, world, n_pairs)[1] - pair_range(r, world, n_pairs)[0] for r in range(world))
+    if device is not None and str(device).startswith("cuda") and hasattr(dist, "all_gather_into_tensor"):
+        # NCCL: staging buffers made once (pinned on the host), one copy in, one exchange, one copy out
+        key = (world, n_pairs, str(device))
+        c = _GATHER_CACHE.get(key)
+        if c is None:
+            c = dict(h_in=torch.zeros(block * REC, dtype=torch.uint8).pin_memory(), d_in=torch.zeros(block * REC, dtype=torch.uint8, device=device),
+                     d_out=torch.empty(world * block * REC, dtype=torch.uint8, device=device),
+                     h_out=torch.empty(world * block * REC, dtype=torch.uint8).pin_memory())
+            _GATHER_CACHE[key] = c
+        flat = mine.view(np.uint8).reshape(-1)
+        c["h_in"].numpy()[:flat.size] = flat
+        c["d_in"].copy_(c["h_in"], non_blocking=True)
+        dist.all_gather_into_tensor(c["d_out"], c["d_in"])
+        c["h_out"].copy_(c["d_out"], non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+        host = c["h_out"].numpy().reshape(world, block * REC)
+        rows = []
+        for r in range(world):
+            a, b = pair_range(r, world, n_pairs)
+            rows.append(host[r, :(b - a) * REC].copy().view(RECORD))
+        return np.concatenate(rows, axis=0)
     pad = torch.zeros(block * REC, dtype=torch.uint8)
     flat = torch.from_numpy(mine.view(np.uint8).reshape(-1).copy())
     pad[:flat.numel()] = flat

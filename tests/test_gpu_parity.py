@@ -426,6 +426,14 @@ def test_icp_align_batch_equals_separate_aligns(mvr, synth):
             assert np.array_equal(got[k]["final"], one["final"]) and got[k]["mse"] == one["mse"]
     iters = [g["iterations"] for k, g in enumerate(got) if sizes[k]]
     assert all(1 <= it <= 25 for it in iters)
+    # the FIRST context of a batch drops out (empty source): the rest regroups and still equals the separate aligns
+    order = [3, 0, 1, 2, 4]
+    prm = mvr.default_params(max_iterations=7, max_dist=4.0, reciprocal=1, fixed_iterations=1)
+    got = mvr.icp_align_batch([ctxs[k] for k in order], prm, [guesses[k] for k in order])
+    assert got[0]["status"] == mvr.ERR_NO_INPUT
+    for j, k in enumerate(order[1:], start=1):
+        one = ctxs[k].icp_align(prm, guess=guesses[k], n_source=sizes[k])
+        assert got[j]["status"] == one["status"] == 0 and np.array_equal(got[j]["final"], one["final"]) and got[j]["n_corr"] == one["n_corr"]
     for c in ctxs:
         c.close()
 
