@@ -29,7 +29,6 @@ struct KnnList {
   float wd; int wid;
   __device__ __forceinline__ void rescan() {
     worst = 0; wd = d[0]; wid = id[0];
-#pragma unroll 4
     for (int a = 1; a < k; ++a) {
       const float da = d[a * KN_THREADS]; const int ia = id[a * KN_THREADS];
       if (lex_less(wd, wid, da, ia)) { worst = a; wd = da; wid = ia; }
@@ -76,28 +75,13 @@ __global__ void __launch_bounds__(KN_THREADS) k_normals(const float4* __restrict
       L.push(d2_pinned(q.x, q.y, q.z, p.x, p.y, p.z), __float_as_int(p.w), (int)a);
     }
   };
-  // The 3 x 3 x 3 block, NEAREST rows first (the point's own row, the four rows sharing a face with it, the four diagonal ones):
-  // the list fills with near candidates early and most of the later ones fail the single comparison with its worst member
-  // (every accepted candidate costs a rescan of the list: in arbitrary order ~36 of ~55 candidates are accepted at some point).
-  {
-    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
-    const int order[9] = {4, 1, 3, 5, 7, 0, 2, 6, 8};
-#pragma unroll
-    for (int o = 0; o < 9; ++o) {
-      const int y = cy + order[o] % 3 - 1, z = cz + order[o] / 3 - 1;
-      if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
-      const uint32_t* row = start + ((size_t)z * g.ny + y) * g.nx;
-      scan(__ldg(row + x0), __ldg(row + x1 + 1));
-    }
-  }
   for (int h = 1;; ++h) {
-    // the shell between the cubes of half-width h - 1 and h (the block of h = 1 has been scanned above)
+    // the shell between the cubes of half-width h - 1 and h (h = 1: the whole 3 x 3 x 3 block)
     const int x0 = max(cx - h, 0), x1 = min(cx + h, g.nx - 1);
-    if (h > 1)
     for (int z = max(cz - h, 0); z <= min(cz + h, g.nz - 1); ++z)
       for (int y = max(cy - h, 0); y <= min(cy + h, g.ny - 1); ++y) {
         const uint32_t* row = start + ((size_t)z * g.ny + y) * g.nx;
-        const bool face = z == cz - h || z == cz + h || y == cy - h || y == cy + h;
+        const bool face = h == 1 || z == cz - h || z == cz + h || y == cy - h || y == cy + h;
         if (face) {
           scan(__ldg(row + x0), __ldg(row + x1 + 1));
         } else {   // an inner row: only its two end cells are new
