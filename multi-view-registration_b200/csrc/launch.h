@@ -134,7 +134,6 @@ enum { BUILD_MAX_JOBS = 48 };
 struct BuildBatch { BuildJob j[BUILD_MAX_JOBS]; };
 cudaError_t launch_pair_builds(const BuildBatch& batch, int count, cudaStream_t s);
 cudaError_t launch_scan_cells_batch(const BuildBatch& batch, int count, int max_tiles, cudaStream_t s);
-cudaError_t launch_fill_u32(uint32_t* p, size_t n, uint32_t v, cudaStream_t s);
 // Gate mask of an index (pair_index.cu): occ and mask hold ny * nz * wstride words, wstride = ceil(nx / 32); D / Dx = dilation in
 // y-z / x cells.
 cudaError_t launch_gate_mask(const uint32_t* start, PairGrid g, int wstride, int D, int Dx, uint32_t* occ, uint32_t* mask, cudaStream_t s);

@@ -136,18 +136,6 @@ cudaError_t launch_gate_mask(const uint32_t* start, PairGrid g, int wstride, int
   return cudaGetLastError();
 }
 
-__global__ void k_fill_u32(uint32_t* __restrict__ p, size_t n, uint32_t v) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
-}
-
-cudaError_t launch_fill_u32(uint32_t* p, size_t n, uint32_t v, cudaStream_t s) {
-  if (n == 0) return cudaSuccess;
-  const size_t want = (n + 255) / 256;
-  const int blocks = (int)(want < (size_t)(148 * 8) ? want : (size_t)(148 * 8));
-  k_fill_u32<<<blocks, 256, 0, s>>>(p, n, v); count_launch();
-  return cudaGetLastError();
-}
-
 // The four phases of `count` index builds (<= BUILD_MAX_JOBS) on stream s.
 cudaError_t launch_pair_builds(const BuildBatch& batch, int count, cudaStream_t s) {
   if (count <= 0) return cudaSuccess;
