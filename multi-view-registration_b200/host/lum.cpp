@@ -205,9 +205,10 @@ int ringClose(const std::vector<Matrix4d>& rel_in, const std::vector<double>& we
   // With vertex 0 fixed the ring's unknowns 1 .. V-1 form a CHAIN (the edges 0 -> 1 and V-1 -> 0 touch one unknown
   // each): the normal equations are block tridiagonal with 6 x 6 blocks, half bandwidth 11.
   const int band = 11;
-  std::vector<double> H((size_t)n * n, 0.0), g((size_t)n, 0.0), Hd, gd;
+  // (dense row-major storage, but only the band is ever cleared, copied or read: 23 of 138 columns per row for 24 views)
+  std::vector<double> H((size_t)n * n, 0.0), g((size_t)n, 0.0), Hd((size_t)n * n, 0.0), gd;
   for (int it = 0; it < iterations; ++it) {
-    std::fill(H.begin(), H.end(), 0.0);
+    for (int i = 0; i < n; ++i) std::fill(H.begin() + (size_t)i * n + std::max(0, i - band), H.begin() + (size_t)i * n + std::min(n - 1, i + band) + 1, 0.0);
     std::fill(g.begin(), g.end(), 0.0);
     double cost = 0;
     for (int p = 0; p < V; ++p) {
@@ -258,8 +259,12 @@ int ringClose(const std::vector<Matrix4d>& rel_in, const std::vector<double>& we
     if (!(dmax > 0) || !std::isfinite(dmax)) break;
     bool solved = false;
     for (double lambda = 1e-12 * dmax; lambda <= 1e3 * dmax; lambda *= 1e3) {
-      Hd = H; gd = g;
-      for (int i = 0; i < n; ++i) Hd[(size_t)i * n + i] += lambda;
+      gd = g;
+      for (int i = 0; i < n; ++i) {   // the factorisation reads the lower band only
+        const size_t lo = (size_t)i * n + std::max(0, i - band), hi = (size_t)i * n + i + 1;
+        std::copy(H.begin() + lo, H.begin() + hi, Hd.begin() + lo);
+        Hd[(size_t)i * n + i] += lambda;
+      }
       if (chol_solve(Hd, gd, n, band)) { g.swap(gd); solved = true; break; }
     }
     if (!solved) return MVR_ERR_NOT_SPD;
