@@ -127,6 +127,20 @@ def test_pack_unpack_records_and_pair_ranges(mvr):
     back = ring.unpack_records(ring.pack_reports(reps, 2, 5))
     assert [b["n_corr"] for b in back] == [102, 103, 104] and back[0]["nn_queries"] == (1 << 30) + 2
     assert np.array_equal(back[1]["pose"], (np.eye(4) * 4).astype(np.float32))
+    # the raw path (numpy view of the C report array, no per-pair Python objects) packs the same bytes, and the ring closes
+    # the same from either
+    raw = np.zeros(6, dtype=mvr.REPORT)
+    rng = np.random.default_rng(3)
+    for p in range(6):
+        T = np.eye(4, dtype=np.float32); T[:3, 3] = rng.normal(size=3)
+        reps[p]["pose"] = T
+        raw[p]["pose"] = mvr.pose_from_numpy(T); raw[p]["n_correspondences"] = reps[p]["n_corr"]; raw[p]["mse"] = reps[p]["mse"]
+        raw[p]["iterations"] = 30; raw[p]["status"] = 0; raw[p]["nn_queries"] = reps[p]["nn_queries"]
+    a, b = ring.pack_reports(reps, 1, 6), ring.records_from_reports(raw, 1, 6)
+    assert a.tobytes() == b.tobytes() and ring.pose_checksum(a) == ring.pose_checksum(b)
+    flat = ring.close_ring(ring.pack_reports(reps, 0, 6), [0.0, 0.0, 0.0], 100.0)
+    listed = mvr.ring_close([r["pose"] for r in reps], [float(r["n_corr"]) for r in reps], centre=[0.0, 0.0, 0.0], rot_scale=100.0)
+    assert all(np.array_equal(x, y) for x, y in zip(flat, listed))
 
 
 WORKER = r"""
