@@ -23,7 +23,7 @@
 
 // x cells per y/z cell edge of the per-align indices of the fused ICP iteration (pair_search.cuh); measured in DESIGN.md section 7
 #ifndef MVR_PG_XRATIO
-#define MVR_PG_XRATIO 2
+#define MVR_PG_XRATIO 4
 #endif
 
 using namespace mvr;
