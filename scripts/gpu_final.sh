@@ -9,7 +9,7 @@ python -m pytest tests -m gpu -x -q 2>&1 | tail -6 | tee gpurun_out/${TAG}_pytes
 python __graft_entry__.py smoke 2>&1 | tail -3 | tee gpurun_out/${TAG}_smoke.log
 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; cut -c1-300 gpurun_out/${TAG}_bench_n1.json
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_ref.json 2>> gpurun_out/${TAG}_bench.err; echo "reference arm rc=$?"
-python bench.py --workload nn_sweep --steps 5 --warmup 3 > gpurun_out/${TAG}_nn_sweep.json 2>> gpurun_out/${TAG}_bench.err; echo "nn_sweep rc=$?"
+python bench.py --workload nn_sweep --steps 3 --warmup 3 > gpurun_out/${TAG}_nn_sweep.json 2>> gpurun_out/${TAG}_bench.err; echo "nn_sweep rc=$?"
 python scripts/gpu_normals_time.py 2>&1 | tail -1 | tee gpurun_out/${TAG}_normals.log
 SMALL="python bench.py --steps 2 --warmup 1 --no-e2e --cpu-sample-pairs 0"
 $SMALL > gpurun_out/${TAG}_plain.log 2>&1 &&
