@@ -506,3 +506,21 @@ def test_pcl_adapter_header_compiles_and_links(mvr, tmp_path):
     assert out.returncode == 0, out.stderr
     if not torch.cuda.is_available():
         assert "no usable CUDA device" in out.stdout
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU oracle port timed on the host cores) on a tiny configuration: one JSON line with the
+    keys the driver reads; under torchrun only rank 0 prints."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--views", "4", "--points", "3000", "--iters", "4",
+           "--steps", "1", "--warmup", "0", "--cpu-sample-pairs", "2"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="0"))
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["unit"] == "queries/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["views"] == 4 and d["config"]["points_per_view"] == 3000
+    quiet = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1"))
+    assert quiet.returncode == 0 and quiet.stdout.strip() == ""
