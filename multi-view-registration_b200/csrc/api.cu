@@ -110,7 +110,7 @@ struct mvr_ctx {
   PairIndex pt, ps;              // target / source index of the running align
   PairIndex nt, nq;              // target / query index of the dense NN pass (cell_nn.cu)
   double nn_ppc = 8.0;           // its target points per occupied cell
-  double nn_dense_ratio = 8.0;   // queries per target point from which the dense pass is used (0: never)
+  double nn_dense_ratio = 8.0;   // kept for mvr_ctx_set_nn_options (unused: batches above nn_sorted_from are sorted and seeded)
   int nn_mode = MVR_NN_AUTO;     // mvr_ctx_set_nn_mode
   int nn_sorted_from = 262144;   // AUTO: batches larger than this are sorted by cell and answered by the seeded pass
   bool gate_mask = false;        // mvr_ctx_set_gate_mask

@@ -16,10 +16,9 @@
 //   k_pair_rerank  : the final position of a point = start[key] + number of points of its cell with a SMALLER
 //                    original index (its cell is ~10 contiguous records of tmp), so points of a cell end up in
 //                    ascending original index whatever order the atomics ran in: every sorted position, and with
-//                    it the order of every later reduction, is reproducible run to run.  The source also gets a
-//                    second copy s0 = its binning-time coordinates next to the coordinates that move.
+//                    it the order of every later reduction, is reproducible run to run.
 //
-// Algorithmic bytes per point: 16 read + 16 (32 with the s0 copy) written, + 8 B per cell.
+// Algorithmic bytes per point: 16 read + 16 written, + 8 B per cell.
 #include <algorithm>
 
 #include "launch.h"
