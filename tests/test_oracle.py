@@ -170,3 +170,62 @@ def test_normals_golden_and_plane(orc):
     n = orc.estimate_normals(pl, 12, viewpoint=(0, 0, 0))
     assert np.allclose(np.abs(n[:, 2]), 1.0, atol=1e-6) and np.all(n[:, 2] < 0)        # flipped towards the origin
     assert np.allclose(n[:, 3], 0.0, atol=1e-6)                                          # curvature of a plane
+
+
+def _xform_pinned(M, p):
+    """x' = ((m00*x + m01*y) + m02*z) + m03 in float32 without FMA (ICP's in-place transformCloud)."""
+    M = M.astype(np.float32)
+    x, y, z = p[:, 0].astype(np.float32), p[:, 1].astype(np.float32), p[:, 2].astype(np.float32)
+    out = np.ones_like(p, dtype=np.float32)
+    for r in range(3):
+        out[:, r] = ((M[r, 0] * x + M[r, 1] * y) + M[r, 2] * z) + M[r, 3]
+    return out
+
+
+def _kabsch(a, b):
+    """Eigen::umeyama(with_scaling = false) on double centroids / cross-covariance: b ~ R a + t."""
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    ma, mb = a.mean(axis=0), b.mean(axis=0)
+    S = (b - mb).T @ (a - ma) / len(a)
+    U, _, Vt = np.linalg.svd(S)
+    D = np.eye(3)
+    if np.linalg.det(U) * np.linalg.det(Vt) < 0:
+        D[2, 2] = -1.0
+    R = U @ D @ Vt
+    T = np.eye(4)
+    T[:3, :3] = R
+    T[:3, 3] = mb - R @ ma
+    return T
+
+
+@pytest.mark.parametrize("reciprocal", [True, False])
+def test_icp_loop_against_an_independent_numpy_restatement(orc, synth, reciprocal):
+    """The WHOLE loop of pcl::IterativeClosestPoint::computeTransformation (SURVEY.md A3-A10) restated with numpy brute force
+    and numpy's SVD -- guess applied in float, exact NN with lowest-index ties, (reciprocal test,) double gate, Kabsch on
+    double sums, increment cast to float and applied in place, final = increment * final -- against the oracle's C loop:
+    the correspondence count of every iteration equal, every increment and the final pose equal to float rounding."""
+    views, poses = synth.turntable_sequence(12, 1500)
+    src, tgt = views[1], views[0]
+    guess = (synth.perturbation() @ np.linalg.inv(poses[0]) @ poses[1]).astype(np.float32)
+    iters, max_dist = 6, 4.0
+    o = orc.icp_align(src, tgt, orc.make_params(max_iterations=iters, max_dist=max_dist, reciprocal=reciprocal, fixed_iterations=True), guess=guess)
+    assert o["status"] == 0 and o["iterations"] == iters
+    cur = _xform_pinned(guess, src)
+    final = guess.astype(np.float64)
+    for it in range(iters):
+        D = d2_pinned(cur, tgt)
+        j = D.argmin(axis=1)
+        d = D[np.arange(len(cur)), j]
+        keep = ~(d.astype(np.float64) > max_dist * max_dist)
+        if reciprocal:
+            keep &= D.T.argmin(axis=1)[j] == np.arange(len(cur))
+        rec = o["log"][it]
+        assert rec["n_corr"] == int(keep.sum()), "iteration %d" % it
+        assert rec["mse"] == pytest.approx(float(d[keep].astype(np.float64).mean()), rel=1e-12)
+        T = _kabsch(cur[keep, :3], tgt[j[keep], :3]).astype(np.float32)
+        assert np.allclose(rec["delta"], T.astype(np.float64), rtol=0, atol=2e-6 * max(1.0, np.abs(T[:3, 3]).max()))
+        Tf = rec["delta"].astype(np.float32)      # continue from the oracle's own increment: rounding does not accumulate
+        cur = _xform_pinned(Tf, cur)
+        final = Tf.astype(np.float64) @ final
+    assert np.array_equal(o["final"], final.astype(np.float32))
+    assert np.array_equal(o["cloud"][:, :3], _xform_pinned(o["final"], src)[:, :3])
