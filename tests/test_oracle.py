@@ -229,3 +229,45 @@ def test_icp_loop_against_an_independent_numpy_restatement(orc, synth, reciproca
         final = Tf.astype(np.float64) @ final
     assert np.array_equal(o["final"], final.astype(np.float32))
     assert np.array_equal(o["cloud"][:, :3], _xform_pinned(o["final"], src)[:, :3])
+
+
+def test_point_to_plane_and_normals_against_numpy(orc, synth):
+    """TransformationEstimationPointToPlaneLLS and the kNN-PCA normals (A13) restated with numpy: the 6-vector
+    from numpy's least squares over the rows [cross(s, n), n | n.(d - s)], the pose from the same Rz Ry Rx composition;
+    normals from numpy's brute-force k nearest neighbours and numpy's symmetric eigen-solver."""
+    rng = np.random.default_rng(11)
+    tgt = synth.full_object(3000, seed=5)
+    k = 12
+    nrm, nbr = orc.estimate_normals(tgt, k, viewpoint=(0, 0, 0), want_neighbours=True)
+    # normals: brute-force kNN (self included, (d2, index) order) + smallest eigenvector of the neighbours' covariance
+    D = d2_pinned(tgt, tgt)
+    order = np.lexsort((np.broadcast_to(np.arange(len(tgt)), D.shape), D), axis=1)[:, :k]
+    assert np.array_equal(nbr, order.astype(np.int32))
+    for i in rng.integers(0, len(tgt), 200):
+        P = tgt[order[i], :3].astype(np.float64)
+        C = np.cov(P.T, bias=True)
+        w, V = np.linalg.eigh(C)
+        n = V[:, 0]
+        if n @ (0.0 - tgt[i, :3].astype(np.float64)) < 0:
+            n = -n
+        assert abs(float(n @ nrm[i, :3].astype(np.float64))) > 1 - 1e-6 and float(n @ nrm[i, :3]) > 0
+        assert nrm[i, 3] == pytest.approx(w[0] / w.sum(), rel=1e-4, abs=1e-7)
+    # point-to-plane: a small known motion, correspondences by index
+    T = synth.rotation_about_axis(np.deg2rad(0.4), axis=(0.2, 1.0, -0.5))
+    T[:3, 3] += [0.3, -0.2, 0.1]
+    Ti = np.linalg.inv(T)
+    src = np.ones_like(tgt)
+    src[:, :3] = (tgt[:, :3].astype(np.float64) @ Ti[:3, :3].T + Ti[:3, 3]).astype(np.float32)
+    idx = np.arange(len(tgt), dtype=np.int32)
+    rc, To = orc.estimate_point_to_plane(src, tgt, nrm, idx, idx)
+    assert rc == 1 or rc == 0
+    s, d, n = src[:, :3].astype(np.float64), tgt[:, :3].astype(np.float64), nrm[:, :3].astype(np.float64)
+    A = np.concatenate([np.cross(s, n), n], axis=1)
+    b = np.einsum("ij,ij->i", n, d - s)
+    x = np.linalg.lstsq(A, b, rcond=None)[0]
+    ca, sa, cb, sb, cg, sg = np.cos(x[0]), np.sin(x[0]), np.cos(x[1]), np.sin(x[1]), np.cos(x[2]), np.sin(x[2])
+    R = np.array([[cg * cb, -sg * ca + cg * sb * sa, sg * sa + cg * sb * ca],
+                  [sg * cb, cg * ca + sg * sb * sa, -cg * sa + sg * sb * ca],
+                  [-sb, cb * sa, cb * ca]])
+    assert np.allclose(To[:3, :3], R, atol=1e-9) and np.allclose(To[:3, 3], x[3:], atol=1e-7)
+    assert np.allclose(To[:3, :3], T[:3, :3], atol=5e-5)          # one linearised step lands close to the motion
