@@ -271,3 +271,33 @@ def test_point_to_plane_and_normals_against_numpy(orc, synth):
                   [-sb, cb * sa, cb * ca]])
     assert np.allclose(To[:3, :3], R, atol=1e-9) and np.allclose(To[:3, 3], x[3:], atol=1e-7)
     assert np.allclose(To[:3, :3], T[:3, :3], atol=5e-5)          # one linearised step lands close to the motion
+
+
+def test_denoise_oracle_equals_the_delaunay_construction(orc, synth):
+    """PointCloud::denoise takes its edges from a 3-D Delaunay triangulation (mvr/src/point_cloud.cpp:469-497: every edge no
+    longer than triangle_length) and labels connected components; the oracle (and the GPU kernel) use the plain radius
+    graph.  The two have the same components (the short edges of the Euclidean minimum spanning tree lie in both): checked
+    here against scipy's Delaunay triangulation, kept points and their output order."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(21)
+    obj = synth.full_object(2500, seed=9)[:, :3].astype(np.float64)
+    blobs = np.concatenate([c + rng.normal(size=(m, 3)) * 0.8 for c, m in (((150.0, 0.0, 900.0), 14), ((-150.0, 30.0, 905.0), 6), ((0.0, 160.0, 880.0), 9))])
+    lone = rng.uniform(-200, 200, size=(25, 3)) + [0, 0, 900]
+    pts = np.concatenate([obj, blobs, lone])
+    pts = pts[rng.permutation(len(pts))].astype(np.float32).astype(np.float64)   # the oracle gets float records: the same coordinates
+    n = len(pts)
+    for length, thr in ((6.0, 10), (4.0, 8), (9.0, 12)):
+        tri = Delaunay(pts)
+        e = np.concatenate([tri.simplices[:, [a, b]] for a in range(4) for b in range(a + 1, 4)])
+        e = e[np.linalg.norm(pts[e[:, 0]] - pts[e[:, 1]], axis=1) <= length]
+        _, label = connected_components(coo_matrix((np.ones(len(e), np.int8), (e[:, 0], e[:, 1])), shape=(n, n)), directed=False)
+        size = np.bincount(label)
+        first = np.full(len(size), n)
+        np.minimum.at(first, label, np.arange(n))
+        keep = np.flatnonzero(size[label] >= thr)
+        keep = keep[np.lexsort((keep, first[label[keep]]))]
+        okeep, onoise = orc.denoise(np.concatenate([pts, np.ones((n, 1))], axis=1).astype(np.float32), thr, length)
+        assert onoise == n - len(keep) and np.array_equal(okeep, keep.astype(np.int32))
+        assert 0 < onoise < n
