@@ -301,3 +301,45 @@ def test_denoise_oracle_equals_the_delaunay_construction(orc, synth):
         okeep, onoise = orc.denoise(np.concatenate([pts, np.ones((n, 1))], axis=1).astype(np.float32), thr, length)
         assert onoise == n - len(keep) and np.array_equal(okeep, keep.astype(np.int32))
         assert 0 < onoise < n
+
+
+def test_convergence_criteria_and_fitness_against_numpy(orc, synth):
+    """DefaultConvergenceCriteria replayed in numpy over the oracle's own iteration log -- iteration cap,
+    transform epsilon, absolute and relative mse, in that order, prev_mse starting at DBL_MAX -- must stop where the oracle
+    stopped and for the same reason; getFitnessScore (A9) = mean of the un-gated NN d2 of the aligned cloud within max_range."""
+    import sys
+    views, poses = synth.turntable_sequence(12, 1500)
+    src, tgt = views[1], views[0]
+    guess = (synth.perturbation() @ np.linalg.inv(poses[0]) @ poses[1]).astype(np.float32)
+    cases = [dict(max_iterations=50, transformation_epsilon=1e-7, euclidean_fitness_epsilon=1e-9),
+             dict(max_iterations=50, transformation_epsilon=0.0, euclidean_fitness_epsilon=1e-3),
+             dict(max_iterations=4, transformation_epsilon=0.0, euclidean_fitness_epsilon=0.0),
+             dict(max_iterations=50, transformation_epsilon=1e-4, euclidean_fitness_epsilon=0.0)]
+    seen = set()
+    for c in cases:
+        o = orc.icp_align(src, tgt, orc.make_params(max_dist=4.0, reciprocal=True, **c), guess=guess)
+        full = orc.icp_align(src, tgt, orc.make_params(max_iterations=c["max_iterations"], max_dist=4.0, reciprocal=True, fixed_iterations=True), guess=guess)
+        prev, stop, why = sys.float_info.max, None, None
+        for it, rec in enumerate(full["log"], start=1):
+            T = rec["delta"]
+            cos_angle = 0.5 * (np.trace(T[:3, :3]) - 1.0)
+            t2 = float(T[:3, 3] @ T[:3, 3])
+            if it >= c["max_iterations"]:
+                stop, why = it, 1
+            elif cos_angle >= 1.0 - c["transformation_epsilon"] and t2 <= c["transformation_epsilon"]:
+                stop, why = it, 2
+            elif abs(rec["mse"] - prev) < 1e-12:
+                stop, why = it, 3
+            elif abs(rec["mse"] - prev) / prev < c["euclidean_fitness_epsilon"]:
+                stop, why = it, 4
+            if stop:
+                break
+            prev = rec["mse"]
+        assert (o["iterations"], o["reason"]) == (stop, why), c
+        assert [r["n_corr"] for r in o["log"]] == [r["n_corr"] for r in full["log"][:stop]]
+        seen.add(why)
+    assert {1, 2, 4} <= seen
+    D = d2_pinned(o["cloud"], tgt).min(axis=1).astype(np.float64)
+    assert orc.fitness_score(o["cloud"], tgt) == pytest.approx(D.mean(), rel=1e-13)
+    lim = float(np.median(D))
+    assert orc.fitness_score(o["cloud"], tgt, max_range=lim) == pytest.approx(D[D <= lim].mean(), rel=1e-13)
