@@ -187,10 +187,13 @@ int mvr_correspondences(mvr_ctx* ctx, double max_dist, int reciprocal, int32_t* 
 int mvr_icp_align(mvr_ctx* ctx, const mvr_icp_params* params, const float* guess, float* out_pose, float* out_xyzw,
                   mvr_icp_report* report);
 /* `count` aligns in lock-step: context k holds pair k's source and target, every pair advances one iteration per
- * kernel launch (one launch serves the whole batch -- a single scan pair does not fill a B200).  Results are those of
- * `count` separate mvr_icp_align calls.  guesses: count x float[16] (nullable: identities), out_poses: count x
- * float[16], statuses: count x mvr_status of the individual aligns; the return value reports batch-level failures.
- * All contexts must live on one device; the work runs on the first context's stream. */
+ * kernel launch (one launch serves a group of pairs -- a single scan pair does not fill a B200; the groups of a batch,
+ * by default a quarter of it each, run concurrently on the streams of their first contexts).  Results are those of
+ * `count` separate mvr_icp_align calls, bit for bit, whatever the grouping.  guesses: count x float[16] (nullable:
+ * identities), out_poses: count x float[16], statuses: count x mvr_status of the individual aligns; the return value
+ * reports batch-level failures.  All contexts must live on one device.  Afterwards every context answers
+ * mvr_icp_get_iterations, mvr_fitness_score and mvr_copy_aligned_device for its own align (the log is fetched and the
+ * aligned cloud computed at that moment). */
 int mvr_icp_align_batch(mvr_ctx* const* ctxs, int count, const mvr_icp_params* params, const float* guesses, float* out_poses,
                         mvr_icp_report* reports, int* statuses);
 /* Pairs per kernel launch of the batches this context leads (1..24; 0 = automatic, the default: a quarter of the batch).  The
