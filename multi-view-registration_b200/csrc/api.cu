@@ -924,15 +924,15 @@ int mvr_correspondences(mvr_ctx* ctx, double max_dist, int reciprocal, int32_t* 
 }
 
 // ---- the align behind mvr_icp_align, mvr_icp_align_batch and mvr_pair_moments_compute ------------------------------
-// An align is split in three so that many of them can advance in lock-step, ONE launch per iteration half for the
-// whole batch (a single 200k-point pair fills a fraction of a B200):
-//   align_plan / align_prepare_batch : per context on the host -- grids, buffers, initial state, kernel arguments; then for
-//                   the whole batch on the first context's stream -- every per-align index (four launches), the seeds,
-//                   gates and initial states (one launch);
+// An align is split in three so that many of them can advance in lock-step, ONE launch per iteration half for a
+// group of pairs (a single 200k-point pair fills a fraction of a B200):
+//   align_plan / align_prepare_batch : per context on the host -- grids, buffers, initial state, kernel arguments; then per
+//                   group of pairs, on the group's stream -- every per-align index (four launches), the seeds, gates and
+//                   initial states (one launch);
 //   align_run     : the iterations of every context of the batch (groups of pairs, each group on the stream of its first context);
 //   align_finish  : per context -- report; the aligned cloud and the iteration log are produced when asked for.
 // est = EST_MOM accumulates second moments next to the point-to-point sums (those of the LAST iteration's pairs).
-// S: the stream the batch's preparation runs on; jobs: receives the index builds this align needs.
+// S: the stream the pair's group prepares and runs on; jobs: receives the index builds this align needs.
 static int align_plan(mvr_ctx* ctx, const mvr_icp_params* prm, const float* guess, int est, cudaStream_t S, std::vector<BuildJob>& jobs) {
   cudaSetDevice(ctx->device);
   if (ctx->tgt.gen == 0 || ctx->src.gen == 0) return fail(ctx, MVR_ERR_NO_INPUT, "source/target not set");
